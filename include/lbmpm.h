@@ -1,0 +1,198 @@
+/*
+ * lbmpm.h -- C ABI of liblbmpm.so: the B200-native collision + streaming hot path of
+ * openLBMPM (multiphase lattice Boltzmann, D2Q9 and D3Q19).
+ *
+ * This is the drop-in boundary.  The reference has no native layer: its host
+ * drivers call Numba-CUDA kernels as `K[grid, block](scalars..., device arrays...)`
+ * from a per-step Python loop.  Each entry point below replaces one block of that
+ * driver code; the citation after every prototype is the reference code it stands
+ * in for (paths relative to the reference repository, commit 3d84189).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative LBM_E* code, and never
+ *     throws; `lbm_last_error` gives the message of the last failure on a handle
+ *     (or of the last failed `lbm_create` when called with NULL);
+ *   - host buffers are owned by the caller, C-contiguous, float64 / int64 / uint8;
+ *     device buffers are owned by the handle;
+ *   - dense arrays are `[z][y][x]` row-major (2-D: nz = 1, i.e. the reference's
+ *     `[y][x]`); population arrays are the reference's AoS `[z][y][x][Q]`
+ *     (RKD2Q9.py:451-452); the SoA <-> AoS transposition happens in
+ *     upload/download, never on the timed path;
+ *   - one host thread per handle; all device work is stream-ordered on a
+ *     handle-owned stream; `lbm_step` is asynchronous, downloads synchronise;
+ *   - there is NO CPU fallback: every entry point that computes needs the GPU.
+ */
+#ifndef LBMPM_H
+#define LBMPM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_ABI_VERSION 1
+
+/* error codes */
+#define LBM_OK          0
+#define LBM_EINVAL     -1   /* bad argument / unsupported combination            */
+#define LBM_ECUDA      -2   /* a CUDA runtime call failed                        */
+#define LBM_ESTATE     -3   /* call order (e.g. step before geometry/state)      */
+#define LBM_ENOMEM     -4
+#define LBM_ENCCL      -5
+
+/* lbm_config.model */
+#define LBM_MODEL_CG    0   /* Rothman-Keller colour gradient, CSF   (RKCG2D/)          */
+#define LBM_MODEL_SC    1   /* original Shan-Chen                    (ShanChen2D/Optimized...)  */
+#define LBM_MODEL_EFS   2   /* explicit-forcing Shan-Chen SRT/MRT    (ShanChen2D/Explicit...)   */
+
+/* lbm_config.relax */
+#define LBM_RELAX_SRT   0
+#define LBM_RELAX_MRT   1
+
+/* lbm_config.inlet  (top of the flow axis: y in 2-D, z in 3-D) */
+#define LBM_BC_PERIODIC          0
+#define LBM_INLET_VELOCITY       1   /* ini: BoundaryTypeInlet = 'Neumann'   */
+#define LBM_INLET_PRESSURE       2   /* ini: BoundaryTypeInlet = 'Dirichlet' */
+/* lbm_config.outlet (bottom of the flow axis) */
+#define LBM_OUTLET_CONVECTIVE    1   /* ini: BoundaryTypeOutlet = 'Convective' */
+#define LBM_OUTLET_PRESSURE      2   /* ini: BoundaryTypeOutlet = 'Dirichlet'  */
+
+/* lbm_config.flags */
+#define LBM_FLAG_GENERIC_KERNELS 1u  /* force the unfused reference-ordered kernel sequence */
+
+typedef struct lbm_handle lbm_handle;
+
+/* Plain-old-data configuration: the numbers the reference reads from IniFiles/*.ini
+ * (RKD2Q9.py:24-297, ShanChenD2Q9.py:39-496).  Zero-initialise, then fill.        */
+typedef struct lbm_config {
+    int32_t abi_version;       /* = LBM_ABI_VERSION                                         */
+    int32_t lattice;           /* 9 (D2Q9) or 19 (D3Q19)                                    */
+    int32_t model;             /* LBM_MODEL_*                                               */
+    int32_t nx, ny, nz;        /* xDomain, yDomain, zDomain (nz = 1 for D2Q9)               */
+    int32_t relax;             /* [RelaxationType] Type                                     */
+    int32_t tau_type;          /* [FluidParameters] TauType 1|2        (CG)                 */
+    int32_t wetting_type;      /* [SurfaceTension] WettingType 1|2     (CG)                 */
+    int32_t inlet, outlet;     /* LBM_BC_* / LBM_INLET_* / LBM_OUTLET_*                     */
+    int32_t device;            /* CUDA device ordinal                                       */
+    uint32_t flags;
+    int32_t n_components;      /* SC/EFS: number of fluids (1..4); CG: ignored (2 colours)  */
+    int32_t reserved_i[3];
+    /* colour gradient */
+    double sigma;              /* [SurfaceTension] SurfaceTension(Value)                    */
+    double contact_angle_deg;  /* [SurfaceTension] ContactAngle                             */
+    double beta;               /* [RKParameters] BetaThickness                              */
+    double delta;              /* [RKParameters] DeltaValue                                 */
+    double tauR, tauB;         /* [FluidParameters] TauR, TauB                              */
+    double inlet_velocity;     /* velocityYR + velocityYB (RKD2Q9.py:1300)                  */
+    double rhoBH, rhoRH;       /* densityBH, densityRH  (pressure inlet)                    */
+    double rhoBL, rhoRL;       /* densityBL, densityRL  (pressure outlet)                   */
+    /* Shan-Chen / explicit forcing (per component, up to 4) */
+    double sc_tau[4];          /* [FluidProperties] tau                                     */
+    double sc_G[16];           /* interaction matrix G[s][s'] row-major (n x n used)        */
+    double sc_Gsolid[4];       /* fluid-solid interaction strengths                         */
+    double sc_inlet_velocity[4];
+    double sc_rho_in[4], sc_rho_out[4];
+    double reserved_d[8];
+} lbm_config;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Replaces the constructor side of the drivers: constants, MRT matrices and all
+ * `cuda.to_device` allocations (RKD2Q9.py:299-340, 1243-1287; ShanChenD2Q9.py:1447-1485). */
+int lbm_create(const lbm_config* cfg, lbm_handle** out);
+int lbm_destroy(lbm_handle* h);
+const char* lbm_last_error(const lbm_handle* h);
+int lbm_abi_version(void);
+
+/* ---- geometry and indexing -------------------------------------------------------------- */
+
+/* is_domain: uint8 dense [nz][ny][nx], 1 = void (fluid), 0 = solid -- the `isDomain` array
+ * produced by SimpleGeometry.defineGeometry / the structure image (RKD2Q9.py:417-443).
+ * Builds on the device everything the reference builds with Python loops:
+ * node classes, wetting-solid set, fluid nodes next to solid and the unit normals n_s
+ * (RKD2Q9.py:657-892).                                                                     */
+int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain);
+
+/* Sizes of the reference's index structures for the current geometry:
+ * n_fluid = fluidNodes.size, n_wet_solid = wettingSolidNodes.size,
+ * n_fluid_near_solid = fluidNodesWithSolidGPU.size.                                        */
+int lbm_index_sizes(lbm_handle* h, int64_t* n_fluid, int64_t* n_wet_solid, int64_t* n_fluid_near_solid);
+
+/* Bit-exact export of the reference's integer structures (any pointer may be NULL):
+ *   fluid_nodes[n_fluid]                 fluidNodes                     RKD2Q9.py:665-676
+ *   neighbors[8|18 * n_fluid]            neighboringNodes               AcceleratedRKGPU2D.py:14-52
+ *   wet_solid_nodes[n_wet_solid]         wettingSolidNodes              RKD2Q9.py:677-689
+ *   wet_solid_neighbors[8|18 * n_wet]    neighboringWettingSolidNodes   AcceleratedRKGPU2D.py:57-95
+ *   near_solid_compact[n_near]           fluidNodesWithSolidGPU         RKD2Q9.py:741-760
+ *   near_solid_flat[n_near]              fluidNodesWithSolidOriginal
+ *   ns[D * n_near]                       nsX, nsY(, nsZ) component-major RKD2Q9.py:768-892
+ * Compact ids: >= 0 fluid rank, -1 solid away from fluid, <= -2 wetting solid (-2 - rank).  */
+int lbm_export_indexing(lbm_handle* h, int64_t* fluid_nodes, int64_t* neighbors,
+                        int64_t* wet_solid_nodes, int64_t* wet_solid_neighbors,
+                        int64_t* near_solid_compact, int64_t* near_solid_flat, double* ns);
+
+/* ---- state ------------------------------------------------------------------------------ */
+
+/* f = w_i * rho at rest for every void node: the reference's initial condition
+ * (RKD2Q9.py:561-585 with zero velocity; ShanChenD2Q9.py:734-786).
+ * CG: rho[0] = rhoR, rho[1] = rhoB; SC/EFS: one dense array per component.
+ * rho: n_comp pointers to dense [nz][ny][nx].  Resets the lagged force to zero.            */
+int lbm_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp);
+
+/* Upload populations in the reference's dense AoS layout [nz][ny][nx][Q] per component
+ * (fluidPDFR / fluidPDFB, RKD2Q9.py:451-452; fluidPDF[nf], ShanChenD2Q9.py:740) and the
+ * matching densities (NULL entries: computed as the population sums) -- the restart path
+ * of RKD2Q9.py:491-559.                                                                    */
+int lbm_upload_state(lbm_handle* h, const double* const* pdf, const double* const* rho, int32_t n_comp);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+
+/* Advance nsteps iterations of the reference's per-step loop
+ * (CG: RKD2Q9.py:1295-1490; SC: ShanChenD2Q9.py:1492-1629; EFS: ShanChenD2Q9.py:1852-2087),
+ * asynchronously on the handle's stream.                                                   */
+int lbm_step(lbm_handle* h, int32_t nsteps);
+int lbm_synchronize(lbm_handle* h);
+
+/* ---- results ---------------------------------------------------------------------------- */
+
+/* What the reference copies to the host at an output interval (RKD2Q9.py:1382-1393,
+ * convertOptTo2D :902-911): densities after this step's boundary treatment and the
+ * velocity evaluated with the lagged force.  Dense [nz][ny][nx], zero on solid nodes.
+ * rho: n_comp pointers; u: up to 3 pointers (x, y, z); any pointer may be NULL.            */
+int lbm_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u);
+
+/* Populations in the reference's dense AoS layout [nz][ny][nx][Q] per component
+ * (fluidPDFR/B at the same output point).                                                  */
+int lbm_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp);
+
+/* Auxiliary per-node fields of the last completed step, dense [nz][ny][nx] (NULL = skip):
+ * phi (colour field incl. wetting-solid values), G (D arrays), F (D arrays), K.            */
+int lbm_download_fields(lbm_handle* h, double* phi, double* const* G, double* const* F, double* K);
+
+/* Sum of each component's density over the void nodes (mass check).                        */
+int lbm_total_mass(lbm_handle* h, double* mass, int32_t n_comp);
+
+/* ---- measurement ------------------------------------------------------------------------ */
+
+/* CUDA-event time of the last lbm_step call (ms, on the handle's stream), number of kernel
+ * launches it issued and number of void nodes it updated per step.                         */
+int lbm_get_timing(lbm_handle* h, double* last_step_call_ms, int64_t* kernel_launches, int64_t* nodes_per_step);
+
+/* Device-resident benchmark initialiser: spinodal start rhoR = 0.5 + amp*(U-0.5), rhoB = 1-rhoR
+ * with a counter-based hash of (seed, node id) -- no host buffers involved.                */
+int lbm_init_spinodal_device(lbm_handle* h, double amplitude, uint64_t seed);
+
+/* ---- multi-GPU slab decomposition (one handle per rank, one rank per GPU) --------------- */
+
+/* Fills 128 bytes with an NCCL unique id (rank 0 calls it, the host framework broadcasts it). */
+int lbm_nccl_unique_id(uint8_t id_out[128]);
+/* Declares this handle to be slab `rank` of `nranks` along the flow axis (z in 3-D, y in 2-D):
+ * cfg.nz (ny) is the LOCAL slab thickness; ghost planes are exchanged every step with
+ * ncclSend/ncclRecv to rank+-1 (periodic ring).  Must precede lbm_set_geometry.              */
+int lbm_comm_init(lbm_handle* h, int32_t rank, int32_t nranks, const uint8_t id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBMPM_H */
