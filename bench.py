@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the D3Q19 colour-gradient MRT collision + streaming step on a periodic box.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                      (CPU arm: the oracle port on the host cores)
+
+One "step" = one lattice time step of the whole box (every void node collides, is recoloured and
+streams once).  N = 1: the metric's own configuration, 512^3 periodic spinodal start (BASELINE.json
+`metric`); N > 1: the same box slab-partitioned along z ("strong" scaling, ghost planes over NCCL).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = {19: 2 * 19 * 8 * 2, 9: 2 * 9 * 8 * 2}     # one read + one write of every population
+SPIN_AMP, SPIN_SEED = 0.01, 20260117
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def pinned_empty(shape):
+    """host buffer in pinned memory (torch is only the allocator here)"""
+    import torch
+    t = torch.empty(shape, dtype=torch.float64, pin_memory=torch.cuda.is_available())
+    return t, t.numpy()
+
+
+def spinodal_host(shape, rank=0):
+    rng = np.random.default_rng(SPIN_SEED + rank)
+    return 0.5 + SPIN_AMP * (rng.random(shape) - 0.5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement on the host cores (bounded sample of the same workload)
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_mlups(lattice, n, steps, threads=None):
+    from oracle import cg_c
+    threads = threads or os.cpu_count()
+    shape = (n, n, n) if lattice == 19 else (n, n)
+    rhoR = spinodal_host(shape)
+    sim = cg_c.CGC(lattice, np.ones(shape, bool), threads=threads)
+    sim.set_densities(rhoR, 1.0 - rhoR)
+    sim.step(1)
+    t0 = time.perf_counter()
+    sim.step(steps)
+    dt = time.perf_counter() - t0
+    return rhoR.size * steps / dt / 1e6, threads, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lattice = args.lattice
+    n = args.cpu_size
+    cores = os.cpu_count()
+    per_step = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_mlups(lattice, n, 1, cores)
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        v, cores, dt = cpu_oracle_mlups(lattice, n, args.cpu_steps, cores)
+        vals.append(v); per_step.append(dt / args.cpu_steps * 1e3)
+    v = float(np.median(vals))
+    sample = "%s periodic spinodal box, %d steps per sample, oracle/cg_c (C + OpenMP restatement of the reference loop)" % (
+        "x".join([str(n)] * (3 if lattice == 19 else 2)), args.cpu_steps)
+    line = {"impl": "reference", "metric": "MLUPS D3Q19 CG-MRT periodic box" if lattice == 19 else "MLUPS D2Q9 CG-MRT periodic box",
+            "value": v, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.median(per_step)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    if args.lattice == 19:
+        return "D3Q19 colour-gradient CSF MRT, %d^3 periodic all-fluid box, spinodal start (BASELINE metric)" % args.size
+    return "D2Q9 colour-gradient CSF MRT, %d^2 periodic all-fluid box, spinodal start" % args.size
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--lattice", type=int, default=19)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--general", action="store_true", help="force the general (unfused) kernels")
+    ap.add_argument("--cpu-size", type=int, default=128)
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from openlbmpm_b200 import _lib
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE")
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); the CPU arm is --impl reference")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    Q, n = args.lattice, args.size
+    if n % world:
+        raise SystemExit("size must be divisible by the number of GPUs")
+    nloc = n // world
+    shape = (nloc, n, n) if Q == 19 else (nloc, n)
+    flags = _lib.FLAG_GENERIC_KERNELS if args.general else 0
+    eng = _lib.Engine(Q, shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, device=local, flags=flags,
+                      sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.from_numpy(eng.nccl_unique_id().copy())
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        eng.comm_init(rank, world, uid.cpu().numpy())
+    eng.set_geometry(np.ones(shape, np.uint8))
+    eng.init_spinodal_device(SPIN_AMP, SPIN_SEED)
+    nodes_total = float(n) ** (3 if Q == 19 else 2)
+
+    def barrier():
+        eng.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the timed region: K steps in one asynchronous lbm_step call -----------------
+    eng.step(args.warmup)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    eng.profile(True)
+    t0 = time.perf_counter()
+    eng.step(args.steps)
+    eng.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    tm = eng.timing()               # CUDA events on the handle's stream around the lbm_step call
+    prof = eng.profile_report()
+    eng.profile(False)
+    barrier()
+    clocks = sampler.summary() if sampler else None
+    dev_ms = tm["ms"]
+    if dist is not None:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = nodes_total / (ms_per_step * 1e-3) / 1e6
+    mass = eng.total_mass()
+
+    # ---- end to end through the C ABI with host buffers: upload densities -> K steps -> download macros
+    e2e = None
+    if not args.no_e2e:
+        keep = []
+        t_r, rhoR = pinned_empty(shape); keep.append(t_r)
+        t_b, rhoB = pinned_empty(shape); keep.append(t_b)
+        rhoR[...] = spinodal_host(shape, rank); rhoB[...] = 1.0 - rhoR
+        outs = [pinned_empty(shape) for _ in range(2 + eng.D)]
+        out_rho = [o[1] for o in outs[:2]]; out_u = [o[1] for o in outs[2:]]
+        barrier()
+        t0 = time.perf_counter()
+        eng.init_equilibrium(rhoR, rhoB)                 # H2D of this batch's input
+        eng.step(args.steps)
+        eng.download_macros(out_rho, out_u)              # D2H of the result (synchronises)
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": nodes_total * args.steps / e2e_s / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": 2 * rhoR.nbytes * world / args.steps,
+               "d2h_bytes_per_step": (2 + eng.D) * rhoR.nbytes * world / args.steps,
+               "batch": "init_equilibrium(host rhoR, rhoB) -> lbm_step(%d) -> download_macros(host), wall clock" % args.steps,
+               "finite": bool(np.isfinite(out_rho[0]).all())}
+
+    if rank != 0:
+        eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the step (all kernels of one time step; dominant kernel listed) ------------------
+    peak, peak_src = measured_peaks()
+    tot_prof = sum(ms for _, ms in prof.values()) or 1.0
+    kernels = sorted(({"name": k, "launches": c, "ms_per_launch": ms / c, "share": ms / tot_prof}
+                      for k, (c, ms) in prof.items()), key=lambda r: -r["share"])
+    step_kernel_ms = tot_prof / args.steps
+    alg_bytes = B_ALG[Q] * nodes_total / world           # per rank and step
+    achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "scope": "all kernels of one time step (%d launches/step), %d B per lattice update x %d nodes per GPU" % (
+                    round(sum(c for c, _ in prof.values()) / args.steps), B_ALG[Q], int(nodes_total / world)),
+                "kernels": kernels[:6]}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_step")
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        try:
+            v, cores, dt = cpu_oracle_mlups(Q, args.cpu_size, args.cpu_steps)
+            cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
+                   "sample": "%d^%d periodic spinodal box x %d steps (%.1f s), oracle/cg_c: C + OpenMP restatement of the "
+                             "reference's kernel-per-phase loop (the reference has no D3Q19 code and its Numba-CUDA "
+                             "kernels cannot run on host cores)" % (args.cpu_size, 3 if Q == 19 else 2, args.cpu_steps, dt)}
+        except Exception as e:       # the oracle is a checker; its absence must not hide the GPU number
+            cpu = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port", "sample": "unavailable: %r" % (e,)}
+
+    line = {"metric": "MLUPS D3Q19 CG-MRT 512^3" if (Q == 19 and n == 512) else "MLUPS %s CG-MRT %d" % ("D3Q19" if Q == 19 else "D2Q9", n),
+            "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "l2": "working set (%.1f GB) far larger than the 126 MB L2" % (
+                           2 * 2 * Q * 8 * nodes_total / 1e9),
+                       "path": "general kernels" if args.general else "fused fast path", "slab": list(shape)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["launches"],
+            "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
+            "mass": [float(mass[0]), float(mass[1])], "pct_hbm_roofline": 100.0 * achieved / peak}
+    print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -179,6 +179,11 @@ int lbm_total_mass(lbm_handle* h, double* mass, int32_t n_comp);
  * launches it issued and number of void nodes it updated per step.                         */
 int lbm_get_timing(lbm_handle* h, double* last_step_call_ms, int64_t* kernel_launches, int64_t* nodes_per_step);
 
+/* Per-kernel timing for the roofline leg of bench.py: while enabled, every kernel launch is bracketed by
+ * CUDA events on the handle's stream; the report is one line per kernel, "name<TAB>launches<TAB>total_ms". */
+int lbm_profile_enable(lbm_handle* h, int32_t on);
+int lbm_profile_report(lbm_handle* h, char* buf, int64_t buflen);
+
 /* Device-resident benchmark initialiser: spinodal start rhoR = 0.5 + amp*(U-0.5), rhoB = 1-rhoR
  * with a counter-based hash of (seed, node id) -- no host buffers involved.                */
 int lbm_init_spinodal_device(lbm_handle* h, double amplitude, uint64_t seed);

@@ -1,0 +1,143 @@
+// backend.h -- the few runtime services the library needs (device memory, copies, one-thread-
+// per-node launches, an exclusive scan), so that the SAME operator code builds
+//   * with nvcc for sm_100a  -> liblbmpm.so, the product, and
+//   * with g++ (LBM_HOSTCHECK) -> tests/hostcheck/libhostcheck.so, a test hook that lets the
+//     CPU-only test tier check the node arithmetic against the oracle without a GPU.
+// The Python package only ever loads liblbmpm.so; there is no CPU fallback in the product.
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <typeinfo>
+#include <vector>
+
+#ifndef LBM_HOSTCHECK
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#endif
+
+namespace lbm {
+
+#ifndef LBM_HOSTCHECK
+// ------------------------------------------------------------------ CUDA backend
+typedef cudaStream_t stream_t;
+
+struct BackendError {
+    std::string msg;
+};
+
+#define LBM_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            throw ::lbm::BackendError{std::string(#expr) + ": " + cudaGetErrorString(_e)};    \
+    } while (0)
+
+inline void* dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    LBM_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
+    return p;
+}
+inline void dev_free(void* p) {
+    if (p) cudaFree(p);
+}
+inline void dev_zero(void* p, size_t bytes, stream_t s) { LBM_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, s)); }
+inline void dev_h2d(void* d, const void* h, size_t bytes, stream_t s) {
+    LBM_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+    LBM_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+inline void dev_d2h(void* h, const void* d, size_t bytes, stream_t s) {
+    LBM_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+    LBM_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+inline void dev_d2d(void* d, const void* s_, size_t bytes, stream_t s) {
+    LBM_CUDA_CHECK(cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, s));
+}
+inline void dev_sync(stream_t s) { LBM_CUDA_CHECK(cudaStreamSynchronize(s)); }
+
+template <class Op>
+__global__ void __launch_bounds__(256) node_kernel(const Op op, const int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) op(i);
+}
+
+// one thread per item; counts launches for lbm_get_timing
+extern thread_local int64_t g_launch_counter;
+
+// optional per-launch CUDA-event timing on the launching stream (lbm_profile_enable / _report)
+struct ProfRecord { const char* name; cudaEvent_t e0, e1; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRecord> recs;
+    void begin(const char* name, stream_t s) {
+        ProfRecord r; r.name = name;
+        LBM_CUDA_CHECK(cudaEventCreate(&r.e0)); LBM_CUDA_CHECK(cudaEventCreate(&r.e1));
+        LBM_CUDA_CHECK(cudaEventRecord(r.e0, s));
+        recs.push_back(r);
+    }
+    void end(stream_t s) { LBM_CUDA_CHECK(cudaEventRecord(recs.back().e1, s)); }
+    void clear() {
+        for (auto& r : recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        recs.clear();
+    }
+};
+extern thread_local Profiler g_prof;
+
+template <class Op>
+inline void launch(const Op& op, int64_t n, stream_t s) {
+    if (n <= 0) return;
+    const int block = 256;
+    const int64_t grid = (n + block - 1) / block;
+    if (g_prof.on) g_prof.begin(typeid(Op).name(), s);
+    node_kernel<Op><<<(unsigned)grid, block, 0, s>>>(op, n);
+    if (g_prof.on) g_prof.end(s);
+    LBM_CUDA_CHECK(cudaGetLastError());
+    ++g_launch_counter;
+}
+
+inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, stream_t s) {
+    size_t tmp_bytes = 0;
+    LBM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, s));
+    void* tmp = dev_alloc(tmp_bytes);
+    LBM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, n, s));
+    LBM_CUDA_CHECK(cudaStreamSynchronize(s));
+    dev_free(tmp);
+    ++g_launch_counter;
+}
+
+#else
+// ------------------------------------------------------------------ host test hook
+typedef int stream_t;
+struct BackendError {
+    std::string msg;
+};
+inline void* dev_alloc(size_t bytes) {
+    void* p = malloc(bytes ? bytes : 8);
+    if (!p) throw BackendError{"malloc failed"};
+    return p;
+}
+inline void dev_free(void* p) { free(p); }
+inline void dev_zero(void* p, size_t bytes, stream_t) { memset(p, 0, bytes); }
+inline void dev_h2d(void* d, const void* h, size_t bytes, stream_t) { memcpy(d, h, bytes); }
+inline void dev_d2h(void* h, const void* d, size_t bytes, stream_t) { memcpy(h, d, bytes); }
+inline void dev_d2d(void* d, const void* s_, size_t bytes, stream_t) { memmove(d, s_, bytes); }
+inline void dev_sync(stream_t) {}
+extern thread_local int64_t g_launch_counter;
+template <class Op>
+inline void launch(const Op& op, int64_t n, stream_t) {
+    for (int64_t i = 0; i < n; ++i) op(i);
+    ++g_launch_counter;
+}
+inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, stream_t) {
+    int64_t acc = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = in[i];
+        out[i] = acc;
+        acc += v;
+    }
+}
+#endif
+
+}  // namespace lbm

@@ -1,0 +1,356 @@
+// cg_ops.cuh -- colour-gradient (CSF) step as one-thread-per-node operators on the dense grid, in the
+// order of the reference's loop body (RKD2Q9.py:1295-1490).  This is the GENERAL path: any mask,
+// wetting, open boundaries, SRT/MRT, D2Q9/D3Q19.  Populations are structure-of-arrays [Q][vol].
+// The fused fast path for closed (periodic / bounce-back) boxes lives in cg_fast.cu.
+#pragma once
+#include "grid.cuh"
+
+namespace lbm {
+
+struct CGFields {
+    Grid g;
+    CGParams p;
+    double* fS[2];      // streamed populations (what the reference holds between iterations), R and B
+    double* fC[2];      // post-collision populations
+    double* rho[2];     // rhoR, rhoB
+    double* u;          // [3][vol]
+    double* phi;        // colour field; on wetting solids: calColorValueOnSolid's value
+    double* G;          // [3][vol] colour gradient (after the wetting correction)
+    double* nrm;        // [3][vol] interface unit normal
+    double* F;          // [3][vol] CSF force (lagged by one step when the velocity is evaluated)
+    double* K;          // curvature
+    const uint8_t* cls;
+    const double* ns;   // [3][vol] solid normals
+    // open boundaries (global plane numbers along axis 2; -1000 = not on this slab)
+    int inlet, outlet;
+    int z_in, z_in_ghost, z_out, z_out_ghost, z_out2;
+    double v_in, rhoBH, rhoRH, rhoBL, rhoRL;
+};
+
+// f = w_i rho at rest (RKD2Q9.py:561-585 with u = 0); also clears the lagged force
+template <class L>
+struct InitEquilibriumOp {
+    CGFields c; const double* rhoR_in; const double* rhoB_in;    // dense owned [n2][n1][n0] on device
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)NG * c.g.plane + i;
+        const bool fl = c.cls[id] & CLS_FLUID;
+        const double r[2] = {fl ? rhoR_in[i] : 0.0, fl ? rhoB_in[i] : 0.0};
+        for (int k = 0; k < 2; ++k) {
+            c.rho[k][id] = r[k];
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) c.fS[k][q * c.g.vol + id] = L::w(q) * r[k];
+        }
+        for (int a = 0; a < 3; ++a) { c.F[a * c.g.vol + id] = 0.0; c.u[a * c.g.vol + id] = 0.0; }
+    }
+};
+
+// AoS [node][Q] (reference layout, RKD2Q9.py:451-452) <-> SoA [Q][vol]
+template <class L>
+struct AosToSoaOp {
+    Grid g; const double* aos; double* soa; const uint8_t* cls; double* rho; const double* rho_in;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)NG * g.plane + i;
+        const bool fl = cls[id] & CLS_FLUID;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) {
+            const double v = fl ? aos[i * L::Q + q] : 0.0;
+            soa[q * g.vol + id] = v;
+            s = q == 0 ? v : s + v;
+        }
+        rho[id] = fl ? (rho_in ? rho_in[i] : s) : 0.0;
+    }
+};
+template <class L>
+struct SoaToAosOp {
+    Grid g; const double* soa; double* aos;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)NG * g.plane + i;
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) aos[i * L::Q + q] = soa[q * g.vol + id];
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// open boundaries of the reference's 2-D driver (rows along the flow axis; inlet = top, outlet = bottom)
+// ------------------------------------------------------------------------------------------------
+// constantTotalVelocityInlet (AcceleratedRKGPU2D.py:2345-2423): non-equilibrium bounce-back of the
+// unknown populations of the TOTAL distribution on row z_in with u = (0, v), split by mass fraction.
+// Items: one row of n0 nodes.  (D2Q9 only: the reference has no 3-D code.)
+struct InletVelocity2DOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t x) const {
+        const Grid& g = c.g;
+        const int64_t id = g.at((int)x, 0, c.z_in);
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        const int64_t V = g.vol;
+        double* fR = c.fS[0]; double* fB = c.fS[1];
+        double fT[9];
+        for (int q = 0; q < 9; ++q) fT[q] = fR[q * V + id] + fB[q * V + id];
+        const double v = c.v_in;
+        const double rho = (fT[0] + fT[1] + fT[3] + 2.0 * (fT[2] + fT[5] + fT[6])) / (1.0 + v);
+        const double vv = v * v;
+        auto eq = [&](double w, double ev) { return rho * w * (1.0 + 3.0 * ev + 4.5 * ev * ev - 1.5 * vv); };
+        fT[4] = eq(1.0 / 9.0, -v) + (fT[2] - eq(1.0 / 9.0, v));
+        fT[7] = eq(1.0 / 36.0, -v) + (fT[5] - eq(1.0 / 36.0, v));
+        fT[8] = eq(1.0 / 36.0, -v) + (fT[6] - eq(1.0 / 36.0, v));
+        double rR = c.rho[0][id], rB = c.rho[1][id];
+        const double ratioR = rR / (rR + rB);
+        rR = ratioR * rho;
+        const double ratioB = rB / (rR + rB);     // uses the already-updated rhoR, like :2399-2407
+        rB = ratioB * rho;
+        c.rho[0][id] = rR; c.rho[1][id] = rB;
+        const int unk[3] = {4, 7, 8};
+        for (int k = 0; k < 3; ++k) {
+            fR[unk[k] * V + id] = ratioR * fT[unk[k]];
+            fB[unk[k] * V + id] = ratioB * fT[unk[k]];
+        }
+    }
+};
+// calConstPressureInletGPU (AcceleratedRKGPU2D.py:923-961): Zou-He pressure per colour on row z_in
+struct InletPressure2DOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t x) const {
+        const Grid& g = c.g;
+        const int64_t id = g.at((int)x, 0, c.z_in);
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        const int64_t V = g.vol;
+        for (int k = 0; k < 2; ++k) {
+            double* f = c.fS[k];
+            const double p = k == 0 ? c.rhoRH : c.rhoBH;
+            const double f1 = f[1 * V + id], f3 = f[3 * V + id];
+            const double v = -1.0 + (f[id] + f1 + f3 + 2.0 * (f[2 * V + id] + f[5 * V + id] + f[6 * V + id])) / p;
+            f[4 * V + id] = f[2 * V + id] - 2.0 / 3.0 * p * v;
+            f[7 * V + id] = f[5 * V + id] + 1.0 / 2.0 * (f1 - f3) - 1.0 / 6.0 * p * v;
+            f[8 * V + id] = f[6 * V + id] - 1.0 / 2.0 * (f1 - f3) - 1.0 / 6.0 * p * v;
+            c.rho[k][id] = p;
+        }
+    }
+};
+// calConstPressureLowerGPUTotal (AcceleratedRKGPU2D.py:2557-2602): Zou-He pressure on the total
+// distribution on row z_out with p = rhoBL + rhoRL (RKD2Q9.py:1344), split by mass fraction
+struct OutletPressure2DOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t x) const {
+        const Grid& g = c.g;
+        const int64_t id = g.at((int)x, 0, c.z_out);
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        const int64_t V = g.vol;
+        double* fR = c.fS[0]; double* fB = c.fS[1];
+        double fT[9];
+        for (int q = 0; q < 9; ++q) fT[q] = fR[q * V + id] + fB[q * V + id];
+        const double p = c.rhoBL + c.rhoRL;
+        const double v = 1.0 - 1.0 / p * (fT[0] + fT[1] + fT[3] + 2.0 * (fT[4] + fT[7] + fT[8]));
+        fT[2] = fT[4] + 2.0 / 3.0 * (p * v);
+        fT[5] = fT[7] + 0.5 * (fT[3] - fT[1]) + 1.0 / 6.0 * p * v;
+        fT[6] = fT[8] + 0.5 * (fT[1] - fT[3]) + 1.0 / 6.0 * p * v;
+        const double rR = c.rho[0][id], rB = c.rho[1][id];
+        const double ratioR = rR / (rR + rB), ratioB = rB / (rR + rB);
+        const int unk[3] = {2, 5, 6};
+        for (int k = 0; k < 3; ++k) {
+            fR[unk[k] * V + id] = ratioR * fT[unk[k]];
+            fB[unk[k] * V + id] = ratioB * fT[unk[k]];
+        }
+    }
+};
+// Row copies: ghostPointsConstantVelocityRK (604-650), ghostPointsConstPressureInletRK (966-1001),
+// ghostPointsConstPressureLowerRK (1043-1080), convectiveOutletGPU/Ghost2/Ghost3 (698-784):
+// row z_dst <- row z_src (populations of both colours); density = sum (sum_rho) or copied.
+// Rows are whole planes of axis 2, so the operator is lattice-generic.
+template <class L>
+struct RowCopyOp {
+    CGFields c; int z_dst, z_src; int sum_rho;
+    LBM_HD void operator()(int64_t r) const {
+        const Grid& g = c.g;
+        const int64_t d = (int64_t)(z_dst + NG) * g.plane + r, s = (int64_t)(z_src + NG) * g.plane + r;
+        if (!(c.cls[d] & CLS_FLUID) || !(c.cls[s] & CLS_FLUID)) return;
+        for (int k = 0; k < 2; ++k) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) {
+                const double v = c.fS[k][q * g.vol + s];
+                c.fS[k][q * g.vol + d] = v;
+                acc = q == 0 ? v : acc + v;
+            }
+            c.rho[k][d] = sum_rho ? acc : c.rho[k][s];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the loop body
+// ------------------------------------------------------------------------------------------------
+// calTotalFluidPDF (1413-1422) + calPhysicalVelocityRKGPU2DNew1 (2632-2653) + calPhaseFieldPhi
+// (1347-1356): u = (sum e fT + F_lagged / 2) / (rhoR + rhoB), phi = (rhoR - rhoB) / (rhoR + rhoB)
+template <class L>
+struct HeadOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        const int64_t id = (int64_t)NG * g.plane + i, V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        double mom[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            const double fT = c.fS[0][q * V + id] + c.fS[1][q * V + id];
+#pragma unroll
+            for (int a = 0; a < L::D; ++a)
+                if (L::c(q, a) != 0) mom[a] += L::c(q, a) * fT;
+        }
+        const double rR = c.rho[0][id], rB = c.rho[1][id];
+        const double rho = rB + rR;
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) c.u[a * V + id] = (mom[a] + 0.5 * c.F[a * V + id]) / rho;
+        c.phi[id] = (rR - rB) / (rR + rB);
+    }
+};
+
+// calColorValueOnSolid (1559-1580): phi_s = sum_{fluid nb} w phi / sum w, planes [-2, n2+2)
+template <class L>
+struct PhiSolidOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 2, x, y, z);
+        const int64_t id = g.at(x, y, z);
+        if (!(c.cls[id] & CLS_WET)) return;
+        double num = 0.0, den = 0.0;
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            const int64_t n = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
+            if (c.cls[n] & CLS_FLUID) { num += L::w(q) * c.phi[n]; den += L::w(q); }
+        }
+        c.phi[id] = den > 0.0 ? num / den : 0.0;
+    }
+};
+
+// calRKInitialGradient (1582-1632) + updateColorGradientOnWetting[New] (1637-1679 / 2428-2492) and the
+// unit normal that the curvature stencil gathers; planes [-1, n2+1)
+template <class L>
+struct GradientOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 1, x, y, z);
+        const int64_t id = g.at(x, y, z), V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        double G[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            const double v = L::w(q) * c.phi[g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q))];
+#pragma unroll
+            for (int a = 0; a < L::D; ++a)
+                if (L::c(q, a) != 0) G[a] += v * L::c(q, a);
+        }
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) G[a] *= 3.0;
+        if (c.cls[id] & CLS_NEAR) {
+            double ns[3] = {c.ns[id], c.ns[V + id], L::D == 3 ? c.ns[2 * V + id] : 0.0};
+            cg_wetting<L::D>(G, ns, c.p.cosT, c.p.sinT, c.p.wetting_type);
+        }
+        double n[3];
+        cg_unit_normal<L::D>(G, c.p.wetting_type, n);
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) { c.G[a * V + id] = G[a]; c.nrm[a * V + id] = n[a]; }
+    }
+};
+
+// curvature and CSF force from the neighbours' unit normals: calForceTermInColorGradient[New]2D
+// (1684-1735 / 2497-2552), K = n_a n_b d_a n_b - (n.n) d_a n_a (== the reference's 2-D expression)
+template <class L>
+LBM_HD void cg_force_at(const CGFields& c, int x, int y, int z, int64_t id, const double* G, const double* n,
+                        double* F, double* Kout) {
+    const Grid& g = c.g; const int64_t V = g.vol;
+    double dn[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};   // dn[a][b] = d_a n_b
+#pragma unroll
+    for (int q = 1; q < L::Q; ++q) {
+        const int64_t nbid = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
+        double nk[3];
+#pragma unroll
+        for (int b = 0; b < L::D; ++b) nk[b] = c.nrm[b * V + nbid];   // zero on solid nodes
+#pragma unroll
+        for (int a = 0; a < L::D; ++a)
+            if (L::c(q, a) != 0)
+#pragma unroll
+                for (int b = 0; b < L::D; ++b) dn[a][b] += 3.0 * L::w(q) * L::c(q, a) * nk[b];
+    }
+    double K = 0.0, nn = 0.0, div = 0.0;
+#pragma unroll
+    for (int a = 0; a < L::D; ++a) {
+        nn += n[a] * n[a]; div += dn[a][a];
+#pragma unroll
+        for (int b = 0; b < L::D; ++b) K += n[a] * n[b] * dn[a][b];
+    }
+    K -= nn * div;
+    const double sgn = c.p.wetting_type == 1 ? 0.5 : -0.5;
+#pragma unroll
+    for (int a = 0; a < L::D; ++a) F[a] = sgn * c.p.sigma * K * G[a];
+    *Kout = K;
+    (void)id;
+}
+
+// force + collision of the total population + recolouring, fS -> fC
+// (calForceTermInColorGradient*, calRKCollision1TotalGPU2D{SRT,MRT}M, calPerturbationFromForce2D[MRT],
+//  calRecoloringProcessM; RKD2Q9.py:1419-1465)
+template <class L>
+struct CollideOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 0, x, y, z);
+        const int64_t id = g.at(x, y, z), V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        double G[3] = {0, 0, 0}, n[3] = {0, 0, 0}, u[3] = {0, 0, 0}, F[3] = {0, 0, 0}, K;
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) { G[a] = c.G[a * V + id]; n[a] = c.nrm[a * V + id]; u[a] = c.u[a * V + id]; }
+        cg_force_at<L>(c, x, y, z, id, G, n, F, &K);
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) c.F[a * V + id] = F[a];
+        c.K[id] = K;
+        double fT[L::Q], fR[L::Q], fB[L::Q];
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) fT[q] = c.fS[0][q * V + id] + c.fS[1][q * V + id];
+        const double rR = c.rho[0][id], rB = c.rho[1][id];
+        const double tau = cg_tau(c.phi[id], rR, rB, c.p);
+        cg_collide<L>(fT, rR + rB, u, F, tau, c.p.relax);
+        cg_recolour<L>(fT, rR, rB, G, c.p.beta, fR, fB);
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) { c.fC[0][q * V + id] = fR[q]; c.fC[1][q * V + id] = fB[q]; }
+    }
+};
+
+// pull streaming with half-way bounce back + densities: calStreaming1GPU/2GPU (338-417) and
+// calMacroDensityRKGPU2D (101-118).  fC -> fS
+template <class L>
+struct StreamOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 0, x, y, z);
+        const int64_t id = g.at(x, y, z), V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        int64_t src[L::Q]; bool fl[L::Q];
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            src[q] = g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q));
+            fl[q] = c.cls[src[q]] & CLS_FLUID;
+        }
+        for (int k = 0; k < 2; ++k) {
+            const double* fC = c.fC[k]; double* fS = c.fS[k];
+            double acc = fC[id];
+            fS[id] = acc;
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                const double v = fl[q] ? fC[q * V + src[q]] : fC[L::opp(q) * V + id];
+                fS[q * V + id] = v;
+                acc += v;
+            }
+            c.rho[k][id] = acc;
+        }
+    }
+};
+
+// sum of a density over the owned void nodes is done on the host side of the ABI from a download
+// (mass check only; never on the timed path)
+
+}  // namespace lbm

@@ -1,0 +1,132 @@
+// comm.cu -- slab decomposition along the flow axis: one handle per rank, one rank per GPU, ghost
+// planes exchanged with ncclSend/ncclRecv between ring neighbours over NVLink.  Planes of axis 2 are
+// contiguous in every array, so they are sent in place: no packing kernels, no staging buffers.
+// (The reference is single-GPU: RKD2Q9.py / ShanChenD2Q9.py hold the whole lattice on one device.)
+#ifndef LBM_HOSTCHECK
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is bound at run time (see nccl_api)
+
+#include "internal.h"
+
+using namespace lbm;
+
+// NCCL is resolved with dlopen/dlsym instead of a link-time dependency: a host process that has already
+// loaded its own libnccl.so.2 (PyTorch bundles one) must keep using exactly that copy, and a process
+// that never goes multi-GPU should not need NCCL at all.
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    const char* (*GetErrorString)(ncclResult_t);
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    if (api.ok) return api;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // the copy the process already has
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) throw BackendError{std::string("cannot load libnccl.so.2: ") + dlerror()};
+    auto sym = [&](const char* name) {
+        void* p = dlsym(lib, name);
+        if (!p) throw BackendError{std::string("libnccl lacks ") + name};
+        return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.ok = true;
+    return api;
+}
+}  // namespace
+#define ncclGetUniqueId nccl_api().GetUniqueId
+#define ncclCommInitRank nccl_api().CommInitRank
+#define ncclCommDestroy nccl_api().CommDestroy
+#define ncclGroupStart nccl_api().GroupStart
+#define ncclGroupEnd nccl_api().GroupEnd
+#define ncclSend nccl_api().Send
+#define ncclRecv nccl_api().Recv
+#define ncclGetErrorString nccl_api().GetErrorString
+
+#define LBM_NCCL_CHECK(expr)                                                               \
+    do {                                                                                   \
+        ncclResult_t _r = (expr);                                                          \
+        if (_r != ncclSuccess)                                                             \
+            throw ::lbm::BackendError{std::string(#expr) + ": " + ncclGetErrorString(_r)}; \
+    } while (0)
+
+static_assert(sizeof(ncclUniqueId) == 128, "lbm_nccl_unique_id assumes a 128-byte NCCL id");
+
+extern "C" int lbm_nccl_unique_id(uint8_t id_out[128]) {
+    if (!id_out) return LBM_EINVAL;
+    try {
+        ncclUniqueId id;
+        if (ncclGetUniqueId(&id) != ncclSuccess) return LBM_ENCCL;
+        memcpy(id_out, &id, 128);
+    } catch (const BackendError&) { return LBM_ENCCL; }
+    return LBM_OK;
+}
+
+extern "C" int lbm_comm_init(lbm_handle* h, int32_t rank, int32_t nranks, const uint8_t id_in[128]) {
+    if (!h) return LBM_EINVAL;
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id_in) { h->err = "bad rank / nranks / id"; return LBM_EINVAL; }
+    if (h->has_geometry) { h->err = "lbm_comm_init must precede lbm_set_geometry"; return LBM_ESTATE; }
+    try {
+        LBM_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+        if (nranks > 1) {
+            ncclUniqueId id;
+            memcpy(&id, id_in, 128);
+            ncclComm_t comm;
+            LBM_NCCL_CHECK(ncclCommInitRank(&comm, nranks, id, rank));
+            h->nccl = comm;
+        }
+        h->rank = rank; h->nranks = nranks;
+    } catch (const BackendError& e) { h->err = e.msg; return LBM_ENCCL; }
+    return LBM_OK;
+}
+
+namespace lbm {
+
+template <class T>
+static void ring_exchange(lbm_handle* h, T* base, int64_t stride, int narr, int gp, ncclDataType_t dt) {
+    const Grid& g = h->g;
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    const int up = (h->rank + 1) % h->nranks, down = (h->rank + h->nranks - 1) % h->nranks;
+    const size_t count = (size_t)gp * g.plane;
+    LBM_NCCL_CHECK(ncclGroupStart());
+    for (int a = 0; a < narr; ++a) {
+        T* f = base + a * stride;
+        // my top planes -> low ghost of the rank above; my low ghost <- top planes of the rank below
+        LBM_NCCL_CHECK(ncclSend(f + (int64_t)(NG + g.n2 - gp) * g.plane, count, dt, up, comm, h->stream));
+        LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG - gp) * g.plane, count, dt, down, comm, h->stream));
+        // my bottom planes -> high ghost of the rank below; my high ghost <- bottom planes of the rank above
+        LBM_NCCL_CHECK(ncclSend(f + (int64_t)NG * g.plane, count, dt, down, comm, h->stream));
+        LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG + g.n2) * g.plane, count, dt, up, comm, h->stream));
+    }
+    LBM_NCCL_CHECK(ncclGroupEnd());
+    ++g_launch_counter;
+}
+
+void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp) {
+    ring_exchange<double>(h, base, stride, narr, gp, ncclDouble);
+}
+void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp) { ring_exchange<uint8_t>(h, base, 0, 1, gp, ncclUint8); }
+void comm_destroy(lbm_handle* h) {
+    if (h->nccl) {
+        try { ncclCommDestroy((ncclComm_t)h->nccl); } catch (const BackendError&) {}
+        h->nccl = nullptr;
+    }
+}
+
+}  // namespace lbm
+#endif

@@ -1,0 +1,153 @@
+// grid.cuh -- the dense masked lattice of one slab and the geometry operators.
+//
+// Every field is a dense array over the padded slab [n2 + 2*NG][n1][n0], x (axis 0) fastest; axis 2 is
+// the flow / slab axis (z in 3-D, the reference's y in 2-D, where n1 = 1).  NG ghost planes on each
+// side of axis 2 hold the periodic images (one GPU) or the neighbouring ranks' planes (slab
+// decomposition); axes 0 and 1 wrap inside the kernels.  The reference instead keeps a compact
+// fluid-node list with an int64 neighbour table (RKD2Q9.py:657-736); that structure is only
+// exported on request (lbm_export_indexing), never used on the hot path.
+#pragma once
+#include "lattice.cuh"
+
+namespace lbm {
+
+constexpr int NG = 3;   // phi needs radius 3 when wetting solids are present (phi_s -> G -> n -> K)
+
+enum : uint8_t { CLS_FLUID = 1, CLS_WET = 2, CLS_NEAR = 4 };
+
+struct Grid {
+    int n0, n1, n2;
+    int64_t plane;   // n0 * n1
+    int64_t vol;     // plane * (n2 + 2 NG)
+    LBM_HD int64_t at(int x, int y, int z) const { return (int64_t)(z + NG) * plane + (int64_t)y * n0 + x; }
+    // neighbour (x+dx, y+dy, z+dz): periodic in axes 0 and 1, ghost planes along axis 2
+    LBM_HD int64_t nb(int x, int y, int z, int dx, int dy, int dz) const {
+        int xn = x + dx, yn = y + dy;
+        if (xn < 0) xn += n0; else if (xn >= n0) xn -= n0;
+        if (yn < 0) yn += n1; else if (yn >= n1) yn -= n1;
+        return at(xn, yn, z + dz);
+    }
+    // item i of a launch over planes [-ext, n2 + ext)
+    LBM_HD void decode(int64_t i, int ext, int& x, int& y, int& z) const {
+        z = (int)(i / plane) - ext;
+        const int r = (int)(i % plane);
+        y = r / n0;
+        x = r - y * n0;
+    }
+    int64_t count(int ext) const { return plane * (int64_t)(n2 + 2 * ext); }
+};
+
+// Fill the ghost planes of `narr` arrays (stride `stride` elements apart) from the slab's own opposite
+// planes: periodic wrap on one GPU.  item = (array, side, ghost plane j, node in plane)
+template <class T>
+struct GhostWrapOp {
+    Grid g; T* base; int64_t stride; int narr; int gp;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t r = i % g.plane; int64_t q = i / g.plane;
+        const int j = (int)(q % gp); q /= gp;
+        const int side = (int)(q % 2); const int a = (int)(q / 2);
+        T* f = base + a * stride;
+        if (side == 0) f[(int64_t)(NG - 1 - j) * g.plane + r] = f[(int64_t)(NG + g.n2 - 1 - j) * g.plane + r];
+        else f[(int64_t)(NG + g.n2 + j) * g.plane + r] = f[(int64_t)(NG + j) * g.plane + r];
+    }
+    int64_t items() const { return (int64_t)narr * 2 * gp * g.plane; }
+};
+
+// Node classes from the void mask (1 = void): the dense equivalent of optimizeFluidandSolidArray's
+// wetting-solid marking (RKD2Q9.py:677-689) and of sortOutFluidNodesToSolid (RKD2Q9.py:741-760).
+template <int D>
+struct ClassifyOp {
+    Grid g; const uint8_t* dom; uint8_t* cls;
+    LBM_HD void operator()(int64_t i) const {
+        int x, y, z; g.decode(i, 2, x, y, z);
+        int nfl = 0;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = (D == 3 ? -1 : 0); dy <= (D == 3 ? 1 : 0); ++dy)
+                for (int dx = -1; dx <= 1; ++dx) nfl += dom[g.nb(x, y, z, dx, dy, dz)] ? 1 : 0;
+        const int full = D == 3 ? 27 : 9;
+        const int64_t id = g.at(x, y, z);
+        cls[id] = dom[id] ? (uint8_t)(CLS_FLUID | (nfl < full ? CLS_NEAR : 0)) : (uint8_t)(nfl > 0 ? CLS_WET : 0);
+    }
+};
+
+// Unit normal of the solid surface seen from a fluid node next to solid: calVectorNormaltoSolid
+// (RKD2Q9.py:768-892), n_s = sum over solid cells c in the 5^D box of w(|c|^2) c, normalised.
+// 2-D weights are the reference's (RKD2Q9.py:806-880); 3-D uses the 8th-order isotropic set.
+template <int D>
+struct SolidNormalOp {
+    Grid g; const uint8_t* dom; const uint8_t* cls; double* ns;   // ns: [3][vol]
+    LBM_HD static double weight(int c2) {
+        if (D == 2) {
+            switch (c2) { case 1: return 4.0 / 21.0; case 2: return 4.0 / 45.0; case 4: return 1.0 / 60.0;
+                          case 5: return 2.0 / 315.0; case 8: return 1.0 / 5040.0; default: return 0.0; }
+        }
+        switch (c2) { case 1: return 4.0 / 45.0; case 2: return 1.0 / 21.0; case 3: return 2.0 / 105.0;
+                      case 4: return 5.0 / 504.0; case 5: return 1.0 / 315.0; case 6: return 1.0 / 630.0;
+                      case 8: return 1.0 / 5040.0; default: return 0.0; }
+    }
+    LBM_HD void operator()(int64_t i) const {
+        int x, y, z; g.decode(i, 1, x, y, z);
+        const int64_t id = g.at(x, y, z);
+        if (!(cls[id] & CLS_NEAR)) return;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;    // along array axes 0, 1, 2
+        for (int dz = -2; dz <= 2; ++dz)
+            for (int dy = (D == 3 ? -2 : 0); dy <= (D == 3 ? 2 : 0); ++dy)
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const double w = weight(dx * dx + dy * dy + dz * dz);
+                    if (w == 0.0) continue;
+                    int xn = x + dx, yn = y + dy;     // |d| = 2 may wrap twice on tiny grids
+                    xn = ((xn % g.n0) + g.n0) % g.n0; yn = ((yn % g.n1) + g.n1) % g.n1;
+                    if (!dom[g.at(xn, yn, z + dz)]) { s0 += w * dx; s1 += w * dy; s2 += w * dz; }
+                }
+        const double nrm = sqrt(s0 * s0 + s1 * s1 + s2 * s2);
+        // physical components: 2-D (x, y) = axes (0, 2); 3-D (x, y, z) = axes (0, 1, 2)
+        if (D == 2) { ns[id] = s0 / nrm; ns[g.vol + id] = s2 / nrm; }
+        else { ns[id] = s0 / nrm; ns[g.vol + id] = s1 / nrm; ns[2 * g.vol + id] = s2 / nrm; }
+    }
+};
+
+// ---- export of the reference's compact index structures (single slab; bit-exact contract) -------
+struct FlagOp {          // flag[i] = 1 where the owned node has all bits of `mask` set, row-major order
+    Grid g; const uint8_t* cls; uint8_t mask; int64_t* flag;
+    LBM_HD void operator()(int64_t i) const { flag[i] = (cls[(int64_t)NG * g.plane + i] & mask) ? 1 : 0; }
+};
+// list[rank[i]] = i for flagged nodes; id[i] = (negate ? -2 - rank : rank)
+struct CompactOp {
+    const int64_t* flag; const int64_t* rank; int64_t* list; int64_t* id; int negate;
+    LBM_HD void operator()(int64_t i) const {
+        if (!flag[i]) return;
+        list[rank[i]] = i;
+        if (id) id[i] = negate ? -2 - rank[i] : rank[i];
+    }
+};
+// neighbour table of the listed nodes: slot k <-> direction k+1, periodic in every axis
+// (fillNeighboringNodes / fillNeighboringWettingNodes, AcceleratedRKGPU2D.py:14-95)
+template <class L>
+struct NeighbourTableOp {
+    Grid g; const int64_t* list; const int64_t* id; int64_t* out;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t node = list[i];
+        int x, y, z; g.decode(node, 0, x, y, z);
+#pragma unroll
+        for (int k = 1; k < L::Q; ++k) {
+            int zn = z + L::d2(k);
+            if (zn < 0) zn += g.n2; else if (zn >= g.n2) zn -= g.n2;
+            const int64_t nbn = g.nb(x, y, zn, L::d0(k), L::d1(k), 0) - (int64_t)NG * g.plane;
+            out[i * (L::Q - 1) + (k - 1)] = id[nbn];
+        }
+    }
+};
+// fluid nodes next to solid: compact id, flat id and unit normal (component-major)
+struct NearSolidExportOp {
+    Grid g; int D; const int64_t* list; const int64_t* id; const double* ns; int64_t n;
+    int64_t* compact; int64_t* flat; double* ns_out;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t node = list[i];
+        if (compact) compact[i] = id[node];
+        if (flat) flat[i] = node;
+        if (ns_out)
+            for (int a = 0; a < D; ++a) ns_out[a * n + i] = ns[a * g.vol + (int64_t)NG * g.plane + node];
+    }
+};
+
+}  // namespace lbm

@@ -1,0 +1,54 @@
+// handle.h -- the state behind an lbm_handle (device arrays are owned by the handle).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/lbmpm.h"
+#include "backend.h"
+#include "cg_ops.cuh"
+
+struct lbm_handle {
+    lbm_config cfg;
+    lbm::Grid g;
+    int D = 0, Q = 0;
+    lbm::stream_t stream = 0;
+    int rank = 0, nranks = 1;
+    std::string err;
+
+    // geometry
+    uint8_t* dom = nullptr;     // [vol] 1 = void
+    uint8_t* cls = nullptr;     // [vol] node classes
+    double* ns = nullptr;       // [3][vol]
+    int64_t n_fluid = 0, n_wet = 0, n_near = 0;
+    bool has_geometry = false;
+
+    // colour-gradient state (general path)
+    double* fS = nullptr;       // [2][Q][vol] streamed populations
+    double* fC = nullptr;       // [2][Q][vol] post-collision populations
+    double* rho = nullptr;      // [2][vol]
+    double* u = nullptr;        // [3][vol]
+    double* phi = nullptr;
+    double* G = nullptr;        // [3][vol]
+    double* nrm = nullptr;      // [3][vol]
+    double* F = nullptr;        // [3][vol]
+    double* K = nullptr;
+    bool has_state = false;
+    bool head_done = false;     // boundary treatment + velocity + phi of the current iteration already applied
+
+    // fast path (cg_fast.cu): state kept post-collision in factored form
+    void* fast = nullptr;
+    bool fast_pending_stream = false;
+
+    // Shan-Chen / explicit forcing state (sc_ops)
+    void* sc = nullptr;
+
+    // measurement
+    double last_ms = 0.0;
+    int64_t last_launches = 0;
+#ifndef LBM_HOSTCHECK
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* nccl = nullptr;       // ncclComm_t
+#endif
+
+    lbm::CGFields fields() const;
+};

@@ -1,0 +1,37 @@
+// internal.h -- functions shared between the translation units of liblbmpm.so
+#pragma once
+#include "handle.h"
+
+namespace lbm {
+
+// ghost planes along the slab axis (periodic wrap on one GPU, NCCL send/recv between slabs)
+void exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp);
+void exchange_u8(lbm_handle* h, uint8_t* base, int gp);
+void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp);
+void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp);
+void comm_destroy(lbm_handle* h);
+
+// general colour-gradient path (lbm_api.cu)
+void cg_alloc_state(lbm_handle* h);
+void cg_alloc_postcollision(lbm_handle* h);
+void cg_ensure_head(lbm_handle* h);
+void cg_generic_body(lbm_handle* h);
+void cg_generic_forces(lbm_handle* h);
+void cg_open_boundaries_3d(lbm_handle* h, const CGFields& c);
+
+// fused fast path for closed boxes (cg_fast.cu)
+bool cg_fast_eligible(const lbm_handle* h);
+void cg_fast_step(lbm_handle* h, int nsteps);
+void cg_fast_materialise(lbm_handle* h);
+void cg_fast_free(lbm_handle* h);
+
+// Shan-Chen / explicit-forcing models (sc_api.cu)
+int sc_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp);
+int sc_upload_state(lbm_handle* h, const double* const* pdf, const double* const* rho, int32_t n_comp);
+void sc_step(lbm_handle* h, int nsteps);
+int sc_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u);
+int sc_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp);
+int sc_total_mass(lbm_handle* h, double* mass, int32_t n_comp);
+void sc_free(lbm_handle* h);
+
+}  // namespace lbm

@@ -23,6 +23,11 @@ struct D2Q9 {
     LBM_HD static constexpr int cx(int i) { constexpr int t[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}; return t[i]; }
     LBM_HD static constexpr int cy(int i) { constexpr int t[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1}; return t[i]; }
     LBM_HD static constexpr int cz(int) { return 0; }
+    // offsets along the array axes (0 = fastest, 2 = slab axis): the 2-D lattice lives on axes 0 and 2
+    LBM_HD static constexpr int d0(int i) { return cx(i); }
+    LBM_HD static constexpr int d1(int) { return 0; }
+    LBM_HD static constexpr int d2(int i) { return cy(i); }
+    LBM_HD static constexpr int c(int i, int a) { return a == 0 ? cx(i) : (a == 1 ? cy(i) : 0); }
     LBM_HD static constexpr int opp(int i) { constexpr int t[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6}; return t[i]; }
     LBM_HD static constexpr double w(int i) { return i == 0 ? 4.0 / 9.0 : (i < 5 ? 1.0 / 9.0 : 1.0 / 36.0); }
     LBM_HD static constexpr double enorm(int i) { return i == 0 ? 0.0 : (i < 5 ? 1.0 : 1.4142135623730951); }
@@ -95,6 +100,10 @@ struct D3Q19 {
         constexpr int t[19] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
         return t[i];
     }
+    LBM_HD static constexpr int d0(int i) { return cx(i); }
+    LBM_HD static constexpr int d1(int i) { return cy(i); }
+    LBM_HD static constexpr int d2(int i) { return cz(i); }
+    LBM_HD static constexpr int c(int i, int a) { return a == 0 ? cx(i) : (a == 1 ? cy(i) : cz(i)); }
     LBM_HD static constexpr int opp(int i) {
         constexpr int t[19] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
         return t[i];

@@ -1,0 +1,661 @@
+// lbm_api.cu -- the C ABI of liblbmpm.so (include/lbmpm.h): handle lifetime, geometry, state
+// transfer, the step loop of the general colour-gradient path and measurement.
+#include <math.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <new>
+
+#include "handle.h"
+#include "internal.h"
+
+namespace lbm {
+thread_local int64_t g_launch_counter = 0;
+#ifndef LBM_HOSTCHECK
+thread_local Profiler g_prof;
+#endif
+}
+using namespace lbm;
+
+static thread_local std::string g_create_error;
+
+#define API_BEGIN(h)                   \
+    if (!(h)) return LBM_EINVAL;       \
+    try {
+#define API_END(h)                                                      \
+    }                                                                   \
+    catch (const BackendError& e) { (h)->err = e.msg; return LBM_ECUDA; } \
+    catch (const std::bad_alloc&) { (h)->err = "out of host memory"; return LBM_ENOMEM; } \
+    return LBM_OK;
+
+static int fail(lbm_handle* h, int code, const char* msg) {
+    h->err = msg;
+    return code;
+}
+
+CGFields lbm_handle::fields() const {
+    CGFields c;
+    memset(&c, 0, sizeof(c));
+    c.g = g;
+    const double th = cfg.contact_angle_deg / 180.0 * M_PI;      // RKD2Q9.py:86-87
+    c.p.sigma = cfg.sigma; c.p.cosT = cos(th); c.p.sinT = sin(th);
+    c.p.beta = cfg.beta; c.p.delta = cfg.delta; c.p.tauR = cfg.tauR; c.p.tauB = cfg.tauB;
+    c.p.tau_type = cfg.tau_type; c.p.wetting_type = cfg.wetting_type; c.p.relax = cfg.relax;
+    const int64_t cv = (int64_t)Q * g.vol;
+    c.fS[0] = fS; c.fS[1] = fS + cv;
+    c.fC[0] = fC; c.fC[1] = fC ? fC + cv : nullptr;
+    c.rho[0] = rho; c.rho[1] = rho + g.vol;
+    c.u = u; c.phi = phi; c.G = G; c.nrm = nrm; c.F = F; c.K = K;
+    c.cls = cls; c.ns = ns;
+    c.inlet = cfg.inlet; c.outlet = cfg.outlet;
+    // open-boundary rows in local plane numbers; the top rows live on the last rank, the bottom rows on rank 0
+    const int off = -100000;
+    c.z_in = rank == nranks - 1 ? g.n2 - 2 : off;
+    c.z_in_ghost = rank == nranks - 1 ? g.n2 - 1 : off;
+    c.z_out = rank == 0 ? 1 : off; c.z_out_ghost = rank == 0 ? 0 : off; c.z_out2 = rank == 0 ? 2 : off;
+    c.v_in = cfg.inlet_velocity;
+    c.rhoBH = cfg.rhoBH; c.rhoRH = cfg.rhoRH; c.rhoBL = cfg.rhoBL; c.rhoRL = cfg.rhoRL;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ghost planes
+// ------------------------------------------------------------------------------------------------
+void lbm::exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp) {
+    if (h->nranks > 1) { comm_exchange_f64(h, base, stride, narr, gp); return; }
+    GhostWrapOp<double> op{h->g, base, stride, narr, gp};
+    launch(op, op.items(), h->stream);
+}
+void lbm::exchange_u8(lbm_handle* h, uint8_t* base, int gp) {
+    if (h->nranks > 1) { comm_exchange_u8(h, base, gp); return; }
+    GhostWrapOp<uint8_t> op{h->g, base, 0, 1, gp};
+    launch(op, op.items(), h->stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbm_abi_version(void) { return LBM_ABI_VERSION; }
+
+extern "C" const char* lbm_last_error(const lbm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return LBM_EINVAL; }
+    *out = nullptr;
+    if (cfg->abi_version != LBM_ABI_VERSION) { g_create_error = "abi_version mismatch"; return LBM_EINVAL; }
+    if (cfg->lattice != 9 && cfg->lattice != 19) { g_create_error = "lattice must be 9 (D2Q9) or 19 (D3Q19)"; return LBM_EINVAL; }
+    if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 1) { g_create_error = "domain sizes must be positive"; return LBM_EINVAL; }
+    if (cfg->lattice == 9 && cfg->nz != 1) { g_create_error = "D2Q9 needs nz = 1"; return LBM_EINVAL; }
+    if (cfg->model < LBM_MODEL_CG || cfg->model > LBM_MODEL_EFS) { g_create_error = "unknown model"; return LBM_EINVAL; }
+    if (cfg->model != LBM_MODEL_CG && cfg->lattice != 9) { g_create_error = "Shan-Chen models are D2Q9 only"; return LBM_EINVAL; }
+    if (cfg->model != LBM_MODEL_CG && (cfg->n_components < 1 || cfg->n_components > 4)) {
+        g_create_error = "n_components must be 1..4"; return LBM_EINVAL;
+    }
+    if (cfg->relax != LBM_RELAX_SRT && cfg->relax != LBM_RELAX_MRT) { g_create_error = "relax must be SRT or MRT"; return LBM_EINVAL; }
+    if (cfg->model == LBM_MODEL_CG) {
+        if (cfg->tau_type != 1 && cfg->tau_type != 2) { g_create_error = "tau_type must be 1 or 2"; return LBM_EINVAL; }
+        if (cfg->wetting_type != 1 && cfg->wetting_type != 2) { g_create_error = "wetting_type must be 1 or 2"; return LBM_EINVAL; }
+        if (cfg->wetting_type == 1 && cfg->lattice == 19) { g_create_error = "WettingType 1 is a 2-D rotation; use 2 for D3Q19"; return LBM_EINVAL; }
+        if ((cfg->inlet != LBM_BC_PERIODIC || cfg->outlet != LBM_BC_PERIODIC) && cfg->lattice == 19 &&
+            !(cfg->inlet == LBM_INLET_VELOCITY || cfg->inlet == LBM_BC_PERIODIC)) {
+            g_create_error = "D3Q19 open boundaries: velocity inlet / convective or pressure outlet"; return LBM_EINVAL;
+        }
+    }
+    lbm_handle* h = new (std::nothrow) lbm_handle();
+    if (!h) { g_create_error = "out of host memory"; return LBM_ENOMEM; }
+    h->cfg = *cfg;
+    h->Q = cfg->lattice; h->D = cfg->lattice == 9 ? 2 : 3;
+    Grid& g = h->g;
+    if (h->D == 2) { g.n0 = cfg->nx; g.n1 = 1; g.n2 = cfg->ny; }
+    else { g.n0 = cfg->nx; g.n1 = cfg->ny; g.n2 = cfg->nz; }
+    g.plane = (int64_t)g.n0 * g.n1;
+    g.vol = g.plane * (g.n2 + 2 * NG);
+    if (g.n2 < NG) { g_create_error = "the flow axis needs at least 3 planes"; delete h; return LBM_EINVAL; }
+    try {
+#ifndef LBM_HOSTCHECK
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw BackendError{std::string("no CUDA device: ") + cudaGetErrorString(e) + " (liblbmpm has no CPU fallback)"};
+        if (cfg->device < 0 || cfg->device >= ndev) throw BackendError{"device ordinal out of range"};
+        LBM_CUDA_CHECK(cudaSetDevice(cfg->device));
+        LBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        LBM_CUDA_CHECK(cudaEventCreate(&h->ev0));
+        LBM_CUDA_CHECK(cudaEventCreate(&h->ev1));
+#endif
+    } catch (const BackendError& e) {
+        g_create_error = e.msg; delete h; return LBM_ECUDA;
+    }
+    *out = h;
+    return LBM_OK;
+}
+
+static void free_state(lbm_handle* h) {
+    double** arrs[] = {&h->fS, &h->fC, &h->rho, &h->u, &h->phi, &h->G, &h->nrm, &h->F, &h->K};
+    for (double** p : arrs) { dev_free(*p); *p = nullptr; }
+    cg_fast_free(h);
+    sc_free(h);
+    h->has_state = false;
+}
+
+extern "C" int lbm_destroy(lbm_handle* h) {
+    if (!h) return LBM_EINVAL;
+#ifndef LBM_HOSTCHECK
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+#endif
+    free_state(h);
+    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns);
+    comm_destroy(h);
+#ifndef LBM_HOSTCHECK
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+#endif
+    delete h;
+    return LBM_OK;
+}
+
+static inline void set_device(lbm_handle* h) {
+#ifndef LBM_HOSTCHECK
+    LBM_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+#else
+    (void)h;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
+    API_BEGIN(h)
+    if (!is_domain) return fail(h, LBM_EINVAL, "is_domain is NULL");
+    set_device(h);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2;
+    free_state(h);
+    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns);
+    h->dom = (uint8_t*)dev_alloc(g.vol); h->cls = (uint8_t*)dev_alloc(g.vol);
+    h->ns = (double*)dev_alloc(3 * g.vol * sizeof(double));
+    dev_zero(h->dom, g.vol, h->stream); dev_zero(h->cls, g.vol, h->stream);
+    dev_zero(h->ns, 3 * g.vol * sizeof(double), h->stream);
+    std::vector<uint8_t> norm((size_t)owned);
+    int64_t nf = 0;
+    for (int64_t i = 0; i < owned; ++i) { norm[i] = is_domain[i] ? 1 : 0; nf += norm[i]; }
+    h->n_fluid = nf;
+    dev_h2d(h->dom + NG * g.plane, norm.data(), owned, h->stream);
+    exchange_u8(h, h->dom, NG);
+    if (h->D == 2) {
+        launch(ClassifyOp<2>{g, h->dom, h->cls}, g.count(2), h->stream);
+        launch(SolidNormalOp<2>{g, h->dom, h->cls, h->ns}, g.count(1), h->stream);
+    } else {
+        launch(ClassifyOp<3>{g, h->dom, h->cls}, g.count(2), h->stream);
+        launch(SolidNormalOp<3>{g, h->dom, h->cls, h->ns}, g.count(1), h->stream);
+    }
+    dev_sync(h->stream);
+    h->n_wet = h->n_near = -1;
+    h->has_geometry = true;
+    API_END(h)
+}
+
+namespace {
+struct IndexWork {
+    int64_t *flag = nullptr, *rank = nullptr, *id = nullptr;
+    ~IndexWork() { dev_free(flag); dev_free(rank); dev_free(id); }
+};
+// flag + scan of one node class over the owned nodes; returns the count
+int64_t scan_class(lbm_handle* h, IndexWork& w, uint8_t mask) {
+    const int64_t owned = h->g.plane * h->g.n2;
+    launch(FlagOp{h->g, h->cls, mask, w.flag}, owned, h->stream);
+    exclusive_scan_i64(w.flag, w.rank, owned, h->stream);
+    int64_t last_rank = 0, last_flag = 0;
+    dev_d2h(&last_rank, w.rank + owned - 1, sizeof(int64_t), h->stream);
+    dev_d2h(&last_flag, w.flag + owned - 1, sizeof(int64_t), h->stream);
+    return last_rank + last_flag;
+}
+struct FillOp {
+    int64_t* p; int64_t v;
+    LBM_HD void operator()(int64_t i) const { p[i] = v; }
+};
+}  // namespace
+
+extern "C" int lbm_index_sizes(lbm_handle* h, int64_t* n_fluid, int64_t* n_wet_solid, int64_t* n_fluid_near_solid) {
+    API_BEGIN(h)
+    if (!h->has_geometry) return fail(h, LBM_ESTATE, "lbm_set_geometry has not been called");
+    set_device(h);
+    if (h->n_wet < 0) {
+        const int64_t owned = h->g.plane * h->g.n2;
+        IndexWork w;
+        w.flag = (int64_t*)dev_alloc(owned * 8); w.rank = (int64_t*)dev_alloc(owned * 8);
+        h->n_fluid = scan_class(h, w, CLS_FLUID);
+        h->n_wet = scan_class(h, w, CLS_WET);
+        h->n_near = scan_class(h, w, CLS_NEAR);
+    }
+    if (n_fluid) *n_fluid = h->n_fluid;
+    if (n_wet_solid) *n_wet_solid = h->n_wet;
+    if (n_fluid_near_solid) *n_fluid_near_solid = h->n_near;
+    API_END(h)
+}
+
+template <class L>
+static void export_indexing(lbm_handle* h, int64_t* fluid_nodes, int64_t* neighbors, int64_t* wet_nodes,
+                            int64_t* wet_neighbors, int64_t* near_compact, int64_t* near_flat, double* ns) {
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2;
+    IndexWork w;
+    w.flag = (int64_t*)dev_alloc(owned * 8); w.rank = (int64_t*)dev_alloc(owned * 8); w.id = (int64_t*)dev_alloc(owned * 8);
+    launch(FillOp{w.id, -1}, owned, h->stream);
+    struct Buf { int64_t* p = nullptr; ~Buf() { dev_free(p); } };
+    struct DBuf { double* p = nullptr; ~DBuf() { dev_free(p); } };
+    Buf lf, lw, ln, tmp; DBuf nsd;
+    const int64_t nf = scan_class(h, w, CLS_FLUID);
+    lf.p = (int64_t*)dev_alloc(nf * 8);
+    launch(CompactOp{w.flag, w.rank, lf.p, w.id, 0}, owned, h->stream);
+    const int64_t nw = scan_class(h, w, CLS_WET);
+    lw.p = (int64_t*)dev_alloc(nw * 8);
+    launch(CompactOp{w.flag, w.rank, lw.p, w.id, 1}, owned, h->stream);
+    const int64_t nn = scan_class(h, w, CLS_NEAR);
+    ln.p = (int64_t*)dev_alloc(nn * 8);
+    launch(CompactOp{w.flag, w.rank, ln.p, nullptr, 0}, owned, h->stream);
+    h->n_fluid = nf; h->n_wet = nw; h->n_near = nn;
+    const int S = L::Q - 1;
+    if (fluid_nodes) dev_d2h(fluid_nodes, lf.p, nf * 8, h->stream);
+    if (wet_nodes) dev_d2h(wet_nodes, lw.p, nw * 8, h->stream);
+    if (neighbors && nf) {
+        tmp.p = (int64_t*)dev_alloc(nf * S * 8);
+        launch(NeighbourTableOp<L>{g, lf.p, w.id, tmp.p}, nf, h->stream);
+        dev_d2h(neighbors, tmp.p, nf * S * 8, h->stream);
+        dev_free(tmp.p); tmp.p = nullptr;
+    }
+    if (wet_neighbors && nw) {
+        tmp.p = (int64_t*)dev_alloc(nw * S * 8);
+        launch(NeighbourTableOp<L>{g, lw.p, w.id, tmp.p}, nw, h->stream);
+        dev_d2h(wet_neighbors, tmp.p, nw * S * 8, h->stream);
+        dev_free(tmp.p); tmp.p = nullptr;
+    }
+    if ((near_compact || near_flat || ns) && nn) {
+        Buf c, f;
+        c.p = (int64_t*)dev_alloc(nn * 8); f.p = (int64_t*)dev_alloc(nn * 8);
+        nsd.p = (double*)dev_alloc(nn * L::D * 8);
+        launch(NearSolidExportOp{g, L::D, ln.p, w.id, h->ns, nn, c.p, f.p, nsd.p}, nn, h->stream);
+        if (near_compact) dev_d2h(near_compact, c.p, nn * 8, h->stream);
+        if (near_flat) dev_d2h(near_flat, f.p, nn * 8, h->stream);
+        if (ns) dev_d2h(ns, nsd.p, nn * L::D * 8, h->stream);
+    }
+}
+
+extern "C" int lbm_export_indexing(lbm_handle* h, int64_t* fluid_nodes, int64_t* neighbors,
+                                   int64_t* wet_solid_nodes, int64_t* wet_solid_neighbors,
+                                   int64_t* near_solid_compact, int64_t* near_solid_flat, double* ns) {
+    API_BEGIN(h)
+    if (!h->has_geometry) return fail(h, LBM_ESTATE, "lbm_set_geometry has not been called");
+    if (h->nranks > 1) return fail(h, LBM_EINVAL, "index export is defined for a single slab");
+    set_device(h);
+    if (h->Q == 9) export_indexing<D2Q9>(h, fluid_nodes, neighbors, wet_solid_nodes, wet_solid_neighbors, near_solid_compact, near_solid_flat, ns);
+    else export_indexing<D3Q19>(h, fluid_nodes, neighbors, wet_solid_nodes, wet_solid_neighbors, near_solid_compact, near_solid_flat, ns);
+    API_END(h)
+}
+
+// ------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------
+void lbm::cg_alloc_state(lbm_handle* h) {
+    if (h->fS) return;
+    const Grid& g = h->g;
+    const size_t V = (size_t)g.vol * sizeof(double);
+    auto alloc0 = [&](size_t bytes) { double* p = (double*)dev_alloc(bytes); dev_zero(p, bytes, h->stream); return p; };
+    h->fS = alloc0(2 * h->Q * V);
+    h->rho = alloc0(2 * V); h->u = alloc0(3 * V); h->phi = alloc0(V); h->G = alloc0(3 * V);
+    h->nrm = alloc0(3 * V); h->F = alloc0(3 * V); h->K = alloc0(V);
+}
+void lbm::cg_alloc_postcollision(lbm_handle* h) {
+    if (h->fC) return;
+    const size_t bytes = 2 * (size_t)h->Q * h->g.vol * sizeof(double);
+    h->fC = (double*)dev_alloc(bytes);
+    dev_zero(h->fC, bytes, h->stream);
+}
+
+extern "C" int lbm_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp) {
+    API_BEGIN(h)
+    if (!h->has_geometry) return fail(h, LBM_ESTATE, "lbm_set_geometry has not been called");
+    set_device(h);
+    if (h->cfg.model != LBM_MODEL_CG) return sc_init_equilibrium(h, rho, n_comp);
+    if (n_comp != 2 || !rho || !rho[0] || !rho[1]) return fail(h, LBM_EINVAL, "colour gradient needs rho[0] = rhoR and rho[1] = rhoB");
+    cg_fast_free(h);
+    cg_alloc_state(h);
+    const int64_t owned = h->g.plane * h->g.n2;
+    double* tmp = (double*)dev_alloc(2 * owned * 8);
+    try {
+        dev_h2d(tmp, rho[0], owned * 8, h->stream);
+        dev_h2d(tmp + owned, rho[1], owned * 8, h->stream);
+        CGFields c = h->fields();
+        if (h->Q == 9) launch(InitEquilibriumOp<D2Q9>{c, tmp, tmp + owned}, owned, h->stream);
+        else launch(InitEquilibriumOp<D3Q19>{c, tmp, tmp + owned}, owned, h->stream);
+        dev_sync(h->stream);
+    } catch (...) { dev_free(tmp); throw; }
+    dev_free(tmp);
+    h->has_state = true; h->head_done = false; h->fast_pending_stream = false;
+    API_END(h)
+}
+
+extern "C" int lbm_upload_state(lbm_handle* h, const double* const* pdf, const double* const* rho, int32_t n_comp) {
+    API_BEGIN(h)
+    if (!h->has_geometry) return fail(h, LBM_ESTATE, "lbm_set_geometry has not been called");
+    set_device(h);
+    if (h->cfg.model != LBM_MODEL_CG) return sc_upload_state(h, pdf, rho, n_comp);
+    if (n_comp != 2 || !pdf || !pdf[0] || !pdf[1]) return fail(h, LBM_EINVAL, "colour gradient needs pdf[0] = fluidPDFR and pdf[1] = fluidPDFB");
+    cg_fast_free(h);
+    cg_alloc_state(h);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2;
+    double* tmp = (double*)dev_alloc((size_t)owned * (h->Q + 1) * 8);
+    try {
+        CGFields c = h->fields();
+        for (int k = 0; k < 2; ++k) {
+            dev_h2d(tmp, pdf[k], (size_t)owned * h->Q * 8, h->stream);
+            const double* rin = nullptr;
+            if (rho && rho[k]) { dev_h2d(tmp + owned * h->Q, rho[k], owned * 8, h->stream); rin = tmp + owned * h->Q; }
+            if (h->Q == 9) launch(AosToSoaOp<D2Q9>{g, tmp, c.fS[k], h->cls, c.rho[k], rin}, owned, h->stream);
+            else launch(AosToSoaOp<D3Q19>{g, tmp, c.fS[k], h->cls, c.rho[k], rin}, owned, h->stream);
+            dev_sync(h->stream);
+        }
+        dev_zero(h->F, 3 * g.vol * 8, h->stream);
+        dev_sync(h->stream);
+    } catch (...) { dev_free(tmp); throw; }
+    dev_free(tmp);
+    h->has_state = true; h->head_done = false; h->fast_pending_stream = false;
+    API_END(h)
+}
+
+// ------------------------------------------------------------------------------------------------
+// the general colour-gradient step (reference order, RKD2Q9.py:1295-1490)
+// ------------------------------------------------------------------------------------------------
+template <class L>
+static void cg_head(lbm_handle* h) {
+    CGFields c = h->fields();
+    const Grid& g = h->g;
+    if (h->Q == 9) {
+        if (c.inlet == LBM_INLET_VELOCITY && c.z_in >= 0) {
+            launch(InletVelocity2DOp{c}, g.n0, h->stream);
+            launch(RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 1}, g.plane, h->stream);
+        } else if (c.inlet == LBM_INLET_PRESSURE && c.z_in >= 0) {
+            launch(InletPressure2DOp{c}, g.n0, h->stream);
+            launch(RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 0}, g.plane, h->stream);
+        }
+        if (c.outlet == LBM_OUTLET_CONVECTIVE && c.z_out >= 0) {
+            launch(RowCopyOp<L>{c, 2, 3, 1}, g.plane, h->stream);
+            launch(RowCopyOp<L>{c, 1, 2, 1}, g.plane, h->stream);
+            launch(RowCopyOp<L>{c, 0, 1, 1}, g.plane, h->stream);
+        } else if (c.outlet == LBM_OUTLET_PRESSURE && c.z_out >= 0) {
+            launch(OutletPressure2DOp{c}, g.n0, h->stream);
+            launch(RowCopyOp<L>{c, 0, 1, 0}, g.plane, h->stream);
+        }
+    } else {
+        cg_open_boundaries_3d(h, c);
+    }
+    launch(HeadOp<L>{c}, g.count(0), h->stream);
+    h->head_done = true;
+}
+
+template <class L>
+static void cg_forces(lbm_handle* h, const CGFields& c) {
+    const Grid& g = h->g;
+    exchange_f64(h, c.phi, 0, 1, NG);
+    if (h->n_fluid != g.plane * g.n2 || h->nranks > 1) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
+    launch(GradientOp<L>{c}, g.count(1), h->stream);
+}
+
+template <class L>
+static void cg_body(lbm_handle* h) {
+    cg_alloc_postcollision(h);
+    CGFields c = h->fields();
+    const Grid& g = h->g;
+    cg_forces<L>(h, c);
+    launch(CollideOp<L>{c}, g.count(0), h->stream);
+    exchange_f64(h, h->fC, g.vol, 2 * L::Q, 1);
+    launch(StreamOp<L>{c}, g.count(0), h->stream);
+    h->head_done = false;
+}
+
+void lbm::cg_open_boundaries_3d(lbm_handle*, const CGFields&) {}
+
+void lbm::cg_ensure_head(lbm_handle* h) {
+    if (h->head_done) return;
+    if (h->Q == 9) cg_head<D2Q9>(h); else cg_head<D3Q19>(h);
+}
+void lbm::cg_generic_body(lbm_handle* h) {
+    if (h->Q == 9) cg_body<D2Q9>(h); else cg_body<D3Q19>(h);
+}
+void lbm::cg_generic_forces(lbm_handle* h) {
+    CGFields c = h->fields();
+    if (h->Q == 9) cg_forces<D2Q9>(h, c); else cg_forces<D3Q19>(h, c);
+}
+
+extern "C" int lbm_step(lbm_handle* h, int32_t nsteps) {
+    API_BEGIN(h)
+    if (!h->has_state) return fail(h, LBM_ESTATE, "no state: call lbm_init_equilibrium or lbm_upload_state first");
+    if (nsteps < 0) return fail(h, LBM_EINVAL, "nsteps < 0");
+    set_device(h);
+    const int64_t l0 = g_launch_counter;
+#ifndef LBM_HOSTCHECK
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+#endif
+    if (h->cfg.model != LBM_MODEL_CG) {
+        sc_step(h, nsteps);
+    } else if (cg_fast_eligible(h)) {
+        cg_fast_step(h, nsteps);
+    } else {
+        for (int s = 0; s < nsteps; ++s) {
+            cg_ensure_head(h);
+            cg_generic_body(h);
+        }
+    }
+#ifndef LBM_HOSTCHECK
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+#endif
+    h->last_launches = g_launch_counter - l0;
+    API_END(h)
+}
+
+extern "C" int lbm_synchronize(lbm_handle* h) {
+    API_BEGIN(h)
+    set_device(h);
+    dev_sync(h->stream);
+    API_END(h)
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+static void to_output_point(lbm_handle* h) {
+    cg_fast_materialise(h);     // no-op unless the fast path left the streaming pending
+    cg_ensure_head(h);
+}
+
+extern "C" int lbm_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u) {
+    API_BEGIN(h)
+    if (!h->has_state) return fail(h, LBM_ESTATE, "no state");
+    set_device(h);
+    if (h->cfg.model != LBM_MODEL_CG) return sc_download_macros(h, rho, n_comp, u);
+    if (rho && n_comp != 2) return fail(h, LBM_EINVAL, "colour gradient has 2 components");
+    to_output_point(h);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2, off = NG * g.plane;
+    if (rho)
+        for (int k = 0; k < 2; ++k)
+            if (rho[k]) dev_d2h(rho[k], h->rho + k * g.vol + off, owned * 8, h->stream);
+    if (u)
+        for (int a = 0; a < h->D; ++a)
+            if (u[a]) dev_d2h(u[a], h->u + a * g.vol + off, owned * 8, h->stream);
+    dev_sync(h->stream);
+    API_END(h)
+}
+
+extern "C" int lbm_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp) {
+    API_BEGIN(h)
+    if (!h->has_state) return fail(h, LBM_ESTATE, "no state");
+    set_device(h);
+    if (h->cfg.model != LBM_MODEL_CG) return sc_download_pdfs(h, pdf, n_comp);
+    if (!pdf || n_comp != 2) return fail(h, LBM_EINVAL, "colour gradient has 2 components");
+    to_output_point(h);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2;
+    double* tmp = (double*)dev_alloc((size_t)owned * h->Q * 8);
+    try {
+        CGFields c = h->fields();
+        for (int k = 0; k < 2; ++k) {
+            if (!pdf[k]) continue;
+            if (h->Q == 9) launch(SoaToAosOp<D2Q9>{g, c.fS[k], tmp}, owned, h->stream);
+            else launch(SoaToAosOp<D3Q19>{g, c.fS[k], tmp}, owned, h->stream);
+            dev_d2h(pdf[k], tmp, (size_t)owned * h->Q * 8, h->stream);
+        }
+    } catch (...) { dev_free(tmp); throw; }
+    dev_free(tmp);
+    API_END(h)
+}
+
+extern "C" int lbm_download_fields(lbm_handle* h, double* phi, double* const* G, double* const* F, double* K) {
+    API_BEGIN(h)
+    if (!h->has_state) return fail(h, LBM_ESTATE, "no state");
+    if (h->cfg.model != LBM_MODEL_CG) return fail(h, LBM_EINVAL, "colour-gradient fields only");
+    set_device(h);
+    cg_fast_materialise(h);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2, off = NG * g.plane;
+    if (phi) dev_d2h(phi, h->phi + off, owned * 8, h->stream);
+    if (K) dev_d2h(K, h->K + off, owned * 8, h->stream);
+    for (int a = 0; a < h->D; ++a) {
+        if (G && G[a]) dev_d2h(G[a], h->G + a * g.vol + off, owned * 8, h->stream);
+        if (F && F[a]) dev_d2h(F[a], h->F + a * g.vol + off, owned * 8, h->stream);
+    }
+    API_END(h)
+}
+
+extern "C" int lbm_total_mass(lbm_handle* h, double* mass, int32_t n_comp) {
+    API_BEGIN(h)
+    if (!h->has_state || !mass) return fail(h, LBM_ESTATE, "no state");
+    set_device(h);
+    if (h->cfg.model != LBM_MODEL_CG) return sc_total_mass(h, mass, n_comp);
+    if (n_comp != 2) return fail(h, LBM_EINVAL, "colour gradient has 2 components");
+    cg_fast_materialise(h);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2;
+    std::vector<double> buf((size_t)owned);
+    for (int k = 0; k < 2; ++k) {
+        dev_d2h(buf.data(), h->rho + k * g.vol + NG * g.plane, owned * 8, h->stream);
+        long double s = 0.0L;
+        for (int64_t i = 0; i < owned; ++i) s += buf[i];
+        mass[k] = (double)s;
+    }
+    API_END(h)
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbm_get_timing(lbm_handle* h, double* last_step_call_ms, int64_t* kernel_launches, int64_t* nodes_per_step) {
+    API_BEGIN(h)
+    set_device(h);
+#ifndef LBM_HOSTCHECK
+    if (last_step_call_ms) {
+        LBM_CUDA_CHECK(cudaEventSynchronize(h->ev1));
+        float ms = 0.f;
+        LBM_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *last_step_call_ms = ms;
+    }
+#else
+    if (last_step_call_ms) *last_step_call_ms = 0.0;
+#endif
+    if (kernel_launches) *kernel_launches = h->last_launches;
+    if (nodes_per_step) *nodes_per_step = h->n_fluid;
+    API_END(h)
+}
+
+namespace {
+// counter-based uniform in [0, 1): SplitMix64 of (seed, global node id)
+template <class L>
+struct SpinodalInitOp {
+    CGFields c; double amp; uint64_t seed; int64_t node0;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)NG * c.g.plane + i;
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(node0 + i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        const double U = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+        const bool fl = c.cls[id] & CLS_FLUID;
+        const double rR = 0.5 + amp * (U - 0.5);
+        const double r[2] = {fl ? rR : 0.0, fl ? 1.0 - rR : 0.0};
+        for (int k = 0; k < 2; ++k) {
+            c.rho[k][id] = r[k];
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) c.fS[k][q * c.g.vol + id] = L::w(q) * r[k];
+        }
+        for (int a = 0; a < 3; ++a) { c.F[a * c.g.vol + id] = 0.0; c.u[a * c.g.vol + id] = 0.0; }
+    }
+};
+}  // namespace
+
+extern "C" int lbm_init_spinodal_device(lbm_handle* h, double amplitude, uint64_t seed) {
+    API_BEGIN(h)
+    if (!h->has_geometry) return fail(h, LBM_ESTATE, "lbm_set_geometry has not been called");
+    if (h->cfg.model != LBM_MODEL_CG) return fail(h, LBM_EINVAL, "colour-gradient initialiser");
+    set_device(h);
+    cg_fast_free(h);
+    cg_alloc_state(h);
+    const int64_t owned = h->g.plane * h->g.n2;
+    CGFields c = h->fields();
+    const int64_t node0 = (int64_t)h->rank * owned;
+    if (h->Q == 9) launch(SpinodalInitOp<D2Q9>{c, amplitude, seed, node0}, owned, h->stream);
+    else launch(SpinodalInitOp<D3Q19>{c, amplitude, seed, node0}, owned, h->stream);
+    dev_sync(h->stream);
+    h->has_state = true; h->head_done = false; h->fast_pending_stream = false;
+    API_END(h)
+}
+
+// per-kernel CUDA-event timing (bench.py's roofline leg)
+extern "C" int lbm_profile_enable(lbm_handle* h, int32_t on) {
+    API_BEGIN(h)
+#ifndef LBM_HOSTCHECK
+    set_device(h);
+    dev_sync(h->stream);
+    g_prof.clear();
+    g_prof.on = on != 0;
+#else
+    (void)on;
+#endif
+    API_END(h)
+}
+
+#ifndef LBM_HOSTCHECK
+#include <cxxabi.h>
+#include <map>
+#endif
+extern "C" int lbm_profile_report(lbm_handle* h, char* buf, int64_t buflen) {
+    API_BEGIN(h)
+    if (!buf || buflen < 1) return fail(h, LBM_EINVAL, "no buffer");
+    std::string out;
+#ifndef LBM_HOSTCHECK
+    set_device(h);
+    dev_sync(h->stream);
+    struct Acc { int64_t n = 0; double ms = 0.0; };
+    std::map<std::string, Acc> acc;
+    for (auto& r : g_prof.recs) {
+        float ms = 0.f;
+        LBM_CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        int status = 0;
+        char* dm = abi::__cxa_demangle(r.name, nullptr, nullptr, &status);
+        Acc& a = acc[status == 0 && dm ? dm : r.name];
+        free(dm);
+        a.n += 1; a.ms += ms;
+    }
+    for (auto& kv : acc) {
+        char line[512];
+        snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", kv.first.c_str(), (long long)kv.second.n, kv.second.ms);
+        out += line;
+    }
+#endif
+    if ((int64_t)out.size() + 1 > buflen) out.resize((size_t)buflen - 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    API_END(h)
+}

@@ -1,0 +1,45 @@
+"""CPU tier: the library's operator code (openlbmpm_b200/csrc), built for the host by tests/hostcheck
+(test hook, g++ -DLBM_HOSTCHECK), driven through the same C ABI and compared with the reference's golden
+vectors and the oracle.  The GPU tier (test_gpu_*.py) runs the same cases on liblbmpm.so."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "hostcheck"))
+import build as hostcheck_build
+import cases
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return hostcheck_build.build()
+
+
+@pytest.mark.parametrize("path", cases.GOLD_CG2D, ids=[cases.gold_id(p) for p in cases.GOLD_CG2D])
+def test_indexing_bit_exact(path, lib):
+    cases.check_indexing_vs_gold(path, lib)
+
+
+@pytest.mark.parametrize("path", cases.GOLD_CG2D, ids=[cases.gold_id(p) for p in cases.GOLD_CG2D])
+def test_trajectory_vs_reference(path, lib):
+    cases.check_trajectory_vs_gold(path, lib)
+
+
+def test_chunked_steps_equal_single_steps(lib):
+    cases.check_trajectory_vs_gold(cases.GOLD_CG2D[0], lib, chunk=7)
+
+
+@pytest.mark.parametrize("relax", ["MRT", "SRT"])
+def test_d3q19_periodic_vs_oracle(lib, relax):
+    m, mo = cases.case_d3q19_periodic(lib, relax=relax)
+    assert np.allclose(m, mo, rtol=0, atol=1e-9)
+
+
+def test_d3q19_sphere_wetting_vs_oracle(lib):
+    cases.case_d3q19_sphere(lib)
+
+
+def test_d2q9_obstacles_vs_oracle(lib):
+    cases.case_d2q9_random(lib, steps=8)
