@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--general", action="store_true", help="force the general (unfused) kernels")
     ap.add_argument("--cpu-size", type=int, default=128)
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -60,6 +60,7 @@ extern "C" {
 
 /* lbm_config.flags */
 #define LBM_FLAG_GENERIC_KERNELS 1u  /* force the unfused reference-ordered kernel sequence */
+#define LBM_FLAG_NO_TILED_KERNEL 2u  /* factored fast path, but with its one-thread-per-node kernels only */
 
 typedef struct lbm_handle lbm_handle;
 

@@ -1,10 +1,294 @@
-// cg_fast.cu -- fused fast path (placeholder: not yet enabled)
-#ifndef LBM_HOSTCHECK
+// cg_fast.cu -- orchestration of the factored colour-gradient fast path (cg_fast_ops.cuh) and the tiled
+// sm_100a kernel of its collision pass.
+//
+// State machine (handle.h): between lbm_step calls the lattice is either STREAMED (fS, rho: what the
+// reference holds between loop iterations, RKD2Q9.py:1295) or POST-COLLISION FACTORED (fast->buf[cur],
+// streaming pending).  Entering costs one general collision, leaving costs one materialising pull;
+// consecutive lbm_step calls stay in factored form.
+#include "cg_fast_ops.cuh"
 #include "internal.h"
+
 namespace lbm {
-bool cg_fast_eligible(const lbm_handle*) { return false; }
-void cg_fast_step(lbm_handle*, int) {}
-void cg_fast_materialise(lbm_handle*) {}
-void cg_fast_free(lbm_handle*) {}
-}  // namespace lbm
+
+struct FastState {
+    double* buf[2] = {nullptr, nullptr};   // each: gT [Q][vol], kR [vol], a [3][vol]
+    int cur = 0;
+};
+
+static FastFields fast_fields(const lbm_handle* h, int k) {
+    const FastState* f = (const FastState*)h->fast;
+    FastFields o;
+    o.gT = f->buf[k]; o.kR = f->buf[k] + (int64_t)h->Q * h->g.vol; o.a = o.kR + h->g.vol;
+    return o;
+}
+
+bool cg_fast_eligible(const lbm_handle* h) {
+    return h->cfg.model == LBM_MODEL_CG && h->cfg.inlet == LBM_BC_PERIODIC && h->cfg.outlet == LBM_BC_PERIODIC &&
+           !(h->cfg.flags & LBM_FLAG_GENERIC_KERNELS);
+}
+
+void cg_fast_free(lbm_handle* h) {
+    FastState* f = (FastState*)h->fast;
+    if (f) { dev_free(f->buf[0]); dev_free(f->buf[1]); delete f; }
+    h->fast = nullptr;
+    h->fast_pending_stream = false;
+}
+
+static void fast_alloc(lbm_handle* h) {
+    if (h->fast) return;
+    FastState* f = new FastState();
+    h->fast = f;
+    const size_t bytes = (size_t)(h->Q + 4) * h->g.vol * sizeof(double);
+    for (int k = 0; k < 2; ++k) { f->buf[k] = (double*)dev_alloc(bytes); dev_zero(f->buf[k], bytes, h->stream); }
+}
+
+#ifndef LBM_HOSTCHECK
+// ------------------------------------------------------------------------------------------------
+// Tiled collision pass for D3Q19.  One CTA owns a TX x TY column of the lattice and marches along z.
+// phi is staged in shared memory as a rolling window of 5 planes with a 2-node halo, the interface
+// normals n = -+G/|G| (and |G|) of the current 3 planes with a 1-node halo are derived from it in
+// shared memory, so that every node's curvature stencil (18 neighbour normals) is served on chip and
+// phi is read from HBM once.  The 19 pulled populations of a node are requested before the tile
+// synchronises, so the HBM latency overlaps the shared-memory phase.
+// ------------------------------------------------------------------------------------------------
+template <bool SOLIDS, int TX, int TY>
+__global__ void __launch_bounds__(TX* TY, 2)
+cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk) {
+    using L = D3Q19;
+    constexpr int NT = TX * TY;
+    constexpr int PW = TX + 4, PH = TY + 4;     // phi tile
+    constexpr int NW = TX + 2, NH = TY + 2;     // normal tile
+    extern __shared__ double smem_dyn[];
+    double (*sphi)[PH][PW] = reinterpret_cast<double (*)[PH][PW]>(smem_dyn);                    // [5]
+    double (*sn)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn + 5 * PH * PW);  // [3][nx, ny, nz, |G|]
+    const Grid& g = c.g;
+    const int64_t V = g.vol;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int z_begin = blockIdx.z * zchunk;
+    const int z_end = min(z_begin + zchunk, g.n2);
+    const int x = x0 + tx, y = y0 + ty;
+
+    auto wrapx = [&](int v) { return v < 0 ? v + g.n0 : (v >= g.n0 ? v - g.n0 : v); };
+    auto wrapy = [&](int v) { return v < 0 ? v + g.n1 : (v >= g.n1 ? v - g.n1 : v); };
+
+    auto load_phi_plane = [&](int zp) {
+        const int slot = (zp + 10) % 5;
+        const double* src = c.phi + (int64_t)(zp + NG) * g.plane;
+        for (int e = tid; e < PH * PW; e += NT) {
+            const int ly = e / PW, lx = e - ly * PW;
+            sphi[slot][ly][lx] = src[(int64_t)wrapy(y0 + ly - 2) * g.n0 + wrapx(x0 + lx - 2)];
+        }
+    };
+    auto normal_plane = [&](int zp) {
+        const int slot = (zp + 9) % 3;
+        for (int e = tid; e < NH * NW; e += NT) {
+            const int ly = e / NW, lx = e - ly * NW;
+            double G[3] = {0.0, 0.0, 0.0}, n[3] = {0.0, 0.0, 0.0}, gn = 0.0;
+            bool fluid = true;
+            int64_t id = 0;
+            if (SOLIDS) {
+                id = (int64_t)(zp + NG) * g.plane + (int64_t)wrapy(y0 + ly - 1) * g.n0 + wrapx(x0 + lx - 1);
+                fluid = c.cls[id] & CLS_FLUID;
+            }
+            if (fluid) {
+#pragma unroll
+                for (int q = 1; q < L::Q; ++q) {
+                    const double v = mul_rn(L::w(q), sphi[(zp + L::d2(q) + 10) % 5][ly + 1 + L::d1(q)][lx + 1 + L::d0(q)]);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+                        if (L::c(q, d) != 0) G[d] = add_rn(G[d], L::c(q, d) > 0 ? v : -v);
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) G[d] *= 3.0;
+                if (SOLIDS && (c.cls[id] & CLS_NEAR)) {
+                    const double ns[3] = {c.ns[id], c.ns[V + id], c.ns[2 * V + id]};
+                    cg_wetting<3>(G, ns, c.p.cosT, c.p.sinT, c.p.wetting_type);
+                }
+                gn = sqrt(G[0] * G[0] + G[1] * G[1] + G[2] * G[2]);
+                cg_unit_normal<3>(G, c.p.wetting_type, n);
+            }
+            sn[slot][0][ly][lx] = n[0]; sn[slot][1][ly][lx] = n[1]; sn[slot][2][ly][lx] = n[2];
+            sn[slot][3][ly][lx] = gn;
+        }
+    };
+
+    // x / y neighbour offsets of this thread's column (periodic)
+    const int64_t xo[3] = {(int64_t)wrapx(x - 1), (int64_t)x, (int64_t)wrapx(x + 1)};
+    const int64_t yo[3] = {(int64_t)wrapy(y - 1) * g.n0, (int64_t)y * g.n0, (int64_t)wrapy(y + 1) * g.n0};
+
+    for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) load_phi_plane(zp);
+    __syncthreads();
+    normal_plane(z_begin - 1);
+    normal_plane(z_begin);
+
+    const double sgn = c.p.wetting_type == 1 ? 1.0 : -1.0;
+    for (int z = z_begin; z < z_end; ++z) {
+        load_phi_plane(z + 2);
+        // ---- requests to HBM first: pulled populations, densities, lagged force ----
+        const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
+        bool fluid = true;
+        if (SOLIDS) fluid = c.cls[id] & CLS_FLUID;
+        double fT[L::Q];
+        double rR = 1.0, rB = 1.0, Fl[3] = {0.0, 0.0, 0.0}, phi0 = 0.0;
+        if (fluid) {
+            fT[0] = __ldcs(s.gT + id);
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                const int64_t src = (int64_t)(z - L::d2(q) + NG) * g.plane + yo[1 - L::d1(q)] + xo[1 - L::d0(q)];
+                int64_t addr = q * V + src;
+                if (SOLIDS && !(c.cls[src] & CLS_FLUID)) addr = L::opp(q) * V + id;
+                fT[q] = __ldcs(s.gT + addr);
+            }
+            rR = c.rho[0][id]; rB = c.rho[1][id];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) Fl[d] = c.F[d * V + id];
+        }
+        __syncthreads();
+        normal_plane(z + 1);
+        __syncthreads();
+        if (!fluid) continue;
+        phi0 = sphi[(z + 10) % 5][ty + 2][tx + 2];
+        // ---- curvature and force from the normals in shared memory ----
+        const int sl = (z + 9) % 3;
+        double n[3] = {sn[sl][0][ty + 1][tx + 1], sn[sl][1][ty + 1][tx + 1], sn[sl][2][ty + 1][tx + 1]};
+        const double gn = sn[sl][3][ty + 1][tx + 1];
+        double dn[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            const int sq = (z + L::d2(q) + 9) % 3;
+            double nk[3];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) nk[b] = sn[sq][b][ty + 1 + L::d1(q)][tx + 1 + L::d0(q)];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                if (L::c(q, a) != 0)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) dn[a][b] = add_rn(dn[a][b], mul_rn(3.0 * L::w(q) * L::c(q, a), nk[b]));
+        }
+        double K = 0.0, nn = 0.0, div = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            nn += n[a] * n[a]; div += dn[a][a];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) K += n[a] * n[b] * dn[a][b];
+        }
+        K -= nn * div;
+        double G[3], F[3], u[3];
+        const double rho = rB + rR, irho = 1.0 / rho;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            G[d] = sgn * gn * n[d];
+            F[d] = (c.p.wetting_type == 1 ? 0.5 : -0.5) * c.p.sigma * K * G[d];
+        }
+        double mom[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                if (L::c(q, d) != 0) mom[d] += L::c(q, d) * fT[q];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] = (mom[d] + 0.5 * Fl[d]) * irho;
+        const double tau = cg_tau(phi0, rR, rB, c.p);
+        cg_collide<L>(fT, rho, u, F, tau, c.p.relax);
+        const double amp = gn > 1.0e-8 ? c.p.beta * rR * rB * irho : 0.0;   // a = amp G / |G| = amp sgn n
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) __stcs(o.gT + q * V + id, fT[q]);
+        o.kR[id] = rR * irho;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            o.a[d * V + id] = amp * sgn * n[d];
+            c.F[d * V + id] = F[d];
+        }
+    }
+}
+
+constexpr int TILE_X = 32, TILE_Y = 8;
+
+static bool tiled_ok(const lbm_handle* h) {
+    return h->Q == 19 && h->g.n0 % TILE_X == 0 && h->g.n1 % TILE_Y == 0 && !(h->cfg.flags & 2u);
+}
+
+template <bool SOLIDS>
+static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o) {
+    const Grid& g = h->g;
+    int zchunk = g.n2 >= 64 ? 32 : g.n2;
+    dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
+    constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2));
+    static bool configured = false;
+    if (!configured) {
+        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tiled_d3q19<solids>" : "cg_collide_tiled_d3q19<all-fluid>", h->stream);
+    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, o, zchunk);
+    if (g_prof.on) g_prof.end(h->stream);
+    LBM_CUDA_CHECK(cudaGetLastError());
+    ++g_launch_counter;
+}
 #endif
+
+template <class L>
+static void fast_enter(lbm_handle* h) {
+    cg_ensure_head(h);
+    cg_generic_forces(h);
+    CGFields c = h->fields();
+    FastState* f = (FastState*)h->fast;
+    launch(CollideFactoredOp<L>{c, fast_fields(h, f->cur)}, h->g.count(0), h->stream);
+    h->head_done = false;
+    h->fast_pending_stream = true;
+}
+
+template <class L>
+static void fast_one_step(lbm_handle* h) {
+    FastState* f = (FastState*)h->fast;
+    const Grid& g = h->g;
+    CGFields c = h->fields();
+    const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
+    exchange_f64(h, f->buf[f->cur], g.vol, L::Q + 4, 1);
+    if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
+    else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
+    exchange_f64(h, c.phi, 0, 1, h->has_solid ? NG : 2);
+    if (h->has_solid) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
+    bool done = false;
+#ifndef LBM_HOSTCHECK
+    if (tiled_ok(h)) {
+        if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);
+        done = true;
+    }
+#endif
+    if (!done) {
+        launch(GradientOp<L>{c}, g.count(1), h->stream);
+        if (h->has_solid) launch(PullCollideOp<L, true>{c, s, o}, g.count(0), h->stream);
+        else launch(PullCollideOp<L, false>{c, s, o}, g.count(0), h->stream);
+    }
+    f->cur = 1 - f->cur;
+}
+
+void cg_fast_step(lbm_handle* h, int nsteps) {
+    if (nsteps <= 0) return;
+    fast_alloc(h);
+    int left = nsteps;
+    if (!h->fast_pending_stream) {
+        if (h->Q == 9) fast_enter<D2Q9>(h); else fast_enter<D3Q19>(h);
+        --left;
+    }
+    for (int s = 0; s < left; ++s) {
+        if (h->Q == 9) fast_one_step<D2Q9>(h); else fast_one_step<D3Q19>(h);
+    }
+}
+
+void cg_fast_materialise(lbm_handle* h) {
+    if (!h->fast || !h->fast_pending_stream) return;
+    FastState* f = (FastState*)h->fast;
+    const Grid& g = h->g;
+    CGFields c = h->fields();
+    exchange_f64(h, f->buf[f->cur], g.vol, h->Q + 4, 1);
+    if (h->Q == 9) launch(PullMaterialiseOp<D2Q9>{c, fast_fields(h, f->cur)}, g.count(0), h->stream);
+    else launch(PullMaterialiseOp<D3Q19>{c, fast_fields(h, f->cur)}, g.count(0), h->stream);
+    h->fast_pending_stream = false;
+    h->head_done = false;
+}
+
+}  // namespace lbm

@@ -218,7 +218,7 @@ struct PhiSolidOp {
 #pragma unroll
         for (int q = 1; q < L::Q; ++q) {
             const int64_t n = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
-            if (c.cls[n] & CLS_FLUID) { num += L::w(q) * c.phi[n]; den += L::w(q); }
+            if (c.cls[n] & CLS_FLUID) { num = add_rn(num, mul_rn(L::w(q), c.phi[n])); den += L::w(q); }
         }
         c.phi[id] = den > 0.0 ? num / den : 0.0;
     }
@@ -237,10 +237,10 @@ struct GradientOp {
         double G[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int q = 1; q < L::Q; ++q) {
-            const double v = L::w(q) * c.phi[g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q))];
+            const double v = mul_rn(L::w(q), c.phi[g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q))]);
 #pragma unroll
             for (int a = 0; a < L::D; ++a)
-                if (L::c(q, a) != 0) G[a] += v * L::c(q, a);
+                if (L::c(q, a) != 0) G[a] = add_rn(G[a], L::c(q, a) > 0 ? v : -v);
         }
 #pragma unroll
         for (int a = 0; a < L::D; ++a) G[a] *= 3.0;
@@ -272,7 +272,7 @@ LBM_HD void cg_force_at(const CGFields& c, int x, int y, int z, int64_t id, cons
         for (int a = 0; a < L::D; ++a)
             if (L::c(q, a) != 0)
 #pragma unroll
-                for (int b = 0; b < L::D; ++b) dn[a][b] += 3.0 * L::w(q) * L::c(q, a) * nk[b];
+                for (int b = 0; b < L::D; ++b) dn[a][b] = add_rn(dn[a][b], mul_rn(3.0 * L::w(q) * L::c(q, a), nk[b]));
     }
     double K = 0.0, nn = 0.0, div = 0.0;
 #pragma unroll

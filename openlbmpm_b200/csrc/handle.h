@@ -21,6 +21,7 @@ struct lbm_handle {
     double* ns = nullptr;       // [3][vol]
     int64_t n_fluid = 0, n_wet = 0, n_near = 0;
     bool has_geometry = false;
+    bool has_solid = false;     // any solid node in the slab or its ghost planes
 
     // colour-gradient state (general path)
     double* fS = nullptr;       // [2][Q][vol] streamed populations

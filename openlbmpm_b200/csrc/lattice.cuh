@@ -16,6 +16,25 @@
 
 namespace lbm {
 
+// Products inside the gradient / curvature stencils must be rounded before they are summed: the reference
+// relies on EXACT cancellation of w_k phi(x+e_k) against w_k phi(x-e_k) in uniform regions (its type-1
+// force kernel turns any non-zero |G|, even 1e-17 of rounding noise, into a unit normal).  An FMA would
+// keep the product unrounded and break that cancellation.
+LBM_HD double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+LBM_HD double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
 struct D2Q9 {
     static constexpr int Q = 9;
     static constexpr int D = 2;

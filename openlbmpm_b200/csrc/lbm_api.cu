@@ -185,6 +185,12 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
     h->n_fluid = nf;
     dev_h2d(h->dom + NG * g.plane, norm.data(), owned, h->stream);
     exchange_u8(h, h->dom, NG);
+    {
+        std::vector<uint8_t> padded((size_t)g.vol);
+        dev_d2h(padded.data(), h->dom, g.vol, h->stream);
+        h->has_solid = false;
+        for (int64_t i = 0; i < g.vol; ++i) if (!padded[i]) { h->has_solid = true; break; }
+    }
     if (h->D == 2) {
         launch(ClassifyOp<2>{g, h->dom, h->cls}, g.count(2), h->stream);
         launch(SolidNormalOp<2>{g, h->dom, h->cls, h->ns}, g.count(1), h->stream);
@@ -401,7 +407,7 @@ template <class L>
 static void cg_forces(lbm_handle* h, const CGFields& c) {
     const Grid& g = h->g;
     exchange_f64(h, c.phi, 0, 1, NG);
-    if (h->n_fluid != g.plane * g.n2 || h->nranks > 1) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
+    if (h->has_solid) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
     launch(GradientOp<L>{c}, g.count(1), h->stream);
 }
 

@@ -1,7 +1,7 @@
 """Builds tests/hostcheck/libhostcheck.so: the library's operator code (openlbmpm_b200/csrc/*.cuh, *.cu)
 compiled for the HOST with g++ -DLBM_HOSTCHECK.  TEST HOOK ONLY: it lets the CPU-only test tier check
 the node arithmetic and the step orchestration against the oracle without a GPU.  The package never
-loads it (openlbmpm_b200/_lib.py only knows liblbmpm.so) and the fused CUDA fast path is not in it."""
+loads it (openlbmpm_b200/_lib.py only knows liblbmpm.so) and the tiled CUDA kernels are not in it."""
 import os
 import subprocess
 import sys
@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "openlbmpm_b200", "csrc")
 OUT = os.path.join(HERE, "libhostcheck.so")
-SOURCES = ["lbm_api.cu", "sc_api.cu", "host_stubs.cu"]
+SOURCES = ["lbm_api.cu", "sc_api.cu", "cg_fast.cu", "host_stubs.cu"]
 
 
 def build(force=False):

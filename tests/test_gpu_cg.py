@@ -64,3 +64,48 @@ def test_no_state_is_an_error():
     with pytest.raises(_lib.LbmError):
         eng.step(1)
     eng.close()
+
+
+# ---- the factored fast path with the tiled sm_100a collision kernel (needs nx % 32 == 0, ny % 8 == 0) ----
+@pytest.mark.parametrize("relax", ["MRT", "SRT"])
+def test_tiled_kernel_periodic_vs_oracle(relax):
+    cases.case_d3q19_periodic(None, n=(10, 16, 32), steps=8, relax=relax)
+
+
+def test_tiled_kernel_two_tiles_and_chunks_vs_oracle():
+    cases.case_d3q19_periodic(None, n=(70, 16, 64), steps=5)
+
+
+def test_tiled_kernel_sphere_wetting_vs_oracle():
+    cases.case_d3q19_sphere(None, n=(12, 16, 32), steps=8)
+
+
+def test_tiled_kernel_equals_untiled_fast_path():
+    cases.case_d3q19_sphere(None, n=(12, 16, 32), steps=8, flags=2)
+    cases.case_d3q19_periodic(None, n=(10, 16, 32), steps=8, flags=2)
+
+
+def test_large_box_mass_conservation_and_symmetry():
+    """full-size-style property test: colour masses conserved and a mirror-symmetric start stays symmetric"""
+    from openlbmpm_b200 import _lib
+    n = (64, 64, 64)
+    z, y, x = np.mgrid[0:n[0], 0:n[1], 0:n[2]]
+    red = ((x - 31.5) ** 2 + (y - 31.5) ** 2 + (z - 31.5) ** 2) < 15.0 ** 2
+    eng = _lib.Engine(19, n, sigma=0.1, beta=0.7)
+    eng.set_geometry(np.ones(n, bool))
+    eng.init_equilibrium(np.where(red, 1.0, 0.0), np.where(red, 0.0, 1.0))
+    m0 = eng.total_mass()
+    eng.step(200)
+    m1 = eng.total_mass()
+    assert np.allclose(m0, m1, rtol=1e-12)
+    rho, u = eng.download_macros()
+    assert np.isfinite(rho[0]).all()
+    assert np.abs(rho[0] - rho[0][::-1]).max() < 1e-9
+    assert np.abs(rho[0] - rho[0][:, :, ::-1]).max() < 1e-9
+    assert np.abs(rho[0] - rho[0].transpose(1, 0, 2)).max() < 1e-9
+    # Laplace law: pressure jump across the droplet = 2 sigma / R (3-D), p = rho / 3
+    p_in = (rho[0] + rho[1])[28:36, 28:36, 28:36].mean() / 3.0
+    p_out = (rho[0] + rho[1])[0:4, 0:4, 0:4].mean() / 3.0
+    R = (3.0 * (rho[0] > 0.5).sum() / (4.0 * np.pi)) ** (1.0 / 3.0)
+    assert abs((p_in - p_out) - 2 * 0.1 / R) < 0.25 * (2 * 0.1 / R)
+    eng.close()

@@ -43,3 +43,20 @@ def test_d3q19_sphere_wetting_vs_oracle(lib):
 
 def test_d2q9_obstacles_vs_oracle(lib):
     cases.case_d2q9_random(lib, steps=8)
+
+
+# the same cases through the general (reference-ordered) kernels instead of the factored fast path
+@pytest.mark.parametrize("path", [p for p in cases.GOLD_CG2D if "channel" not in p],
+                         ids=[cases.gold_id(p) for p in cases.GOLD_CG2D if "channel" not in p])
+def test_trajectory_vs_reference_general_kernels(path, lib):
+    cases.check_trajectory_vs_gold(path, lib, flags=1)
+
+
+def test_d3q19_general_kernels_vs_oracle(lib):
+    cases.case_d3q19_periodic(lib, flags=1)
+    cases.case_d3q19_sphere(lib, flags=1)
+
+
+def test_fast_and_general_paths_agree_on_mass(lib):
+    m, mo = cases.case_d3q19_periodic(lib, n=(6, 8, 32), steps=5)
+    assert np.allclose(m, mo, rtol=0, atol=1e-9)
