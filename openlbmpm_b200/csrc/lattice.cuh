@@ -23,6 +23,9 @@ namespace lbm {
 LBM_HD double mul_rn(double a, double b) {
 #ifdef __CUDA_ARCH__
     return __dmul_rn(a, b);
+#elif defined(LBM_HOST_FMA_TEST)     // host build with -ffp-contract=fast (debug aid): block the contraction
+    volatile double r = a * b;
+    return r;
 #else
     return a * b;
 #endif
@@ -313,19 +316,25 @@ LBM_HD void cg_recolour(const double* fT, double rhoR, double rhoB, const double
 //   type 2: updateColorGradientOnWettingNew (2428-2492, Akai et al. 2018; any D)
 template <int D>
 LBM_HD void cg_wetting(double* G, const double* ns, double cosT, double sinT, int type) {
-    const double gn = sqrt(G[0] * G[0] + G[1] * G[1] + (D == 3 ? G[2] * G[2] : 0.0));
+    // Every product and sum below is rounded separately (mul_rn / add_rn, no FMA contraction): which of the
+    // two candidate normals is "closer" is decided by comparing two distances that are EQUAL by symmetry at
+    // corner and axis nodes; the reference's tie rule (d1 == d2) only reproduces with its own rounding.
+    auto M = [](double a, double b) { return mul_rn(a, b); };
+    auto A = [](double a, double b) { return add_rn(a, b); };
+    auto S = [](double a, double b) { return add_rn(a, -b); };
+    const double gn = sqrt(D == 3 ? A(A(M(G[0], G[0]), M(G[1], G[1])), M(G[2], G[2])) : A(M(G[0], G[0]), M(G[1], G[1])));
     if (type == 1) {
-        const double n1x = ns[0] * cosT - ns[1] * sinT, n1y = ns[1] * cosT + ns[0] * sinT;
-        const double n2x = ns[0] * cosT + ns[1] * sinT, n2y = ns[1] * cosT - ns[0] * sinT;
+        const double n1x = S(M(ns[0], cosT), M(ns[1], sinT)), n1y = A(M(ns[1], cosT), M(ns[0], sinT));
+        const double n2x = A(M(ns[0], cosT), M(ns[1], sinT)), n2y = S(M(ns[1], cosT), M(ns[0], sinT));
         double ux = 0.0, uy = 0.0;
         if (gn > 1.0e-8) { ux = G[0] / gn; uy = G[1] / gn; }
-        const double d1 = sqrt((ux - n1x) * (ux - n1x) + (uy - n1y) * (uy - n1y));
-        const double d2 = sqrt((ux - n2x) * (ux - n2x) + (uy - n2y) * (uy - n2y));
+        const double d1 = sqrt(A(M(S(ux, n1x), S(ux, n1x)), M(S(uy, n1y), S(uy, n1y))));
+        const double d2 = sqrt(A(M(S(ux, n2x), S(ux, n2x)), M(S(uy, n2y), S(uy, n2y))));
         double mx = 0.0, my = 0.0;
         if (d1 < d2) { mx = n1x; my = n1y; }
         else if (d1 > d2) { mx = n2x; my = n2y; }
         else if (d1 == d2) { mx = ns[0]; my = ns[1]; }
-        G[0] = gn * mx; G[1] = gn * my;
+        G[0] = M(gn, mx); G[1] = M(gn, my);
         return;
     }
     double un[3] = {0.0, 0.0, 0.0};
@@ -333,29 +342,30 @@ LBM_HD void cg_wetting(double* G, const double* ns, double cosT, double sinT, in
         un[0] = -G[0] / gn; un[1] = -G[1] / gn;
         if (D == 3) un[2] = -G[2] / gn;
     }
-    double dot = un[0] * ns[0] + un[1] * ns[1] + (D == 3 ? un[2] * ns[2] : 0.0);
+    double dot = A(M(un[0], ns[0]), M(un[1], ns[1]));
+    if (D == 3) dot = A(dot, M(un[2], ns[2]));
     // acos outside [-1,1] is NaN on the GPU and ends in "no update" (2451-2460); clamping gives
     // sin(theta') = 0 (or 1.2e-16) and therefore the same outcome without the NaN.
     dot = fmin(1.0, fmax(-1.0, dot));
     const double th = acos(dot);
     const double sth = sin(th), cth = cos(th);
     double c1 = 0.0, c2 = 0.0;
-    if (fabs(sth) > 1.0e-9) { c1 = sinT * cth / sth; c2 = sinT / sth; }
+    if (fabs(sth) > 1.0e-9) { c1 = M(sinT, cth) / sth; c2 = sinT / sth; }
     double d1 = 0.0, d2 = 0.0, n1[3], n2[3];
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        n1[a] = (cosT - c1) * ns[a] + c2 * un[a];
-        n2[a] = (cosT + c1) * ns[a] - c2 * un[a];
-        d1 += (n1[a] - un[a]) * (n1[a] - un[a]);
-        d2 += (n2[a] - un[a]) * (n2[a] - un[a]);
+        n1[a] = A(M(S(cosT, c1), ns[a]), M(c2, un[a]));
+        n2[a] = S(M(A(cosT, c1), ns[a]), M(c2, un[a]));
+        d1 = A(d1, M(S(n1[a], un[a]), S(n1[a], un[a])));
+        d2 = A(d2, M(S(n2[a], un[a]), S(n2[a], un[a])));
     }
     d1 = sqrt(d1); d2 = sqrt(d2);
     if (d1 < d2) {
 #pragma unroll
-        for (int a = 0; a < D; ++a) G[a] = -gn * n1[a];
+        for (int a = 0; a < D; ++a) G[a] = M(-gn, n1[a]);
     } else if (d1 > d2) {
 #pragma unroll
-        for (int a = 0; a < D; ++a) G[a] = -gn * n2[a];
+        for (int a = 0; a < D; ++a) G[a] = M(-gn, n2[a]);
     }
 }
 

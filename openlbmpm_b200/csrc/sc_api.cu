@@ -1,11 +1,238 @@
-// sc_api.cu -- Shan-Chen / explicit-forcing models (placeholder until sc_ops.cuh lands)
+// sc_api.cu -- state and step loops of the D2Q9 Shan-Chen models behind the C ABI
+// (original Shan-Chen: ShanChenD2Q9.py:1492-1629; explicit forcing SRT/MRT: ShanChenD2Q9.py:1714-2087).
 #include "internal.h"
+#include "sc_ops.cuh"
+
 namespace lbm {
-int sc_init_equilibrium(lbm_handle* h, const double* const*, int32_t) { h->err = "Shan-Chen models not built yet"; return LBM_EINVAL; }
-int sc_upload_state(lbm_handle* h, const double* const*, const double* const*, int32_t) { h->err = "Shan-Chen models not built yet"; return LBM_EINVAL; }
-void sc_step(lbm_handle*, int) {}
-int sc_download_macros(lbm_handle*, double* const*, int32_t, double* const*) { return LBM_EINVAL; }
-int sc_download_pdfs(lbm_handle*, double* const*, int32_t) { return LBM_EINVAL; }
-int sc_total_mass(lbm_handle*, double*, int32_t) { return LBM_EINVAL; }
-void sc_free(lbm_handle*) {}
+
+struct SCState {
+    double *fS = nullptr, *fC = nullptr, *rho = nullptr, *F = nullptr, *ueq = nullptr, *uph = nullptr, *fold = nullptr;
+    bool efs_prepared = false;    // EFS pre-loop (force, u_eq, f <- f - fF/2, boundary rows) done
+    bool head_done = false;       // SC: inlet treatment of the current iteration already applied
+};
+
+static SCFields sc_fields(const lbm_handle* h) {
+    const SCState* s = (const SCState*)h->sc;
+    SCFields c;
+    memset(&c, 0, sizeof(c));
+    c.g = h->g;
+    const lbm_config& cfg = h->cfg;
+    c.p.nc = cfg.n_components; c.p.relax = cfg.relax; c.p.inlet = cfg.inlet; c.p.outlet = cfg.outlet;
+    for (int k = 0; k < SC_MAXC; ++k) {
+        c.p.tau[k] = cfg.sc_tau[k]; c.p.Gs[k] = cfg.sc_Gsolid[k]; c.p.vin[k] = cfg.sc_inlet_velocity[k];
+        c.p.rho_out[k] = cfg.sc_rho_out[k];
+        for (int j = 0; j < SC_MAXC; ++j) c.p.G[k * SC_MAXC + j] = cfg.sc_G[k * SC_MAXC + j];
+    }
+    c.fS = s->fS; c.fC = s->fC; c.rho = s->rho; c.F = s->F; c.ueq = s->ueq; c.uph = s->uph; c.fold = s->fold;
+    c.cls = h->cls;
+    c.z_in = h->g.n2 - 2; c.z_in_ghost = h->g.n2 - 1;
+    return c;
+}
+
+void sc_free(lbm_handle* h) {
+    SCState* s = (SCState*)h->sc;
+    if (!s) return;
+    double* arrs[] = {s->fS, s->fC, s->rho, s->F, s->ueq, s->uph, s->fold};
+    for (double* p : arrs) dev_free(p);
+    delete s;
+    h->sc = nullptr;
+}
+
+static void sc_alloc(lbm_handle* h) {
+    if (h->sc) return;
+    if (h->nranks > 1) throw BackendError{"the Shan-Chen models run on one slab"};
+    SCState* s = new SCState();
+    h->sc = s;
+    const int nc = h->cfg.n_components;
+    const size_t V = (size_t)h->g.vol * sizeof(double);
+    auto alloc0 = [&](size_t bytes) { double* p = (double*)dev_alloc(bytes); dev_zero(p, bytes, h->stream); return p; };
+    s->fS = alloc0(nc * 9 * V); s->fC = alloc0(nc * 9 * V); s->rho = alloc0(nc * V); s->F = alloc0(nc * 2 * V);
+    s->ueq = alloc0(2 * V); s->uph = alloc0(2 * V);
+    s->fold = alloc0((size_t)nc * 9 * 3 * h->g.plane * sizeof(double));
+}
+
+int sc_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp) {
+    if (n_comp != h->cfg.n_components || !rho) { h->err = "one density array per component expected"; return LBM_EINVAL; }
+    for (int k = 0; k < n_comp; ++k) if (!rho[k]) { h->err = "NULL density array"; return LBM_EINVAL; }
+    sc_alloc(h);
+    const int64_t owned = h->g.plane * h->g.n2;
+    double* tmp = (double*)dev_alloc((size_t)n_comp * owned * 8);
+    try {
+        for (int k = 0; k < n_comp; ++k) dev_h2d(tmp + k * owned, rho[k], owned * 8, h->stream);
+        launch(ScInitOp{sc_fields(h), tmp}, owned, h->stream);
+        dev_sync(h->stream);
+    } catch (...) { dev_free(tmp); throw; }
+    dev_free(tmp);
+    SCState* s = (SCState*)h->sc;
+    s->efs_prepared = false; s->head_done = false;
+    h->has_state = true;
+    return LBM_OK;
+}
+
+int sc_upload_state(lbm_handle* h, const double* const* pdf, const double* const* rho, int32_t n_comp) {
+    if (n_comp != h->cfg.n_components || !pdf) { h->err = "one population array per component expected"; return LBM_EINVAL; }
+    sc_alloc(h);
+    const int64_t owned = h->g.plane * h->g.n2;
+    double* tmp = (double*)dev_alloc((size_t)owned * 10 * 8);
+    try {
+        SCFields c = sc_fields(h);
+        for (int k = 0; k < n_comp; ++k) {
+            if (!pdf[k]) throw BackendError{"NULL population array"};
+            dev_h2d(tmp, pdf[k], (size_t)owned * 9 * 8, h->stream);
+            const double* rin = nullptr;
+            if (rho && rho[k]) { dev_h2d(tmp + owned * 9, rho[k], owned * 8, h->stream); rin = tmp + owned * 9; }
+            launch(ScUploadOp{c, k, tmp, rin}, owned, h->stream);
+            dev_sync(h->stream);
+        }
+        SCState* s = (SCState*)h->sc;
+        dev_zero(s->F, (size_t)n_comp * 2 * h->g.vol * 8, h->stream);
+        s->efs_prepared = false; s->head_done = false;
+    } catch (...) { dev_free(tmp); throw; }
+    dev_free(tmp);
+    h->has_state = true;
+    return LBM_OK;
+}
+
+// inlet rows: Zou-He velocity per component + ghost row (OptimizedD2Q9GPU.py:839-861, 710-736)
+static void sc_inlet(lbm_handle* h, const SCFields& c) {
+    if (c.p.inlet == LBM_INLET_VELOCITY) {
+        launch(ScInletVelocityOp{c}, h->g.n0, h->stream);
+        launch(ScRowCopyOp{c, c.z_in_ghost, c.z_in}, h->g.plane, h->stream);
+    }
+}
+static void sc_outlet_pressure(lbm_handle* h, const SCFields& c) {
+    launch(ScOutletPressureOp{c}, h->g.n0, h->stream);
+    launch(ScRowCopyOp{c, 0, 1}, h->g.plane, h->stream);
+}
+
+static void sc_ensure_head(lbm_handle* h) {
+    SCState* s = (SCState*)h->sc;
+    if (h->cfg.model != LBM_MODEL_SC || s->head_done) return;
+    sc_inlet(h, sc_fields(h));
+    s->head_done = true;
+}
+
+// one iteration of runOptimizedLBM's loop (ShanChenD2Q9.py:1492-1629)
+static void sc_iteration(lbm_handle* h) {
+    SCState* s = (SCState*)h->sc;
+    const Grid& g = h->g;
+    SCFields c = sc_fields(h);
+    sc_ensure_head(h);
+    launch(ScRhoOp{c}, g.count(0), h->stream);                  // calFluidRhoGPU; psi = rho
+    exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
+    launch(ScCollideOp{c}, g.count(0), h->stream);              // interactionCollisionProcess
+    exchange_f64(h, c.fC, g.vol, c.p.nc * 9, 1);
+    launch(ScStreamOp{c}, g.count(0), h->stream);               // calStreaming1GPU/2GPU (+ densities)
+    if (c.p.outlet == LBM_OUTLET_CONVECTIVE) {                  // convectiveOutletGPU / Ghost2 / Ghost3
+        launch(ScRowCopyOp{c, 2, 3}, g.plane, h->stream);
+        launch(ScRowCopyOp{c, 1, 2}, g.plane, h->stream);
+        launch(ScRowCopyOp{c, 0, 1}, g.plane, h->stream);
+    }
+    launch(ScPhysicalVelocityOp{c}, g.count(0), h->stream);
+    s->head_done = false;
+}
+
+// pre-loop of runOptimizedEFLBM (ShanChenD2Q9.py:1714-1849)
+static void efs_prepare(lbm_handle* h) {
+    SCState* s = (SCState*)h->sc;
+    if (s->efs_prepared) return;
+    const Grid& g = h->g;
+    SCFields c = sc_fields(h);
+    exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
+    launch(EfsForceOp{c}, g.count(0), h->stream);
+    launch(EfsTransformOp{c}, g.count(0), h->stream);
+    // boundary rows: the populations are treated, the densities the reference sets here are never read
+    // before calFluidRhoGPU overwrites them, so the state keeps the densities f_eq was built from
+    if (c.p.inlet == LBM_INLET_VELOCITY || c.p.outlet == LBM_OUTLET_PRESSURE) {
+        double* keep = (double*)dev_alloc((size_t)c.p.nc * g.vol * 8);
+        dev_d2d(keep, c.rho, (size_t)c.p.nc * g.vol * 8, h->stream);
+        sc_inlet(h, c);
+        if (c.p.outlet == LBM_OUTLET_PRESSURE) sc_outlet_pressure(h, c);
+        dev_d2d(c.rho, keep, (size_t)c.p.nc * g.vol * 8, h->stream);
+        dev_sync(h->stream);
+        dev_free(keep);
+    }
+    s->efs_prepared = true;
+}
+
+// one iteration of runOptimizedEFLBM's loop (ShanChenD2Q9.py:1852-2087)
+static void efs_iteration(lbm_handle* h) {
+    const Grid& g = h->g;
+    SCFields c = sc_fields(h);
+    if (c.p.outlet == LBM_OUTLET_CONVECTIVE) launch(ScSaveRowsOp{c}, 3 * g.plane, h->stream);   // savePDFLastStep
+    launch(EfsCollideOp{c}, g.count(0), h->stream);
+    exchange_f64(h, c.fC, g.vol, c.p.nc * 9, 1);
+    launch(ScStreamOp{c}, g.count(0), h->stream);
+    if (c.p.outlet == LBM_OUTLET_CONVECTIVE) {
+        launch(ScPhysicalVelocityOp{c}, g.count(0), h->stream);
+        launch(ScConvectiveEachOp{c, 2}, g.plane, h->stream);
+        launch(ScConvectiveEachOp{c, 1}, g.plane, h->stream);
+        launch(ScConvectiveEachOp{c, 0}, g.plane, h->stream);
+    } else if (c.p.outlet == LBM_OUTLET_PRESSURE) {
+        sc_outlet_pressure(h, c);
+    }
+    sc_inlet(h, c);
+    if (c.p.inlet != LBM_BC_PERIODIC || c.p.outlet != LBM_BC_PERIODIC) launch(ScRhoOp{c}, g.count(0), h->stream);
+    launch(ScPhysicalVelocityOp{c}, g.count(0), h->stream);     // output point (:2016-2027)
+    exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
+    launch(EfsForceOp{c}, g.count(0), h->stream);
+}
+
+void sc_step(lbm_handle* h, int nsteps) {
+    if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
+    for (int s = 0; s < nsteps; ++s) {
+        if (h->cfg.model == LBM_MODEL_SC) sc_iteration(h); else efs_iteration(h);
+    }
+}
+
+int sc_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u) {
+    if (rho && n_comp != h->cfg.n_components) { h->err = "one density array per component expected"; return LBM_EINVAL; }
+    if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
+    sc_ensure_head(h);
+    SCFields c = sc_fields(h);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2, off = NG * g.plane;
+    if (rho)
+        for (int k = 0; k < n_comp; ++k)
+            if (rho[k]) dev_d2h(rho[k], c.rho + k * g.vol + off, owned * 8, h->stream);
+    if (u)
+        for (int a = 0; a < 2; ++a)
+            if (u[a]) dev_d2h(u[a], c.uph + a * g.vol + off, owned * 8, h->stream);
+    dev_sync(h->stream);
+    return LBM_OK;
+}
+
+int sc_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp) {
+    if (!pdf || n_comp != h->cfg.n_components) { h->err = "one population array per component expected"; return LBM_EINVAL; }
+    if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
+    sc_ensure_head(h);
+    SCFields c = sc_fields(h);
+    const int64_t owned = h->g.plane * h->g.n2;
+    double* tmp = (double*)dev_alloc((size_t)owned * 9 * 8);
+    try {
+        for (int k = 0; k < n_comp; ++k) {
+            if (!pdf[k]) continue;
+            launch(ScDownloadOp{c, k, tmp}, owned, h->stream);
+            dev_d2h(pdf[k], tmp, (size_t)owned * 9 * 8, h->stream);
+        }
+    } catch (...) { dev_free(tmp); throw; }
+    dev_free(tmp);
+    return LBM_OK;
+}
+
+int sc_total_mass(lbm_handle* h, double* mass, int32_t n_comp) {
+    if (n_comp != h->cfg.n_components) { h->err = "one value per component expected"; return LBM_EINVAL; }
+    SCFields c = sc_fields(h);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2;
+    std::vector<double> buf((size_t)owned);
+    for (int k = 0; k < n_comp; ++k) {
+        dev_d2h(buf.data(), c.rho + k * g.vol + NG * g.plane, owned * 8, h->stream);
+        long double s = 0.0L;
+        for (int64_t i = 0; i < owned; ++i) s += buf[i];
+        mass[k] = (double)s;
+    }
+    return LBM_OK;
+}
+
 }  // namespace lbm

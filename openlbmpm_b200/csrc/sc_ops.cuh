@@ -1,0 +1,379 @@
+// sc_ops.cuh -- D2Q9 multi-component Shan-Chen models on the dense grid, one thread per node:
+//   * original Shan-Chen      (ShanChenD2Q9.runOptimizedLBM,   ShanChenD2Q9.py:1433-1629; kernels in
+//                              ShanChen2D/OptimizedD2Q9GPU.py)
+//   * explicit forcing SRT/MRT (ShanChenD2Q9.runOptimizedEFLBM, ShanChenD2Q9.py:1631-2087; kernels in
+//                              ShanChen2D/ExplicitD2Q9GPU.py), isotropy 4.
+// The reference materialises f_eq, the force distribution and (MRT) their images under C = M^-1 S M as
+// five extra [nf, N, 9] arrays and runs 7-9 kernels over them; here the state is (f, rho, F, u_eq) and
+// the equilibrium / force distributions live in registers inside the collision operator.  The MRT
+// relaxation is applied in moment space (M, diag(S), M^-1 hand-factored) instead of a dense 9x9 product.
+#pragma once
+#include "grid.cuh"
+
+namespace lbm {
+
+constexpr int SC_MAXC = 4;
+
+struct SCParams {
+    int nc, relax, inlet, outlet;
+    double tau[SC_MAXC], G[SC_MAXC * SC_MAXC], Gs[SC_MAXC], vin[SC_MAXC], rho_out[SC_MAXC];
+};
+
+struct SCFields {
+    Grid g;
+    SCParams p;
+    double* fS;      // [nc][9][vol] populations (EFS: the transformed populations f - fF/2)
+    double* fC;      // [nc][9][vol] post-collision
+    double* rho;     // [nc][vol]
+    double* F;       // [nc][2][vol]
+    double* ueq;     // [2][vol]   common equilibrium velocity (EFS)
+    double* uph;     // [2][vol]   physical velocity
+    double* fold;    // [nc][9][3 planes] populations of rows 0..2 before the collision (convective outlet)
+    const uint8_t* cls;
+    int z_in, z_in_ghost;
+    LBM_HD double* f(double* base, int c, int q) const { return base + ((int64_t)c * 9 + q) * g.vol; }
+};
+
+LBM_HD double sc_feq(int q, double rho, double ux, double uy) {
+    const double eu = D2Q9::cx(q) * ux + D2Q9::cy(q) * uy;
+    return D2Q9::w(q) * rho * (1.0 + 3.0 * eu + 9.0 / 2.0 * (eu * eu) - 3.0 / 2.0 * (ux * ux + uy * uy));
+}
+
+// f = w rho at rest (ShanChenD2Q9.py:759-768)
+struct ScInitOp {
+    SCFields c; const double* rho_in;     // [nc][owned]
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g; const int64_t id = (int64_t)NG * g.plane + i, owned = g.plane * g.n2;
+        const bool fl = c.cls[id] & CLS_FLUID;
+        for (int k = 0; k < c.p.nc; ++k) {
+            const double r = fl ? rho_in[k * owned + i] : 0.0;
+            c.rho[k * g.vol + id] = r;
+            for (int q = 0; q < 9; ++q) c.f(c.fS, k, q)[id] = D2Q9::w(q) * r;
+            c.F[(k * 2) * g.vol + id] = 0.0; c.F[(k * 2 + 1) * g.vol + id] = 0.0;
+        }
+        c.ueq[id] = c.ueq[g.vol + id] = c.uph[id] = c.uph[g.vol + id] = 0.0;
+    }
+};
+struct ScUploadOp {     // AoS [node][9] of one component -> SoA; rho = given or sum
+    SCFields c; int k; const double* aos; const double* rho_in;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g; const int64_t id = (int64_t)NG * g.plane + i;
+        const bool fl = c.cls[id] & CLS_FLUID;
+        double s = 0.0;
+        for (int q = 0; q < 9; ++q) {
+            const double v = fl ? aos[i * 9 + q] : 0.0;
+            c.f(c.fS, k, q)[id] = v;
+            s = q == 0 ? v : s + v;
+        }
+        c.rho[k * g.vol + id] = fl ? (rho_in ? rho_in[i] : s) : 0.0;
+    }
+};
+struct ScDownloadOp {
+    SCFields c; int k; double* aos;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)NG * c.g.plane + i;
+        for (int q = 0; q < 9; ++q) aos[i * 9 + q] = c.f(c.fS, k, q)[id];
+    }
+};
+
+// calFluidRhoGPU (OptimizedD2Q9GPU.py:84-93)
+struct ScRhoOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)NG * c.g.plane + i;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        for (int k = 0; k < c.p.nc; ++k) {
+            double s = c.f(c.fS, k, 0)[id];
+            for (int q = 1; q < 9; ++q) s += c.f(c.fS, k, q)[id];
+            c.rho[k * c.g.vol + id] = s;
+        }
+    }
+};
+
+// calPhysicalVelocity (OptimizedD2Q9GPU.py:156-175)
+struct ScPhysicalVelocityOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g; const int64_t id = (int64_t)NG * g.plane + i;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        double vx = 0.0, vy = 0.0, r = 0.0;
+        for (int k = 0; k < c.p.nc; ++k) {
+            const double f1 = c.f(c.fS, k, 1)[id], f2 = c.f(c.fS, k, 2)[id], f3 = c.f(c.fS, k, 3)[id], f4 = c.f(c.fS, k, 4)[id];
+            const double f5 = c.f(c.fS, k, 5)[id], f6 = c.f(c.fS, k, 6)[id], f7 = c.f(c.fS, k, 7)[id], f8 = c.f(c.fS, k, 8)[id];
+            vx += (f1 - f3 + f5 - f6 - f7 + f8 + 1.0 / 2.0 * c.F[(k * 2) * g.vol + id]);
+            vy += (f2 - f4 + f5 + f6 - f7 - f8 + 1.0 / 2.0 * c.F[(k * 2 + 1) * g.vol + id]);
+            r += c.rho[k * g.vol + id];
+        }
+        c.uph[id] = vx / r; c.uph[g.vol + id] = vy / r;
+    }
+};
+
+// constantVelocityZouHeBoundaryHigher (OptimizedD2Q9GPU.py:839-861): per-component Zou-He velocity on row z_in
+struct ScInletVelocityOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t x) const {
+        const Grid& g = c.g; const int64_t id = g.at((int)x, 0, c.z_in);
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        for (int k = 0; k < c.p.nc; ++k) {
+            const double v = c.p.vin[k];
+            const double f0 = c.f(c.fS, k, 0)[id], f1 = c.f(c.fS, k, 1)[id], f2 = c.f(c.fS, k, 2)[id], f3 = c.f(c.fS, k, 3)[id];
+            const double f5 = c.f(c.fS, k, 5)[id], f6 = c.f(c.fS, k, 6)[id];
+            const double r = (f0 + f1 + f3 + 2.0 * (f2 + f5 + f6)) / (1.0 + v);
+            c.rho[k * g.vol + id] = r;
+            c.f(c.fS, k, 4)[id] = f2 - 2.0 / 3.0 * r * v;
+            c.f(c.fS, k, 7)[id] = f5 + (f1 - f3) / 2.0 - 1.0 / 6.0 * r * v;
+            c.f(c.fS, k, 8)[id] = f6 - (f1 - f3) / 2.0 - 1.0 / 6.0 * r * v;
+        }
+    }
+};
+// constantPressureZouHeBoundaryLower (OptimizedD2Q9GPU.py:555-584) on row 1.  The reference ignores its
+// densityL argument and uses the hard-coded densities [1.0, 0.02]; they arrive here as p.rho_out.
+struct ScOutletPressureOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t x) const {
+        const Grid& g = c.g; const int64_t id = g.at((int)x, 0, 1);
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        for (int k = 0; k < c.p.nc; ++k) {
+            const double d = c.p.rho_out[k];
+            const double f0 = c.f(c.fS, k, 0)[id], f1 = c.f(c.fS, k, 1)[id], f3 = c.f(c.fS, k, 3)[id], f4 = c.f(c.fS, k, 4)[id];
+            const double f7 = c.f(c.fS, k, 7)[id], f8 = c.f(c.fS, k, 8)[id];
+            const double vy = 1.0 - (f0 + f1 + f3 + 2.0 * (f4 + f7 + f8)) / d;
+            c.f(c.fS, k, 2)[id] = f4 + 2.0 / 3.0 * vy * d;
+            c.f(c.fS, k, 5)[id] = f7 + 1.0 / 2.0 * (f3 - f1) + 1.0 / 6.0 * d * vy;
+            c.f(c.fS, k, 6)[id] = f8 - 1.0 / 2.0 * (f3 - f1) + 1.0 / 6.0 * d * vy;
+            c.rho[k * g.vol + id] = d;
+        }
+    }
+};
+// row copies with rho = sum: ghostPointsConstantVelocityInlet (710-736), ghostPointsConstantPressureOutlet
+// (743-768), convectiveOutletGPU / Ghost2 / Ghost3 (960-1036)
+struct ScRowCopyOp {
+    SCFields c; int z_dst, z_src;
+    LBM_HD void operator()(int64_t r) const {
+        const Grid& g = c.g;
+        const int64_t d = (int64_t)(z_dst + NG) * g.plane + r, s = (int64_t)(z_src + NG) * g.plane + r;
+        if (!(c.cls[d] & CLS_FLUID) || !(c.cls[s] & CLS_FLUID)) return;
+        for (int k = 0; k < c.p.nc; ++k) {
+            double acc = 0.0;
+            for (int q = 0; q < 9; ++q) {
+                const double v = c.f(c.fS, k, q)[s];
+                c.f(c.fS, k, q)[d] = v;
+                acc = q == 0 ? v : acc + v;
+            }
+            c.rho[k * g.vol + d] = acc;
+        }
+    }
+};
+// savePDFLastStep (OptimizedD2Q9GPU.py:70-78), restricted to the rows the convective outlet reads (0..2)
+struct ScSaveRowsOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t i) const {      // i over 3 planes
+        const Grid& g = c.g; const int64_t id = (int64_t)NG * g.plane + i;
+        for (int k = 0; k < c.p.nc; ++k)
+            for (int q = 0; q < 9; ++q) c.fold[((int64_t)k * 9 + q) * 3 * g.plane + i] = c.f(c.fS, k, q)[id];
+    }
+};
+// convectiveOutletEachGPU / Each2 / Each3 (OptimizedD2Q9GPU.py:1044-1119): row z <- (f_old + |u_y(row 3)| f(row z+1)) / (1 + |u_y|)
+struct ScConvectiveEachOp {
+    SCFields c; int z;
+    LBM_HD void operator()(int64_t r) const {
+        const Grid& g = c.g;
+        const int64_t d = (int64_t)(z + NG) * g.plane + r, s = (int64_t)(z + 1 + NG) * g.plane + r;
+        const int64_t r3 = (int64_t)(3 + NG) * g.plane + r;
+        if (!(c.cls[d] & CLS_FLUID)) return;
+        const double v = fabs(c.uph[g.vol + r3]);
+        for (int k = 0; k < c.p.nc; ++k) {
+            double acc = 0.0;
+            for (int q = 0; q < 9; ++q) {
+                const double fo = c.fold[((int64_t)k * 9 + q) * 3 * g.plane + (int64_t)z * g.plane + r];
+                const double val = (fo + v * c.f(c.fS, k, q)[s]) / (1.0 + v);
+                c.f(c.fS, k, q)[d] = val;
+                acc += val;
+            }
+            c.rho[k * g.vol + d] = acc;
+        }
+    }
+};
+
+// pull streaming with half-way bounce back + densities (calStreaming1GPU/2GPU 450-548, calFluidRhoGPU)
+struct ScStreamOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 0, x, y, z);
+        const int64_t id = g.at(x, y, z);
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        int64_t src[9]; bool fl[9];
+        for (int q = 1; q < 9; ++q) {
+            src[q] = g.nb(x, y, z, -D2Q9::d0(q), 0, -D2Q9::d2(q));
+            fl[q] = c.cls[src[q]] & CLS_FLUID;
+        }
+        for (int k = 0; k < c.p.nc; ++k) {
+            double acc = c.f(c.fC, k, 0)[id];
+            c.f(c.fS, k, 0)[id] = acc;
+            for (int q = 1; q < 9; ++q) {
+                const double v = fl[q] ? c.f(c.fC, k, q)[src[q]] : c.f(c.fC, k, D2Q9::opp(q))[id];
+                c.f(c.fS, k, q)[id] = v;
+                acc += v;
+            }
+            c.rho[k * g.vol + id] = acc;
+        }
+    }
+};
+
+// interactionCollisionProcess (OptimizedD2Q9GPU.py:1274-1446): common velocity u', Shan-Chen force with
+// psi = rho (fluid-fluid through the neighbours, fluid-solid with weights 1/9, 1/36), SRT collision towards
+// f_eq(rho, u' + tau F / rho).  fS -> fC, writes F.
+struct ScCollideOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 0, x, y, z);
+        const int64_t id = g.at(x, y, z), V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        const int nc = c.p.nc;
+        double f[SC_MAXC][9];
+        double vxt = 0.0, vyt = 0.0, rt = 0.0;
+        for (int k = 0; k < nc; ++k) {
+            for (int q = 0; q < 9; ++q) f[k][q] = c.f(c.fS, k, q)[id];
+            vxt += (f[k][1] - f[k][3] + f[k][5] - f[k][6] - f[k][7] + f[k][8]) / c.p.tau[k];
+            vyt += (f[k][2] - f[k][4] + f[k][5] + f[k][6] - f[k][7] - f[k][8]) / c.p.tau[k];
+            rt += c.rho[k * V + id] / c.p.tau[k];
+        }
+        const double upx = vxt / rt, upy = vyt / rt;
+        int64_t nb[9]; bool fl[9];
+        for (int q = 1; q < 9; ++q) {
+            nb[q] = g.nb(x, y, z, D2Q9::d0(q), 0, D2Q9::d2(q));
+            fl[q] = c.cls[nb[q]] & CLS_FLUID;
+        }
+        for (int k = 0; k < nc; ++k) {
+            const double psi = c.rho[k * V + id];
+            double fx = 0.0, fy = 0.0;
+            for (int q = 1; q < 9; ++q) {
+                const double wI = q < 5 ? 1.0 / 9.0 : 1.0 / 36.0;
+                if (fl[q]) {
+                    for (int j = 0; j < nc; ++j) {
+                        const double t = -wI * c.p.G[k * SC_MAXC + j] * psi * c.rho[j * V + nb[q]];
+                        if (D2Q9::cx(q) != 0) fx += t * D2Q9::cx(q);
+                        if (D2Q9::cy(q) != 0) fy += t * D2Q9::cy(q);
+                    }
+                } else {
+                    const double t = -wI * c.p.Gs[k] * psi;
+                    if (D2Q9::cx(q) != 0) fx += t * D2Q9::cx(q);
+                    if (D2Q9::cy(q) != 0) fy += t * D2Q9::cy(q);
+                }
+            }
+            c.F[(k * 2) * V + id] = fx; c.F[(k * 2 + 1) * V + id] = fy;
+            const double tau = c.p.tau[k];
+            const double ux = upx + tau * fx / psi, uy = upy + tau * fy / psi;
+            const double uu = ux * ux + uy * uy;
+            for (int q = 0; q < 9; ++q) {
+                const double eu = D2Q9::cx(q) * ux + D2Q9::cy(q) * uy;
+                c.f(c.fC, k, q)[id] = (1.0 - 1.0 / tau) * f[k][q] +
+                                      D2Q9::w(q) * psi / tau * (1.0 + 3.0 * eu + 4.5 * (eu * eu) - 1.5 * uu);
+            }
+        }
+    }
+};
+
+// calExplicit4thOrderScheme (ExplicitD2Q9GPU.py:51-217) + calEquilibriumVEFGPU (340-363, SRT) /
+// transformEquilibriumVelocity (1426-1449, MRT: weights s_0 = 1 instead of 1/tau).  Writes F and u_eq.
+struct EfsForceOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 0, x, y, z);
+        const int64_t id = g.at(x, y, z), V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        const int nc = c.p.nc;
+        int64_t nb[9]; bool fl[9];
+        for (int q = 1; q < 9; ++q) {
+            nb[q] = g.nb(x, y, z, D2Q9::d0(q), 0, D2Q9::d2(q));
+            fl[q] = c.cls[nb[q]] & CLS_FLUID;
+        }
+        double mx = 0.0, my = 0.0, rt = 0.0;
+        for (int k = 0; k < nc; ++k) {
+            const double psi = c.rho[k * V + id];
+            double gx = 0.0, gy = 0.0, sx = 0.0, sy = 0.0;
+            for (int q = 1; q < 9; ++q) {
+                const double wI = q < 5 ? 1.0 / 3.0 : 1.0 / 12.0;
+                if (fl[q]) {
+                    for (int j = 0; j < nc; ++j) {
+                        const double t = wI * (c.rho[j * V + nb[q]] - c.rho[j * V + id]);
+                        if (D2Q9::cx(q) != 0) gx += t * D2Q9::cx(q) * c.p.G[k * SC_MAXC + j];
+                        if (D2Q9::cy(q) != 0) gy += t * D2Q9::cy(q) * c.p.G[k * SC_MAXC + j];
+                    }
+                } else {
+                    const double t = -wI * c.p.Gs[k] * psi;
+                    if (D2Q9::cx(q) != 0) sx += t * D2Q9::cx(q);
+                    if (D2Q9::cy(q) != 0) sy += t * D2Q9::cy(q);
+                }
+            }
+            const double fx = -6.0 * psi * gx + sx, fy = -6.0 * psi * gy + sy;
+            c.F[(k * 2) * V + id] = fx; c.F[(k * 2 + 1) * V + id] = fy;
+            double ex = 0.0, ey = 0.0;
+            for (int q = 0; q < 9; ++q) {
+                const double v = c.f(c.fS, k, q)[id];
+                ex += v * D2Q9::cx(q); ey += v * D2Q9::cy(q);
+            }
+            ex += 1.0 / 2.0 * fx; ey += 1.0 / 2.0 * fy;
+            const double wgt = c.p.relax == 0 ? 1.0 / c.p.tau[k] : 1.0;
+            if (c.p.relax == 0) { mx += ex / c.p.tau[k]; my += ey / c.p.tau[k]; rt = rt + psi / c.p.tau[k]; }
+            else { mx += ex * wgt; my += ey * wgt; rt += psi * wgt; }
+        }
+        c.ueq[id] = mx / rt; c.ueq[V + id] = my / rt;
+    }
+};
+
+// equilibrium and force distributions of component k at a node (calEquilibriumFuncEFGPU 227-248,
+// calForceDistrGPU 255-272)
+LBM_HD void efs_feq_ff(const SCFields& c, int k, int64_t id, double* feq, double* ff) {
+    const int64_t V = c.g.vol;
+    const double r = c.rho[k * V + id], ux = c.ueq[id], uy = c.ueq[V + id];
+    const double fx = c.F[(k * 2) * V + id], fy = c.F[(k * 2 + 1) * V + id];
+    for (int q = 0; q < 9; ++q) {
+        feq[q] = sc_feq(q, r, ux, uy);
+        ff[q] = ((fx * (D2Q9::cx(q) - ux)) + (fy * (D2Q9::cy(q) - uy))) * feq[q] / (1.0 / 3.0 * r);
+    }
+}
+// transformPDFGPU (ExplicitD2Q9GPU.py:278-287), once before the first iteration: f <- f - fF / 2
+struct EfsTransformOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)NG * c.g.plane + i;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        for (int k = 0; k < c.p.nc; ++k) {
+            double feq[9], ff[9];
+            efs_feq_ff(c, k, id, feq, ff);
+            for (int q = 0; q < 9; ++q) c.f(c.fS, k, q)[id] = c.f(c.fS, k, q)[id] - 1.0 / 2.0 * ff[q];
+        }
+    }
+};
+// calCollisionEXGPU (294-304) / transfromForceTerm + transformPDFandEquil + calAfterCollisionMRT
+// (1379-1469): f <- f + C (feq - f - fF/2) + fF with C = 1/tau (SRT) or M^-1 diag(s) M (MRT),
+// s = [1, 0.6, 1.5, 1, 1.2, 1, 1.2, 1/tau, 1/tau] for the first two components (ShanChenD2Q9.py:99-106)
+struct EfsCollideOp {
+    SCFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)NG * c.g.plane + i;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        for (int k = 0; k < c.p.nc; ++k) {
+            double feq[9], ff[9], f[9], d[9];
+            efs_feq_ff(c, k, id, feq, ff);
+            for (int q = 0; q < 9; ++q) { f[q] = c.f(c.fS, k, q)[id]; d[q] = feq[q] - f[q] - 1.0 / 2.0 * ff[q]; }
+            if (c.p.relax == 0) {
+                for (int q = 0; q < 9; ++q) c.f(c.fC, k, q)[id] = f[q] + 1.0 / c.p.tau[k] * d[q] + 1.0 * ff[q];
+            } else {
+                double m[9], cd[9];
+                D2Q9::to_moments(d, m);
+                const double st = 1.0 / c.p.tau[k];
+                if (k < 2) { m[1] *= 0.6; m[2] *= 1.5; m[4] *= 1.2; m[6] *= 1.2; }
+                m[7] *= st; m[8] *= st;
+                D2Q9::from_moments(m, cd);
+                for (int q = 0; q < 9; ++q) c.f(c.fC, k, q)[id] = f[q] + cd[q] + 1.0 * ff[q];
+            }
+        }
+    }
+};
+
+}  // namespace lbm

@@ -95,7 +95,7 @@ def test_large_box_mass_conservation_and_symmetry():
     eng.set_geometry(np.ones(n, bool))
     eng.init_equilibrium(np.where(red, 1.0, 0.0), np.where(red, 0.0, 1.0))
     m0 = eng.total_mass()
-    eng.step(200)
+    eng.step(800)       # the pressure wave of the start-up has decayed (oracle: ratio 1.005 at step 800)
     m1 = eng.total_mass()
     assert np.allclose(m0, m1, rtol=1e-12)
     rho, u = eng.download_macros()
@@ -107,5 +107,20 @@ def test_large_box_mass_conservation_and_symmetry():
     p_in = (rho[0] + rho[1])[28:36, 28:36, 28:36].mean() / 3.0
     p_out = (rho[0] + rho[1])[0:4, 0:4, 0:4].mean() / 3.0
     R = (3.0 * (rho[0] > 0.5).sum() / (4.0 * np.pi)) ** (1.0 / 3.0)
-    assert abs((p_in - p_out) - 2 * 0.1 / R) < 0.25 * (2 * 0.1 / R)
+    assert abs((p_in - p_out) - 2 * 0.1 / R) < 0.1 * (2 * 0.1 / R)
     eng.close()
+
+
+def test_slab_decomposition_bit_equal_to_single_gpu():
+    """2 ranks over NCCL (when the box has >= 2 GPUs): tests/mgpu_check.py"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "mgpu_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "MGPU OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
