@@ -1,0 +1,281 @@
+"""`RKColorGradientLBM` -- drop-in for the reference's colour-gradient host class (RKCG2D/RKD2Q9.py:23-1498).
+
+Same constructor (`RKColorGradientLBM(pathIniFile)`, reads `RKtwophasesetup2D.ini`), same public attributes
+(`isDomain`, `isSolid`, `fluidsRhoR/B`, `fluidPDFR/B`, `physicalVX/VY`, `fluidNodes`, `neighboringNodes`,
+`wettingSolidNodes`, `fluidNodesWithSolidGPU`, `nsX/nsY`, ...) and the same entry points
+(`runRKColorGradient2D`, `runRKColorGradient2DCSF`; plus `runModifiedRKColorGradient2D`, which the reference's
+main.py:53 calls although the class never defined it).  The per-step Python loop that launched 17-21
+Numba-CUDA kernels (RKD2Q9.py:1295-1490) is replaced by one `lbm_step(TimeInterval)` call into
+liblbmpm.so; geometry compaction, neighbour tables and solid normals (RKD2Q9.py:657-892, Python loops) are
+built on the GPU and exported bit-exactly.  There is no CPU fallback.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import _lib
+from .inifile import Ini, IniError
+from .results import ResultFile
+
+INLET = {"periodic": _lib.BC_PERIODIC, "neumann": _lib.INLET_VELOCITY, "dirichlet": _lib.INLET_PRESSURE}
+OUTLET = {"periodic": _lib.BC_PERIODIC, "convective": _lib.OUTLET_CONVECTIVE, "dirichlet": _lib.OUTLET_PRESSURE}
+
+
+class RKColorGradientLBM:
+    INI_NAME = "RKtwophasesetup2D.ini"
+    LATTICE = 9
+
+    def __init__(self, pathIniFile, verbose=True):
+        self.pathIni = pathIniFile
+        self.verbose = verbose
+        ini = Ini(pathIniFile, self.INI_NAME)
+        self.imageExist = ini.quoted("ImageSetup", "Existance", default="no")
+        self._read_domain(ini)
+        # surface tension / recolouring (RKD2Q9.py:60-140)
+        self.surfaceTensionType = ini.quoted("SurfaceTension", "SurfaceTensionType", default="CSF")
+        if self.surfaceTensionType != "'CSF'":
+            raise IniError("Only SurfaceTensionType 'CSF' is a live path of the reference "
+                           "(runRKColorGradient2DPerturbation is unfinished upstream: RKD2Q9.py:1218-1223).")
+        self.surfaceTension = ini.number("SurfaceTension", "SurfaceTensionValue", "SurfaceTension", default=0.1)
+        self.contactAngle = ini.number("SurfaceTension", "ContactAngle", default=90.0)
+        self.cosTheta = np.cos(self.contactAngle / 180. * np.pi)
+        self.sinTheta = np.sin(self.contactAngle / 180. * np.pi)
+        self.wettingType = ini.integer("SurfaceTension", "WettingType", default=2)
+        self.betaThickness = ini.number("RKParameters", "BetaThickness", default=0.7)
+        self.deltaValue = ini.number("RKParameters", "DeltaValue", default=0.98)
+        self.alphaR = ini.number("RKParameters", "AlphaR", default=4. / 9.)
+        self.alphaB = ini.number("RKParameters", "AlphaB", default=4. / 9.)
+        self.tauR = ini.number("FluidParameters", "TauR")
+        self.tauB = ini.number("FluidParameters", "TauB")
+        self.initialRhoR = ini.number("FluidParameters", "InitialRhoR")
+        self.initialRhoB = ini.number("FluidParameters", "InitialRhoB")
+        self.tauCalculation = ini.integer("FluidParameters", "TauType", default=2)
+        self.isBodyForce = ini.quoted("BodyForce", "isBodyForce", default="no")
+        if self.isBodyForce == "'yes'":
+            raise IniError("A body force is read but never applied by the reference's CSF loop (RKD2Q9.py:1225-1490).")
+        self._read_time(ini)
+        self.Parallel = ini.quoted("Parallelism", "Parallel", default="yes")
+        self.xDimension = ini.integer("Parallelism", "xDimension", default=128)    # kept for compatibility, unused
+        self.threadNum = ini.integer("Parallelism", "ThreadsNum", default=32)
+        self.numGPUs = ini.integer("Parallelism", "NumGPUs", default=1)
+        self.relaxationType = ini.quoted("RelaxationType", "Type", default="MRT")
+        self._read_boundaries(ini)
+        self.isCycles = ini.quoted("CyclesSetup", "IsCycle", default="no")
+        if self.isCycles == "'yes'":
+            self.lastStep = ini.integer("CyclesSetup", "LastStep")
+        # lattice constants (RKD2Q9.py:299-303)
+        self.weightsCoeff = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
+        self.unitEX = np.array([0., 1., 0., -1., 0., 1., -1., -1., 1.])
+        self.unitEY = np.array([0., 0., 1., 0., -1., 1., 1., -1., -1.])
+        self.engine = None
+        self._results = None
+
+    # -- ini pieces (overridden by the 3-D class) ---------------------------------------------------
+    def _read_domain(self, ini):
+        self.xDomain = ini.integer("DomainSize", "xDomain")
+        self.yDomain = ini.integer("DomainSize", "yDomain")
+        self.numBufferingLayers = ini.integer("DomainSize", "numBufferingLayers", default=0)
+        self.ratioTopToBottom = ini.number("DomainSize", "ratioTopToBottom", default=0.5)
+
+    def _read_time(self, ini):
+        self.timeSteps = ini.integer("TimeSetup", "TimeSteps")
+        self.timeInterval = ini.integer("TimeSetup", "TimeInterval", default=max(1, self.timeSteps))
+
+    def _read_boundaries(self, ini):
+        self.boundaryTypeInlet = ini.quoted("BoundaryCondition", "BoundaryTypeInlet", default="Periodic")
+        self.boundaryTypeOutlet = ini.quoted("BoundaryCondition", "BoundaryTypeOutlet", default="Periodic")
+        self.velocityYR = self.velocityYB = 0.0
+        self.densityRhoBH = self.densityRhoRH = self.densityRhoBL = self.densityRhoRL = 0.0
+        if self.boundaryTypeInlet == "'Neumann'":
+            self.neumannType = ini.quoted("BoundaryCondition", "NeumannType", default="ZouHe")
+            self.velocityYR = ini.number("BoundaryCondition", "VelocityYR", default=0.0)
+            self.velocityYB = ini.number("BoundaryCondition", "VelocityYB", default=0.0)
+        elif self.boundaryTypeInlet == "'Dirichlet'":
+            self.densityRhoBH = ini.number("BoundaryCondition", "densityBH")
+            self.densityRhoRH = ini.number("BoundaryCondition", "densityRH")
+        if self.boundaryTypeOutlet == "'Dirichlet'":
+            self.densityRhoBL = ini.number("BoundaryCondition", "densityBL")
+            self.densityRhoRL = ini.number("BoundaryCondition", "densityRL")
+
+    def _say(self, *a):
+        if self.verbose:
+            print(*a)
+
+    # -- geometry and initial condition ---------------------------------------------------------------
+    def _shape(self):
+        return (self.yDomain, self.xDomain)
+
+    def initializeDomainBorder(self):
+        """RKD2Q9.py:417-443: `defineGeometry(xDomain, yDomain)` or ~/StructureImage/structure.png (0 = solid)"""
+        if self.imageExist == "'yes'":
+            self._process_image()
+        else:
+            try:
+                from SimpleGeometryRK import defineGeometry       # a user's own module on sys.path wins
+            except ImportError:
+                from .SimpleGeometryRK import defineGeometry
+            self.isDomain, self.isSolid = defineGeometry(self.xDomain, self.yDomain)
+        self.isDomain = np.ascontiguousarray(self.isDomain, dtype=bool)
+        self.isSolid = ~self.isDomain
+        self.voidSpace = int(np.count_nonzero(self.isDomain))
+        self._say('The number of vexls in void space is %g.' % self.voidSpace)
+        self._say('The porosity of the layout is %f.' % (self.voidSpace / self.isDomain.size))
+
+    def _process_image(self):
+        """RKD2Q9.py:373-414: 0 = solid, 255 = void, buffering layers of void rows above and below"""
+        path = os.path.expanduser("~/StructureImage/structure.png")
+        img = None
+        for loader in ("imageio", "PIL.Image", "matplotlib.image"):
+            try:
+                mod = __import__(loader, fromlist=["x"])
+                img = np.asarray(mod.imread(path) if hasattr(mod, "imread") else mod.open(path))
+                break
+            except Exception:
+                continue
+        if img is None:
+            raise IniError("Cannot read %s (needs imageio, Pillow or matplotlib)" % path)
+        if img.ndim == 3:
+            img = img[..., 0]
+        void = img > (0.5 * img.max())
+        nb = self.numBufferingLayers
+        top = int(round(nb * self.ratioTopToBottom * 2)) if nb else 0
+        bottom = 2 * nb - top if nb else 0
+        void = np.vstack([np.ones((bottom, void.shape[1]), bool), void, np.ones((top, void.shape[1]), bool)])
+        self.isDomain = void
+        self.yDomain, self.xDomain = void.shape
+
+    def initializeDomainCondition(self):
+        """RKD2Q9.py:445-490: droplet of R with radius 16 around the centre, B elsewhere, at rest; assign
+        `self.initialRedRegion` (boolean array) beforehand for another layout."""
+        shape = self._shape()
+        red = getattr(self, "initialRedRegion", None)
+        if red is None:
+            idx = np.indices(shape)
+            centre = [int(n / 2) for n in shape]
+            red = np.sqrt(sum((idx[a] - centre[a]) ** 2 for a in range(len(shape)))) <= 16.
+        red = np.asarray(red, bool) & self.isDomain
+        self.fluidsRhoR = np.where(red, self.initialRhoR, 0.0) * self.isDomain
+        self.fluidsRhoB = np.where(red, 0.0, self.initialRhoB) * self.isDomain
+        self.fluidPDFR = self.fluidsRhoR[..., None] * self._weights()
+        self.fluidPDFB = self.fluidsRhoB[..., None] * self._weights()
+        self.physicalVX = np.zeros(shape); self.physicalVY = np.zeros(shape)
+        if len(shape) == 3:
+            self.physicalVZ = np.zeros(shape)
+
+    def _weights(self):
+        return self.weightsCoeff
+
+    # -- engine ---------------------------------------------------------------------------------------
+    def _make_engine(self):
+        inlet = self.boundaryTypeInlet.strip("'").lower(); outlet = self.boundaryTypeOutlet.strip("'").lower()
+        if inlet not in INLET or outlet not in OUTLET:
+            raise IniError("Unknown boundary type %s / %s" % (self.boundaryTypeInlet, self.boundaryTypeOutlet))
+        relax = _lib.RELAX_MRT if self.relaxationType == "'MRT'" else _lib.RELAX_SRT
+        self.engine = _lib.Engine(self.LATTICE, self._shape(), model=_lib.MODEL_CG, relax=relax,
+                                  sigma=self.surfaceTension, contact_angle_deg=self.contactAngle,
+                                  wetting_type=self.wettingType, beta=self.betaThickness, delta=self.deltaValue,
+                                  tauR=self.tauR, tauB=self.tauB, tau_type=self.tauCalculation,
+                                  inlet=INLET[inlet], outlet=OUTLET[outlet], inlet_velocity=self._inlet_velocity(),
+                                  rhoBH=self.densityRhoBH, rhoRH=self.densityRhoRH, rhoBL=self.densityRhoBL,
+                                  rhoRL=self.densityRhoRL)
+        self.engine.set_geometry(self.isDomain)
+
+    def _inlet_velocity(self):
+        return self.velocityYB + self.velocityYR            # RKD2Q9.py:1300
+
+    def optimizeFluidandSolidArray(self):
+        """RKD2Q9.py:657-736 (+ sortOutFluidNodesToSolid 741-760, calVectorNormaltoSolid 768-892): the
+        compact index structures, built on the device and exported bit-exactly."""
+        if self.engine is None:
+            self._make_engine()
+        idx = self.engine.export_indexing()
+        self.fluidNodes = idx["fluidNodes"]
+        self.neighboringNodes = idx["neighboringNodes"]
+        self.wettingSolidNodes = idx["wettingSolidNodes"]
+        self.neighboringWettingSolidNodes = idx["neighboringWettingSolidNodes"]
+        self.fluidNodesWithSolidGPU = idx["fluidNodesWithSolidGPU"]
+        self.fluidNodesWithSolidOriginal = idx["fluidNodesWithSolidOriginal"]
+        self.nsX, self.nsY = idx["nsX"], idx["nsY"]
+        if "nsZ" in idx:
+            self.nsZ = idx["nsZ"]
+        flat = self.fluidNodes
+        Q = self.LATTICE
+        self.optFluidPDFR = self.fluidPDFR.reshape(-1, Q)[flat]
+        self.optFluidPDFB = self.fluidPDFB.reshape(-1, Q)[flat]
+        self.optFluidRhoR = self.fluidsRhoR.ravel()[flat]
+        self.optFluidRhoB = self.fluidsRhoB.ravel()[flat]
+
+    sortOutFluidNodesToSolid = calVectorNormaltoSolid = lambda self: None    # folded into optimizeFluidandSolidArray
+
+    def convertOptTo2D(self):
+        """RKD2Q9.py:902-911: refresh the dense host arrays from the device state (output point of the loop)"""
+        rho, u = self.engine.download_macros()
+        self.fluidsRhoR, self.fluidsRhoB = rho
+        self.physicalVX, self.physicalVY = u[0], u[1]
+        if len(u) == 3:
+            self.physicalVZ = u[2]
+        self.fluidPDFR, self.fluidPDFB = self.engine.download_pdfs()
+
+    def resultInHDF5(self, iStep):
+        """RKD2Q9.py:938-957, same group / dataset names"""
+        if self._results is None:
+            self._results = ResultFile("SimulationResultsRK.h5")
+        arrays = {"/FluidMacro/FluidDensityRin%g" % iStep: self.fluidsRhoR,
+                  "/FluidMacro/FluidDensityBin%g" % iStep: self.fluidsRhoB,
+                  "/FluidPDF/FluidPDFBat%g" % iStep: self.fluidPDFB,
+                  "/FluidPDF/FluidPDFRat%g" % iStep: self.fluidPDFR,
+                  "/FluidVelocity/FluidVelocityXAt%g" % iStep: self.physicalVX,
+                  "/FluidVelocity/FluidVelocityYAt%g" % iStep: self.physicalVY}
+        if hasattr(self, "physicalVZ"):
+            arrays["/FluidVelocity/FluidVelocityZAt%g" % iStep] = self.physicalVZ
+        self._results.write(iStep, arrays)
+
+    def plotDensityDistributionOPT(self, iStep):
+        """RKD2Q9.py:959-975 (PNG snapshots; skipped when matplotlib is absent)"""
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+        except Exception:
+            return
+        from .results import results_dir
+        for name, a in (("FluidRsDistributionAt%05d.png", self.fluidsRhoR), ("FluidBsDistributionAt%05d.png", self.fluidsRhoB)):
+            img = a if a.ndim == 2 else a[:, a.shape[1] // 2, :]
+            plt.imshow(img, origin="lower"); plt.colorbar()
+            plt.savefig(os.path.join(results_dir(), name % iStep)); plt.close()
+
+    # -- the run loop (RKD2Q9.py:1225-1490) ------------------------------------------------------------
+    def runRKColorGradient2DCSF(self):
+        self._say("Start to run R-K color gradient lattice Boltzmann method.")
+        self.initializeDomainBorder()
+        self.initializeDomainCondition()
+        self._make_engine()
+        self.optimizeFluidandSolidArray()
+        self.engine.upload_state([self.fluidPDFR, self.fluidPDFB], [self.fluidsRhoR, self.fluidsRhoB])
+        iStep = 0
+        recordStep = 0
+        t0 = time.perf_counter()
+        while iStep < self.timeSteps:
+            if iStep % self.timeInterval == 0:                       # RKD2Q9.py:1382-1393
+                self.convertOptTo2D()
+                self.resultInHDF5(recordStep)
+                self.plotDensityDistributionOPT(recordStep)
+                recordStep += 1
+                m = self.engine.total_mass()
+                self._say("step %d: mass R %.12g, mass B %.12g" % (iStep, m[0], m[1]))
+            n = min(self.timeInterval - iStep % self.timeInterval, self.timeSteps - iStep)
+            self.engine.step(n)
+            iStep += n
+        self.engine.synchronize()
+        dt = time.perf_counter() - t0
+        self.convertOptTo2D()
+        self._say("%d steps, %.3f s, %.1f MLUPS (output included)" % (self.timeSteps, dt, self.voidSpace * self.timeSteps / dt / 1e6))
+
+    def runRKColorGradient2D(self):
+        """RKD2Q9.py:1495-1498"""
+        if self.surfaceTensionType == "'CSF'":
+            self.runRKColorGradient2DCSF()
+
+    runModifiedRKColorGradient2D = runRKColorGradient2D     # the name main.py:53 calls

@@ -1,0 +1,190 @@
+"""`ShanChenD2Q9` -- drop-in for the reference's Shan-Chen host class (ShanChen2D/ShanChenD2Q9.py:38-2094).
+
+Constructor `ShanChenD2Q9(pathIniFile)` reads twophasesetup.ini + shanchen2D.ini | efs2D.ini (basicsetup.ini,
+which the reference demands but does not ship, is optional); entry points `runTypeSCmodel`,
+`runOptimizedLBM`, `runOptimizedEFLBM`; public arrays `isDomain`, `isSolid`, `fluidsDensity[nf, ny, nx]`,
+`fluidPDF[nf, ny, nx, 9]`, `physicalVX/VY`, `fluidNodes`, `neighboringNodes`, `optFluidRho`, `optFluidPDF`.
+The per-step loops (ShanChenD2Q9.py:1492-1629, 1852-2087; 15-20 kernel launches each) run inside liblbmpm.so."""
+import time
+
+import numpy as np
+
+from . import _lib
+from .inifile import Ini, IniError
+from .results import ResultFile
+
+
+class ShanChenD2Q9:
+    def __init__(self, pathIniFile, verbose=True):
+        self.path = pathIniFile
+        self.verbose = verbose
+        ini = Ini(pathIniFile, "twophasesetup.ini")
+        self.PictureExistance = ini.quoted("PictureSetup", "Exist", default="no")
+        if self.PictureExistance == "'yes'":
+            raise IniError("image input for the Shan-Chen class: provide the geometry through SimpleGeometry.defineGeometry")
+        self.nx = self.borderX = ini.integer("SeparationBorder", "xGrid")
+        self.ny = self.borderY = ini.integer("SeparationBorder", "yGrid")
+        self.typesFluids = ini.integer("FluidsTypes", "NumberOfFluids", default=2)
+        if not 1 <= self.typesFluids <= 4:
+            raise IniError("1..4 fluids are supported")
+        self.interactionType = ini.quoted("InterType", "InteractionType", default="ShanChen")
+        self.Parallel = ini.quoted("Parallelism", "Parallel", default="yes")
+        self.xDimension = ini.integer("Parallelism", "xDimension", default=128)
+        self.threadNum = ini.integer("Parallelism", "ThreadsNum", default=32)
+        self.relaxationType = ini.quoted("RelaxationType", "Type", default="SRT")
+        if self.relaxationType == "'TRT'":
+            raise IniError("TRT is read by the reference but never launched by a live driver")
+        self.duplicateDomain = ini.quoted("DuplicateDomain", "Option", default="no")
+        self.isCycles = ini.quoted("DICycles", "Option", default="no")
+        self.unitEX = np.array([0., 1., 0., -1., 0., 1., -1., -1., 1.])
+        self.unitEY = np.array([0., 0., 1., 0., -1., 1., 1., -1., -1.])
+        self.weightsCoeff = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
+        efs = self.interactionType == "'EFS'"
+        self._read_model(Ini(pathIniFile, "efs2D.ini" if efs else "shanchen2D.ini"), "EFSParameters" if efs else "ShanChenParameters")
+        self.engine = None
+        self._results = None
+
+    def _say(self, *a):
+        if self.verbose:
+            print(*a)
+
+    def _read_model(self, ini, section):
+        """ShanChenD2Q9.py:164-321 / 323-499"""
+        nf = self.typesFluids
+        self.initialDensities = np.array(ini.numbers("FluidProperties", "InitialDensities"))
+        self.backgroundDensities = np.array(ini.numbers("FluidProperties", "BackgroundDensities"))
+        self.tau = np.array(ini.numbers("FluidProperties", "FluidsTau"))
+        if not (self.initialDensities.size == self.backgroundDensities.size == self.tau.size == nf):
+            raise IniError("The number of fluids does not match the number of densities / taus.")
+        pairs = ini.numbers(section, "InteractionFluid")
+        self.interCoeff = np.zeros((nf, nf))
+        k = 0
+        for i in range(nf - 1):
+            for j in range(i + 1, nf):
+                self.interCoeff[i, j] = self.interCoeff[j, i] = pairs[k]
+                k += 1
+        self.interactionSolid = np.array(ini.numbers(section, "InteractionSolid"))
+        if self.interactionSolid.size != nf:
+            raise IniError("The number of fluids does not match the number of interaction coeff with solid.")
+        self.explicitScheme = ini.integer("ForceScheme", "ExplicitScheme", default=4)
+        if self.interactionType == "'EFS'" and self.explicitScheme != 4:
+            raise IniError("ExplicitScheme 8 / 10 (higher isotropy) is not built yet (SURVEY.md 8 f-1); use 4")
+        self.boundaryTypeInlet = ini.quoted("BoundaryDefinition", "BoundaryTypeInlet", default="Periodic")
+        self.boundaryMethod = ini.quoted("BoundaryDefinition", "BoundaryMethod", default="ZouHe")
+        self.boundaryTypeOutlet = ini.quoted("BoundaryDefinition", "BoundaryTypeOutlet", default="Periodic")
+        self.velocityYInlet = np.zeros(nf); self.velocityXInlet = np.zeros(nf)
+        if self.boundaryTypeInlet == "'Neumann'":
+            if self.boundaryMethod != "'ZouHe'":
+                raise IniError("BoundaryMethod 'Chang' is not built; use 'ZouHe'")
+            self.velocityXInlet = np.array(ini.numbers("VelocityBoundary", "velocityX"))
+            self.velocityYInlet = np.array(ini.numbers("VelocityBoundary", "velocityY"))
+        elif self.boundaryTypeInlet == "'Dirichlet'":
+            raise IniError("The reference's pressure inlet reads self.specificRho1Upper, which is never set "
+                           "(ShanChenD2Q9.py:1498): that path cannot run upstream either")
+        self.numTimeStep = ini.integer("Time", "numberTimeStep")
+
+    # -- geometry / initial condition --------------------------------------------------------------
+    def initializeDomainBorder(self):
+        try:
+            from SimpleGeometry import defineGeometry
+        except ImportError:
+            from .SimpleGeometry import defineGeometry
+        self.isDomain, self.isSolid = defineGeometry(self.nx, self.ny)
+        self.isDomain = np.ascontiguousarray(self.isDomain, dtype=bool)
+        self.isSolid = ~self.isDomain
+        self.voidSpace = int(np.count_nonzero(self.isDomain))
+        self._say('The porosity of the layout is %f.' % (self.voidSpace / self.isDomain.size))
+
+    def initializeDomainCondition(self):
+        """ShanChenD2Q9.py:734-768: fluid 0 below row ny-10, fluid 1 above; assign `self.initialRegion0`
+        (boolean [ny, nx]) beforehand for another layout"""
+        reg = getattr(self, "initialRegion0", None)
+        if reg is None:
+            reg = np.indices((self.ny, self.nx))[0] < self.ny - 10
+        nf = self.typesFluids
+        self.fluidsDensity = np.zeros((nf, self.ny, self.nx))
+        for k in range(nf):
+            inside = self.initialDensities[k] if k == 0 else self.backgroundDensities[k]
+            outside = self.backgroundDensities[k] if k == 0 else self.initialDensities[k]
+            self.fluidsDensity[k] = np.where(reg, inside, outside) * self.isDomain
+        self.fluidPDF = self.fluidsDensity[..., None] * self.weightsCoeff
+        self.physicalVX = np.zeros((self.ny, self.nx)); self.physicalVY = np.zeros((self.ny, self.nx))
+
+    def _make_engine(self, model):
+        inlet = {"'Periodic'": _lib.BC_PERIODIC, "'Neumann'": _lib.INLET_VELOCITY}.get(self.boundaryTypeInlet)
+        outlet = {"'Periodic'": _lib.BC_PERIODIC, "'Convective'": _lib.OUTLET_CONVECTIVE,
+                  "'Dirichlet'": _lib.OUTLET_PRESSURE}.get(self.boundaryTypeOutlet)
+        if inlet is None or outlet is None:
+            raise IniError("Unknown boundary type %s / %s" % (self.boundaryTypeInlet, self.boundaryTypeOutlet))
+        if model == _lib.MODEL_SC and outlet == _lib.OUTLET_PRESSURE:
+            raise IniError("the original Shan-Chen loop has no pressure outlet (ShanChenD2Q9.py:1603-1621)")
+        G = np.zeros((4, 4)); G[:self.typesFluids, :self.typesFluids] = self.interCoeff
+        self.engine = _lib.Engine(9, (self.ny, self.nx), model=model,
+                                  relax=_lib.RELAX_MRT if self.relaxationType == "'MRT'" else _lib.RELAX_SRT,
+                                  n_components=self.typesFluids, inlet=inlet, outlet=outlet, sc_tau=self.tau,
+                                  sc_G=G.ravel(), sc_Gsolid=self.interactionSolid, sc_inlet_velocity=self.velocityYInlet,
+                                  sc_rho_out=[1.0, 0.02])      # hard-coded upstream: OptimizedD2Q9GPU.py:560-561
+        self.engine.set_geometry(self.isDomain)
+
+    def optimizeFluidArray(self):
+        """ShanChenD2Q9.py:587-659: compact node list and neighbour table (solids are -1 in this class)"""
+        idx = self.engine.export_indexing()
+        self.fluidNodes = idx["fluidNodes"]
+        nb = idx["neighboringNodes"].copy()
+        nb[nb < 0] = -1
+        self.neighboringNodes = nb
+        self.optFluidRho = self.fluidsDensity.reshape(self.typesFluids, -1)[:, self.fluidNodes]
+        self.optFluidPDF = self.fluidPDF.reshape(self.typesFluids, -1, 9)[:, self.fluidNodes]
+
+    def convertOptTo2D(self):
+        rho, u = self.engine.download_macros()
+        self.fluidsDensity = np.stack(rho)
+        self.physicalVX, self.physicalVY = u
+        self.fluidPDF = np.stack(self.engine.download_pdfs())
+
+    def resultInHDF5(self, iStep):
+        """ShanChenD2Q9.py:940-955"""
+        if self._results is None:
+            self._results = ResultFile("SimulationResults.h5", groups=("FluidMacro", "FluidVelocity"))
+        arrays = {"/FluidMacro/FluidDensityType%gin%g" % (k, iStep): self.fluidsDensity[k] for k in range(self.typesFluids)}
+        arrays["/FluidVelocity/FluidVelocityXAt%g" % iStep] = self.physicalVX
+        arrays["/FluidVelocity/FluidVelocityYAt%g" % iStep] = self.physicalVY
+        self._results.write(iStep, arrays)
+
+    def _run(self, model, interval):
+        self.initializeDomainBorder()
+        self.initializeDomainCondition()
+        self._make_engine(model)
+        self.optimizeFluidArray()
+        self.engine.upload_state(list(self.fluidPDF), list(self.fluidsDensity))
+        step = record = 0
+        total = self.numTimeStep + 1                 # both loops run numTimeStep + 1 iterations
+        t0 = time.perf_counter()
+        while step < total:
+            if step % interval == 0:
+                self.convertOptTo2D()
+                self.resultInHDF5(record)
+                record += 1
+                self._say("step %d: masses %s" % (step, self.engine.total_mass()))
+            n = min(interval - step % interval, total - step)
+            self.engine.step(n)
+            step += n
+        self.engine.synchronize()
+        dt = time.perf_counter() - t0
+        self.convertOptTo2D()
+        self._say("%d steps, %.3f s, %.1f MLUPS (output included)" % (total, dt, self.voidSpace * total / dt / 1e6))
+
+    def runOptimizedLBM(self):
+        """ShanChenD2Q9.py:1433-1629 (results every 80 iterations, :1561)"""
+        self._run(_lib.MODEL_SC, 80)
+
+    def runOptimizedEFLBM(self):
+        """ShanChenD2Q9.py:1631-2087 (results every 1000 iterations, :2029)"""
+        self._run(_lib.MODEL_EFS, 1000)
+
+    def runTypeSCmodel(self):
+        """ShanChenD2Q9.py:2089-2094"""
+        if self.interactionType == "'ShanChen'":
+            self.runOptimizedLBM()
+        elif self.interactionType == "'EFS'":
+            self.runOptimizedEFLBM()

@@ -59,7 +59,12 @@ template <int D>
 struct ClassifyOp {
     Grid g; const uint8_t* dom; uint8_t* cls;
     LBM_HD void operator()(int64_t i) const {
-        int x, y, z; g.decode(i, 2, x, y, z);
+        int x, y, z; g.decode(i, NG, x, y, z);
+        if (z < -2 || z >= g.n2 + 2) {      // outermost ghost planes: only the fluid bit is known (and needed)
+            const int64_t id = g.at(x, y, z);
+            cls[id] = dom[id] ? (uint8_t)CLS_FLUID : (uint8_t)0;
+            return;
+        }
         int nfl = 0;
         for (int dz = -1; dz <= 1; ++dz)
             for (int dy = (D == 3 ? -1 : 0); dy <= (D == 3 ? 1 : 0); ++dy)

@@ -192,10 +192,10 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
         for (int64_t i = 0; i < g.vol; ++i) if (!padded[i]) { h->has_solid = true; break; }
     }
     if (h->D == 2) {
-        launch(ClassifyOp<2>{g, h->dom, h->cls}, g.count(2), h->stream);
+        launch(ClassifyOp<2>{g, h->dom, h->cls}, g.count(NG), h->stream);
         launch(SolidNormalOp<2>{g, h->dom, h->cls, h->ns}, g.count(1), h->stream);
     } else {
-        launch(ClassifyOp<3>{g, h->dom, h->cls}, g.count(2), h->stream);
+        launch(ClassifyOp<3>{g, h->dom, h->cls}, g.count(NG), h->stream);
         launch(SolidNormalOp<3>{g, h->dom, h->cls, h->ns}, g.count(1), h->stream);
     }
     dev_sync(h->stream);

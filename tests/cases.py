@@ -172,8 +172,11 @@ def case_d3q19_periodic(lib_path, n=(10, 12, 14), steps=6, relax="MRT", **par):
     return run_dense_case(19, dom, rhoR, 1.0 - rhoR, steps, lib_path, relax=relax, chunk=[2, steps - 2], **par)
 
 
-def case_d3q19_sphere(lib_path, n=(12, 12, 12), steps=6, theta=70.0, relax="MRT", **par):
-    dom = sphere_geometry(n, 2.6)
+def case_d3q19_sphere(lib_path, n=(12, 12, 12), steps=6, theta=70.0, relax="MRT", centre=None, **par):
+    dom = sphere_geometry(n, 2.6, centre)
+    if centre is not None:        # periodic images of a sphere that straddles the box faces
+        for sh in ((n[0], 0, 0), (0, n[1], 0), (0, 0, n[2]), (n[0], n[1], 0), (n[0], 0, n[2]), (0, n[1], n[2]), tuple(n)):
+            dom &= sphere_geometry(n, 2.6, [c + s for c, s in zip(centre, sh)])
     z = np.mgrid[0:n[0], 0:n[1], 0:n[2]][0]
     red = z < n[0] // 2
     return run_dense_case(19, dom, np.where(red, 1.0, 0.0), np.where(red, 0.0, 1.0), steps, lib_path,

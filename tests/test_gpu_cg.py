@@ -124,3 +124,8 @@ def test_slab_decomposition_bit_equal_to_single_gpu():
                           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "mgpu_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert "MGPU OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_d3q19_solid_across_the_periodic_faces():
+    cases.case_d3q19_sphere(None, n=(12, 16, 32), centre=[0.3, 0.2, 0.4])
+    cases.case_d3q19_sphere(None, centre=[0.3, 0.2, 0.4], flags=1)

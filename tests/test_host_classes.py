@@ -1,0 +1,86 @@
+"""Host-side mirror of the reference's class surface (RKColorGradientLBM, ShanChenD2Q9, RKColorGradient3D, main.py):
+ini parsing, attribute names, index export, result files.  CPU tier: the classes are pointed at the host test
+hook (tests/hostcheck) instead of liblbmpm.so; the GPU tier (test_gpu_classes.py) runs them unmodified."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "hostcheck"))
+import build as hostcheck_build
+
+from openlbmpm_b200 import _lib
+from oracle import cg2d
+
+REF_INI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ini")
+
+
+@pytest.fixture()
+def hostlib(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "LIB_PATH", hostcheck_build.build())
+    monkeypatch.setenv("LBM_RESULTS_DIR", str(tmp_path / "results"))
+    return tmp_path
+
+
+def run_cg2d(hostlib):
+    from openlbmpm_b200.RKD2Q9 import RKColorGradientLBM
+    sim = RKColorGradientLBM(os.path.join(REF_INI, "cg2d"), verbose=False)
+    sim.runModifiedRKColorGradient2D()
+    return sim
+
+
+def test_cg2d_class_runs_with_reference_style_ini(hostlib):
+    sim = run_cg2d(hostlib)
+    assert sim.relaxationType == "'MRT'" and sim.boundaryTypeInlet == "'Neumann'"
+    assert sim.surfaceTension == 0.1 and sim.wettingType == 2       # `SurfaceTension` spelling of the shipped ini
+    assert sim.fluidsRhoR.shape == (sim.yDomain, sim.xDomain) and sim.fluidPDFR.shape == (sim.yDomain, sim.xDomain, 9)
+    assert np.isfinite(sim.fluidsRhoR).all() and np.isfinite(sim.physicalVY).all()
+    idx = cg2d.build_indexing(sim.isDomain)
+    for k in ("fluidNodes", "neighboringNodes", "wettingSolidNodes", "fluidNodesWithSolidGPU"):
+        assert np.array_equal(getattr(sim, k), idx[k]), k
+    np.testing.assert_allclose(sim.nsX, idx["nsX"], atol=1e-15)
+    files = glob.glob(str(hostlib / "results" / "SimulationResultsRK*"))
+    assert files, "no result file written"
+    # trajectory equals the oracle driven with the same parameters
+    ref = cg2d.CG2D(sim.isDomain, sigma=0.1, theta_deg=60.0, wetting=2, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0,
+                    tautype=2, relax="MRT", inlet="Neumann", outlet="Dirichlet", vy_inlet=-1e-4, dBL=1.0, dRL=5e-8)
+    yy, xx = np.indices(sim.isDomain.shape)
+    red = (np.sqrt((yy - sim.yDomain // 2) ** 2 + (xx - sim.xDomain // 2) ** 2) <= 16.) & sim.isDomain
+    ref.set_densities(np.where(red, 1.0, 0.0) * sim.isDomain, np.where(red, 0.0, 1.0) * sim.isDomain)
+    ref.step(sim.timeSteps)
+    ref.head()
+    d = ref.to_dense()
+    np.testing.assert_allclose(sim.fluidsRhoR, d["rhoR"], atol=1e-9)
+    np.testing.assert_allclose(sim.physicalVY, d["uy"], atol=1e-9)
+
+
+@pytest.mark.parametrize("which", ["sc", "efs"])
+def test_shanchen_class(hostlib, which):
+    from openlbmpm_b200.ShanChenD2Q9 import ShanChenD2Q9
+    sim = ShanChenD2Q9(os.path.join(REF_INI, which), verbose=False)
+    sim.runTypeSCmodel()
+    assert sim.fluidsDensity.shape == (2, sim.ny, sim.nx) and sim.fluidPDF.shape == (2, sim.ny, sim.nx, 9)
+    assert sim.neighboringNodes.min() == -1 and sim.fluidNodes.size == sim.voidSpace
+    assert np.isfinite(sim.fluidsDensity).all()
+    m = sim.fluidsDensity.sum(axis=(1, 2))
+    assert m[0] > 0 and m[1] > 0
+
+
+def test_cg3d_class_and_main(hostlib, monkeypatch):
+    import main
+    monkeypatch.chdir(os.path.join(REF_INI, "cg3d"))
+    assert main.main(["3D", "flow", "CG", "--ini", os.path.join(REF_INI, "cg3d")]) == 0
+    assert main.main(["2D", "transport", "CG"]) == 2
+    from openlbmpm_b200.ShanChenD3Q19 import ShanChenD3Q19
+    with pytest.raises(NotImplementedError):
+        ShanChenD3Q19("x").runEFS4LBM3DGPU()
+
+
+def test_missing_key_exits_like_the_reference(hostlib, tmp_path):
+    from openlbmpm_b200.RKD2Q9 import RKColorGradientLBM
+    d = tmp_path / "bad"; d.mkdir()
+    (d / "RKtwophasesetup2D.ini").write_text("[DomainSize]\nxDomain = 8\n")
+    with pytest.raises(SystemExit):
+        RKColorGradientLBM(str(d))

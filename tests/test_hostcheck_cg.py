@@ -60,3 +60,9 @@ def test_d3q19_general_kernels_vs_oracle(lib):
 def test_fast_and_general_paths_agree_on_mass(lib):
     m, mo = cases.case_d3q19_periodic(lib, n=(6, 8, 32), steps=5)
     assert np.allclose(m, mo, rtol=0, atol=1e-9)
+
+
+def test_d3q19_solid_across_the_periodic_faces(lib):
+    """a sphere centred on the box corner: wetting solids and their colour values live in the ghost planes"""
+    cases.case_d3q19_sphere(lib, centre=[0.3, 0.2, 0.4])
+    cases.case_d3q19_sphere(lib, centre=[0.3, 0.2, 0.4], flags=1)
