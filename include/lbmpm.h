@@ -61,6 +61,7 @@ extern "C" {
 /* lbm_config.flags */
 #define LBM_FLAG_GENERIC_KERNELS 1u  /* force the unfused reference-ordered kernel sequence */
 #define LBM_FLAG_NO_TILED_KERNEL 2u  /* factored fast path, but with its one-thread-per-node kernels only */
+#define LBM_FLAG_NO_TILED_DENSITY 4u /* keep the tiled collision pass, use the one-thread-per-node density pass */
 
 typedef struct lbm_handle lbm_handle;
 

@@ -203,6 +203,102 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled density pass for D3Q19 (pass 1).  Same column-marching layout as the collision pass: the four
+// recolouring scalars (kR, a) of the neighbours are served from a rolling 4-plane shared-memory window
+// with a 1-node halo (each value is read from L2/HBM once per CTA instead of 19 times), and the 19
+// pulled populations of the NEXT plane are requested before the current plane is reduced, so one full
+// plane of HBM requests per thread is always in flight.
+// ------------------------------------------------------------------------------------------------
+template <bool SOLIDS, int TX, int TY>
+__global__ void __launch_bounds__(TX* TY, 2)
+cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk) {
+    using L = D3Q19;
+    constexpr int NT = TX * TY;
+    constexpr int NW = TX + 2, NH = TY + 2;
+    extern __shared__ double smem_dyn[];
+    double (*ss)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn);   // [4 slots][kR, ax, ay, az]
+    const Grid& g = c.g;
+    const int64_t V = g.vol;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int z_begin = blockIdx.z * zchunk;
+    const int z_end = min(z_begin + zchunk, g.n2);
+    const int x = x0 + tx, y = y0 + ty;
+    auto wrapx = [&](int v) { return v < 0 ? v + g.n0 : (v >= g.n0 ? v - g.n0 : v); };
+    auto wrapy = [&](int v) { return v < 0 ? v + g.n1 : (v >= g.n1 ? v - g.n1 : v); };
+    const double* fld[4] = {s.kR, s.a, s.a + V, s.a + 2 * V};
+
+    auto load_scalar_plane = [&](int zp) {
+        const int slot = (zp + 8) % 4;
+        const int64_t base = (int64_t)(zp + NG) * g.plane;
+        for (int e = tid; e < NH * NW; e += NT) {
+            const int ly = e / NW, lx = e - ly * NW;
+            const int64_t off = base + (int64_t)wrapy(y0 + ly - 1) * g.n0 + wrapx(x0 + lx - 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ss[slot][k][ly][lx] = fld[k][off];
+        }
+    };
+    const int64_t xo[3] = {(int64_t)wrapx(x - 1), (int64_t)x, (int64_t)wrapx(x + 1)};
+    const int64_t yo[3] = {(int64_t)wrapy(y - 1) * g.n0, (int64_t)y * g.n0, (int64_t)wrapy(y + 1) * g.n0};
+
+    // request the pulled populations of plane z: values + bit mask of the directions whose upstream node is fluid
+    auto request = [&](int z, double* f, unsigned& mask, bool& fluid) {
+        const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
+        fluid = true; mask = 0xFFFFFFFFu;
+        if (SOLIDS) fluid = c.cls[id] & CLS_FLUID;
+        if (!fluid) return;
+        f[0] = __ldcs(s.gT + id);
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            const int64_t src = (int64_t)(z - L::d2(q) + NG) * g.plane + yo[1 - L::d1(q)] + xo[1 - L::d0(q)];
+            int64_t addr = q * V + src;
+            if (SOLIDS && !(c.cls[src] & CLS_FLUID)) { addr = L::opp(q) * V + id; mask &= ~(1u << q); }
+            f[q] = __ldcs(s.gT + addr);
+        }
+    };
+
+    load_scalar_plane(z_begin - 1);
+    load_scalar_plane(z_begin);
+    double cur[L::Q], nxt[L::Q];
+    unsigned mcur = 0, mnxt = 0;
+    bool fcur = true, fnxt = true;
+    request(z_begin, cur, mcur, fcur);
+    for (int z = z_begin; z < z_end; ++z) {
+        load_scalar_plane(z + 1);
+        if (z + 1 < z_end) request(z + 1, nxt, mnxt, fnxt);
+        __syncthreads();
+        if (fcur) {
+            const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
+            const int s0 = (z + 8) % 4;
+            const double kR0 = ss[s0][0][ty + 1][tx + 1];
+            const double a0[3] = {ss[s0][1][ty + 1][tx + 1], ss[s0][2][ty + 1][tx + 1], ss[s0][3][ty + 1][tx + 1]};
+            double accR = kR0 * cur[0], accB = cur[0] - accR;
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                double fr;
+                if (!SOLIDS || (mcur & (1u << q))) {
+                    const int sq = (z - L::d2(q) + 8) % 4;
+                    const int ly = ty + 1 - L::d1(q), lx = tx + 1 - L::d0(q);
+                    double ea = 0.0;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+                        if (L::c(q, d) != 0) ea += L::c(q, d) * ss[sq][1 + d][ly][lx];
+                    fr = ss[sq][0][ly][lx] * cur[q] + L::w(q) * ea;
+                } else {
+                    fr = cg_red_part<L>(L::opp(q), cur[q], kR0, a0);
+                }
+                accR += fr; accB += cur[q] - fr;
+            }
+            c.rho[0][id] = accR; c.rho[1][id] = accB;
+            c.phi[id] = (accR - accB) / (accR + accB);
+        }
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) cur[q] = nxt[q];
+        mcur = mnxt; fcur = fnxt;
+    }
+}
+
 constexpr int TILE_X = 32, TILE_Y = 8;
 
 static bool tiled_ok(const lbm_handle* h) {
@@ -227,6 +323,25 @@ static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, 
     LBM_CUDA_CHECK(cudaGetLastError());
     ++g_launch_counter;
 }
+
+template <bool SOLIDS>
+static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s) {
+    const Grid& g = h->g;
+    int zchunk = g.n2 >= 64 ? 32 : g.n2;
+    dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
+    constexpr size_t smem = sizeof(double) * 4 * 4 * (TILE_Y + 2) * (TILE_X + 2);
+    static bool configured = false;
+    if (!configured) {
+        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    if (g_prof.on) g_prof.begin(SOLIDS ? "cg_density_tiled_d3q19<solids>" : "cg_density_tiled_d3q19<all-fluid>", h->stream);
+    cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, zchunk);
+    if (g_prof.on) g_prof.end(h->stream);
+    LBM_CUDA_CHECK(cudaGetLastError());
+    ++g_launch_counter;
+}
 #endif
 
 template <class L>
@@ -247,8 +362,17 @@ static void fast_one_step(lbm_handle* h) {
     CGFields c = h->fields();
     const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
     exchange_f64(h, f->buf[f->cur], g.vol, L::Q + 4, 1);
-    if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
-    else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
+    bool dens_done = false;
+#ifndef LBM_HOSTCHECK
+    if (tiled_ok(h) && !(h->cfg.flags & 4u)) {
+        if (h->has_solid) launch_density_tiled<true>(h, c, s); else launch_density_tiled<false>(h, c, s);
+        dens_done = true;
+    }
+#endif
+    if (!dens_done) {
+        if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
+        else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
+    }
     exchange_f64(h, c.phi, 0, 1, h->has_solid ? NG : 2);
     if (h->has_solid) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
     bool done = false;

@@ -72,84 +72,129 @@ struct SoaToAosOp {
 };
 
 // ------------------------------------------------------------------------------------------------
-// open boundaries of the reference's 2-D driver (rows along the flow axis; inlet = top, outlet = bottom)
+// open boundaries of the reference's driver (planes along the flow axis; inlet = top, outlet = bottom)
 // ------------------------------------------------------------------------------------------------
+// The three row treatments below are written for any lattice: "up" is the slab axis (y in 2-D, z in 3-D),
+// the unknown populations are those pointing into the domain, N_t = 1/2 sum_{in-plane} c_t f is the
+// transverse momentum that Zou-He redistributes over the diagonal unknowns.  For D2Q9 they are the
+// reference's formulas term by term; D3Q19 (no reference code) is their Hecht-Harting generalisation.
+// Items: one plane of n0 * n1 nodes.
+
 // constantTotalVelocityInlet (AcceleratedRKGPU2D.py:2345-2423): non-equilibrium bounce-back of the
-// unknown populations of the TOTAL distribution on row z_in with u = (0, v), split by mass fraction.
-// Items: one row of n0 nodes.  (D2Q9 only: the reference has no 3-D code.)
-struct InletVelocity2DOp {
+// unknown populations of the TOTAL distribution on plane z_in with u = v e_up, split by mass fraction.
+template <class L>
+struct InletVelocityOp {
     CGFields c;
-    LBM_HD void operator()(int64_t x) const {
+    LBM_HD void operator()(int64_t r) const {
         const Grid& g = c.g;
-        const int64_t id = g.at((int)x, 0, c.z_in);
+        const int64_t id = (int64_t)(c.z_in + NG) * g.plane + r;
         if (!(c.cls[id] & CLS_FLUID)) return;
         const int64_t V = g.vol;
         double* fR = c.fS[0]; double* fB = c.fS[1];
-        double fT[9];
-        for (int q = 0; q < 9; ++q) fT[q] = fR[q * V + id] + fB[q * V + id];
+        double fT[L::Q];
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) fT[q] = fR[q * V + id] + fB[q * V + id];
         const double v = c.v_in;
-        const double rho = (fT[0] + fT[1] + fT[3] + 2.0 * (fT[2] + fT[5] + fT[6])) / (1.0 + v);
+        double s0 = 0.0, sp = 0.0;
+        bool first0 = true, firstp = true;
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) {
+            if (L::d2(q) == 0) { s0 = first0 ? fT[q] : s0 + fT[q]; first0 = false; }
+            if (L::d2(q) == 1) { sp = firstp ? fT[q] : sp + fT[q]; firstp = false; }
+        }
+        const double rho = (s0 + 2.0 * sp) / (1.0 + v);
         const double vv = v * v;
-        auto eq = [&](double w, double ev) { return rho * w * (1.0 + 3.0 * ev + 4.5 * ev * ev - 1.5 * vv); };
-        fT[4] = eq(1.0 / 9.0, -v) + (fT[2] - eq(1.0 / 9.0, v));
-        fT[7] = eq(1.0 / 36.0, -v) + (fT[5] - eq(1.0 / 36.0, v));
-        fT[8] = eq(1.0 / 36.0, -v) + (fT[6] - eq(1.0 / 36.0, v));
         double rR = c.rho[0][id], rB = c.rho[1][id];
         const double ratioR = rR / (rR + rB);
         rR = ratioR * rho;
         const double ratioB = rB / (rR + rB);     // uses the already-updated rhoR, like :2399-2407
         rB = ratioB * rho;
         c.rho[0][id] = rR; c.rho[1][id] = rB;
-        const int unk[3] = {4, 7, 8};
-        for (int k = 0; k < 3; ++k) {
-            fR[unk[k] * V + id] = ratioR * fT[unk[k]];
-            fB[unk[k] * V + id] = ratioB * fT[unk[k]];
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            if (L::d2(q) != -1) continue;
+            const double ev = -v, evo = v;        // e_q . u and e_opp . u
+            const double eq = rho * L::w(q) * (1.0 + 3.0 * ev + 4.5 * ev * ev - 1.5 * vv);
+            const double eqo = rho * L::w(q) * (1.0 + 3.0 * evo + 4.5 * evo * evo - 1.5 * vv);
+            const double t = eq + (fT[L::opp(q)] - eqo);
+            fR[q * V + id] = ratioR * t;
+            fB[q * V + id] = ratioB * t;
         }
     }
 };
-// calConstPressureInletGPU (AcceleratedRKGPU2D.py:923-961): Zou-He pressure per colour on row z_in
-struct InletPressure2DOp {
+// calConstPressureInletGPU (AcceleratedRKGPU2D.py:923-961): Zou-He pressure per colour on plane z_in
+template <class L>
+struct InletPressureOp {
     CGFields c;
-    LBM_HD void operator()(int64_t x) const {
+    LBM_HD void operator()(int64_t r) const {
         const Grid& g = c.g;
-        const int64_t id = g.at((int)x, 0, c.z_in);
+        const int64_t id = (int64_t)(c.z_in + NG) * g.plane + r;
         if (!(c.cls[id] & CLS_FLUID)) return;
         const int64_t V = g.vol;
         for (int k = 0; k < 2; ++k) {
             double* f = c.fS[k];
             const double p = k == 0 ? c.rhoRH : c.rhoBH;
-            const double f1 = f[1 * V + id], f3 = f[3 * V + id];
-            const double v = -1.0 + (f[id] + f1 + f3 + 2.0 * (f[2 * V + id] + f[5 * V + id] + f[6 * V + id])) / p;
-            f[4 * V + id] = f[2 * V + id] - 2.0 / 3.0 * p * v;
-            f[7 * V + id] = f[5 * V + id] + 1.0 / 2.0 * (f1 - f3) - 1.0 / 6.0 * p * v;
-            f[8 * V + id] = f[6 * V + id] - 1.0 / 2.0 * (f1 - f3) - 1.0 / 6.0 * p * v;
+            double fl[L::Q];
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) fl[q] = f[q * V + id];
+            double s0 = 0.0, sp = 0.0, N[3] = {0.0, 0.0, 0.0};
+            bool first0 = true, firstp = true;
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) {
+                if (L::d2(q) == 0) {
+                    s0 = first0 ? fl[q] : s0 + fl[q]; first0 = false;
+                    if (L::d0(q) != 0) N[0] += L::d0(q) * fl[q];
+                    if (L::d1(q) != 0) N[1] += L::d1(q) * fl[q];
+                }
+                if (L::d2(q) == 1) { sp = firstp ? fl[q] : sp + fl[q]; firstp = false; }
+            }
+            const double v = -1.0 + (s0 + 2.0 * sp) / p;
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                if (L::d2(q) != -1) continue;
+                // f_q = f_opp - 1/2 (e_q . N) - 6 w_q p v      (2-D: f4 = f2 - 2/3 p v, f7 = f5 + (f1-f3)/2 - p v/6, ...)
+                f[q * V + id] = fl[L::opp(q)] + 1.0 / 2.0 * (-(L::d0(q) * N[0] + L::d1(q) * N[1])) - 6.0 * L::w(q) * p * v;
+            }
             c.rho[k][id] = p;
         }
     }
 };
 // calConstPressureLowerGPUTotal (AcceleratedRKGPU2D.py:2557-2602): Zou-He pressure on the total
-// distribution on row z_out with p = rhoBL + rhoRL (RKD2Q9.py:1344), split by mass fraction
-struct OutletPressure2DOp {
+// distribution on plane z_out with p = rhoBL + rhoRL (RKD2Q9.py:1344), split by mass fraction
+template <class L>
+struct OutletPressureOp {
     CGFields c;
-    LBM_HD void operator()(int64_t x) const {
+    LBM_HD void operator()(int64_t r) const {
         const Grid& g = c.g;
-        const int64_t id = g.at((int)x, 0, c.z_out);
+        const int64_t id = (int64_t)(c.z_out + NG) * g.plane + r;
         if (!(c.cls[id] & CLS_FLUID)) return;
         const int64_t V = g.vol;
         double* fR = c.fS[0]; double* fB = c.fS[1];
-        double fT[9];
-        for (int q = 0; q < 9; ++q) fT[q] = fR[q * V + id] + fB[q * V + id];
+        double fT[L::Q];
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) fT[q] = fR[q * V + id] + fB[q * V + id];
         const double p = c.rhoBL + c.rhoRL;
-        const double v = 1.0 - 1.0 / p * (fT[0] + fT[1] + fT[3] + 2.0 * (fT[4] + fT[7] + fT[8]));
-        fT[2] = fT[4] + 2.0 / 3.0 * (p * v);
-        fT[5] = fT[7] + 0.5 * (fT[3] - fT[1]) + 1.0 / 6.0 * p * v;
-        fT[6] = fT[8] + 0.5 * (fT[1] - fT[3]) + 1.0 / 6.0 * p * v;
+        double s0 = 0.0, sm = 0.0, N[3] = {0.0, 0.0, 0.0};
+        bool first0 = true, firstm = true;
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) {
+            if (L::d2(q) == 0) {
+                s0 = first0 ? fT[q] : s0 + fT[q]; first0 = false;
+                if (L::d0(q) != 0) N[0] += L::d0(q) * fT[q];
+                if (L::d1(q) != 0) N[1] += L::d1(q) * fT[q];
+            }
+            if (L::d2(q) == -1) { sm = firstm ? fT[q] : sm + fT[q]; firstm = false; }
+        }
+        const double v = 1.0 - 1.0 / p * (s0 + 2.0 * sm);
         const double rR = c.rho[0][id], rB = c.rho[1][id];
         const double ratioR = rR / (rR + rB), ratioB = rB / (rR + rB);
-        const int unk[3] = {2, 5, 6};
-        for (int k = 0; k < 3; ++k) {
-            fR[unk[k] * V + id] = ratioR * fT[unk[k]];
-            fB[unk[k] * V + id] = ratioB * fT[unk[k]];
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            if (L::d2(q) != 1) continue;
+            // f_q = f_opp - 1/2 (e_q . N) + 6 w_q p v       (2-D: f2 = f4 + 2/3 p v, f5 = f7 + (f3-f1)/2 + p v/6, ...)
+            const double t = fT[L::opp(q)] + 0.5 * (-(L::d0(q) * N[0] + L::d1(q) * N[1])) + 6.0 * L::w(q) * (p * v);
+            fR[q * V + id] = ratioR * t;
+            fB[q * V + id] = ratioB * t;
         }
     }
 };

@@ -17,7 +17,6 @@ void cg_alloc_postcollision(lbm_handle* h);
 void cg_ensure_head(lbm_handle* h);
 void cg_generic_body(lbm_handle* h);
 void cg_generic_forces(lbm_handle* h);
-void cg_open_boundaries_3d(lbm_handle* h, const CGFields& c);
 
 // fused fast path for closed boxes (cg_fast.cu)
 bool cg_fast_eligible(const lbm_handle* h);

@@ -96,9 +96,8 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
         if (cfg->tau_type != 1 && cfg->tau_type != 2) { g_create_error = "tau_type must be 1 or 2"; return LBM_EINVAL; }
         if (cfg->wetting_type != 1 && cfg->wetting_type != 2) { g_create_error = "wetting_type must be 1 or 2"; return LBM_EINVAL; }
         if (cfg->wetting_type == 1 && cfg->lattice == 19) { g_create_error = "WettingType 1 is a 2-D rotation; use 2 for D3Q19"; return LBM_EINVAL; }
-        if ((cfg->inlet != LBM_BC_PERIODIC || cfg->outlet != LBM_BC_PERIODIC) && cfg->lattice == 19 &&
-            !(cfg->inlet == LBM_INLET_VELOCITY || cfg->inlet == LBM_BC_PERIODIC)) {
-            g_create_error = "D3Q19 open boundaries: velocity inlet / convective or pressure outlet"; return LBM_EINVAL;
+        if (cfg->inlet < 0 || cfg->inlet > LBM_INLET_PRESSURE || cfg->outlet < 0 || cfg->outlet > LBM_OUTLET_PRESSURE) {
+            g_create_error = "unknown inlet / outlet type"; return LBM_EINVAL;
         }
     }
     lbm_handle* h = new (std::nothrow) lbm_handle();
@@ -380,24 +379,20 @@ template <class L>
 static void cg_head(lbm_handle* h) {
     CGFields c = h->fields();
     const Grid& g = h->g;
-    if (h->Q == 9) {
-        if (c.inlet == LBM_INLET_VELOCITY && c.z_in >= 0) {
-            launch(InletVelocity2DOp{c}, g.n0, h->stream);
-            launch(RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 1}, g.plane, h->stream);
-        } else if (c.inlet == LBM_INLET_PRESSURE && c.z_in >= 0) {
-            launch(InletPressure2DOp{c}, g.n0, h->stream);
-            launch(RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 0}, g.plane, h->stream);
-        }
-        if (c.outlet == LBM_OUTLET_CONVECTIVE && c.z_out >= 0) {
-            launch(RowCopyOp<L>{c, 2, 3, 1}, g.plane, h->stream);
-            launch(RowCopyOp<L>{c, 1, 2, 1}, g.plane, h->stream);
-            launch(RowCopyOp<L>{c, 0, 1, 1}, g.plane, h->stream);
-        } else if (c.outlet == LBM_OUTLET_PRESSURE && c.z_out >= 0) {
-            launch(OutletPressure2DOp{c}, g.n0, h->stream);
-            launch(RowCopyOp<L>{c, 0, 1, 0}, g.plane, h->stream);
-        }
-    } else {
-        cg_open_boundaries_3d(h, c);
+    if (c.inlet == LBM_INLET_VELOCITY && c.z_in >= 0) {
+        launch(InletVelocityOp<L>{c}, g.plane, h->stream);
+        launch(RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 1}, g.plane, h->stream);
+    } else if (c.inlet == LBM_INLET_PRESSURE && c.z_in >= 0) {
+        launch(InletPressureOp<L>{c}, g.plane, h->stream);
+        launch(RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 0}, g.plane, h->stream);
+    }
+    if (c.outlet == LBM_OUTLET_CONVECTIVE && c.z_out >= 0) {
+        launch(RowCopyOp<L>{c, 2, 3, 1}, g.plane, h->stream);
+        launch(RowCopyOp<L>{c, 1, 2, 1}, g.plane, h->stream);
+        launch(RowCopyOp<L>{c, 0, 1, 1}, g.plane, h->stream);
+    } else if (c.outlet == LBM_OUTLET_PRESSURE && c.z_out >= 0) {
+        launch(OutletPressureOp<L>{c}, g.plane, h->stream);
+        launch(RowCopyOp<L>{c, 0, 1, 0}, g.plane, h->stream);
     }
     launch(HeadOp<L>{c}, g.count(0), h->stream);
     h->head_done = true;
@@ -422,8 +417,6 @@ static void cg_body(lbm_handle* h) {
     launch(StreamOp<L>{c}, g.count(0), h->stream);
     h->head_done = false;
 }
-
-void lbm::cg_open_boundaries_3d(lbm_handle*, const CGFields&) {}
 
 void lbm::cg_ensure_head(lbm_handle* h) {
     if (h->head_done) return;

@@ -92,8 +92,11 @@ def shift(a, e):
 
 class CGDense:
     def __init__(self, lattice, is_domain, sigma=0.1, theta_deg=60.0, wetting=2, beta=0.7, delta=0.98,
-                 tauR=1.0, tauB=1.0, tautype=2, relax="MRT"):
+                 tauR=1.0, tauB=1.0, tautype=2, relax="MRT", inlet="Periodic", outlet="Periodic",
+                 v_inlet=0.0, dBH=5e-8, dRH=1.0, dBL=1.0, dRL=5e-8):
         L = self.L = lattice
+        self.inlet, self.outlet, self.v_in = inlet, outlet, v_inlet
+        self.dBH, self.dRH, self.dBL, self.dRL = dBH, dRH, dBL, dRL
         dom = np.asarray(is_domain, bool)
         if dom.ndim == 2:
             dom = dom[None]
@@ -133,8 +136,100 @@ class CGDense:
         self.rhoR = _qsum(self.fR); self.rhoB = _qsum(self.fB)
         self.F = np.zeros((3,) + self.shape); self.u = np.zeros((3,) + self.shape)
 
+    # -- open boundaries: planes along the flow axis ("up" = y in 2-D, z in 3-D; inlet on top, outlet at the
+    # bottom).  For D2Q9 these are the reference's row kernels term by term (AcceleratedRKGPU2D.py:2345-2423,
+    # 923-961, 2557-2602, 604-784, 966-1080); for D3Q19 their Hecht-Harting generalisation: unknown = the
+    # populations pointing into the domain, N_t = 1/2 sum_{in-plane} c_t f the transverse momentum.
+    def _pl(self, a, k):
+        """view of plane k (along the flow axis) of a [..., z, y, x] array"""
+        return a[..., k, :, :] if self.L.D == 3 else a[..., 0, k, :][..., None, :]
+
+    def _up(self, q):
+        return int(self.L.e[q, self.L.D - 1])
+
+    def _copy_plane(self, dst, src, sum_rho):
+        m = self._pl(self.dom, dst) & self._pl(self.dom, src)
+        for f in (self.fR, self.fB):
+            self._pl(f, dst)[...] = np.where(m, self._pl(f, src), self._pl(f, dst))
+        for f, r in ((self.fR, self.rhoR), (self.fB, self.rhoB)):
+            new = _qsum(self._pl(f, dst)) if sum_rho else self._pl(r, src)
+            self._pl(r, dst)[...] = np.where(m, new, self._pl(r, dst))
+
+    def _inplane_sums(self, f, sign):
+        L = self.L
+        s0 = None; s1 = None; N = [0.0, 0.0]
+        for q in range(L.Q):
+            if self._up(q) == 0:
+                s0 = f[q] if s0 is None else s0 + f[q]
+                for t in range(L.D - 1):
+                    if L.e[q, t] != 0:
+                        N[t] = N[t] + float(L.e[q, t]) * f[q]
+            if self._up(q) == sign:
+                s1 = f[q] if s1 is None else s1 + f[q]
+        return s0, s1, N
+
+    def boundaries(self):
+        L = self.L
+        n_up = self.shape[0] if L.D == 3 else self.shape[1]
+        zin, zgh = n_up - 2, n_up - 1
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if self.inlet == "Neumann":
+                m = self._pl(self.dom, zin)
+                fR, fB = self._pl(self.fR, zin), self._pl(self.fB, zin)
+                fT = fR + fB
+                s0, sp, _ = self._inplane_sums(fT, 1)
+                v = self.v_in
+                rho = (s0 + 2. * sp) / (1. + v)
+                rR, rB = self._pl(self.rhoR, zin), self._pl(self.rhoB, zin)
+                ratioR = rR / (rR + rB)
+                rRn = ratioR * rho
+                ratioB = rB / (rRn + rB)                      # updated rhoR (2399-2407)
+                rBn = ratioB * rho
+                for q in range(1, L.Q):
+                    if self._up(q) != -1:
+                        continue
+                    eq = rho * L.w[q] * (1. + 3. * (-v) + 4.5 * v * v - 1.5 * v * v)
+                    eqo = rho * L.w[q] * (1. + 3. * v + 4.5 * v * v - 1.5 * v * v)
+                    t = eq + (fT[L.opp[q]] - eqo)
+                    fR[q] = np.where(m, ratioR * t, fR[q]); fB[q] = np.where(m, ratioB * t, fB[q])
+                rR[...] = np.where(m, rRn, rR); rB[...] = np.where(m, rBn, rB)
+                self._copy_plane(zgh, zin, True)
+            elif self.inlet == "Dirichlet":
+                m = self._pl(self.dom, zin)
+                for f, r, p in ((self._pl(self.fB, zin), self._pl(self.rhoB, zin), self.dBH),
+                                (self._pl(self.fR, zin), self._pl(self.rhoR, zin), self.dRH)):
+                    s0, sp, N = self._inplane_sums(f, 1)
+                    v = -1. + (s0 + 2. * sp) / p
+                    old = f.copy()
+                    for q in range(1, L.Q):
+                        if self._up(q) != -1:
+                            continue
+                        eN = sum(float(L.e[q, t]) * N[t] for t in range(L.D - 1))
+                        f[q] = np.where(m, old[L.opp[q]] + 0.5 * (-eN) - 6. * L.w[q] * p * v, old[q])
+                    r[...] = np.where(m, p, r)
+                self._copy_plane(zgh, zin, False)
+            if self.outlet == "Convective":
+                self._copy_plane(2, 3, True); self._copy_plane(1, 2, True); self._copy_plane(0, 1, True)
+            elif self.outlet == "Dirichlet":
+                m = self._pl(self.dom, 1)
+                fR, fB = self._pl(self.fR, 1), self._pl(self.fB, 1)
+                fT = fR + fB
+                p = self.dBL + self.dRL
+                s0, sm, N = self._inplane_sums(fT, -1)
+                v = 1. - 1. / p * (s0 + 2. * sm)
+                rR, rB = self._pl(self.rhoR, 1), self._pl(self.rhoB, 1)
+                ratioR = rR / (rR + rB); ratioB = rB / (rR + rB)
+                for q in range(1, L.Q):
+                    if self._up(q) != 1:
+                        continue
+                    eN = sum(float(L.e[q, t]) * N[t] for t in range(L.D - 1))
+                    t = fT[L.opp[q]] + 0.5 * (-eN) + 6. * L.w[q] * (p * v)
+                    fR[q] = np.where(m, ratioR * t, fR[q]); fB[q] = np.where(m, ratioB * t, fB[q])
+                self._copy_plane(0, 1, False)
+
     def head(self):
         L = self.L
+        self.boundaries()
         self.fT = self.fR + self.fB
         with np.errstate(invalid="ignore", divide="ignore"):
             rho = self.rhoB + self.rhoR

@@ -130,12 +130,17 @@ def sphere_geometry(n, radius, centre=None):
     return ((x - c[2]) ** 2 + (y - c[1]) ** 2 + (z - c[0]) ** 2) > radius ** 2
 
 
-def run_dense_case(lattice, dom, rhoR, rhoB, steps, lib_path, atol=1e-10, relax="MRT", chunk=None, **par):
+def run_dense_case(lattice, dom, rhoR, rhoB, steps, lib_path, atol=1e-10, relax="MRT", chunk=None, bc=None, **par):
     """CUDA path vs oracle/cg_dense.py on the same input: densities, velocities and populations"""
     L = cg_dense.d2q9() if lattice == 9 else cg_dense.d3q19()
     opar = dict(sigma=par.get("sigma", 0.1), theta_deg=par.get("contact_angle_deg", 60.0),
                 wetting=par.get("wetting_type", 2), beta=par.get("beta", 0.7), delta=par.get("delta", 0.98),
                 tauR=par.get("tauR", 1.0), tauB=par.get("tauB", 1.0), tautype=par.get("tau_type", 2), relax=relax)
+    if bc:      # open boundaries: dict(inlet=, outlet=, v_inlet=, dBH=, dRH=, dBL=, dRL=)
+        opar.update(bc)
+        par.update(inlet=INLET[bc.get("inlet", "Periodic")], outlet=OUTLET[bc.get("outlet", "Periodic")],
+                   inlet_velocity=bc.get("v_inlet", 0.0), rhoBH=bc.get("dBH", 5e-8), rhoRH=bc.get("dRH", 1.0),
+                   rhoBL=bc.get("dBL", 1.0), rhoRL=bc.get("dRL", 5e-8))
     sim = cg_dense.CGDense(L, dom, **opar)
     sim.set_densities(rhoR, rhoB)
     par.setdefault("contact_angle_deg", 60.0)
@@ -243,3 +248,14 @@ def check_sc_vs_gold(path, lib_path, chunk=1):
             for k in range(2):
                 np.testing.assert_allclose(pdf[k][rows], ref[k][rows], rtol=0, atol=ATOL_GOLD)
     eng.close()
+
+
+def case_d3q19_open_boundaries(lib_path, inlet="Neumann", outlet="Convective", n=(22, 10, 12), steps=10, relax="MRT", **par):
+    """D3Q19 channel along z with a solid obstacle: velocity / pressure inlet on top, convective / pressure outlet"""
+    dom = np.ones(n, bool)
+    dom[9:13, 3:7, 4:8] = False
+    z = np.mgrid[0:n[0], 0:n[1], 0:n[2]][0]
+    red = z >= n[0] - 7
+    bc = dict(inlet=inlet, outlet=outlet, v_inlet=-2.0e-3, dBH=5e-8, dRH=1.004, dBL=1.0, dRL=5e-8)
+    return run_dense_case(19, dom, np.where(red, 1.0, 5e-8), np.where(red, 5e-8, 1.0), steps, lib_path, atol=1e-9,
+                          relax=relax, chunk=[1, 3, steps - 4], bc=bc, contact_angle_deg=65.0, **par)

@@ -83,6 +83,8 @@ def test_tiled_kernel_sphere_wetting_vs_oracle():
 def test_tiled_kernel_equals_untiled_fast_path():
     cases.case_d3q19_sphere(None, n=(12, 16, 32), steps=8, flags=2)
     cases.case_d3q19_periodic(None, n=(10, 16, 32), steps=8, flags=2)
+    cases.case_d3q19_sphere(None, n=(12, 16, 32), steps=8, flags=4)
+    cases.case_d3q19_periodic(None, n=(70, 16, 64), steps=5, flags=4)
 
 
 def test_large_box_mass_conservation_and_symmetry():
@@ -129,3 +131,9 @@ def test_slab_decomposition_bit_equal_to_single_gpu():
 def test_d3q19_solid_across_the_periodic_faces():
     cases.case_d3q19_sphere(None, n=(12, 16, 32), centre=[0.3, 0.2, 0.4])
     cases.case_d3q19_sphere(None, centre=[0.3, 0.2, 0.4], flags=1)
+
+
+@pytest.mark.parametrize("inlet,outlet", [("Neumann", "Convective"), ("Neumann", "Dirichlet"), ("Dirichlet", "Convective")])
+def test_d3q19_open_boundaries_vs_oracle(inlet, outlet):
+    cases.case_d3q19_open_boundaries(None, inlet, outlet)
+    cases.case_d3q19_open_boundaries(None, inlet, outlet, n=(40, 16, 32), steps=12, relax="SRT")

@@ -66,3 +66,8 @@ def test_d3q19_solid_across_the_periodic_faces(lib):
     """a sphere centred on the box corner: wetting solids and their colour values live in the ghost planes"""
     cases.case_d3q19_sphere(lib, centre=[0.3, 0.2, 0.4])
     cases.case_d3q19_sphere(lib, centre=[0.3, 0.2, 0.4], flags=1)
+
+
+@pytest.mark.parametrize("inlet,outlet", [("Neumann", "Convective"), ("Neumann", "Dirichlet"), ("Dirichlet", "Convective")])
+def test_d3q19_open_boundaries_vs_oracle(lib, inlet, outlet):
+    cases.case_d3q19_open_boundaries(lib, inlet, outlet)
