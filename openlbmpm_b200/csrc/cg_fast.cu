@@ -7,6 +7,9 @@
 // consecutive lbm_step calls stay in factored form.
 #include "cg_fast_ops.cuh"
 #include "internal.h"
+#ifndef LBM_HOSTCHECK
+#include <cuda_pipeline.h>
+#endif
 
 namespace lbm {
 
@@ -72,12 +75,14 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     auto wrapx = [&](int v) { return v < 0 ? v + g.n0 : (v >= g.n0 ? v - g.n0 : v); };
     auto wrapy = [&](int v) { return v < 0 ? v + g.n1 : (v >= g.n1 ? v - g.n1 : v); };
 
+    // phi plane zp -> shared memory with cp.async (LDGSTS): the copy is issued one plane step before the
+    // plane is needed, so its HBM/L2 latency never stalls the tile
     auto load_phi_plane = [&](int zp) {
         const int slot = (zp + 10) % 5;
         const double* src = c.phi + (int64_t)(zp + NG) * g.plane;
         for (int e = tid; e < PH * PW; e += NT) {
             const int ly = e / PW, lx = e - ly * PW;
-            sphi[slot][ly][lx] = src[(int64_t)wrapy(y0 + ly - 2) * g.n0 + wrapx(x0 + lx - 2)];
+            __pipeline_memcpy_async(&sphi[slot][ly][lx], src + (int64_t)wrapy(y0 + ly - 2) * g.n0 + wrapx(x0 + lx - 2), 8);
         }
     };
     auto normal_plane = [&](int zp) {
@@ -118,13 +123,18 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     const int64_t yo[3] = {(int64_t)wrapy(y - 1) * g.n0, (int64_t)y * g.n0, (int64_t)wrapy(y + 1) * g.n0};
 
     for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) load_phi_plane(zp);
+    __pipeline_commit();
+    load_phi_plane(z_begin + 2);
+    __pipeline_commit();
+    __pipeline_wait_prior(1);
     __syncthreads();
     normal_plane(z_begin - 1);
     normal_plane(z_begin);
 
     const double sgn = c.p.wetting_type == 1 ? 1.0 : -1.0;
     for (int z = z_begin; z < z_end; ++z) {
-        load_phi_plane(z + 2);
+        if (z + 1 < z_end) load_phi_plane(z + 3);       // needed by the NEXT plane step
+        __pipeline_commit();
         // ---- requests to HBM first: pulled populations, densities, lagged force ----
         const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
         bool fluid = true;
@@ -144,6 +154,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 #pragma unroll
             for (int d = 0; d < 3; ++d) Fl[d] = c.F[d * V + id];
         }
+        __pipeline_wait_prior(1);                       // plane z + 2 (requested one step ago) has landed
         __syncthreads();
         normal_plane(z + 1);
         __syncthreads();
@@ -205,7 +216,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 
 // ------------------------------------------------------------------------------------------------
 // Tiled density pass for D3Q19 (pass 1).  Same column-marching layout as the collision pass: the four
-// recolouring scalars (kR, a) of the neighbours are served from a rolling 4-plane shared-memory window
+// recolouring scalars (kR, a) of the neighbours are served from a rolling 5-plane shared-memory window
 // with a 1-node halo (each value is read from L2/HBM once per CTA instead of 19 times), and the 19
 // pulled populations of the NEXT plane are requested before the current plane is reduced, so one full
 // plane of HBM requests per thread is always in flight.
@@ -217,7 +228,7 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk) {
     constexpr int NT = TX * TY;
     constexpr int NW = TX + 2, NH = TY + 2;
     extern __shared__ double smem_dyn[];
-    double (*ss)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn);   // [4 slots][kR, ax, ay, az]
+    double (*ss)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn);   // [5 slots][kR, ax, ay, az]
     const Grid& g = c.g;
     const int64_t V = g.vol;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
@@ -230,13 +241,13 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk) {
     const double* fld[4] = {s.kR, s.a, s.a + V, s.a + 2 * V};
 
     auto load_scalar_plane = [&](int zp) {
-        const int slot = (zp + 8) % 4;
+        const int slot = (zp + 10) % 5;
         const int64_t base = (int64_t)(zp + NG) * g.plane;
         for (int e = tid; e < NH * NW; e += NT) {
             const int ly = e / NW, lx = e - ly * NW;
             const int64_t off = base + (int64_t)wrapy(y0 + ly - 1) * g.n0 + wrapx(x0 + lx - 1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ss[slot][k][ly][lx] = fld[k][off];
+            for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(&ss[slot][k][ly][lx], fld[k] + off, 8);
         }
     };
     const int64_t xo[3] = {(int64_t)wrapx(x - 1), (int64_t)x, (int64_t)wrapx(x + 1)};
@@ -260,17 +271,22 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk) {
 
     load_scalar_plane(z_begin - 1);
     load_scalar_plane(z_begin);
+    __pipeline_commit();
+    load_scalar_plane(z_begin + 1);
+    __pipeline_commit();
     double cur[L::Q], nxt[L::Q];
     unsigned mcur = 0, mnxt = 0;
     bool fcur = true, fnxt = true;
     request(z_begin, cur, mcur, fcur);
     for (int z = z_begin; z < z_end; ++z) {
-        load_scalar_plane(z + 1);
+        if (z + 1 < z_end) load_scalar_plane(z + 2);    // cp.async, needed by the next plane step
+        __pipeline_commit();
         if (z + 1 < z_end) request(z + 1, nxt, mnxt, fnxt);
+        __pipeline_wait_prior(1);                       // plane z + 1 has landed
         __syncthreads();
         if (fcur) {
             const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
-            const int s0 = (z + 8) % 4;
+            const int s0 = (z + 10) % 5;
             const double kR0 = ss[s0][0][ty + 1][tx + 1];
             const double a0[3] = {ss[s0][1][ty + 1][tx + 1], ss[s0][2][ty + 1][tx + 1], ss[s0][3][ty + 1][tx + 1]};
             double accR = kR0 * cur[0], accB = cur[0] - accR;
@@ -278,7 +294,7 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk) {
             for (int q = 1; q < L::Q; ++q) {
                 double fr;
                 if (!SOLIDS || (mcur & (1u << q))) {
-                    const int sq = (z - L::d2(q) + 8) % 4;
+                    const int sq = (z - L::d2(q) + 10) % 5;
                     const int ly = ty + 1 - L::d1(q), lx = tx + 1 - L::d0(q);
                     double ea = 0.0;
 #pragma unroll
@@ -329,7 +345,7 @@ static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFie
     const Grid& g = h->g;
     int zchunk = g.n2 >= 64 ? 32 : g.n2;
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
-    constexpr size_t smem = sizeof(double) * 4 * 4 * (TILE_Y + 2) * (TILE_X + 2);
+    constexpr size_t smem = sizeof(double) * 5 * 4 * (TILE_Y + 2) * (TILE_X + 2);
     static bool configured = false;
     if (!configured) {
         LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y>,
