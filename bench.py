@@ -172,12 +172,8 @@ def main():
     eng = _lib.Engine(Q, shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, device=local, flags=flags,
                       sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            uid = torch.from_numpy(eng.nccl_unique_id().copy())
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        eng.comm_init(rank, world, uid.cpu().numpy())
+        from openlbmpm_b200 import slab
+        eng.comm_init(rank, world, slab.share_unique_id(dist, eng, rank, device="cuda"))
     eng.set_geometry(np.ones(shape, np.uint8))
     eng.init_spinodal_device(SPIN_AMP, SPIN_SEED)
     nodes_total = float(n) ** (3 if Q == 19 else 2)

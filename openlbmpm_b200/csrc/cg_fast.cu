@@ -367,6 +367,16 @@ static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFie
 }
 #endif
 
+// which ghost planes of the factored state are ever read: population q is pulled from z - c_z(q), so it has
+// to travel upwards (c_z = +1) or downwards (c_z = -1) only, in-plane directions never cross a slab face
+template <class L>
+static const int8_t* factored_dirs() {
+    static int8_t d[L::Q + 4];
+    for (int q = 0; q < L::Q; ++q) d[q] = L::d2(q) == 0 ? 2 : (int8_t)L::d2(q);
+    for (int k = 0; k < 4; ++k) d[L::Q + k] = 0;
+    return d;
+}
+
 template <class L>
 static void fast_enter(lbm_handle* h) {
     cg_ensure_head(h);
@@ -384,7 +394,7 @@ static void fast_one_step(lbm_handle* h) {
     const Grid& g = h->g;
     CGFields c = h->fields();
     const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
-    exchange_f64(h, f->buf[f->cur], g.vol, L::Q + 4, 1);
+    exchange_f64(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
     bool dens_done = false;
 #ifndef LBM_HOSTCHECK
     if (tiled_ok(h) && !(h->cfg.flags & 4u)) {

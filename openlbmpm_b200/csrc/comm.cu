@@ -97,8 +97,11 @@ extern "C" int lbm_comm_init(lbm_handle* h, int32_t rank, int32_t nranks, const 
 
 namespace lbm {
 
+// dirs (optional, one entry per array): 0 = ghost planes on both sides, +1 = only the planes that travel upwards
+// (needed in the low ghost of the rank above), -1 = only downwards, 2 = none
 template <class T>
-static void ring_exchange(lbm_handle* h, T* base, int64_t stride, int narr, int gp, ncclDataType_t dt) {
+static void ring_exchange(lbm_handle* h, T* base, int64_t stride, int narr, int gp, ncclDataType_t dt,
+                          const int8_t* dirs = nullptr) {
     const Grid& g = h->g;
     ncclComm_t comm = (ncclComm_t)h->nccl;
     const int up = (h->rank + 1) % h->nranks, down = (h->rank + h->nranks - 1) % h->nranks;
@@ -106,19 +109,24 @@ static void ring_exchange(lbm_handle* h, T* base, int64_t stride, int narr, int 
     LBM_NCCL_CHECK(ncclGroupStart());
     for (int a = 0; a < narr; ++a) {
         T* f = base + a * stride;
-        // my top planes -> low ghost of the rank above; my low ghost <- top planes of the rank below
-        LBM_NCCL_CHECK(ncclSend(f + (int64_t)(NG + g.n2 - gp) * g.plane, count, dt, up, comm, h->stream));
-        LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG - gp) * g.plane, count, dt, down, comm, h->stream));
-        // my bottom planes -> high ghost of the rank below; my high ghost <- bottom planes of the rank above
-        LBM_NCCL_CHECK(ncclSend(f + (int64_t)NG * g.plane, count, dt, down, comm, h->stream));
-        LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG + g.n2) * g.plane, count, dt, up, comm, h->stream));
+        const int dir = dirs ? dirs[a] : 0;
+        if (dir == 0 || dir == 1) {
+            // my top planes -> low ghost of the rank above; my low ghost <- top planes of the rank below
+            LBM_NCCL_CHECK(ncclSend(f + (int64_t)(NG + g.n2 - gp) * g.plane, count, dt, up, comm, h->stream));
+            LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG - gp) * g.plane, count, dt, down, comm, h->stream));
+        }
+        if (dir == 0 || dir == -1) {
+            // my bottom planes -> high ghost of the rank below; my high ghost <- bottom planes of the rank above
+            LBM_NCCL_CHECK(ncclSend(f + (int64_t)NG * g.plane, count, dt, down, comm, h->stream));
+            LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG + g.n2) * g.plane, count, dt, up, comm, h->stream));
+        }
     }
     LBM_NCCL_CHECK(ncclGroupEnd());
     ++g_launch_counter;
 }
 
-void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp) {
-    ring_exchange<double>(h, base, stride, narr, gp, ncclDouble);
+void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+    ring_exchange<double>(h, base, stride, narr, gp, ncclDouble, dirs);
 }
 void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp) { ring_exchange<uint8_t>(h, base, 0, 1, gp, ncclUint8); }
 void comm_destroy(lbm_handle* h) {

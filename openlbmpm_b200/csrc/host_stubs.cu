@@ -3,7 +3,7 @@
 #ifdef LBM_HOSTCHECK
 #include "internal.h"
 namespace lbm {
-void comm_exchange_f64(lbm_handle*, double*, int64_t, int, int) { throw BackendError{"multi-rank needs the CUDA build"}; }
+void comm_exchange_f64(lbm_handle*, double*, int64_t, int, int, const int8_t*) { throw BackendError{"multi-rank needs the CUDA build"}; }
 void comm_exchange_u8(lbm_handle*, uint8_t*, int) { throw BackendError{"multi-rank needs the CUDA build"}; }
 void comm_destroy(lbm_handle*) {}
 }  // namespace lbm

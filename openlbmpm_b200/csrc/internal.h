@@ -5,9 +5,9 @@
 namespace lbm {
 
 // ghost planes along the slab axis (periodic wrap on one GPU, NCCL send/recv between slabs)
-void exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp);
+void exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs = nullptr);
 void exchange_u8(lbm_handle* h, uint8_t* base, int gp);
-void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp);
+void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs);
 void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp);
 void comm_destroy(lbm_handle* h);
 

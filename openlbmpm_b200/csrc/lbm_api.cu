@@ -61,8 +61,8 @@ CGFields lbm_handle::fields() const {
 // ------------------------------------------------------------------------------------------------
 // ghost planes
 // ------------------------------------------------------------------------------------------------
-void lbm::exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp) {
-    if (h->nranks > 1) { comm_exchange_f64(h, base, stride, narr, gp); return; }
+void lbm::exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+    if (h->nranks > 1) { comm_exchange_f64(h, base, stride, narr, gp, dirs); return; }
     GhostWrapOp<double> op{h->g, base, stride, narr, gp};
     launch(op, op.items(), h->stream);
 }

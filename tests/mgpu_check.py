@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
 
-from openlbmpm_b200 import _lib
+from openlbmpm_b200 import _lib, slab
 
 
 def run(shape_global, dom, rhoR, steps, rank, world, **kw):
@@ -19,12 +19,7 @@ def run(shape_global, dom, rhoR, steps, rank, world, **kw):
     sl = slice(rank * nz, (rank + 1) * nz)
     eng = _lib.Engine(19, (nz,) + tuple(shape_global[1:]), device=int(os.environ.get("LOCAL_RANK", "0")), **kw)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            uid = torch.from_numpy(eng.nccl_unique_id().copy())
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        eng.comm_init(rank, world, uid.cpu().numpy())
+        eng.comm_init(rank, world, slab.share_unique_id(dist, eng, rank, device="cuda"))
     eng.set_geometry(dom[sl])
     eng.init_equilibrium(np.where(dom[sl], rhoR[sl], 0.0), np.where(dom[sl], 1.0 - rhoR[sl], 0.0))
     eng.step(steps)
