@@ -199,16 +199,25 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             G[d] = sgn * gn * n[d];
             F[d] = (c.p.wetting_type == 1 ? 0.5 : -0.5) * c.p.sigma * K * G[d];
         }
-        double mom[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int q = 1; q < L::Q; ++q)
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-                if (L::c(q, d) != 0) mom[d] += L::c(q, d) * fT[q];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) u[d] = (mom[d] + 0.5 * Fl[d]) * irho;
         const double tau = c.p.tauR == c.p.tauB ? c.p.tauR : cg_tau(phi0, rR, rB, c.p);   // equal viscosities: tau(phi) is constant
-        cg_collide<L>(fT, rho, u, F, tau, c.p.relax);
+        if (c.p.relax != 0) {
+            // MRT: the momentum is three of the moments, so the transform is done once
+            double m[L::NMOM];
+            L::to_moments(fT, m);
+            u[0] = (m[3] + 0.5 * Fl[0]) * irho; u[1] = (m[5] + 0.5 * Fl[1]) * irho; u[2] = (m[7] + 0.5 * Fl[2]) * irho;
+            L::relax_moments(m, rho, u, F, 1.0 / tau);
+            L::from_moments(m, fT);
+        } else {
+            double mom[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q)
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    if (L::c(q, d) != 0) mom[d] += L::c(q, d) * fT[q];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) u[d] = (mom[d] + 0.5 * Fl[d]) * irho;
+            cg_collide<L>(fT, rho, u, F, tau, 0);
+        }
         const double amp = gn > 1.0e-8 ? c.p.beta * rR * rB * irho : 0.0;   // a = amp G / |G| = amp sgn n
 #pragma unroll
         for (int q = 0; q < L::Q; ++q) __stcs(o.gT + q * V + id, fT[q]);
