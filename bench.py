@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="lbm_config.flags (LBM_FLAG_*), for A/B measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -168,7 +169,7 @@ def main():
         raise SystemExit("size must be divisible by the number of GPUs")
     nloc = n // world
     shape = (nloc, n, n) if Q == 19 else (nloc, n)
-    flags = _lib.FLAG_GENERIC_KERNELS if args.general else 0
+    flags = (_lib.FLAG_GENERIC_KERNELS if args.general else 0) | args.flags
     eng = _lib.Engine(Q, shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, device=local, flags=flags,
                       sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2)
     if world > 1:

@@ -97,6 +97,42 @@ inline void launch(const Op& op, int64_t n, stream_t s) {
     ++g_launch_counter;
 }
 
+// Replay of a launch-bound unit of work: small lattices (the 2-D configurations) spend their time in launch
+// overhead, so `body` (which only enqueues kernels on `s`) is captured once into a CUDA graph and the graph is
+// launched `reps` times.  The executable graph is parked in *keep and destroyed by the next call / the owner.
+struct GraphKeep { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; };
+inline void graph_release(GraphKeep* k, stream_t s) {
+    if (!k->exec && !k->graph) return;
+    cudaStreamSynchronize(s);
+    if (k->exec) cudaGraphExecDestroy(k->exec);
+    if (k->graph) cudaGraphDestroy(k->graph);
+    k->exec = nullptr; k->graph = nullptr;
+}
+template <class F>
+inline void replay(int reps, bool use_graph, GraphKeep* keep, stream_t s, F body) {
+    if (reps <= 0) return;
+    if (!use_graph || reps < 8 || g_prof.on) {
+        for (int i = 0; i < reps; ++i) body();
+        return;
+    }
+    graph_release(keep, s);
+    const int64_t l0 = g_launch_counter;
+    LBM_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    try {
+        body();
+    } catch (...) {
+        cudaGraph_t dead = nullptr;
+        cudaStreamEndCapture(s, &dead);
+        if (dead) cudaGraphDestroy(dead);
+        throw;
+    }
+    LBM_CUDA_CHECK(cudaStreamEndCapture(s, &keep->graph));
+    const int64_t per = g_launch_counter - l0;
+    LBM_CUDA_CHECK(cudaGraphInstantiate(&keep->exec, keep->graph, 0));
+    for (int i = 0; i < reps; ++i) LBM_CUDA_CHECK(cudaGraphLaunch(keep->exec, s));
+    g_launch_counter += per * (reps - 1);
+}
+
 inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, stream_t s) {
     size_t tmp_bytes = 0;
     LBM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, n, s));
@@ -129,6 +165,12 @@ template <class Op>
 inline void launch(const Op& op, int64_t n, stream_t) {
     for (int64_t i = 0; i < n; ++i) op(i);
     ++g_launch_counter;
+}
+struct GraphKeep { int unused = 0; };
+inline void graph_release(GraphKeep*, stream_t) {}
+template <class F>
+inline void replay(int reps, bool, GraphKeep*, stream_t, F body) {
+    for (int i = 0; i < reps; ++i) body();
 }
 inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, stream_t) {
     int64_t acc = 0;

@@ -440,9 +440,11 @@ void cg_fast_step(lbm_handle* h, int nsteps) {
         if (h->Q == 9) fast_enter<D2Q9>(h); else fast_enter<D3Q19>(h);
         --left;
     }
-    for (int s = 0; s < left; ++s) {
-        if (h->Q == 9) fast_one_step<D2Q9>(h); else fast_one_step<D3Q19>(h);
-    }
+    auto one = [&] { if (h->Q == 9) fast_one_step<D2Q9>(h); else fast_one_step<D3Q19>(h); };
+    if (left > 0) { one(); --left; }          // outside the graph: configures the tiled kernels on first use
+    // the double buffer flips every step, so the replayed unit is a pair of steps
+    replay(left / 2, h->graph_ok(), &h->graph, h->stream, [&] { one(); one(); });
+    if (left & 1) one();
 }
 
 void cg_fast_materialise(lbm_handle* h) {

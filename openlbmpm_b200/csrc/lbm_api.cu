@@ -143,6 +143,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
 #endif
+    graph_release(&h->graph, h->stream);
     free_state(h);
     dev_free(h->dom); dev_free(h->cls); dev_free(h->ns);
     comm_destroy(h);
@@ -443,11 +444,10 @@ extern "C" int lbm_step(lbm_handle* h, int32_t nsteps) {
         sc_step(h, nsteps);
     } else if (cg_fast_eligible(h)) {
         cg_fast_step(h, nsteps);
-    } else {
-        for (int s = 0; s < nsteps; ++s) {
-            cg_ensure_head(h);
-            cg_generic_body(h);
-        }
+    } else if (nsteps > 0) {
+        cg_ensure_head(h);          // first iteration outside the graph: it allocates the scratch arrays
+        cg_generic_body(h);
+        replay(nsteps - 1, h->graph_ok(), &h->graph, h->stream, [&] { cg_ensure_head(h); cg_generic_body(h); });
     }
 #ifndef LBM_HOSTCHECK
     LBM_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));

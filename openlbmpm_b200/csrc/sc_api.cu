@@ -180,9 +180,10 @@ static void efs_iteration(lbm_handle* h) {
 
 void sc_step(lbm_handle* h, int nsteps) {
     if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
-    for (int s = 0; s < nsteps; ++s) {
-        if (h->cfg.model == LBM_MODEL_SC) sc_iteration(h); else efs_iteration(h);
-    }
+    auto one = [&] { if (h->cfg.model == LBM_MODEL_SC) sc_iteration(h); else efs_iteration(h); };
+    if (nsteps <= 0) return;
+    one();      // outside the graph: whether the inlet treatment of this iteration is still due depends on the host state
+    replay(nsteps - 1, h->graph_ok(), &h->graph, h->stream, one);
 }
 
 int sc_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u) {

@@ -137,3 +137,10 @@ def test_d3q19_solid_across_the_periodic_faces():
 def test_d3q19_open_boundaries_vs_oracle(inlet, outlet):
     cases.case_d3q19_open_boundaries(None, inlet, outlet)
     cases.case_d3q19_open_boundaries(None, inlet, outlet, n=(40, 16, 32), steps=12, relax="SRT")
+
+
+# ---- small lattices replay a captured CUDA graph of the step when many steps are requested at once ----
+@pytest.mark.parametrize("path", cases.GOLD_CG2D, ids=[cases.gold_id(p) for p in cases.GOLD_CG2D])
+@pytest.mark.parametrize("flags", [0, 1, 8])
+def test_trajectory_vs_reference_graph_replay(path, flags):
+    cases.check_trajectory_vs_gold(path, None, chunk=19, flags=flags)

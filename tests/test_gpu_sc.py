@@ -14,3 +14,8 @@ def test_trajectory_vs_reference(path):
 
 def test_chunked():
     cases.check_sc_vs_gold(cases.GOLD_SC2D[0], None, chunk=13)
+
+
+@pytest.mark.parametrize("path", cases.GOLD_SC2D, ids=[cases.gold_id(p) for p in cases.GOLD_SC2D])
+def test_trajectory_vs_reference_graph_replay(path):
+    cases.check_sc_vs_gold(path, None, chunk=20)
