@@ -169,8 +169,9 @@ int lbm_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, doubl
  * (fluidPDFR/B at the same output point).                                                  */
 int lbm_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp);
 
-/* Auxiliary per-node fields of the last completed step, dense [nz][ny][nx] (NULL = skip):
- * phi (colour field incl. wetting-solid values), G (D arrays), F (D arrays), K.            */
+/* Auxiliary per-node fields at the output point, dense [nz][ny][nx] (NULL = skip): phi (colour field incl.
+ * wetting-solid values), G (D arrays, after the wetting correction) and curvature K of the current time level,
+ * F (D arrays) = the CSF force of the PREVIOUS step (the lagged force the velocity is evaluated with).        */
 int lbm_download_fields(lbm_handle* h, double* phi, double* const* G, double* const* F, double* K);
 
 /* Sum of each component's density over the void nodes (mass check).                        */

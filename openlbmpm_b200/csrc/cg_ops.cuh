@@ -334,6 +334,23 @@ LBM_HD void cg_force_at(const CGFields& c, int x, int y, int z, int64_t id, cons
     (void)id;
 }
 
+// curvature only (lbm_download_fields): same stencil as the collision operators, the force state is left alone
+template <class L>
+struct CurvatureOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 0, x, y, z);
+        const int64_t id = g.at(x, y, z), V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        double G[3] = {0, 0, 0}, n[3] = {0, 0, 0}, F[3], K;
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) { G[a] = c.G[a * V + id]; n[a] = c.nrm[a * V + id]; }
+        cg_force_at<L>(c, x, y, z, id, G, n, F, &K);
+        c.K[id] = K;
+    }
+};
+
 // force + collision of the total population + recolouring, fS -> fC
 // (calForceTermInColorGradient*, calRKCollision1TotalGPU2D{SRT,MRT}M, calPerturbationFromForce2D[MRT],
 //  calRecoloringProcessM; RKD2Q9.py:1419-1465)

@@ -518,7 +518,13 @@ extern "C" int lbm_download_fields(lbm_handle* h, double* phi, double* const* G,
     if (!h->has_state) return fail(h, LBM_ESTATE, "no state");
     if (h->cfg.model != LBM_MODEL_CG) return fail(h, LBM_EINVAL, "colour-gradient fields only");
     set_device(h);
-    cg_fast_materialise(h);
+    to_output_point(h);
+    cg_generic_forces(h);           // phi on the wetting solids, G, unit normals of the current time level
+    {
+        CGFields c = h->fields();
+        if (h->Q == 9) launch(CurvatureOp<D2Q9>{c}, h->g.count(0), h->stream);
+        else launch(CurvatureOp<D3Q19>{c}, h->g.count(0), h->stream);
+    }
     const Grid& g = h->g;
     const int64_t owned = g.plane * g.n2, off = NG * g.plane;
     if (phi) dev_d2h(phi, h->phi + off, owned * 8, h->stream);
