@@ -56,7 +56,7 @@ static void fast_alloc(lbm_handle* h) {
 // ------------------------------------------------------------------------------------------------
 template <bool SOLIDS, int TX, int TY>
 __global__ void __launch_bounds__(TX* TY, 2)
-cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk) {
+cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi) {
     using L = D3Q19;
     constexpr int NT = TX * TY;
     constexpr int PW = TX + 4, PH = TY + 4;     // phi tile
@@ -68,8 +68,8 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     const int64_t V = g.vol;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int z_begin = blockIdx.z * zchunk;
-    const int z_end = min(z_begin + zchunk, g.n2);
+    const int z_begin = z_lo + blockIdx.z * zchunk;
+    const int z_end = min(z_begin + zchunk, z_hi);
     const int x = x0 + tx, y = y0 + ty;
 
     auto wrapx = [&](int v) { return v < 0 ? v + g.n0 : (v >= g.n0 ? v - g.n0 : v); };
@@ -239,7 +239,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 // ------------------------------------------------------------------------------------------------
 template <bool SOLIDS, int TX, int TY>
 __global__ void __launch_bounds__(TX* TY, 2)
-cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk) {
+cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, const int z_lo, const int z_hi) {
     using L = D3Q19;
     constexpr int NT = TX * TY;
     constexpr int NW = TX + 2, NH = TY + 2;
@@ -249,8 +249,8 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk) {
     const int64_t V = g.vol;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int z_begin = blockIdx.z * zchunk;
-    const int z_end = min(z_begin + zchunk, g.n2);
+    const int z_begin = z_lo + blockIdx.z * zchunk;
+    const int z_end = min(z_begin + zchunk, z_hi);
     const int x = x0 + tx, y = y0 + ty;
     auto wrapx = [&](int v) { return v < 0 ? v + g.n0 : (v >= g.n0 ? v - g.n0 : v); };
     auto wrapy = [&](int v) { return v < 0 ? v + g.n1 : (v >= g.n1 ? v - g.n1 : v); };
@@ -338,10 +338,12 @@ static bool tiled_ok(const lbm_handle* h) {
 }
 
 template <bool SOLIDS>
-static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o) {
+static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo = 0, int z_hi = -1) {
     const Grid& g = h->g;
+    if (z_hi < 0) z_hi = g.n2;
+    if (z_hi <= z_lo) return;
     int zchunk = g.n2 >= 64 ? 32 : g.n2;
-    dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
+    dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2));
     static bool configured = false;
     if (!configured) {
@@ -350,17 +352,19 @@ static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, 
         configured = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tiled_d3q19<solids>" : "cg_collide_tiled_d3q19<all-fluid>", h->stream);
-    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, o, zchunk);
+    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
     ++g_launch_counter;
 }
 
 template <bool SOLIDS>
-static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s) {
+static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo = 0, int z_hi = -1) {
     const Grid& g = h->g;
+    if (z_hi < 0) z_hi = g.n2;
+    if (z_hi <= z_lo) return;
     int zchunk = g.n2 >= 64 ? 32 : g.n2;
-    dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
+    dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * 5 * 4 * (TILE_Y + 2) * (TILE_X + 2);
     static bool configured = false;
     if (!configured) {
@@ -369,7 +373,7 @@ static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFie
         configured = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_density_tiled_d3q19<solids>" : "cg_density_tiled_d3q19<all-fluid>", h->stream);
-    cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, zchunk);
+    cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, zchunk, z_lo, z_hi);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
     ++g_launch_counter;
@@ -397,10 +401,50 @@ static void fast_enter(lbm_handle* h) {
     h->fast_pending_stream = true;
 }
 
+#ifndef LBM_HOSTCHECK
+// Slab decomposition, all-fluid slab, tiled kernels: the two ghost-plane exchanges of a step run on the
+// communication stream while the main stream works on the planes that do not need them.
+//   comm:  [factored state, 1 plane]            [phi, 2 planes]
+//   main:  density pass planes 1..n-2 | 0, n-1   collision pass planes 2..n-3 | 0,1, n-2,n-1
+static void fast_one_step_overlapped(lbm_handle* h) {
+    using L = D3Q19;
+    FastState* f = (FastState*)h->fast;
+    const Grid& g = h->g;
+    CGFields c = h->fields();
+    const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
+    const int n = g.n2;
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_main, h->stream));             // previous collision pass complete
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
+    h->xstream = h->comm_stream;
+    exchange_f64(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_comm, h->comm_stream));
+    launch_density_tiled<false>(h, c, s, 1, n - 1);                     // needs no ghost plane
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    launch_density_tiled<false>(h, c, s, 0, 1);
+    launch_density_tiled<false>(h, c, s, n - 1, n);
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_main, h->stream));             // phi complete on the owned planes
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
+    exchange_f64(h, c.phi, 0, 1, 2);
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_comm, h->comm_stream));
+    h->xstream = nullptr;
+    launch_tiled<false>(h, c, s, o, 2, n - 2);                          // phi halo of 2 planes stays inside the slab
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    launch_tiled<false>(h, c, s, o, 0, 2);
+    launch_tiled<false>(h, c, s, o, n - 2, n);
+    f->cur = 1 - f->cur;
+}
+#endif
+
 template <class L>
 static void fast_one_step(lbm_handle* h) {
     FastState* f = (FastState*)h->fast;
     const Grid& g = h->g;
+#ifndef LBM_HOSTCHECK
+    if (h->nranks > 1 && !h->has_solid && tiled_ok(h) && g.n2 >= 8 && !(h->cfg.flags & (4u | 16u))) {
+        fast_one_step_overlapped(h);
+        return;
+    }
+#endif
     CGFields c = h->fields();
     const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
     exchange_f64(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());

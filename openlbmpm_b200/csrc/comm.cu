@@ -22,6 +22,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)();
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     const char* (*GetErrorString)(ncclResult_t);
     bool ok = false;
 };
@@ -44,6 +45,7 @@ NcclApi& nccl_api() {
     api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.Send = (decltype(api.Send))sym("ncclSend");
     api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     api.ok = true;
     return api;
@@ -89,6 +91,9 @@ extern "C" int lbm_comm_init(lbm_handle* h, int32_t rank, int32_t nranks, const 
             ncclComm_t comm;
             LBM_NCCL_CHECK(ncclCommInitRank(&comm, nranks, id, rank));
             h->nccl = comm;
+            LBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+            LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+            LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
         }
         h->rank = rank; h->nranks = nranks;
     } catch (const BackendError& e) { h->err = e.msg; return LBM_ENCCL; }
@@ -104,6 +109,7 @@ static void ring_exchange(lbm_handle* h, T* base, int64_t stride, int narr, int 
                           const int8_t* dirs = nullptr) {
     const Grid& g = h->g;
     ncclComm_t comm = (ncclComm_t)h->nccl;
+    cudaStream_t st = h->xstream ? h->xstream : h->stream;
     const int up = (h->rank + 1) % h->nranks, down = (h->rank + h->nranks - 1) % h->nranks;
     const size_t count = (size_t)gp * g.plane;
     LBM_NCCL_CHECK(ncclGroupStart());
@@ -112,13 +118,13 @@ static void ring_exchange(lbm_handle* h, T* base, int64_t stride, int narr, int 
         const int dir = dirs ? dirs[a] : 0;
         if (dir == 0 || dir == 1) {
             // my top planes -> low ghost of the rank above; my low ghost <- top planes of the rank below
-            LBM_NCCL_CHECK(ncclSend(f + (int64_t)(NG + g.n2 - gp) * g.plane, count, dt, up, comm, h->stream));
-            LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG - gp) * g.plane, count, dt, down, comm, h->stream));
+            LBM_NCCL_CHECK(ncclSend(f + (int64_t)(NG + g.n2 - gp) * g.plane, count, dt, up, comm, st));
+            LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG - gp) * g.plane, count, dt, down, comm, st));
         }
         if (dir == 0 || dir == -1) {
             // my bottom planes -> high ghost of the rank below; my high ghost <- bottom planes of the rank above
-            LBM_NCCL_CHECK(ncclSend(f + (int64_t)NG * g.plane, count, dt, down, comm, h->stream));
-            LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG + g.n2) * g.plane, count, dt, up, comm, h->stream));
+            LBM_NCCL_CHECK(ncclSend(f + (int64_t)NG * g.plane, count, dt, down, comm, st));
+            LBM_NCCL_CHECK(ncclRecv(f + (int64_t)(NG + g.n2) * g.plane, count, dt, up, comm, st));
         }
     }
     LBM_NCCL_CHECK(ncclGroupEnd());
@@ -129,11 +135,28 @@ void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, in
     ring_exchange<double>(h, base, stride, narr, gp, ncclDouble, dirs);
 }
 void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp) { ring_exchange<uint8_t>(h, base, 0, 1, gp, ncclUint8); }
+// maximum of an integer over all slabs (used for decisions every rank must take identically)
+int comm_allreduce_max(lbm_handle* h, int v) {
+    if (h->nranks <= 1) return v;
+    int* d = (int*)dev_alloc(sizeof(int));
+    int out = v;
+    try {
+        dev_h2d(d, &v, sizeof(int), h->stream);
+        LBM_NCCL_CHECK(nccl_api().AllReduce(d, d, 1, ncclInt32, ncclMax, (ncclComm_t)h->nccl, h->stream));
+        dev_d2h(&out, d, sizeof(int), h->stream);
+    } catch (...) { dev_free(d); throw; }
+    dev_free(d);
+    return out;
+}
+
 void comm_destroy(lbm_handle* h) {
     if (h->nccl) {
         try { ncclCommDestroy((ncclComm_t)h->nccl); } catch (const BackendError&) {}
         h->nccl = nullptr;
     }
+    if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); h->comm_stream = nullptr; }
+    if (h->ev_main) { cudaEventDestroy(h->ev_main); h->ev_main = nullptr; }
+    if (h->ev_comm) { cudaEventDestroy(h->ev_comm); h->ev_comm = nullptr; }
 }
 
 }  // namespace lbm

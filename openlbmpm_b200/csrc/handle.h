@@ -53,6 +53,9 @@ struct lbm_handle {
 #ifndef LBM_HOSTCHECK
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* nccl = nullptr;       // ncclComm_t
+    // slab decomposition: ghost-plane exchanges run on their own stream, overlapped with the interior planes
+    cudaStream_t comm_stream = nullptr, xstream = nullptr;   // xstream: where exchange_* currently enqueues (null = stream)
+    cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
 #endif
 
     lbm::CGFields fields() const;

@@ -10,6 +10,7 @@ void exchange_u8(lbm_handle* h, uint8_t* base, int gp);
 void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs);
 void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp);
 void comm_destroy(lbm_handle* h);
+int comm_allreduce_max(lbm_handle* h, int v);
 
 // general colour-gradient path (lbm_api.cu)
 void cg_alloc_state(lbm_handle* h);

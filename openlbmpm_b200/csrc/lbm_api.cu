@@ -190,6 +190,9 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
         dev_d2h(padded.data(), h->dom, g.vol, h->stream);
         h->has_solid = false;
         for (int64_t i = 0; i < g.vol; ++i) if (!padded[i]) { h->has_solid = true; break; }
+        // every slab must take the same code path (number of ghost planes, kernel variants): a solid anywhere
+        // in the lattice switches all of them to the solid-aware variants
+        h->has_solid = comm_allreduce_max(h, h->has_solid ? 1 : 0) != 0;
     }
     if (h->D == 2) {
         launch(ClassifyOp<2>{g, h->dom, h->cls}, g.count(NG), h->stream);

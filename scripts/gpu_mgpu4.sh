@@ -1,0 +1,9 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 170 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531 tests/mgpu_check.py > gpurun_out/mgpu_check4.log 2>&1
+grep -E "bit-equal|MGPU" gpurun_out/mgpu_check4.log || tail -20 gpurun_out/mgpu_check4.log
+for fl in 0 16; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 2955$fl bench.py --gpus 4 --steps 50 --warmup 5 --no-e2e --flags $fl > gpurun_out/scale4_f$fl.json 2> gpurun_out/scale4_f$fl.err
+  python scripts/bench_brief.py gpurun_out/scale4_f$fl.json || tail -5 gpurun_out/scale4_f$fl.err
+done
