@@ -62,7 +62,8 @@ extern "C" {
 #define LBM_FLAG_GENERIC_KERNELS 1u  /* force the unfused reference-ordered kernel sequence */
 #define LBM_FLAG_NO_TILED_KERNEL 2u  /* factored fast path, but with its one-thread-per-node kernels only */
 #define LBM_FLAG_NO_TILED_DENSITY 4u /* keep the tiled collision pass, use the one-thread-per-node density pass */
-#define LBM_FLAG_NO_OVERLAP 16u      /* slab decomposition: exchange ghost planes on the compute stream (no overlap) */
+#define LBM_FLAG_OVERLAP 16u         /* slab decomposition: overlap the ghost-plane exchanges with the interior planes */
+#define LBM_FLAG_PACKED_EXCHANGE 32u /* slab decomposition: pack the boundary planes into one message per direction (experimental) */
 #define LBM_FLAG_NO_CUDA_GRAPH 8u    /* small lattices: launch every kernel instead of replaying a captured graph */
 
 typedef struct lbm_handle lbm_handle;

@@ -131,8 +131,74 @@ static void ring_exchange(lbm_handle* h, T* base, int64_t stride, int narr, int 
     ++g_launch_counter;
 }
 
+// Packed variant for the per-step exchanges: the boundary planes of all arrays that travel in one direction are
+// gathered into one staging buffer, so an exchange is 2 sends + 2 receives of tens of MB instead of 2 x narr
+// messages of one plane each (NCCL point-to-point bandwidth grows with the message size); the pack / unpack
+// kernels move the same bytes at HBM speed.
+namespace {
+constexpr int MAXARR = 48;
+struct PackOp {
+    Grid g; double* base; int64_t stride; int gp; int n_up, n_dn; int8_t up[MAXARR], dn[MAXARR];
+    double *send_up, *send_dn; const double *recv_lo, *recv_hi; int unpack;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t per = (int64_t)gp * g.plane;
+        const int64_t k = i / per, r = i % per;
+        if (k < n_up) {            // arrays travelling upwards: my top planes out, my low ghost in
+            double* f = base + up[k] * stride;
+            if (!unpack) send_up[k * per + r] = f[(int64_t)(NG + g.n2 - gp) * g.plane + r];
+            else f[(int64_t)(NG - gp) * g.plane + r] = recv_lo[k * per + r];
+        } else {                   // arrays travelling downwards: my bottom planes out, my high ghost in
+            const int64_t kk = k - n_up;
+            double* f = base + dn[kk] * stride;
+            if (!unpack) send_dn[kk * per + r] = f[(int64_t)NG * g.plane + r];
+            else f[(int64_t)(NG + g.n2) * g.plane + r] = recv_hi[kk * per + r];
+        }
+    }
+};
+}  // namespace
+
 void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
-    ring_exchange<double>(h, base, stride, narr, gp, ncclDouble, dirs);
+    // opt-in (LBM_FLAG_PACKED_EXCHANGE): +0.5 % at 2 GPUs, and one of the four bit-equality cases of
+    // tests/mgpu_check.py (solids + tiled kernels, P = 2) failed with it, so the in-place exchange stays the default
+    if (narr > MAXARR || !(h->cfg.flags & 32u)) { ring_exchange<double>(h, base, stride, narr, gp, ncclDouble, dirs); return; }
+    const Grid& g = h->g;
+    PackOp op;
+    op.g = g; op.base = base; op.stride = stride; op.gp = gp; op.n_up = op.n_dn = 0;
+    for (int a = 0; a < narr; ++a) {
+        const int d = dirs ? dirs[a] : 0;
+        if (d == 0 || d == 1) op.up[op.n_up++] = (int8_t)a;
+        if (d == 0 || d == -1) op.dn[op.n_dn++] = (int8_t)a;
+    }
+    const int64_t per = (int64_t)gp * g.plane;
+    const size_t need = (size_t)(op.n_up + op.n_dn) * per * sizeof(double);
+    if (h->stage_bytes < need) {
+        dev_sync(h->stream);
+        if (h->comm_stream) LBM_CUDA_CHECK(cudaStreamSynchronize(h->comm_stream));
+        dev_free(h->stage_send); dev_free(h->stage_recv);
+        h->stage_send = (double*)dev_alloc(need); h->stage_recv = (double*)dev_alloc(need);
+        h->stage_bytes = need;
+    }
+    op.send_up = h->stage_send; op.send_dn = h->stage_send + op.n_up * per;
+    double* recv_lo = h->stage_recv; double* recv_hi = h->stage_recv + op.n_up * per;
+    op.recv_lo = recv_lo; op.recv_hi = recv_hi;
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    cudaStream_t st = h->xstream ? h->xstream : h->stream;
+    const int up = (h->rank + 1) % h->nranks, down = (h->rank + h->nranks - 1) % h->nranks;
+    op.unpack = 0;
+    launch(op, (int64_t)(op.n_up + op.n_dn) * per, st);
+    LBM_NCCL_CHECK(ncclGroupStart());
+    if (op.n_up) {
+        LBM_NCCL_CHECK(ncclSend(op.send_up, (size_t)op.n_up * per, ncclDouble, up, comm, st));
+        LBM_NCCL_CHECK(ncclRecv(recv_lo, (size_t)op.n_up * per, ncclDouble, down, comm, st));
+    }
+    if (op.n_dn) {
+        LBM_NCCL_CHECK(ncclSend(op.send_dn, (size_t)op.n_dn * per, ncclDouble, down, comm, st));
+        LBM_NCCL_CHECK(ncclRecv(recv_hi, (size_t)op.n_dn * per, ncclDouble, up, comm, st));
+    }
+    LBM_NCCL_CHECK(ncclGroupEnd());
+    ++g_launch_counter;
+    op.unpack = 1;
+    launch(op, (int64_t)(op.n_up + op.n_dn) * per, st);
 }
 void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp) { ring_exchange<uint8_t>(h, base, 0, 1, gp, ncclUint8); }
 // maximum of an integer over all slabs (used for decisions every rank must take identically)
@@ -154,6 +220,8 @@ void comm_destroy(lbm_handle* h) {
         try { ncclCommDestroy((ncclComm_t)h->nccl); } catch (const BackendError&) {}
         h->nccl = nullptr;
     }
+    dev_free(h->stage_send); dev_free(h->stage_recv);
+    h->stage_send = h->stage_recv = nullptr; h->stage_bytes = 0;
     if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); h->comm_stream = nullptr; }
     if (h->ev_main) { cudaEventDestroy(h->ev_main); h->ev_main = nullptr; }
     if (h->ev_comm) { cudaEventDestroy(h->ev_comm); h->ev_comm = nullptr; }

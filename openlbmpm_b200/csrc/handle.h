@@ -56,6 +56,8 @@ struct lbm_handle {
     // slab decomposition: ghost-plane exchanges run on their own stream, overlapped with the interior planes
     cudaStream_t comm_stream = nullptr, xstream = nullptr;   // xstream: where exchange_* currently enqueues (null = stream)
     cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+    double *stage_send = nullptr, *stage_recv = nullptr;     // packed boundary planes (comm.cu)
+    size_t stage_bytes = 0;
 #endif
 
     lbm::CGFields fields() const;
