@@ -250,14 +250,16 @@ def main():
     alg_bytes = B_ALG[Q] * nodes_total / world           # per rank and step
     achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
                 "scope": "all kernels of one time step (%d launches/step), %d B per lattice update x %d nodes per GPU" % (
                     round(sum(c for c, _ in prof.values()) / args.steps), B_ALG[Q], int(nodes_total / world)),
                 "kernels": kernels[:6]}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
-        try:
-            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_step")
+    if os.path.exists(tr) and Q == 19 and not args.general:
+        try:       # dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels (ncu --set full at 512^3), scaled to this slab
+            t = json.load(open(tr))
+            roofline["traffic"] = t["dram_bytes_per_step"] * (nodes_total / world) / t["nodes"]
+            roofline["traffic_source"] = "profiles/traffic.json (ncu --set full, 512^3)"
         except Exception:
             pass
 

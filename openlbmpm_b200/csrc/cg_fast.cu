@@ -137,6 +137,9 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     __syncthreads();
     normal_plane(z_begin - 1);
     normal_plane(z_begin);
+    // the first asynchronous copy of the loop lands in the slot of plane z_begin - 2, which normal_plane(z_begin - 1)
+    // has just read: every thread must be done with it first (found as a run-to-run difference at 256^3)
+    __syncthreads();
 
     const double sgn = c.p.wetting_type == 1 ? 1.0 : -1.0;
     for (int z = z_begin; z < z_end; ++z) {

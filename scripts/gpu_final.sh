@@ -7,7 +7,7 @@ grep -E "passed|failed|FAILED|rc=" gpurun_out/pytest_gpu.log | tail -8
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench_512.json 2> gpurun_out/bench_512.err; tail -2 gpurun_out/bench_512.err; python scripts/bench_brief.py gpurun_out/bench_512.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-300 gpurun_out/bench_ref.json
-for fl in 0 8; do
+for fl in 0; do
   timeout 300 python bench.py --lattice 9 --size 512 --steps 2000 --warmup 20 --no-cpu --no-e2e --flags $fl > gpurun_out/bench_2d512_f$fl.json 2>> gpurun_out/bench_2d.err; python scripts/bench_brief.py gpurun_out/bench_2d512_f$fl.json
 done
 timeout 300 python bench.py --lattice 9 --size 1024 --steps 2000 --warmup 20 --no-cpu --no-e2e > gpurun_out/bench_2d1024.json 2>> gpurun_out/bench_2d.err; python scripts/bench_brief.py gpurun_out/bench_2d1024.json
