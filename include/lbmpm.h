@@ -82,7 +82,8 @@ typedef struct lbm_config {
     int32_t device;            /* CUDA device ordinal                                       */
     uint32_t flags;
     int32_t n_components;      /* SC/EFS: number of fluids (1..4); CG: ignored (2 colours)  */
-    int32_t reserved_i[3];
+    int32_t sc_isotropy;       /* EFS: [ForceScheme] ExplicitScheme 4 | 8 | 10 (0 = 4)      */
+    int32_t reserved_i[2];
     /* colour gradient */
     double sigma;              /* [SurfaceTension] SurfaceTension(Value)                    */
     double contact_angle_deg;  /* [SurfaceTension] ContactAngle                             */

@@ -67,8 +67,8 @@ class ShanChenD2Q9:
         if self.interactionSolid.size != nf:
             raise IniError("The number of fluids does not match the number of interaction coeff with solid.")
         self.explicitScheme = ini.integer("ForceScheme", "ExplicitScheme", default=4)
-        if self.interactionType == "'EFS'" and self.explicitScheme != 4:
-            raise IniError("ExplicitScheme 8 / 10 (higher isotropy) is not built yet (SURVEY.md 8 f-1); use 4")
+        if self.interactionType == "'EFS'" and self.explicitScheme not in (4, 8, 10):
+            raise IniError("ExplicitScheme must be 4, 8 or 10")
         self.boundaryTypeInlet = ini.quoted("BoundaryDefinition", "BoundaryTypeInlet", default="Periodic")
         self.boundaryMethod = ini.quoted("BoundaryDefinition", "BoundaryMethod", default="ZouHe")
         self.boundaryTypeOutlet = ini.quoted("BoundaryDefinition", "BoundaryTypeOutlet", default="Periodic")
@@ -81,6 +81,10 @@ class ShanChenD2Q9:
         elif self.boundaryTypeInlet == "'Dirichlet'":
             raise IniError("The reference's pressure inlet reads self.specificRho1Upper, which is never set "
                            "(ShanChenD2Q9.py:1498): that path cannot run upstream either")
+        if (self.interactionType == "'EFS'" and self.explicitScheme == 10 and
+                (self.boundaryTypeInlet != "'Periodic'" or self.boundaryTypeOutlet != "'Periodic'")):
+            raise IniError("the reference's explicit-forcing loop has open boundaries for ExplicitScheme 4 and 8 only "
+                           "(ShanChenD2Q9.py:1933-2014)")
         self.numTimeStep = ini.integer("Time", "numberTimeStep")
 
     # -- geometry / initial condition --------------------------------------------------------------
@@ -123,7 +127,8 @@ class ShanChenD2Q9:
                                   relax=_lib.RELAX_MRT if self.relaxationType == "'MRT'" else _lib.RELAX_SRT,
                                   n_components=self.typesFluids, inlet=inlet, outlet=outlet, sc_tau=self.tau,
                                   sc_G=G.ravel(), sc_Gsolid=self.interactionSolid, sc_inlet_velocity=self.velocityYInlet,
-                                  sc_rho_out=[1.0, 0.02])      # hard-coded upstream: OptimizedD2Q9GPU.py:560-561
+                                  sc_rho_out=[1.0, 0.02],      # hard-coded upstream: OptimizedD2Q9GPU.py:560-561
+                                  sc_isotropy=self.explicitScheme if model == _lib.MODEL_EFS else 4)
         self.engine.set_geometry(self.isDomain)
 
     def optimizeFluidArray(self):

@@ -26,7 +26,8 @@ class LbmConfig(ctypes.Structure):
         ("nx", ctypes.c_int32), ("ny", ctypes.c_int32), ("nz", ctypes.c_int32),
         ("relax", ctypes.c_int32), ("tau_type", ctypes.c_int32), ("wetting_type", ctypes.c_int32),
         ("inlet", ctypes.c_int32), ("outlet", ctypes.c_int32), ("device", ctypes.c_int32),
-        ("flags", ctypes.c_uint32), ("n_components", ctypes.c_int32), ("reserved_i", ctypes.c_int32 * 3),
+        ("flags", ctypes.c_uint32), ("n_components", ctypes.c_int32), ("sc_isotropy", ctypes.c_int32),
+        ("reserved_i", ctypes.c_int32 * 2),
         ("sigma", ctypes.c_double), ("contact_angle_deg", ctypes.c_double), ("beta", ctypes.c_double),
         ("delta", ctypes.c_double), ("tauR", ctypes.c_double), ("tauB", ctypes.c_double),
         ("inlet_velocity", ctypes.c_double),

@@ -55,7 +55,7 @@ static void fast_alloc(lbm_handle* h) {
 // synchronises, so the HBM latency overlaps the shared-memory phase.
 // ------------------------------------------------------------------------------------------------
 template <bool SOLIDS, int TX, int TY>
-__global__ void __launch_bounds__(TX* TY, 2)
+__global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
 cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi) {
     using L = D3Q19;
     constexpr int NT = TX * TY;
@@ -241,7 +241,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 // plane of HBM requests per thread is always in flight.
 // ------------------------------------------------------------------------------------------------
 template <bool SOLIDS, int TX, int TY>
-__global__ void __launch_bounds__(TX* TY, 2)
+__global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
 cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, const int z_lo, const int z_hi) {
     using L = D3Q19;
     constexpr int NT = TX * TY;
@@ -334,14 +334,25 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
     }
 }
 
-constexpr int TILE_X = 32, TILE_Y = 8;
-
-static bool tiled_ok(const lbm_handle* h) {
-    return h->Q == 19 && h->g.n0 % TILE_X == 0 && h->g.n1 % TILE_Y == 0 && !(h->cfg.flags & 2u);
+constexpr int TILE_X = 32;
+// rows of a tile: 8 by default (2 CTAs of 256 threads per SM); LBM_TILE_Y = 4 | 8 | 16 selects the other instantiations
+// (tuning knob, read once)
+static int tile_y() {
+    static int ty = 0;
+    if (!ty) {
+        const char* e = getenv("LBM_TILE_Y");
+        ty = e ? atoi(e) : 8;
+        if (ty != 4 && ty != 8 && ty != 16) ty = 8;
+    }
+    return ty;
 }
 
-template <bool SOLIDS>
-static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo = 0, int z_hi = -1) {
+static bool tiled_ok(const lbm_handle* h) {
+    return h->Q == 19 && h->g.n0 % TILE_X == 0 && h->g.n1 % tile_y() == 0 && !(h->cfg.flags & 2u);
+}
+
+template <bool SOLIDS, int TILE_Y>
+static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi) {
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
@@ -362,7 +373,16 @@ static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, 
 }
 
 template <bool SOLIDS>
-static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo = 0, int z_hi = -1) {
+static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo = 0, int z_hi = -1) {
+    switch (tile_y()) {
+        case 4: launch_tiled_t<SOLIDS, 4>(h, c, s, o, z_lo, z_hi); break;
+        case 16: launch_tiled_t<SOLIDS, 16>(h, c, s, o, z_lo, z_hi); break;
+        default: launch_tiled_t<SOLIDS, 8>(h, c, s, o, z_lo, z_hi);
+    }
+}
+
+template <bool SOLIDS, int TILE_Y>
+static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo, int z_hi) {
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
@@ -380,6 +400,14 @@ static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFie
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
     ++g_launch_counter;
+}
+template <bool SOLIDS>
+static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo = 0, int z_hi = -1) {
+    switch (tile_y()) {
+        case 4: launch_density_tiled_t<SOLIDS, 4>(h, c, s, z_lo, z_hi); break;
+        case 16: launch_density_tiled_t<SOLIDS, 16>(h, c, s, z_lo, z_hi); break;
+        default: launch_density_tiled_t<SOLIDS, 8>(h, c, s, z_lo, z_hi);
+    }
 }
 #endif
 

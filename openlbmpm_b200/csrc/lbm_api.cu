@@ -91,6 +91,9 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     if (cfg->model != LBM_MODEL_CG && (cfg->n_components < 1 || cfg->n_components > 4)) {
         g_create_error = "n_components must be 1..4"; return LBM_EINVAL;
     }
+    if (cfg->sc_isotropy != 0 && cfg->sc_isotropy != 4 && cfg->sc_isotropy != 8 && cfg->sc_isotropy != 10) {
+        g_create_error = "sc_isotropy must be 4, 8 or 10"; return LBM_EINVAL;
+    }
     if (cfg->relax != LBM_RELAX_SRT && cfg->relax != LBM_RELAX_MRT) { g_create_error = "relax must be SRT or MRT"; return LBM_EINVAL; }
     if (cfg->model == LBM_MODEL_CG) {
         if (cfg->tau_type != 1 && cfg->tau_type != 2) { g_create_error = "tau_type must be 1 or 2"; return LBM_EINVAL; }

@@ -25,7 +25,11 @@ static SCFields sc_fields(const lbm_handle* h) {
     }
     c.fS = s->fS; c.fC = s->fC; c.rho = s->rho; c.F = s->F; c.ueq = s->ueq; c.uph = s->uph; c.fold = s->fold;
     c.cls = h->cls;
-    c.z_in = h->g.n2 - 2; c.z_in_ghost = h->g.n2 - 1;
+    c.p.scheme = cfg.sc_isotropy == 8 || cfg.sc_isotropy == 10 ? cfg.sc_isotropy : 4;
+    // isotropy 8 moves the treated rows one node inwards and keeps two ghost rows
+    // (constantVelocityZouHeBoundaryHigher8, constantPressureZouHeBoundaryLower8: OptimizedD2Q9GPU.py:590-620, 868-890)
+    const int deep = c.p.scheme == 8 && cfg.model == LBM_MODEL_EFS ? 1 : 0;
+    c.z_in = h->g.n2 - 2 - deep; c.z_in_ghost = h->g.n2 - 1; c.z_out = 1 + deep;
     return c;
 }
 
@@ -97,12 +101,14 @@ int sc_upload_state(lbm_handle* h, const double* const* pdf, const double* const
 static void sc_inlet(lbm_handle* h, const SCFields& c) {
     if (c.p.inlet == LBM_INLET_VELOCITY) {
         launch(ScInletVelocityOp{c}, h->g.n0, h->stream);
-        launch(ScRowCopyOp{c, c.z_in_ghost, c.z_in}, h->g.plane, h->stream);
+        for (int zr = c.z_in; zr < c.z_in_ghost; ++zr)         // ghost rows, one after the other (ghostPointsConstantVelocity8/82)
+            launch(ScRowCopyOp{c, zr + 1, zr}, h->g.plane, h->stream);
     }
 }
 static void sc_outlet_pressure(lbm_handle* h, const SCFields& c) {
     launch(ScOutletPressureOp{c}, h->g.n0, h->stream);
-    launch(ScRowCopyOp{c, 0, 1}, h->g.plane, h->stream);
+    for (int zr = c.z_out; zr > 0; --zr)                        // ghostPointsConstantPressureOutlet8/82
+        launch(ScRowCopyOp{c, zr - 1, zr}, h->g.plane, h->stream);
 }
 
 static void sc_ensure_head(lbm_handle* h) {
@@ -138,7 +144,7 @@ static void efs_prepare(lbm_handle* h) {
     if (s->efs_prepared) return;
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
-    exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
+    exchange_f64(h, c.rho, g.vol, c.p.nc, c.p.scheme == 4 ? 1 : NG);
     launch(EfsForceOp{c}, g.count(0), h->stream);
     launch(EfsTransformOp{c}, g.count(0), h->stream);
     // boundary rows: the populations are treated, the densities the reference sets here are never read
@@ -174,7 +180,7 @@ static void efs_iteration(lbm_handle* h) {
     sc_inlet(h, c);
     if (c.p.inlet != LBM_BC_PERIODIC || c.p.outlet != LBM_BC_PERIODIC) launch(ScRhoOp{c}, g.count(0), h->stream);
     launch(ScPhysicalVelocityOp{c}, g.count(0), h->stream);     // output point (:2016-2027)
-    exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
+    exchange_f64(h, c.rho, g.vol, c.p.nc, c.p.scheme == 4 ? 1 : NG);
     launch(EfsForceOp{c}, g.count(0), h->stream);
 }
 

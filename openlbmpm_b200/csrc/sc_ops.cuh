@@ -2,7 +2,7 @@
 //   * original Shan-Chen      (ShanChenD2Q9.runOptimizedLBM,   ShanChenD2Q9.py:1433-1629; kernels in
 //                              ShanChen2D/OptimizedD2Q9GPU.py)
 //   * explicit forcing SRT/MRT (ShanChenD2Q9.runOptimizedEFLBM, ShanChenD2Q9.py:1631-2087; kernels in
-//                              ShanChen2D/ExplicitD2Q9GPU.py), isotropy 4.
+//                              ShanChen2D/ExplicitD2Q9GPU.py), isotropy 4, 8 and 10.
 // The reference materialises f_eq, the force distribution and (MRT) their images under C = M^-1 S M as
 // five extra [nf, N, 9] arrays and runs 7-9 kernels over them; here the state is (f, rho, F, u_eq) and
 // the equilibrium / force distributions live in registers inside the collision operator.  The MRT
@@ -16,6 +16,7 @@ constexpr int SC_MAXC = 4;
 
 struct SCParams {
     int nc, relax, inlet, outlet;
+    int scheme;      // isotropy of the explicit force: 4 (8 neighbours), 8 (24) or 10 (36)
     double tau[SC_MAXC], G[SC_MAXC * SC_MAXC], Gs[SC_MAXC], vin[SC_MAXC], rho_out[SC_MAXC];
 };
 
@@ -30,7 +31,7 @@ struct SCFields {
     double* uph;     // [2][vol]   physical velocity
     double* fold;    // [nc][9][3 planes] populations of rows 0..2 before the collision (convective outlet)
     const uint8_t* cls;
-    int z_in, z_in_ghost;
+    int z_in, z_in_ghost, z_out;
     LBM_HD double* f(double* base, int c, int q) const { return base + ((int64_t)c * 9 + q) * g.vol; }
 };
 
@@ -131,7 +132,7 @@ struct ScInletVelocityOp {
 struct ScOutletPressureOp {
     SCFields c;
     LBM_HD void operator()(int64_t x) const {
-        const Grid& g = c.g; const int64_t id = g.at((int)x, 0, 1);
+        const Grid& g = c.g; const int64_t id = g.at((int)x, 0, c.z_out);
         if (!(c.cls[id] & CLS_FLUID)) return;
         for (int k = 0; k < c.p.nc; ++k) {
             const double d = c.p.rho_out[k];
@@ -276,6 +277,57 @@ struct ScCollideOp {
     }
 };
 
+// Higher-isotropy explicit force: calExplicit8thOrderScheme (ExplicitD2Q9GPU.py:627-953, 24 neighbours) and
+// calExplicit10thOrderScheme (957-1372, 36 neighbours).  Neighbour slots in the order of fillNeighboringNodesISO8/10
+// (392-592).  A far neighbour only contributes when it is fluid AND "visible": the nearer node(s) on the way are
+// fluid (the gates below, read off the kernels' if-conditions).  Solid neighbours act through the first 8 slots
+// only, with the hard-coded weights 1/9 and 1/36.  The 8th-order kernel uses psi_j(x+e) - psi_j(x), the
+// 10th-order kernel plain psi_j(x+e).
+LBM_HD void efs_force_iso(const SCFields& c, int x, int y, int z, int64_t id, int k, double* fx_out, double* fy_out) {
+    constexpr int OX[36] = {1, 0, -1, 0, 1, -1, -1, 1, 2, 0, -2, 0, 2, -2, -2, 2, 2, 1, -1, -2, -2, -1, 1, 2,
+                            3, 0, -3, 0, 3, 1, -1, -3, -3, -1, 1, 3};
+    constexpr int OY[36] = {0, 1, 0, -1, 1, 1, -1, -1, 0, 2, 0, -2, 2, 2, -2, -2, 1, 2, 2, 1, -1, -2, -2, -1,
+                            0, 3, 0, -3, 1, 3, 3, 1, -1, -3, -3, -1};
+    constexpr int KA[8] = {0, 1, 1, 2, 2, 3, 3, 0}, KB[8] = {4, 4, 5, 5, 6, 6, 7, 7};    // knight moves: axis / diagonal gate
+    const Grid& g = c.g; const int64_t V = g.vol;
+    const int ns = c.p.scheme == 8 ? 24 : 36;
+    int64_t nb[36]; bool fl[36];
+    for (int s = 0; s < ns; ++s) {
+        nb[s] = g.nb(x, y, z, OX[s], 0, OY[s]);
+        fl[s] = c.cls[nb[s]] & CLS_FLUID;
+    }
+    const double psi = c.rho[k * V + id];
+    double fx = 0.0, fy = 0.0;
+    for (int s = 0; s < ns; ++s) {
+        bool gate = true;
+        double w;
+        if (c.p.scheme == 8) w = s < 4 ? 4.0 / 21.0 : s < 8 ? 4.0 / 45.0 : s < 12 ? 1.0 / 60.0 : s < 16 ? 1.0 / 5040.0 : 2.0 / 315.0;
+        else w = s < 4 ? 262.0 / 1785.0 : s < 8 ? 93.0 / 1190.0 : s < 12 ? 7.0 / 340.0 : s < 16 ? 9.0 / 9520.0 :
+                 s < 24 ? 6.0 / 595.0 : s < 28 ? 2.0 / 5355.0 : 1.0 / 7140.0;
+        if (s >= 8 && s < 16) gate = fl[s - 8];
+        else if (s >= 16 && s < 24) gate = fl[KA[s - 16]] || fl[KB[s - 16]];
+        else if (s >= 24 && s < 28) gate = fl[s - 24] && fl[s - 16];
+        else if (s >= 28) {
+            const int t = s - 28;                       // same quadrant pairing as the knight moves
+            const int axis = KA[t], diag = KB[t];
+            gate = (fl[axis] && fl[axis + 8]) || (fl[diag] && fl[16 + t]);
+        }
+        if (fl[s] && gate) {
+            for (int j = 0; j < c.p.nc; ++j) {
+                const double d = c.p.scheme == 8 ? c.rho[j * V + nb[s]] - c.rho[j * V + id] : c.rho[j * V + nb[s]];
+                const double t = -6.0 * w * c.p.G[k * SC_MAXC + j] * psi * d;
+                if (OX[s] != 0) fx += OX[s] * t;
+                if (OY[s] != 0) fy += OY[s] * t;
+            }
+        } else if (s < 8 && !fl[s]) {
+            const double t = -(s < 4 ? 1.0 / 9.0 : 1.0 / 36.0) * c.p.Gs[k] * psi;
+            if (OX[s] != 0) fx += t * OX[s];
+            if (OY[s] != 0) fy += t * OY[s];
+        }
+    }
+    *fx_out = fx; *fy_out = fy;
+}
+
 // calExplicit4thOrderScheme (ExplicitD2Q9GPU.py:51-217) + calEquilibriumVEFGPU (340-363, SRT) /
 // transformEquilibriumVelocity (1426-1449, MRT: weights s_0 = 1 instead of 1/tau).  Writes F and u_eq.
 struct EfsForceOp {
@@ -309,7 +361,8 @@ struct EfsForceOp {
                     if (D2Q9::cy(q) != 0) sy += t * D2Q9::cy(q);
                 }
             }
-            const double fx = -6.0 * psi * gx + sx, fy = -6.0 * psi * gy + sy;
+            double fx = -6.0 * psi * gx + sx, fy = -6.0 * psi * gy + sy;
+            if (c.p.scheme != 4) efs_force_iso(c, x, y, z, id, k, &fx, &fy);
             c.F[(k * 2) * V + id] = fx; c.F[(k * 2 + 1) * V + id] = fy;
             double ex = 0.0, ey = 0.0;
             for (int q = 0; q < 9; ++q) {

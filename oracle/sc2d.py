@@ -4,7 +4,7 @@ NumPy restatement of the two live Shan-Chen drivers of openLBMPM (reference comm
   * original Shan-Chen:        ShanChenD2Q9.runOptimizedLBM   (ShanChen2D/ShanChenD2Q9.py:1433-1629)
     kernels in ShanChen2D/OptimizedD2Q9GPU.py
   * explicit forcing SRT/MRT:  ShanChenD2Q9.runOptimizedEFLBM (ShanChen2D/ShanChenD2Q9.py:1631-2087)
-    kernels in ShanChen2D/ExplicitD2Q9GPU.py, isotropy 4
+    kernels in ShanChen2D/ExplicitD2Q9GPU.py, isotropy 4, 8 and 10
 in the reference's kernel order, keeping its materialised f_eq / force-distribution arrays and its dense
 C = M^-1 S M product for MRT.
 
@@ -34,7 +34,7 @@ def shift(a, k):
 
 class SC2D:
     def __init__(self, is_domain, model="ShanChen", relax="SRT", tau=(1., 1.), G=3.8, Gs=(-0.4, 0.4),
-                 inlet="Periodic", outlet="Periodic", vy=(0., 0.), rho_out=(1.0, 0.02)):
+                 inlet="Periodic", outlet="Periodic", vy=(0., 0.), rho_out=(1.0, 0.02), scheme=4):
         self.dom = np.asarray(is_domain, bool)
         self.ny, self.nx = self.dom.shape
         self.model, self.relax, self.inlet, self.outlet = model, relax, inlet, outlet
@@ -51,6 +51,9 @@ class SC2D:
                     s[1], s[2], s[4], s[6] = 0.6, 1.5, 1.2, 1.2
                 s[7] = s[8] = 1. / self.tau[k]
                 self.C.append(Mi @ np.diag(s) @ M)
+        self.scheme = int(scheme)         # [ForceScheme] ExplicitScheme: 4, 8 or 10
+        deep = 1 if (self.scheme == 8 and model == "EFS") else 0      # ...Higher8 / ...Lower8 act one row further in
+        self.z_in, self.z_out = self.ny - 2 - deep, 1 + deep
         self.prepared = False
 
     def set_densities(self, rho):
@@ -93,7 +96,7 @@ class SC2D:
         """constantVelocityZouHeBoundaryHigher (839-861) + ghostPointsConstantVelocityInlet (710-736)"""
         if self.inlet != "Neumann":
             return
-        r, g = self.ny - 2, self.ny - 1
+        r = self.z_in
         m = self.dom[r]
         for k in range(self.nc):
             f = self.f[k, r]; v = self.vy[k]
@@ -104,7 +107,8 @@ class SC2D:
             f8 = f[:, 6] - (f[:, 1] - f[:, 3]) / 2. - 1. / 6. * rho * v
             for q, val in ((4, f4), (7, f7), (8, f8)):
                 f[:, q] = np.where(m, val, f[:, q])
-        self._row_copy(g, r)
+        for row in range(r, self.ny - 1):          # ghost rows, one after the other (ghostPointsConstantVelocity8 / 82)
+            self._row_copy(row + 1, row)
 
     def _row_copy(self, dst, src):
         m = self.dom[dst] & self.dom[src]
@@ -116,17 +120,19 @@ class SC2D:
 
     def _outlet_pressure(self):
         """constantPressureZouHeBoundaryLower (555-584, densities hard-coded) + ghostPointsConstantPressureOutlet (743-768)"""
-        m = self.dom[1]
+        zo = self.z_out
+        m = self.dom[zo]
         for k in range(self.nc):
-            f = self.f[k, 1]; d = self.rho_out[k]
+            f = self.f[k, zo]; d = self.rho_out[k]
             vy = 1. - (f[:, 0] + f[:, 1] + f[:, 3] + 2. * (f[:, 4] + f[:, 7] + f[:, 8])) / d
             f2 = f[:, 4] + 2. / 3. * vy * d
             f5 = f[:, 7] + 1. / 2. * (f[:, 3] - f[:, 1]) + 1. / 6. * d * vy
             f6 = f[:, 8] - 1. / 2. * (f[:, 3] - f[:, 1]) + 1. / 6. * d * vy
             for q, val in ((2, f2), (5, f5), (6, f6)):
                 f[:, q] = np.where(m, val, f[:, q])
-            self.rho[k, 1] = np.where(m, d, 0.)
-        self._row_copy(0, 1)
+            self.rho[k, zo] = np.where(m, d, 0.)
+        for row in range(zo, 0, -1):               # ghostPointsConstantPressureOutlet8 / 82
+            self._row_copy(row - 1, row)
 
     # -- original Shan-Chen ---------------------------------------------------------------------
     def _sc_iteration(self):
@@ -179,6 +185,8 @@ class SC2D:
                 s = -wI * self.Gs[k] * psi[k]
                 sx = sx + np.where(fl, 0., s * EX[q]); sy = sy + np.where(fl, 0., s * EY[q])
             fx = -6.0 * psi[k] * gx + sx; fy = -6.0 * psi[k] * gy + sy
+            if self.scheme != 4:
+                fx, fy = self._force_iso(k)
             self.F[k, 0] = np.where(self.dom, fx, 0.); self.F[k, 1] = np.where(self.dom, fy, 0.)
             ex = (self.f[k] * EX).sum(-1) + 0.5 * self.F[k, 0]; ey = (self.f[k] * EY).sum(-1) + 0.5 * self.F[k, 1]
             wgt = 1. / self.tau[k] if self.relax == "SRT" else 1.0
@@ -193,6 +201,52 @@ class SC2D:
             self.fF = (self.F[:, 0, ..., None] * (EX - ux[..., None]) + self.F[:, 1, ..., None] * (EY - uy[..., None])) * \
                 self.feq / (1. / 3. * self.rho[..., None])
         self.fF = np.where(self.dom[None, :, :, None], self.fF, 0.)
+
+    # neighbour slots of fillNeighboringNodesISO8 / ISO10 (ExplicitD2Q9GPU.py:392-592), (dx, dy)
+    ISO_OFF = [(1, 0), (0, 1), (-1, 0), (0, -1), (1, 1), (-1, 1), (-1, -1), (1, -1),
+               (2, 0), (0, 2), (-2, 0), (0, -2), (2, 2), (-2, 2), (-2, -2), (2, -2),
+               (2, 1), (1, 2), (-1, 2), (-2, 1), (-2, -1), (-1, -2), (1, -2), (2, -1),
+               (3, 0), (0, 3), (-3, 0), (0, -3), (3, 1), (1, 3), (-1, 3), (-3, 1), (-3, -1), (-1, -3), (1, -3), (3, -1)]
+    ISO_W = {8: [4. / 21.] * 4 + [4. / 45.] * 4 + [1. / 60.] * 4 + [1. / 5040.] * 4 + [2. / 315.] * 8,
+             10: [262. / 1785.] * 4 + [93. / 1190.] * 4 + [7. / 340.] * 4 + [9. / 9520.] * 4 + [6. / 595.] * 8 +
+                 [2. / 5355.] * 4 + [1. / 7140.] * 8}        # ShanChenD2Q9.py:1677-1689
+    KA = [0, 1, 1, 2, 2, 3, 3, 0]
+    KB = [4, 4, 5, 5, 6, 6, 7, 7]
+
+    def _force_iso(self, k):
+        """calExplicit8thOrderScheme (ExplicitD2Q9GPU.py:627-953) / calExplicit10thOrderScheme (957-1372): a far
+        neighbour contributes only if it is fluid and the nearer node(s) towards it are fluid; solids act through
+        the first 8 slots with weights 1/9, 1/36; order 8 uses psi(x+e) - psi(x), order 10 plain psi(x+e)."""
+        ns = 24 if self.scheme == 8 else 36
+        w = self.ISO_W[self.scheme]
+        sh = lambda a, d: np.roll(a, (-d[1], -d[0]), axis=(-2, -1))
+        fl = [sh(self.dom, self.ISO_OFF[s]) for s in range(ns)]
+        psi = self.rho
+        fx = np.zeros((self.ny, self.nx)); fy = np.zeros((self.ny, self.nx))
+        for s in range(ns):
+            dx, dy = self.ISO_OFF[s]
+            if s < 8:
+                gate = np.ones_like(self.dom)
+            elif s < 16:
+                gate = fl[s - 8]
+            elif s < 24:
+                gate = fl[self.KA[s - 16]] | fl[self.KB[s - 16]]
+            elif s < 28:
+                gate = fl[s - 24] & fl[s - 16]
+            else:
+                t = s - 28
+                gate = (fl[self.KA[t]] & fl[self.KA[t] + 8]) | (fl[self.KB[t]] & fl[16 + t])
+            term = np.zeros((self.ny, self.nx))
+            for j in range(self.nc):
+                d = sh(psi[j], (dx, dy)) - psi[j] if self.scheme == 8 else sh(psi[j], (dx, dy))
+                term = term + (-6.0 * w[s] * self.G[k, j]) * psi[k] * d
+            on = fl[s] & gate
+            fx = fx + np.where(on, term * dx, 0.); fy = fy + np.where(on, term * dy, 0.)
+            if s < 8:
+                ws = 1. / 9. if s < 4 else 1. / 36.
+                sol = -ws * self.Gs[k] * psi[k]
+                fx = fx + np.where(fl[s], 0., sol * dx); fy = fy + np.where(fl[s], 0., sol * dy)
+        return fx, fy
 
     def _efs_prepare(self):
         """pre-loop, ShanChenD2Q9.py:1714-1849"""

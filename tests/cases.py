@@ -213,7 +213,7 @@ def sc_engine_for_gold(g, p, lib_path, **extra):
                       sc_Gsolid=[float(p["Gs0"]), float(p["Gs1"])],
                       sc_inlet_velocity=[float(p["vy0"]), float(p["vy1"])],
                       sc_rho_out=[1.0, 0.02],       # hard-coded in OptimizedD2Q9GPU.py:560-561
-                      **extra)
+                      sc_isotropy=int(p.get("scheme", 4)), **extra)
     eng.set_geometry(dom)
     reg = g["region0"]
     rho0 = np.where(dom, np.where(reg, float(p["rho0"]), float(p["bg0"])), 0.0)

@@ -92,7 +92,7 @@ FluidsTau = {tau0},{tau1}
 InteractionFluid = {G}
 InteractionSolid = {Gs0},{Gs1}
 [ForceScheme]
-ExplicitScheme = 4
+ExplicitScheme = {scheme}
 [BoundaryDefinition]
 BoundaryTypeInlet = '{inlet}'
 BoundaryMethod = 'ZouHe'
@@ -110,7 +110,7 @@ numberTimeStep = {steps}
 """
 
 DEFAULTS = dict(relax="SRT", rho0=1.0, rho1=1.0, bg0=0.06, bg1=0.06, tau0=1.0, tau1=1.0, G=3.8, Gs0=-0.4, Gs1=0.4,
-                inlet="Periodic", outlet="Periodic", vy0=0.0, vy1=-1.0e-3, steps=39)
+                inlet="Periodic", outlet="Periodic", vy0=0.0, vy1=-1.0e-3, steps=39, scheme=4)
 
 
 def geom_open(nx, ny):
@@ -160,6 +160,17 @@ CASES = {
     "efs_channel_neumann_convective_srt": ("EFS", 12, 26, geom_walls, init_bottom,
                                            dict(relax="SRT", G=0.2, Gs0=-0.14, Gs1=0.14, inlet="Neumann",
                                                 outlet="Convective", vy1=-5.03e-4, steps=39)),
+    # higher-isotropy explicit forcing (24 / 36 neighbours): ExplicitD2Q9GPU.py:392-1372
+    "efs_iso8_block_srt": ("EFS", 16, 16, geom_block,
+                           lambda nx, ny: init_droplet(nx, ny, cx=nx / 2 + 1, cy=ny / 2 + 4, r=3.6),
+                           dict(relax="SRT", G=0.2, Gs0=-0.14, Gs1=0.14, tau1=0.9, scheme=8)),
+    "efs_iso8_droplet_mrt": ("EFS", 16, 16, geom_open, init_droplet, dict(relax="MRT", G=0.2, Gs0=-0.14, Gs1=0.14, scheme=8)),
+    "efs_iso10_block_mrt": ("EFS", 16, 16, geom_block,
+                            lambda nx, ny: init_droplet(nx, ny, cx=nx / 2 + 1, cy=ny / 2 + 4, r=3.6),
+                            dict(relax="MRT", G=0.2, Gs0=-0.14, Gs1=0.14, tau1=0.8, scheme=10)),
+    "efs_iso8_channel_neumann_dirichlet_srt": ("EFS", 12, 26, geom_walls, init_bottom,
+                                               dict(relax="SRT", G=0.2, Gs0=-0.14, Gs1=0.14, inlet="Neumann",
+                                                    outlet="Dirichlet", vy1=-5.03e-4, scheme=8)),
 }
 
 

@@ -13,7 +13,7 @@ def test_trajectory_matches_reference(path):
     dom = g["is_domain"]
     sim = sc2d.SC2D(dom, model=str(g["model"]), relax=p["relax"], tau=(float(p["tau0"]), float(p["tau1"])),
                     G=float(p["G"]), Gs=(float(p["Gs0"]), float(p["Gs1"])), inlet=p["inlet"], outlet=p["outlet"],
-                    vy=(float(p["vy0"]), float(p["vy1"])))
+                    vy=(float(p["vy0"]), float(p["vy1"])), scheme=int(p.get("scheme", 4)))
     reg = g["region0"]
     sim.set_densities(np.stack([np.where(reg, float(p["rho0"]), float(p["bg0"])),
                                 np.where(reg, float(p["bg1"]), float(p["rho1"]))]))
