@@ -65,6 +65,8 @@ class RKColorGradientLBM:
         self.isCycles = ini.quoted("CyclesSetup", "IsCycle", default="no")
         if self.isCycles == "'yes'":
             self.lastStep = ini.integer("CyclesSetup", "LastStep")
+            raise IniError("[CyclesSetup] IsCycle = 'yes' (restart from ~/LBMInitial/*.h5, RKD2Q9.py:491-559) is not built: "
+                           "assign fluidsRhoR/B and call engine.upload_state instead (SURVEY.md section 8, f-4)")
         # lattice constants (RKD2Q9.py:299-303)
         self.weightsCoeff = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
         self.unitEX = np.array([0., 1., 0., -1., 0., 1., -1., -1., 1.])

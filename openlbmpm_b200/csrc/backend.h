@@ -26,6 +26,7 @@ typedef cudaStream_t stream_t;
 
 struct BackendError {
     std::string msg;
+    bool oom = false;
 };
 
 #define LBM_CUDA_CHECK(expr)                                                                  \
@@ -37,7 +38,11 @@ struct BackendError {
 
 inline void* dev_alloc(size_t bytes) {
     void* p = nullptr;
-    LBM_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
+    const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw BackendError{"cudaMalloc of " + std::to_string(bytes) + " bytes: " + cudaGetErrorString(e), e == cudaErrorMemoryAllocation};
+    }
     return p;
 }
 inline void dev_free(void* p) {
@@ -148,6 +153,7 @@ inline void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, strea
 typedef int stream_t;
 struct BackendError {
     std::string msg;
+    bool oom = false;
 };
 inline void* dev_alloc(size_t bytes) {
     void* p = malloc(bytes ? bytes : 8);

@@ -335,20 +335,30 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
 }
 
 constexpr int TILE_X = 32;
-// rows of a tile: 8 by default (2 CTAs of 256 threads per SM); LBM_TILE_Y = 4 | 8 | 16 selects the other instantiations
-// (tuning knob, read once)
-static int tile_y() {
+// rows of a tile (tuning knobs, read once): the collision pass runs best with 32 x 4 tiles (4 CTAs of 128 threads
+// per SM: their barriers interleave; 512^3: 10.1 ms vs 10.7 ms with 32 x 8 and 12.4 ms with 32 x 16), the density
+// pass with 32 x 8 (4.8 vs 5.0 ms).  LBM_TILE_Y_COLLIDE / LBM_TILE_Y_DENSITY = 4 | 8 | 16, LBM_ZCHUNK = planes per CTA.
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static int tile_y_collide() {
     static int ty = 0;
-    if (!ty) {
-        const char* e = getenv("LBM_TILE_Y");
-        ty = e ? atoi(e) : 8;
-        if (ty != 4 && ty != 8 && ty != 16) ty = 8;
-    }
+    if (!ty) { ty = env_int("LBM_TILE_Y_COLLIDE", 4); if (ty != 4 && ty != 8 && ty != 16) ty = 4; }
     return ty;
 }
-
+static int tile_y_density() {
+    static int ty = 0;
+    if (!ty) { ty = env_int("LBM_TILE_Y_DENSITY", 8); if (ty != 4 && ty != 8 && ty != 16) ty = 8; }
+    return ty;
+}
+static int z_chunk(int n2) {
+    static int zc = 0;
+    if (!zc) { zc = env_int("LBM_ZCHUNK", 32); if (zc < 4) zc = 32; }
+    return n2 >= 2 * zc ? zc : n2;
+}
 static bool tiled_ok(const lbm_handle* h) {
-    return h->Q == 19 && h->g.n0 % TILE_X == 0 && h->g.n1 % tile_y() == 0 && !(h->cfg.flags & 2u);
+    return h->Q == 19 && h->g.n0 % TILE_X == 0 && h->g.n1 % tile_y_collide() == 0 && h->g.n1 % tile_y_density() == 0 && !(h->cfg.flags & 2u);
 }
 
 template <bool SOLIDS, int TILE_Y>
@@ -356,7 +366,7 @@ static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
-    int zchunk = g.n2 >= 64 ? 32 : g.n2;
+    const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2));
     static bool configured = false;
@@ -374,7 +384,7 @@ static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s
 
 template <bool SOLIDS>
 static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo = 0, int z_hi = -1) {
-    switch (tile_y()) {
+    switch (tile_y_collide()) {
         case 4: launch_tiled_t<SOLIDS, 4>(h, c, s, o, z_lo, z_hi); break;
         case 16: launch_tiled_t<SOLIDS, 16>(h, c, s, o, z_lo, z_hi); break;
         default: launch_tiled_t<SOLIDS, 8>(h, c, s, o, z_lo, z_hi);
@@ -386,7 +396,7 @@ static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastF
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
-    int zchunk = g.n2 >= 64 ? 32 : g.n2;
+    const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * 5 * 4 * (TILE_Y + 2) * (TILE_X + 2);
     static bool configured = false;
@@ -403,7 +413,7 @@ static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastF
 }
 template <bool SOLIDS>
 static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo = 0, int z_hi = -1) {
-    switch (tile_y()) {
+    switch (tile_y_density()) {
         case 4: launch_density_tiled_t<SOLIDS, 4>(h, c, s, z_lo, z_hi); break;
         case 16: launch_density_tiled_t<SOLIDS, 16>(h, c, s, z_lo, z_hi); break;
         default: launch_density_tiled_t<SOLIDS, 8>(h, c, s, z_lo, z_hi);

@@ -24,7 +24,7 @@ static thread_local std::string g_create_error;
     try {
 #define API_END(h)                                                      \
     }                                                                   \
-    catch (const BackendError& e) { (h)->err = e.msg; return LBM_ECUDA; } \
+    catch (const BackendError& e) { (h)->err = e.msg; return e.oom ? LBM_ENOMEM : LBM_ECUDA; } \
     catch (const std::bad_alloc&) { (h)->err = "out of host memory"; return LBM_ENOMEM; } \
     return LBM_OK;
 
