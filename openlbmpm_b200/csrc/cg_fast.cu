@@ -46,6 +46,28 @@ static void fast_alloc(lbm_handle* h) {
 }
 
 #ifndef LBM_HOSTCHECK
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
 // ------------------------------------------------------------------------------------------------
 // Tiled collision pass for D3Q19.  One CTA owns a TX x TY column of the lattice and marches along z.
 // phi is staged in shared memory as a rolling window of 5 planes with a 2-node halo, the interface
@@ -54,16 +76,19 @@ static void fast_alloc(lbm_handle* h) {
 // phi is read from HBM once.  The 19 pulled populations of a node are requested before the tile
 // synchronises, so the HBM latency overlaps the shared-memory phase.
 // ------------------------------------------------------------------------------------------------
-template <bool SOLIDS, int TX, int TY>
+// TMA = true: the phi planes are staged with TMA bulk copies (one cp.async.bulk per tile row, 288 B, issued by one
+// thread, completing on a per-slot mbarrier) instead of 8-byte cp.async copies issued by every thread.
+template <bool SOLIDS, int TX, int TY, bool TMA>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
 cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi) {
     using L = D3Q19;
     constexpr int NT = TX * TY;
     constexpr int PW = TX + 4, PH = TY + 4;     // phi tile
     constexpr int NW = TX + 2, NH = TY + 2;     // normal tile
-    extern __shared__ double smem_dyn[];
+    extern __shared__ __align__(128) double smem_dyn[];
     double (*sphi)[PH][PW] = reinterpret_cast<double (*)[PH][PW]>(smem_dyn);                    // [5]
     double (*sn)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn + 5 * PH * PW);  // [3][nx, ny, nz, |G|]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + 5 * PH * PW + 3 * 4 * NH * NW);     // [5] one mbarrier per phi slot
     const Grid& g = c.g;
     const int64_t V = g.vol;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
@@ -80,6 +105,22 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     auto load_phi_plane = [&](int zp) {
         const int slot = (zp + 10) % 5;
         const double* src = c.phi + (int64_t)(zp + NG) * g.plane;
+        if (TMA) {
+            // one thread: arm the slot's mbarrier with the plane's byte count, then one bulk copy per row; rows of the
+            // first / last tile in x wrap around and are split into two 16-byte-aligned pieces
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bars[slot], PH * PW * 8);
+                for (int ly = 0; ly < PH; ++ly) {
+                    const double* row = src + (int64_t)wrapy(y0 + ly - 2) * g.n0;
+                    double* dst = &sphi[slot][ly][0];
+                    const int c0 = x0 - 2, cs = c0 < 0 ? 0 : c0, ce = x0 + TX + 2 > g.n0 ? g.n0 : x0 + TX + 2;
+                    if (c0 < 0) bulk_g2s(dst, row + g.n0 - 2, 16, &bars[slot]);                    // periodic image on the left
+                    bulk_g2s(dst + (cs - c0), row + cs, (uint32_t)(ce - cs) * 8, &bars[slot]);
+                    if (x0 + TX + 2 > g.n0) bulk_g2s(dst + PW - 2, row, 16, &bars[slot]);         // periodic image on the right
+                }
+            }
+            return;
+        }
         for (int e = tid; e < PH * PW; e += NT) {
             const int ly = e / PW, lx = e - ly * PW;
             __pipeline_memcpy_async(&sphi[slot][ly][lx], src + (int64_t)wrapy(y0 + ly - 2) * g.n0 + wrapx(x0 + lx - 2), 8);
@@ -129,11 +170,23 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     const int64_t xo[3] = {(int64_t)wrapx(x - 1), (int64_t)x, (int64_t)wrapx(x + 1)};
     const int64_t yo[3] = {(int64_t)wrapy(y - 1) * g.n0, (int64_t)y * g.n0, (int64_t)wrapy(y + 1) * g.n0};
 
+    // use number of a slot: plane p is the ((p - (z_begin - 2)) / 5)-th occupant of its slot -> mbarrier parity
+    auto wait_phi_plane = [&](int zp) {
+        if (TMA) mbar_wait(&bars[(zp + 10) % 5], (uint32_t)(((zp - (z_begin - 2)) / 5) & 1));
+    };
+    if (TMA) {
+        if (tid == 0) {
+            for (int k = 0; k < 5; ++k) mbar_init(&bars[k], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) load_phi_plane(zp);
     __pipeline_commit();
     load_phi_plane(z_begin + 2);
     __pipeline_commit();
     __pipeline_wait_prior(1);
+    for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) wait_phi_plane(zp);
     __syncthreads();
     normal_plane(z_begin - 1);
     normal_plane(z_begin);
@@ -165,6 +218,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             for (int d = 0; d < 3; ++d) Fl[d] = c.F[d * V + id];
         }
         __pipeline_wait_prior(1);                       // plane z + 2 (requested one step ago) has landed
+        wait_phi_plane(z + 2);
         __syncthreads();
         normal_plane(z + 1);
         __syncthreads();
@@ -361,22 +415,22 @@ static bool tiled_ok(const lbm_handle* h) {
     return h->Q == 19 && h->g.n0 % TILE_X == 0 && h->g.n1 % tile_y_collide() == 0 && h->g.n1 % tile_y_density() == 0 && !(h->cfg.flags & 2u);
 }
 
-template <bool SOLIDS, int TILE_Y>
+template <bool SOLIDS, int TILE_Y, bool TMA>
 static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi) {
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
-    constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2));
+    constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2) + 8);
     static bool configured = false;
     if (!configured) {
-        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y>,
+        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tiled_d3q19<solids>" : "cg_collide_tiled_d3q19<all-fluid>", h->stream);
-    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi);
+    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
     ++g_launch_counter;
@@ -384,10 +438,11 @@ static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s
 
 template <bool SOLIDS>
 static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo = 0, int z_hi = -1) {
+    static const bool tma = env_int("LBM_PHI_TMA", 1) != 0;      // 0: 8-byte cp.async copies instead of TMA bulk copies
     switch (tile_y_collide()) {
-        case 4: launch_tiled_t<SOLIDS, 4>(h, c, s, o, z_lo, z_hi); break;
-        case 16: launch_tiled_t<SOLIDS, 16>(h, c, s, o, z_lo, z_hi); break;
-        default: launch_tiled_t<SOLIDS, 8>(h, c, s, o, z_lo, z_hi);
+        case 4: if (tma) launch_tiled_t<SOLIDS, 4, true>(h, c, s, o, z_lo, z_hi); else launch_tiled_t<SOLIDS, 4, false>(h, c, s, o, z_lo, z_hi); break;
+        case 16: launch_tiled_t<SOLIDS, 16, false>(h, c, s, o, z_lo, z_hi); break;
+        default: if (tma) launch_tiled_t<SOLIDS, 8, true>(h, c, s, o, z_lo, z_hi); else launch_tiled_t<SOLIDS, 8, false>(h, c, s, o, z_lo, z_hi);
     }
 }
 
