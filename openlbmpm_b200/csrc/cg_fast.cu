@@ -294,14 +294,18 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 // pulled populations of the NEXT plane are requested before the current plane is reduced, so one full
 // plane of HBM requests per thread is always in flight.
 // ------------------------------------------------------------------------------------------------
-template <bool SOLIDS, int TX, int TY>
+// TMA = true: the scalar planes are staged with TMA bulk copies (rows widened to a 2-node halo in x so that they start
+// 16-byte aligned), issued by four threads (one per field) and completing on a per-slot mbarrier.
+template <bool SOLIDS, int TX, int TY, bool TMA>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
 cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, const int z_lo, const int z_hi) {
     using L = D3Q19;
     constexpr int NT = TX * TY;
-    constexpr int NW = TX + 2, NH = TY + 2;
-    extern __shared__ double smem_dyn[];
+    constexpr int XH = TMA ? 2 : 1;                 // halo columns kept in shared memory
+    constexpr int NW = TX + 2 * XH, NH = TY + 2;
+    extern __shared__ __align__(128) double smem_dyn[];
     double (*ss)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn);   // [5 slots][kR, ax, ay, az]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + 5 * 4 * NH * NW);      // [5] one mbarrier per slot
     const Grid& g = c.g;
     const int64_t V = g.vol;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
@@ -316,12 +320,32 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
     auto load_scalar_plane = [&](int zp) {
         const int slot = (zp + 10) % 5;
         const int64_t base = (int64_t)(zp + NG) * g.plane;
+        if (TMA) {
+            if (tid < 32) {
+                if (tid == 0) mbar_arrive_expect_tx(&bars[slot], 4 * NH * NW * 8);
+                __syncwarp();
+                if (tid < 4) {
+                    const int c0 = x0 - 2, cs = c0 < 0 ? 0 : c0, ce = x0 + TX + 2 > g.n0 ? g.n0 : x0 + TX + 2;
+                    for (int ly = 0; ly < NH; ++ly) {
+                        const double* row = fld[tid] + base + (int64_t)wrapy(y0 + ly - 1) * g.n0;
+                        double* dst = &ss[slot][tid][ly][0];
+                        if (c0 < 0) bulk_g2s(dst, row + g.n0 - 2, 16, &bars[slot]);
+                        bulk_g2s(dst + (cs - c0), row + cs, (uint32_t)(ce - cs) * 8, &bars[slot]);
+                        if (x0 + TX + 2 > g.n0) bulk_g2s(dst + NW - 2, row, 16, &bars[slot]);
+                    }
+                }
+            }
+            return;
+        }
         for (int e = tid; e < NH * NW; e += NT) {
             const int ly = e / NW, lx = e - ly * NW;
-            const int64_t off = base + (int64_t)wrapy(y0 + ly - 1) * g.n0 + wrapx(x0 + lx - 1);
+            const int64_t off = base + (int64_t)wrapy(y0 + ly - 1) * g.n0 + wrapx(x0 + lx - XH);
 #pragma unroll
             for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(&ss[slot][k][ly][lx], fld[k] + off, 8);
         }
+    };
+    auto wait_scalar_plane = [&](int zp, int first) {
+        if (TMA) mbar_wait(&bars[(zp + 10) % 5], (uint32_t)(((zp - first) / 5) & 1));
     };
     const int64_t xo[3] = {(int64_t)wrapx(x - 1), (int64_t)x, (int64_t)wrapx(x + 1)};
     const int64_t yo[3] = {(int64_t)wrapy(y - 1) * g.n0, (int64_t)y * g.n0, (int64_t)wrapy(y + 1) * g.n0};
@@ -342,11 +366,20 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
         }
     };
 
+    if (TMA) {
+        if (tid == 0) {
+            for (int k = 0; k < 5; ++k) mbar_init(&bars[k], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     load_scalar_plane(z_begin - 1);
     load_scalar_plane(z_begin);
     __pipeline_commit();
     load_scalar_plane(z_begin + 1);
     __pipeline_commit();
+    wait_scalar_plane(z_begin - 1, z_begin - 1);
+    wait_scalar_plane(z_begin, z_begin - 1);
     double cur[L::Q], nxt[L::Q];
     unsigned mcur = 0, mnxt = 0;
     bool fcur = true, fnxt = true;
@@ -356,19 +389,20 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
         __pipeline_commit();
         if (z + 1 < z_end) request(z + 1, nxt, mnxt, fnxt);
         __pipeline_wait_prior(1);                       // plane z + 1 has landed
+        wait_scalar_plane(z + 1, z_begin - 1);
         __syncthreads();
         if (fcur) {
             const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
             const int s0 = (z + 10) % 5;
-            const double kR0 = ss[s0][0][ty + 1][tx + 1];
-            const double a0[3] = {ss[s0][1][ty + 1][tx + 1], ss[s0][2][ty + 1][tx + 1], ss[s0][3][ty + 1][tx + 1]};
+            const double kR0 = ss[s0][0][ty + 1][tx + XH];
+            const double a0[3] = {ss[s0][1][ty + 1][tx + XH], ss[s0][2][ty + 1][tx + XH], ss[s0][3][ty + 1][tx + XH]};
             double accR = kR0 * cur[0], accB = cur[0] - accR;
 #pragma unroll
             for (int q = 1; q < L::Q; ++q) {
                 double fr;
                 if (!SOLIDS || (mcur & (1u << q))) {
                     const int sq = (z - L::d2(q) + 10) % 5;
-                    const int ly = ty + 1 - L::d1(q), lx = tx + 1 - L::d0(q);
+                    const int ly = ty + 1 - L::d1(q), lx = tx + XH - L::d0(q);
                     double ea = 0.0;
 #pragma unroll
                     for (int d = 0; d < 3; ++d)
@@ -446,32 +480,35 @@ static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, 
     }
 }
 
-template <bool SOLIDS, int TILE_Y>
+template <bool SOLIDS, int TILE_Y, bool TMA>
 static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo, int z_hi) {
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
-    constexpr size_t smem = sizeof(double) * 5 * 4 * (TILE_Y + 2) * (TILE_X + 2);
+    constexpr size_t smem = sizeof(double) * (5 * 4 * (TILE_Y + 2) * (TILE_X + (TMA ? 4 : 2)) + 8);
     static bool configured = false;
     if (!configured) {
-        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y>,
+        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_density_tiled_d3q19<solids>" : "cg_density_tiled_d3q19<all-fluid>", h->stream);
-    cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, zchunk, z_lo, z_hi);
+    cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA><<<grid, block, smem, h->stream>>>(c, s, zchunk, z_lo, z_hi);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
     ++g_launch_counter;
 }
 template <bool SOLIDS>
 static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo = 0, int z_hi = -1) {
+    // TMA bulk copies for the scalar planes exist (LBM_SCALAR_TMA=1) but measured 7.2 ms vs 4.7 ms per 512^3 launch:
+    // 40 row copies per plane step issued by four threads sit on the critical path of this short loop; cp.async stays
+    static const bool tma = env_int("LBM_SCALAR_TMA", 0) != 0;
     switch (tile_y_density()) {
-        case 4: launch_density_tiled_t<SOLIDS, 4>(h, c, s, z_lo, z_hi); break;
-        case 16: launch_density_tiled_t<SOLIDS, 16>(h, c, s, z_lo, z_hi); break;
-        default: launch_density_tiled_t<SOLIDS, 8>(h, c, s, z_lo, z_hi);
+        case 4: launch_density_tiled_t<SOLIDS, 4, false>(h, c, s, z_lo, z_hi); break;
+        case 16: launch_density_tiled_t<SOLIDS, 16, false>(h, c, s, z_lo, z_hi); break;
+        default: if (tma) launch_density_tiled_t<SOLIDS, 8, true>(h, c, s, z_lo, z_hi); else launch_density_tiled_t<SOLIDS, 8, false>(h, c, s, z_lo, z_hi);
     }
 }
 #endif
