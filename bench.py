@@ -124,6 +124,9 @@ def run_reference(args):
 
 
 def workload_name(args):
+    if args.workload == "porous":
+        return ("D3Q19 colour-gradient CSF MRT, %d x %d x %d sphere pack (seed 7, porosity ~0.6, half-way bounce back, contact "
+                "angle 60), velocity inlet along -z, convective outlet (BASELINE config 5 geometry)" % (args.size, args.size, args.nz or args.size))
     if args.lattice == 19:
         return "D3Q19 colour-gradient CSF MRT, %d^3 periodic all-fluid box, spinodal start (BASELINE metric)" % args.size
     return "D2Q9 colour-gradient CSF MRT, %d^2 periodic all-fluid box, spinodal start" % args.size
@@ -146,7 +149,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="lbm_config.flags (LBM_FLAG_*), for A/B measurements")
+    ap.add_argument("--workload", default="box", choices=["box", "porous"],
+                    help="box: the metric's periodic spinodal box; porous: sphere pack with velocity inlet + convective outlet (cfg 5)")
+    ap.add_argument("--nz", type=int, default=0, help="porous: planes along the flow axis (default: --size)")
     args = ap.parse_args()
+    if args.workload == "porous":
+        args.lattice = 19
     if args.impl == "reference":
         return run_reference(args)
 
@@ -165,19 +173,36 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     Q, n = args.lattice, args.size
-    if n % world:
+    porous = args.workload == "porous"
+    nz = (args.nz or n) if porous else n
+    if nz % world:
         raise SystemExit("size must be divisible by the number of GPUs")
-    nloc = n // world
+    nloc = nz // world
     shape = (nloc, n, n) if Q == 19 else (nloc, n)
     flags = (_lib.FLAG_GENERIC_KERNELS if args.general else 0) | args.flags
+    bc = dict(inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_CONVECTIVE, inlet_velocity=-5.0e-4, contact_angle_deg=60.0) if porous else {}
     eng = _lib.Engine(Q, shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, device=local, flags=flags,
-                      sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2)
+                      sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2, **bc)
     if world > 1:
         from openlbmpm_b200 import slab
         eng.comm_init(rank, world, slab.share_unique_id(dist, eng, rank, device="cuda"))
-    eng.set_geometry(np.ones(shape, np.uint8))
-    eng.init_spinodal_device(SPIN_AMP, SPIN_SEED)
-    nodes_total = float(n) ** (3 if Q == 19 else 2)
+    if porous:
+        from openlbmpm_b200 import synthetic
+        sl = slice(rank * nloc, (rank + 1) * nloc)
+        dom = synthetic.sphere_pack((nz, n, n))[sl]
+        eng.set_geometry(dom)
+        red = (np.arange(nz)[sl] >= nz - 30)[:, None, None]           # the invading fluid fills the inlet buffer
+        eng.init_equilibrium(np.where(red, 1.0, 5e-8) * dom, np.where(red, 5e-8, 1.0) * dom)
+        nodes_total = float(dom.sum())
+        if dist is not None:
+            t = torch.tensor([nodes_total], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            nodes_total = float(t.item())
+        del dom
+    else:
+        eng.set_geometry(np.ones(shape, np.uint8))
+        eng.init_spinodal_device(SPIN_AMP, SPIN_SEED)
+        nodes_total = float(n) ** (3 if Q == 19 else 2)
 
     def barrier():
         eng.synchronize()
@@ -212,7 +237,7 @@ def main():
 
     # ---- end to end through the C ABI with host buffers: upload densities -> K steps -> download macros
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not porous:
         keep = []
         t_r, rhoR = pinned_empty(shape); keep.append(t_r)
         t_b, rhoB = pinned_empty(shape); keep.append(t_b)
@@ -255,7 +280,7 @@ def main():
                     round(sum(c for c, _ in prof.values()) / args.steps), B_ALG[Q], int(nodes_total / world)),
                 "kernels": kernels[:6]}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr) and Q == 19 and not args.general:
+    if os.path.exists(tr) and Q == 19 and not args.general and not porous:
         try:       # dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels (ncu --set full at 512^3), scaled to this slab
             t = json.load(open(tr))
             roofline["traffic"] = t["dram_bytes_per_step"] * (nodes_total / world) / t["nodes"]
@@ -264,7 +289,7 @@ def main():
             pass
 
     cpu = None
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and world == 1 and not porous:
         try:
             v, cores, dt = cpu_oracle_mlups(Q, args.cpu_size, args.cpu_steps)
             cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
@@ -274,13 +299,14 @@ def main():
         except Exception as e:       # the oracle is a checker; its absence must not hide the GPU number
             cpu = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port", "sample": "unavailable: %r" % (e,)}
 
-    line = {"metric": "MLUPS D3Q19 CG-MRT 512^3" if (Q == 19 and n == 512) else "MLUPS %s CG-MRT %d" % ("D3Q19" if Q == 19 else "D2Q9", n),
+    line = {"metric": "MLUPS D3Q19 CG-MRT 512^3" if (Q == 19 and n == 512 and not porous) else "MLUPS (void nodes) D3Q19 CG-MRT porous" if porous else "MLUPS %s CG-MRT %d" % ("D3Q19" if Q == 19 else "D2Q9", n),
             "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "l2": "working set (%.1f GB) far larger than the 126 MB L2" % (
                            2 * 2 * Q * 8 * nodes_total / 1e9),
-                       "path": "general kernels" if args.general else "fused fast path", "slab": list(shape)},
+                       "path": "general kernels" if args.general else "fused fast path", "slab": list(shape),
+                       "void_nodes": nodes_total},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["launches"],
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
             "mass": [float(mass[0]), float(mass[1])], "pct_hbm_roofline": 100.0 * achieved / peak}

@@ -25,9 +25,16 @@ static FastFields fast_fields(const lbm_handle* h, int k) {
     return o;
 }
 
+static bool open_box(const lbm_handle* h) { return h->cfg.inlet != LBM_BC_PERIODIC || h->cfg.outlet != LBM_BC_PERIODIC; }
+
 bool cg_fast_eligible(const lbm_handle* h) {
-    return h->cfg.model == LBM_MODEL_CG && h->cfg.inlet == LBM_BC_PERIODIC && h->cfg.outlet == LBM_BC_PERIODIC &&
-           !(h->cfg.flags & LBM_FLAG_GENERIC_KERNELS);
+    // open boundaries: the treated planes are patched around the two passes (fast_open_rows_*), which needs the
+    // inlet and outlet planes of a slab to be apart.  WettingType 1 turns ANY non-zero |G| into a unit normal
+    // (AcceleratedRKGPU2D.py:1700-1706), so its trajectories hang on the exact cancellation of phi between the copied
+    // outlet rows; the factored arithmetic rounds differently there, and that combination stays on the
+    // reference-ordered kernels.
+    if (h->cfg.model != LBM_MODEL_CG || (h->cfg.flags & LBM_FLAG_GENERIC_KERNELS)) return false;
+    return !open_box(h) || (h->g.n2 >= 8 && h->cfg.wetting_type != 1);
 }
 
 void cg_fast_free(lbm_handle* h) {
@@ -523,6 +530,59 @@ static const int8_t* factored_dirs() {
     return d;
 }
 
+// ---- open boundaries on the fast path -------------------------------------------------------------------------
+// The inlet / outlet treatment of the reference (RKD2Q9.py:1299-1352) rewrites the STREAMED populations of a few
+// planes at the top of every iteration, which the factored state cannot express.  Those planes are therefore patched:
+// after the density pass their streamed populations are materialised from the factored state, the reference's row
+// operators run on them, and velocity + phi are re-evaluated there; after the collision pass the same planes are
+// collided again from the treated populations (general-path arithmetic) and overwrite the fast pass's result.
+// Everything else of the lattice stays on the two fused passes.
+template <class Op>
+struct PlaneRangeOp {
+    Op op; int64_t off;
+    LBM_HD void operator()(int64_t i) const { op(i + off); }
+};
+// planes [z_lo, z_hi) of an operator whose item 0 is the first node of plane -ext
+template <class Op>
+static void launch_planes(lbm_handle* h, const Op& op, int ext, int z_lo, int z_hi) {
+    launch(PlaneRangeOp<Op>{op, (int64_t)(z_lo + ext) * h->g.plane}, (int64_t)(z_hi - z_lo) * h->g.plane, h->stream);
+}
+struct OpenRows {
+    int n = 0;
+    int mat_lo[2], mat_hi[2];     // planes whose streamed populations the row operators read
+    int mod_lo[2], mod_hi[2];     // planes they modify
+};
+static OpenRows open_rows(const CGFields& c) {
+    OpenRows r;
+    if (c.outlet != LBM_BC_PERIODIC && c.z_out >= 0) {
+        const bool conv = c.outlet == LBM_OUTLET_CONVECTIVE;      // rows 2 <- 3, 1 <- 2, 0 <- 1 | row 1 treated, 0 <- 1
+        r.mat_lo[r.n] = 0; r.mat_hi[r.n] = conv ? 4 : 2; r.mod_lo[r.n] = 0; r.mod_hi[r.n] = conv ? 3 : 2; ++r.n;
+    }
+    if (c.inlet != LBM_BC_PERIODIC && c.z_in >= 0) {
+        r.mat_lo[r.n] = r.mod_lo[r.n] = c.z_in; r.mat_hi[r.n] = r.mod_hi[r.n] = c.z_in_ghost + 1; ++r.n;
+    }
+    return r;
+}
+template <class L>
+static void fast_open_rows_pre(lbm_handle* h, const CGFields& c, const FastFields& s) {
+    const OpenRows r = open_rows(c);
+    if (!r.n) return;
+    for (int k = 0; k < r.n; ++k) launch_planes(h, PullMaterialiseOp<L>{c, s}, 0, r.mat_lo[k], r.mat_hi[k]);
+    cg_apply_open_rows(h);
+    for (int k = 0; k < r.n; ++k) launch_planes(h, HeadOp<L>{c}, 0, r.mod_lo[k], r.mod_hi[k]);   // u with the lagged force, phi
+}
+template <class L>
+static void fast_open_rows_post(lbm_handle* h, const CGFields& c, const FastFields& o, bool need_gradient) {
+    const OpenRows r = open_rows(c);
+    for (int k = 0; k < r.n; ++k) {
+        // the tiled collision pass keeps G and the normals in shared memory: evaluate them around the patched planes
+        if (need_gradient)
+            launch_planes(h, GradientOp<L>{c}, 1, r.mod_lo[k] - 1 < -1 ? -1 : r.mod_lo[k] - 1,
+                          r.mod_hi[k] + 1 > h->g.n2 + 1 ? h->g.n2 + 1 : r.mod_hi[k] + 1);
+        launch_planes(h, CollideFactoredOp<L>{c, o}, 0, r.mod_lo[k], r.mod_hi[k]);
+    }
+}
+
 template <class L>
 static void fast_enter(lbm_handle* h) {
     cg_ensure_head(h);
@@ -575,7 +635,7 @@ static void fast_one_step(lbm_handle* h) {
     FastState* f = (FastState*)h->fast;
     const Grid& g = h->g;
 #ifndef LBM_HOSTCHECK
-    if (h->nranks > 1 && !h->has_solid && tiled_ok(h) && g.n2 >= 8 && (h->cfg.flags & 16u) && !(h->cfg.flags & 4u)) {
+    if (h->nranks > 1 && !h->has_solid && !open_box(h) && tiled_ok(h) && g.n2 >= 8 && (h->cfg.flags & 16u) && !(h->cfg.flags & 4u)) {
         fast_one_step_overlapped(h);
         return;
     }
@@ -594,6 +654,8 @@ static void fast_one_step(lbm_handle* h) {
         if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
         else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
     }
+    const bool open = open_box(h);
+    if (open) fast_open_rows_pre<L>(h, c, s);
     exchange_f64(h, c.phi, 0, 1, h->has_solid ? NG : 2);
     if (h->has_solid) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
     bool done = false;
@@ -608,6 +670,7 @@ static void fast_one_step(lbm_handle* h) {
         if (h->has_solid) launch(PullCollideOp<L, true>{c, s, o}, g.count(0), h->stream);
         else launch(PullCollideOp<L, false>{c, s, o}, g.count(0), h->stream);
     }
+    if (open) fast_open_rows_post<L>(h, c, o, done);
     f->cur = 1 - f->cur;
 }
 

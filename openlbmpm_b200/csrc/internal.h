@@ -16,6 +16,7 @@ int comm_allreduce_max(lbm_handle* h, int v);
 void cg_alloc_state(lbm_handle* h);
 void cg_alloc_postcollision(lbm_handle* h);
 void cg_ensure_head(lbm_handle* h);
+void cg_apply_open_rows(lbm_handle* h);      // inlet / outlet treatment of the streamed populations (no-op on periodic boxes)
 void cg_generic_body(lbm_handle* h);
 void cg_generic_forces(lbm_handle* h);
 

@@ -382,9 +382,9 @@ extern "C" int lbm_upload_state(lbm_handle* h, const double* const* pdf, const d
 // ------------------------------------------------------------------------------------------------
 // the general colour-gradient step (reference order, RKD2Q9.py:1295-1490)
 // ------------------------------------------------------------------------------------------------
+// boundary treatment of the streamed populations at the top of an iteration (RKD2Q9.py:1299-1352)
 template <class L>
-static void cg_head(lbm_handle* h) {
-    CGFields c = h->fields();
+static void cg_open_rows(lbm_handle* h, const CGFields& c) {
     const Grid& g = h->g;
     if (c.inlet == LBM_INLET_VELOCITY && c.z_in >= 0) {
         launch(InletVelocityOp<L>{c}, g.plane, h->stream);
@@ -401,7 +401,13 @@ static void cg_head(lbm_handle* h) {
         launch(OutletPressureOp<L>{c}, g.plane, h->stream);
         launch(RowCopyOp<L>{c, 0, 1, 0}, g.plane, h->stream);
     }
-    launch(HeadOp<L>{c}, g.count(0), h->stream);
+}
+
+template <class L>
+static void cg_head(lbm_handle* h) {
+    CGFields c = h->fields();
+    cg_open_rows<L>(h, c);
+    launch(HeadOp<L>{c}, h->g.count(0), h->stream);
     h->head_done = true;
 }
 
@@ -428,6 +434,10 @@ static void cg_body(lbm_handle* h) {
 void lbm::cg_ensure_head(lbm_handle* h) {
     if (h->head_done) return;
     if (h->Q == 9) cg_head<D2Q9>(h); else cg_head<D3Q19>(h);
+}
+void lbm::cg_apply_open_rows(lbm_handle* h) {
+    CGFields c = h->fields();
+    if (h->Q == 9) cg_open_rows<D2Q9>(h, c); else cg_open_rows<D3Q19>(h, c);
 }
 void lbm::cg_generic_body(lbm_handle* h) {
     if (h->Q == 9) cg_body<D2Q9>(h); else cg_body<D3Q19>(h);

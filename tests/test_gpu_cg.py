@@ -139,6 +139,14 @@ def test_d3q19_open_boundaries_vs_oracle(inlet, outlet):
     cases.case_d3q19_open_boundaries(None, inlet, outlet, n=(40, 16, 32), steps=12, relax="SRT")
 
 
+@pytest.mark.parametrize("inlet,outlet", [("Neumann", "Convective"), ("Dirichlet", "Dirichlet")])
+def test_d3q19_open_boundaries_tiled_equals_untiled_and_general(inlet, outlet):
+    """open boundaries on the fast path: tiled kernels + patched planes vs the one-thread-per-node fast path (flags 2)
+    vs the reference-ordered kernels (flags 1), all against the oracle"""
+    for flags in (0, 2, 1):
+        cases.case_d3q19_open_boundaries(None, inlet, outlet, n=(40, 16, 32), steps=12, flags=flags)
+
+
 # ---- small lattices replay a captured CUDA graph of the step when many steps are requested at once ----
 @pytest.mark.parametrize("path", cases.GOLD_CG2D, ids=[cases.gold_id(p) for p in cases.GOLD_CG2D])
 @pytest.mark.parametrize("flags", [0, 1, 8])
