@@ -15,6 +15,8 @@ from .results import ResultFile
 
 
 class ShanChenD2Q9:
+    LATTICE = 9
+
     def __init__(self, pathIniFile, verbose=True):
         self.path = pathIniFile
         self.verbose = verbose
@@ -24,6 +26,7 @@ class ShanChenD2Q9:
             raise IniError("image input for the Shan-Chen class: provide the geometry through SimpleGeometry.defineGeometry")
         self.nx = self.borderX = ini.integer("SeparationBorder", "xGrid")
         self.ny = self.borderY = ini.integer("SeparationBorder", "yGrid")
+        self._read_extra_dimensions(ini)
         self.typesFluids = ini.integer("FluidsTypes", "NumberOfFluids", default=2)
         if not 1 <= self.typesFluids <= 4:
             raise IniError("1..4 fluids are supported")
@@ -36,13 +39,33 @@ class ShanChenD2Q9:
             raise IniError("TRT is read by the reference but never launched by a live driver")
         self.duplicateDomain = ini.quoted("DuplicateDomain", "Option", default="no")
         self.isCycles = ini.quoted("DICycles", "Option", default="no")
+        self._set_lattice()
+        efs = self.interactionType == "'EFS'"
+        self._read_model(self._model_ini(pathIniFile, efs), "EFSParameters" if efs else "ShanChenParameters")
+        self.engine = None
+        self._results = None
+
+    # -- lattice-specific pieces (ShanChenD3Q19 overrides them) ------------------------------------
+    def _read_extra_dimensions(self, ini):
+        pass
+
+    def _set_lattice(self):
         self.unitEX = np.array([0., 1., 0., -1., 0., 1., -1., -1., 1.])
         self.unitEY = np.array([0., 0., 1., 0., -1., 1., 1., -1., -1.])
         self.weightsCoeff = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
-        efs = self.interactionType == "'EFS'"
-        self._read_model(Ini(pathIniFile, "efs2D.ini" if efs else "shanchen2D.ini"), "EFSParameters" if efs else "ShanChenParameters")
-        self.engine = None
-        self._results = None
+
+    def _model_ini(self, path, efs):
+        return Ini(path, "efs2D.ini" if efs else "shanchen2D.ini")
+
+    def _shape(self):
+        return (self.ny, self.nx)
+
+    def _define_geometry(self):
+        try:
+            from SimpleGeometry import defineGeometry
+        except ImportError:
+            from .SimpleGeometry import defineGeometry
+        return defineGeometry(self.nx, self.ny)
 
     def _say(self, *a):
         if self.verbose:
@@ -89,11 +112,7 @@ class ShanChenD2Q9:
 
     # -- geometry / initial condition --------------------------------------------------------------
     def initializeDomainBorder(self):
-        try:
-            from SimpleGeometry import defineGeometry
-        except ImportError:
-            from .SimpleGeometry import defineGeometry
-        self.isDomain, self.isSolid = defineGeometry(self.nx, self.ny)
+        self.isDomain, self.isSolid = self._define_geometry()
         self.isDomain = np.ascontiguousarray(self.isDomain, dtype=bool)
         self.isSolid = ~self.isDomain
         self.voidSpace = int(np.count_nonzero(self.isDomain))
@@ -103,16 +122,19 @@ class ShanChenD2Q9:
         """ShanChenD2Q9.py:734-768: fluid 0 below row ny-10, fluid 1 above; assign `self.initialRegion0`
         (boolean [ny, nx]) beforehand for another layout"""
         reg = getattr(self, "initialRegion0", None)
+        shape = self._shape()
         if reg is None:
-            reg = np.indices((self.ny, self.nx))[0] < self.ny - 10
+            reg = np.indices(shape)[0] < shape[0] - 10
         nf = self.typesFluids
-        self.fluidsDensity = np.zeros((nf, self.ny, self.nx))
+        self.fluidsDensity = np.zeros((nf,) + shape)
         for k in range(nf):
             inside = self.initialDensities[k] if k == 0 else self.backgroundDensities[k]
             outside = self.backgroundDensities[k] if k == 0 else self.initialDensities[k]
             self.fluidsDensity[k] = np.where(reg, inside, outside) * self.isDomain
         self.fluidPDF = self.fluidsDensity[..., None] * self.weightsCoeff
-        self.physicalVX = np.zeros((self.ny, self.nx)); self.physicalVY = np.zeros((self.ny, self.nx))
+        self.physicalVX = np.zeros(shape); self.physicalVY = np.zeros(shape)
+        if self.LATTICE == 19:
+            self.physicalVZ = np.zeros(shape)
 
     def _make_engine(self, model):
         inlet = {"'Periodic'": _lib.BC_PERIODIC, "'Neumann'": _lib.INLET_VELOCITY}.get(self.boundaryTypeInlet)
@@ -123,7 +145,7 @@ class ShanChenD2Q9:
         if model == _lib.MODEL_SC and outlet == _lib.OUTLET_PRESSURE:
             raise IniError("the original Shan-Chen loop has no pressure outlet (ShanChenD2Q9.py:1603-1621)")
         G = np.zeros((4, 4)); G[:self.typesFluids, :self.typesFluids] = self.interCoeff
-        self.engine = _lib.Engine(9, (self.ny, self.nx), model=model,
+        self.engine = _lib.Engine(self.LATTICE, self._shape(), model=model,
                                   relax=_lib.RELAX_MRT if self.relaxationType == "'MRT'" else _lib.RELAX_SRT,
                                   n_components=self.typesFluids, inlet=inlet, outlet=outlet, sc_tau=self.tau,
                                   sc_G=G.ravel(), sc_Gsolid=self.interactionSolid, sc_inlet_velocity=self.velocityYInlet,
@@ -139,12 +161,14 @@ class ShanChenD2Q9:
         nb[nb < 0] = -1
         self.neighboringNodes = nb
         self.optFluidRho = self.fluidsDensity.reshape(self.typesFluids, -1)[:, self.fluidNodes]
-        self.optFluidPDF = self.fluidPDF.reshape(self.typesFluids, -1, 9)[:, self.fluidNodes]
+        self.optFluidPDF = self.fluidPDF.reshape(self.typesFluids, -1, self.LATTICE)[:, self.fluidNodes]
 
     def convertOptTo2D(self):
         rho, u = self.engine.download_macros()
         self.fluidsDensity = np.stack(rho)
-        self.physicalVX, self.physicalVY = u
+        self.physicalVX, self.physicalVY = u[0], u[1]
+        if self.LATTICE == 19:
+            self.physicalVZ = u[2]
         self.fluidPDF = np.stack(self.engine.download_pdfs())
 
     def resultInHDF5(self, iStep):
@@ -154,6 +178,8 @@ class ShanChenD2Q9:
         arrays = {"/FluidMacro/FluidDensityType%gin%g" % (k, iStep): self.fluidsDensity[k] for k in range(self.typesFluids)}
         arrays["/FluidVelocity/FluidVelocityXAt%g" % iStep] = self.physicalVX
         arrays["/FluidVelocity/FluidVelocityYAt%g" % iStep] = self.physicalVY
+        if self.LATTICE == 19:
+            arrays["/FluidVelocity/FluidVelocityZAt%g" % iStep] = self.physicalVZ
         self._results.write(iStep, arrays)
 
     def _run(self, model, interval):

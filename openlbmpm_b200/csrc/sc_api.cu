@@ -1,9 +1,18 @@
-// sc_api.cu -- state and step loops of the D2Q9 Shan-Chen models behind the C ABI
+// sc_api.cu -- state and step loops of the Shan-Chen models behind the C ABI
 // (original Shan-Chen: ShanChenD2Q9.py:1492-1629; explicit forcing SRT/MRT: ShanChenD2Q9.py:1714-2087).
+// D2Q9 follows the reference; D3Q19 (`ShanChenD3Q19.runOriginalSC3DGPU / runEFS4LBM3DGPU`, named by main.py:73-77
+// but absent upstream) runs the same lattice-generic operators on closed boxes (oracle/sc_dense.py).
 #include "internal.h"
 #include "sc_ops.cuh"
 
 namespace lbm {
+
+// launch a lattice-generic operator for the handle's lattice
+#define SC_LAUNCH(n, OP, ...)                                                      \
+    do {                                                                           \
+        if (h->Q == 9) launch(OP<D2Q9>{__VA_ARGS__}, n, h->stream);                \
+        else launch(OP<D3Q19>{__VA_ARGS__}, n, h->stream);                         \
+    } while (0)
 
 struct SCState {
     double *fS = nullptr, *fC = nullptr, *rho = nullptr, *F = nullptr, *ueq = nullptr, *uph = nullptr, *fold = nullptr;
@@ -15,7 +24,7 @@ static SCFields sc_fields(const lbm_handle* h) {
     const SCState* s = (const SCState*)h->sc;
     SCFields c;
     memset(&c, 0, sizeof(c));
-    c.g = h->g;
+    c.g = h->g; c.Q = h->Q; c.D = h->D;
     const lbm_config& cfg = h->cfg;
     c.p.nc = cfg.n_components; c.p.relax = cfg.relax; c.p.inlet = cfg.inlet; c.p.outlet = cfg.outlet;
     for (int k = 0; k < SC_MAXC; ++k) {
@@ -50,8 +59,9 @@ static void sc_alloc(lbm_handle* h) {
     const int nc = h->cfg.n_components;
     const size_t V = (size_t)h->g.vol * sizeof(double);
     auto alloc0 = [&](size_t bytes) { double* p = (double*)dev_alloc(bytes); dev_zero(p, bytes, h->stream); return p; };
-    s->fS = alloc0(nc * 9 * V); s->fC = alloc0(nc * 9 * V); s->rho = alloc0(nc * V); s->F = alloc0(nc * 2 * V);
-    s->ueq = alloc0(2 * V); s->uph = alloc0(2 * V);
+    const int Q = h->Q, D = h->D;
+    s->fS = alloc0(nc * Q * V); s->fC = alloc0(nc * Q * V); s->rho = alloc0(nc * V); s->F = alloc0(nc * D * V);
+    s->ueq = alloc0(D * V); s->uph = alloc0(D * V);
     s->fold = alloc0((size_t)nc * 9 * 3 * h->g.plane * sizeof(double));
 }
 
@@ -63,7 +73,7 @@ int sc_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp)
     double* tmp = (double*)dev_alloc((size_t)n_comp * owned * 8);
     try {
         for (int k = 0; k < n_comp; ++k) dev_h2d(tmp + k * owned, rho[k], owned * 8, h->stream);
-        launch(ScInitOp{sc_fields(h), tmp}, owned, h->stream);
+        SC_LAUNCH(owned, ScInitOp, sc_fields(h), tmp);
         dev_sync(h->stream);
     } catch (...) { dev_free(tmp); throw; }
     dev_free(tmp);
@@ -77,19 +87,20 @@ int sc_upload_state(lbm_handle* h, const double* const* pdf, const double* const
     if (n_comp != h->cfg.n_components || !pdf) { h->err = "one population array per component expected"; return LBM_EINVAL; }
     sc_alloc(h);
     const int64_t owned = h->g.plane * h->g.n2;
-    double* tmp = (double*)dev_alloc((size_t)owned * 10 * 8);
+    const int Q = h->Q;
+    double* tmp = (double*)dev_alloc((size_t)owned * (Q + 1) * 8);
     try {
         SCFields c = sc_fields(h);
         for (int k = 0; k < n_comp; ++k) {
             if (!pdf[k]) throw BackendError{"NULL population array"};
-            dev_h2d(tmp, pdf[k], (size_t)owned * 9 * 8, h->stream);
+            dev_h2d(tmp, pdf[k], (size_t)owned * Q * 8, h->stream);
             const double* rin = nullptr;
-            if (rho && rho[k]) { dev_h2d(tmp + owned * 9, rho[k], owned * 8, h->stream); rin = tmp + owned * 9; }
-            launch(ScUploadOp{c, k, tmp, rin}, owned, h->stream);
+            if (rho && rho[k]) { dev_h2d(tmp + owned * Q, rho[k], owned * 8, h->stream); rin = tmp + owned * Q; }
+            SC_LAUNCH(owned, ScUploadOp, c, k, tmp, rin);
             dev_sync(h->stream);
         }
         SCState* s = (SCState*)h->sc;
-        dev_zero(s->F, (size_t)n_comp * 2 * h->g.vol * 8, h->stream);
+        dev_zero(s->F, (size_t)n_comp * h->D * h->g.vol * 8, h->stream);
         s->efs_prepared = false; s->head_done = false;
     } catch (...) { dev_free(tmp); throw; }
     dev_free(tmp);
@@ -124,17 +135,17 @@ static void sc_iteration(lbm_handle* h) {
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
     sc_ensure_head(h);
-    launch(ScRhoOp{c}, g.count(0), h->stream);                  // calFluidRhoGPU; psi = rho
+    SC_LAUNCH(g.count(0), ScRhoOp, c);                      // calFluidRhoGPU; psi = rho
     exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
-    launch(ScCollideOp{c}, g.count(0), h->stream);              // interactionCollisionProcess
-    exchange_f64(h, c.fC, g.vol, c.p.nc * 9, 1);
-    launch(ScStreamOp{c}, g.count(0), h->stream);               // calStreaming1GPU/2GPU (+ densities)
+    SC_LAUNCH(g.count(0), ScCollideOp, c);                  // interactionCollisionProcess
+    exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
+    SC_LAUNCH(g.count(0), ScStreamOp, c);                   // calStreaming1GPU/2GPU (+ densities)
     if (c.p.outlet == LBM_OUTLET_CONVECTIVE) {                  // convectiveOutletGPU / Ghost2 / Ghost3
         launch(ScRowCopyOp{c, 2, 3}, g.plane, h->stream);
         launch(ScRowCopyOp{c, 1, 2}, g.plane, h->stream);
         launch(ScRowCopyOp{c, 0, 1}, g.plane, h->stream);
     }
-    launch(ScPhysicalVelocityOp{c}, g.count(0), h->stream);
+    SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);
     s->head_done = false;
 }
 
@@ -145,8 +156,8 @@ static void efs_prepare(lbm_handle* h) {
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
     exchange_f64(h, c.rho, g.vol, c.p.nc, c.p.scheme == 4 ? 1 : NG);
-    launch(EfsForceOp{c}, g.count(0), h->stream);
-    launch(EfsTransformOp{c}, g.count(0), h->stream);
+    SC_LAUNCH(g.count(0), EfsForceOp, c);
+    SC_LAUNCH(g.count(0), EfsTransformOp, c);
     // boundary rows: the populations are treated, the densities the reference sets here are never read
     // before calFluidRhoGPU overwrites them, so the state keeps the densities f_eq was built from
     if (c.p.inlet == LBM_INLET_VELOCITY || c.p.outlet == LBM_OUTLET_PRESSURE) {
@@ -166,11 +177,11 @@ static void efs_iteration(lbm_handle* h) {
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
     if (c.p.outlet == LBM_OUTLET_CONVECTIVE) launch(ScSaveRowsOp{c}, 3 * g.plane, h->stream);   // savePDFLastStep
-    launch(EfsCollideOp{c}, g.count(0), h->stream);
-    exchange_f64(h, c.fC, g.vol, c.p.nc * 9, 1);
-    launch(ScStreamOp{c}, g.count(0), h->stream);
+    SC_LAUNCH(g.count(0), EfsCollideOp, c);
+    exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
+    SC_LAUNCH(g.count(0), ScStreamOp, c);
     if (c.p.outlet == LBM_OUTLET_CONVECTIVE) {
-        launch(ScPhysicalVelocityOp{c}, g.count(0), h->stream);
+        SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);
         launch(ScConvectiveEachOp{c, 2}, g.plane, h->stream);
         launch(ScConvectiveEachOp{c, 1}, g.plane, h->stream);
         launch(ScConvectiveEachOp{c, 0}, g.plane, h->stream);
@@ -178,10 +189,10 @@ static void efs_iteration(lbm_handle* h) {
         sc_outlet_pressure(h, c);
     }
     sc_inlet(h, c);
-    if (c.p.inlet != LBM_BC_PERIODIC || c.p.outlet != LBM_BC_PERIODIC) launch(ScRhoOp{c}, g.count(0), h->stream);
-    launch(ScPhysicalVelocityOp{c}, g.count(0), h->stream);     // output point (:2016-2027)
+    if (c.p.inlet != LBM_BC_PERIODIC || c.p.outlet != LBM_BC_PERIODIC) SC_LAUNCH(g.count(0), ScRhoOp, c);
+    SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);     // output point (:2016-2027)
     exchange_f64(h, c.rho, g.vol, c.p.nc, c.p.scheme == 4 ? 1 : NG);
-    launch(EfsForceOp{c}, g.count(0), h->stream);
+    SC_LAUNCH(g.count(0), EfsForceOp, c);
 }
 
 void sc_step(lbm_handle* h, int nsteps) {
@@ -203,7 +214,7 @@ int sc_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double
         for (int k = 0; k < n_comp; ++k)
             if (rho[k]) dev_d2h(rho[k], c.rho + k * g.vol + off, owned * 8, h->stream);
     if (u)
-        for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < h->D; ++a)
             if (u[a]) dev_d2h(u[a], c.uph + a * g.vol + off, owned * 8, h->stream);
     dev_sync(h->stream);
     return LBM_OK;
@@ -215,12 +226,12 @@ int sc_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp) {
     sc_ensure_head(h);
     SCFields c = sc_fields(h);
     const int64_t owned = h->g.plane * h->g.n2;
-    double* tmp = (double*)dev_alloc((size_t)owned * 9 * 8);
+    double* tmp = (double*)dev_alloc((size_t)owned * h->Q * 8);
     try {
         for (int k = 0; k < n_comp; ++k) {
             if (!pdf[k]) continue;
-            launch(ScDownloadOp{c, k, tmp}, owned, h->stream);
-            dev_d2h(pdf[k], tmp, (size_t)owned * 9 * 8, h->stream);
+            SC_LAUNCH(owned, ScDownloadOp, c, k, tmp);
+            dev_d2h(pdf[k], tmp, (size_t)owned * h->Q * 8, h->stream);
         }
     } catch (...) { dev_free(tmp); throw; }
     dev_free(tmp);

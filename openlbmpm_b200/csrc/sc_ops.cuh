@@ -1,4 +1,6 @@
-// sc_ops.cuh -- D2Q9 multi-component Shan-Chen models on the dense grid, one thread per node:
+// sc_ops.cuh -- multi-component Shan-Chen models on the dense grid, one thread per node, written once for any
+// lattice (D2Q9: the reference's; D3Q19: `ShanChenD3Q19`, which main.py:17,73-77 names but the reference does not
+// ship -- the direct generalisation fixed in oracle/sc_dense.py, closed boxes, isotropy 4):
 //   * original Shan-Chen      (ShanChenD2Q9.runOptimizedLBM,   ShanChenD2Q9.py:1433-1629; kernels in
 //                              ShanChen2D/OptimizedD2Q9GPU.py)
 //   * explicit forcing SRT/MRT (ShanChenD2Q9.runOptimizedEFLBM, ShanChenD2Q9.py:1631-2087; kernels in
@@ -23,24 +25,46 @@ struct SCParams {
 struct SCFields {
     Grid g;
     SCParams p;
-    double* fS;      // [nc][9][vol] populations (EFS: the transformed populations f - fF/2)
-    double* fC;      // [nc][9][vol] post-collision
+    int Q, D;        // lattice of the run (9 / 2 or 19 / 3)
+    double* fS;      // [nc][Q][vol] populations (EFS: the transformed populations f - fF/2)
+    double* fC;      // [nc][Q][vol] post-collision
     double* rho;     // [nc][vol]
-    double* F;       // [nc][2][vol]
-    double* ueq;     // [2][vol]   common equilibrium velocity (EFS)
-    double* uph;     // [2][vol]   physical velocity
-    double* fold;    // [nc][9][3 planes] populations of rows 0..2 before the collision (convective outlet)
+    double* F;       // [nc][D][vol]
+    double* ueq;     // [D][vol]   common equilibrium velocity (EFS)
+    double* uph;     // [D][vol]   physical velocity
+    double* fold;    // [nc][9][3 planes] populations of rows 0..2 before the collision (convective outlet, D2Q9)
     const uint8_t* cls;
     int z_in, z_in_ghost, z_out;
-    LBM_HD double* f(double* base, int c, int q) const { return base + ((int64_t)c * 9 + q) * g.vol; }
+    LBM_HD double* f(double* base, int c, int q) const { return base + ((int64_t)c * Q + q) * g.vol; }
+    LBM_HD double& Fc(int k, int a, int64_t id) const { return F[((int64_t)k * D + a) * g.vol + id]; }
 };
 
-LBM_HD double sc_feq(int q, double rho, double ux, double uy) {
-    const double eu = D2Q9::cx(q) * ux + D2Q9::cy(q) * uy;
-    return D2Q9::w(q) * rho * (1.0 + 3.0 * eu + 9.0 / 2.0 * (eu * eu) - 3.0 / 2.0 * (ux * ux + uy * uy));
+template <class L>
+LBM_HD double sc_feq(int q, double rho, const double* u) {
+    double eu = 0.0, uu = 0.0;
+#pragma unroll
+    for (int a = 0; a < L::D; ++a) {
+        if (L::c(q, a) != 0) eu += L::c(q, a) * u[a];
+        uu += u[a] * u[a];
+    }
+    return L::w(q) * rho * (1.0 + 3.0 * eu + 9.0 / 2.0 * (eu * eu) - 3.0 / 2.0 * uu);
+}
+// first moment sum_q e_q f_q, summed in the order of q (the reference's f1 - f3 + f5 - f6 - f7 + f8)
+template <class L>
+LBM_HD void sc_momentum(const double* f, double* m) {
+#pragma unroll
+    for (int a = 0; a < L::D; ++a) m[a] = 0.0;
+#pragma unroll
+    for (int q = 1; q < L::Q; ++q)
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) {
+            if (L::c(q, a) > 0) m[a] += f[q];
+            else if (L::c(q, a) < 0) m[a] -= f[q];
+        }
 }
 
 // f = w rho at rest (ShanChenD2Q9.py:759-768)
+template <class L>
 struct ScInitOp {
     SCFields c; const double* rho_in;     // [nc][owned]
     LBM_HD void operator()(int64_t i) const {
@@ -49,35 +73,38 @@ struct ScInitOp {
         for (int k = 0; k < c.p.nc; ++k) {
             const double r = fl ? rho_in[k * owned + i] : 0.0;
             c.rho[k * g.vol + id] = r;
-            for (int q = 0; q < 9; ++q) c.f(c.fS, k, q)[id] = D2Q9::w(q) * r;
-            c.F[(k * 2) * g.vol + id] = 0.0; c.F[(k * 2 + 1) * g.vol + id] = 0.0;
+            for (int q = 0; q < L::Q; ++q) c.f(c.fS, k, q)[id] = L::w(q) * r;
+            for (int a = 0; a < L::D; ++a) c.Fc(k, a, id) = 0.0;
         }
-        c.ueq[id] = c.ueq[g.vol + id] = c.uph[id] = c.uph[g.vol + id] = 0.0;
+        for (int a = 0; a < L::D; ++a) c.ueq[a * g.vol + id] = c.uph[a * g.vol + id] = 0.0;
     }
 };
-struct ScUploadOp {     // AoS [node][9] of one component -> SoA; rho = given or sum
+template <class L>
+struct ScUploadOp {     // AoS [node][Q] of one component -> SoA; rho = given or sum
     SCFields c; int k; const double* aos; const double* rho_in;
     LBM_HD void operator()(int64_t i) const {
         const Grid& g = c.g; const int64_t id = (int64_t)NG * g.plane + i;
         const bool fl = c.cls[id] & CLS_FLUID;
         double s = 0.0;
-        for (int q = 0; q < 9; ++q) {
-            const double v = fl ? aos[i * 9 + q] : 0.0;
+        for (int q = 0; q < L::Q; ++q) {
+            const double v = fl ? aos[i * L::Q + q] : 0.0;
             c.f(c.fS, k, q)[id] = v;
             s = q == 0 ? v : s + v;
         }
         c.rho[k * g.vol + id] = fl ? (rho_in ? rho_in[i] : s) : 0.0;
     }
 };
+template <class L>
 struct ScDownloadOp {
     SCFields c; int k; double* aos;
     LBM_HD void operator()(int64_t i) const {
         const int64_t id = (int64_t)NG * c.g.plane + i;
-        for (int q = 0; q < 9; ++q) aos[i * 9 + q] = c.f(c.fS, k, q)[id];
+        for (int q = 0; q < L::Q; ++q) aos[i * L::Q + q] = c.f(c.fS, k, q)[id];
     }
 };
 
 // calFluidRhoGPU (OptimizedD2Q9GPU.py:84-93)
+template <class L>
 struct ScRhoOp {
     SCFields c;
     LBM_HD void operator()(int64_t i) const {
@@ -85,27 +112,28 @@ struct ScRhoOp {
         if (!(c.cls[id] & CLS_FLUID)) return;
         for (int k = 0; k < c.p.nc; ++k) {
             double s = c.f(c.fS, k, 0)[id];
-            for (int q = 1; q < 9; ++q) s += c.f(c.fS, k, q)[id];
+            for (int q = 1; q < L::Q; ++q) s += c.f(c.fS, k, q)[id];
             c.rho[k * c.g.vol + id] = s;
         }
     }
 };
 
-// calPhysicalVelocity (OptimizedD2Q9GPU.py:156-175)
+// calPhysicalVelocity (OptimizedD2Q9GPU.py:156-175): u = sum_k (sum_q e_q f_k,q + F_k / 2) / sum_k rho_k
+template <class L>
 struct ScPhysicalVelocityOp {
     SCFields c;
     LBM_HD void operator()(int64_t i) const {
         const Grid& g = c.g; const int64_t id = (int64_t)NG * g.plane + i;
         if (!(c.cls[id] & CLS_FLUID)) return;
-        double vx = 0.0, vy = 0.0, r = 0.0;
+        double v[3] = {0.0, 0.0, 0.0}, r = 0.0;
         for (int k = 0; k < c.p.nc; ++k) {
-            const double f1 = c.f(c.fS, k, 1)[id], f2 = c.f(c.fS, k, 2)[id], f3 = c.f(c.fS, k, 3)[id], f4 = c.f(c.fS, k, 4)[id];
-            const double f5 = c.f(c.fS, k, 5)[id], f6 = c.f(c.fS, k, 6)[id], f7 = c.f(c.fS, k, 7)[id], f8 = c.f(c.fS, k, 8)[id];
-            vx += (f1 - f3 + f5 - f6 - f7 + f8 + 1.0 / 2.0 * c.F[(k * 2) * g.vol + id]);
-            vy += (f2 - f4 + f5 + f6 - f7 - f8 + 1.0 / 2.0 * c.F[(k * 2 + 1) * g.vol + id]);
+            double f[L::Q], m[3];
+            for (int q = 1; q < L::Q; ++q) f[q] = c.f(c.fS, k, q)[id];
+            sc_momentum<L>(f, m);
+            for (int a = 0; a < L::D; ++a) v[a] += (m[a] + 1.0 / 2.0 * c.Fc(k, a, id));
             r += c.rho[k * g.vol + id];
         }
-        c.uph[id] = vx / r; c.uph[g.vol + id] = vy / r;
+        for (int a = 0; a < L::D; ++a) c.uph[a * g.vol + id] = v[a] / r;
     }
 };
 
@@ -197,6 +225,7 @@ struct ScConvectiveEachOp {
 };
 
 // pull streaming with half-way bounce back + densities (calStreaming1GPU/2GPU 450-548, calFluidRhoGPU)
+template <class L>
 struct ScStreamOp {
     SCFields c;
     LBM_HD void operator()(int64_t i) const {
@@ -204,16 +233,18 @@ struct ScStreamOp {
         int x, y, z; g.decode(i, 0, x, y, z);
         const int64_t id = g.at(x, y, z);
         if (!(c.cls[id] & CLS_FLUID)) return;
-        int64_t src[9]; bool fl[9];
-        for (int q = 1; q < 9; ++q) {
-            src[q] = g.nb(x, y, z, -D2Q9::d0(q), 0, -D2Q9::d2(q));
+        int64_t src[L::Q]; bool fl[L::Q];
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            src[q] = g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q));
             fl[q] = c.cls[src[q]] & CLS_FLUID;
         }
         for (int k = 0; k < c.p.nc; ++k) {
             double acc = c.f(c.fC, k, 0)[id];
             c.f(c.fS, k, 0)[id] = acc;
-            for (int q = 1; q < 9; ++q) {
-                const double v = fl[q] ? c.f(c.fC, k, q)[src[q]] : c.f(c.fC, k, D2Q9::opp(q))[id];
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                const double v = fl[q] ? c.f(c.fC, k, q)[src[q]] : c.f(c.fC, k, L::opp(q))[id];
                 c.f(c.fS, k, q)[id] = v;
                 acc += v;
             }
@@ -223,8 +254,9 @@ struct ScStreamOp {
 };
 
 // interactionCollisionProcess (OptimizedD2Q9GPU.py:1274-1446): common velocity u', Shan-Chen force with
-// psi = rho (fluid-fluid through the neighbours, fluid-solid with weights 1/9, 1/36), SRT collision towards
-// f_eq(rho, u' + tau F / rho).  fS -> fC, writes F.
+// psi = rho (fluid-fluid through the neighbours, fluid-solid with the lattice weights 1/9, 1/36 | 1/18, 1/36),
+// SRT collision towards f_eq(rho, u' + tau F / rho).  fS -> fC, writes F.
+template <class L>
 struct ScCollideOp {
     SCFields c;
     LBM_HD void operator()(int64_t i) const {
@@ -233,45 +265,63 @@ struct ScCollideOp {
         const int64_t id = g.at(x, y, z), V = g.vol;
         if (!(c.cls[id] & CLS_FLUID)) return;
         const int nc = c.p.nc;
-        double f[SC_MAXC][9];
-        double vxt = 0.0, vyt = 0.0, rt = 0.0;
+        double vt[3] = {0.0, 0.0, 0.0}, rt = 0.0;
         for (int k = 0; k < nc; ++k) {
-            for (int q = 0; q < 9; ++q) f[k][q] = c.f(c.fS, k, q)[id];
-            vxt += (f[k][1] - f[k][3] + f[k][5] - f[k][6] - f[k][7] + f[k][8]) / c.p.tau[k];
-            vyt += (f[k][2] - f[k][4] + f[k][5] + f[k][6] - f[k][7] - f[k][8]) / c.p.tau[k];
+            double f[L::Q], m[3];
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) f[q] = c.f(c.fS, k, q)[id];
+            sc_momentum<L>(f, m);
+#pragma unroll
+            for (int a = 0; a < L::D; ++a) vt[a] += m[a] / c.p.tau[k];
             rt += c.rho[k * V + id] / c.p.tau[k];
         }
-        const double upx = vxt / rt, upy = vyt / rt;
-        int64_t nb[9]; bool fl[9];
-        for (int q = 1; q < 9; ++q) {
-            nb[q] = g.nb(x, y, z, D2Q9::d0(q), 0, D2Q9::d2(q));
+        double up[3];
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) up[a] = vt[a] / rt;
+        int64_t nb[L::Q]; bool fl[L::Q];
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            nb[q] = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
             fl[q] = c.cls[nb[q]] & CLS_FLUID;
         }
         for (int k = 0; k < nc; ++k) {
             const double psi = c.rho[k * V + id];
-            double fx = 0.0, fy = 0.0;
-            for (int q = 1; q < 9; ++q) {
-                const double wI = q < 5 ? 1.0 / 9.0 : 1.0 / 36.0;
+            double F[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                const double wI = L::w(q);
                 if (fl[q]) {
                     for (int j = 0; j < nc; ++j) {
                         const double t = -wI * c.p.G[k * SC_MAXC + j] * psi * c.rho[j * V + nb[q]];
-                        if (D2Q9::cx(q) != 0) fx += t * D2Q9::cx(q);
-                        if (D2Q9::cy(q) != 0) fy += t * D2Q9::cy(q);
+#pragma unroll
+                        for (int a = 0; a < L::D; ++a)
+                            if (L::c(q, a) != 0) F[a] += t * L::c(q, a);
                     }
                 } else {
                     const double t = -wI * c.p.Gs[k] * psi;
-                    if (D2Q9::cx(q) != 0) fx += t * D2Q9::cx(q);
-                    if (D2Q9::cy(q) != 0) fy += t * D2Q9::cy(q);
+#pragma unroll
+                    for (int a = 0; a < L::D; ++a)
+                        if (L::c(q, a) != 0) F[a] += t * L::c(q, a);
                 }
             }
-            c.F[(k * 2) * V + id] = fx; c.F[(k * 2 + 1) * V + id] = fy;
             const double tau = c.p.tau[k];
-            const double ux = upx + tau * fx / psi, uy = upy + tau * fy / psi;
-            const double uu = ux * ux + uy * uy;
-            for (int q = 0; q < 9; ++q) {
-                const double eu = D2Q9::cx(q) * ux + D2Q9::cy(q) * uy;
-                c.f(c.fC, k, q)[id] = (1.0 - 1.0 / tau) * f[k][q] +
-                                      D2Q9::w(q) * psi / tau * (1.0 + 3.0 * eu + 4.5 * (eu * eu) - 1.5 * uu);
+            double u[3];
+#pragma unroll
+            for (int a = 0; a < L::D; ++a) {
+                c.Fc(k, a, id) = F[a];
+                u[a] = up[a] + tau * F[a] / psi;
+            }
+            double uu = 0.0;
+#pragma unroll
+            for (int a = 0; a < L::D; ++a) uu += u[a] * u[a];
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) {
+                double eu = 0.0;
+#pragma unroll
+                for (int a = 0; a < L::D; ++a)
+                    if (L::c(q, a) != 0) eu += L::c(q, a) * u[a];
+                c.f(c.fC, k, q)[id] = (1.0 - 1.0 / tau) * c.f(c.fS, k, q)[id] +
+                                      L::w(q) * psi / tau * (1.0 + 3.0 * eu + 4.5 * (eu * eu) - 1.5 * uu);
             }
         }
     }
@@ -330,6 +380,8 @@ LBM_HD void efs_force_iso(const SCFields& c, int x, int y, int z, int64_t id, in
 
 // calExplicit4thOrderScheme (ExplicitD2Q9GPU.py:51-217) + calEquilibriumVEFGPU (340-363, SRT) /
 // transformEquilibriumVelocity (1426-1449, MRT: weights s_0 = 1 instead of 1/tau).  Writes F and u_eq.
+// Interaction weights 3 w_q (D2Q9: 1/3, 1/12 -- ShanChenD2Q9.py:1675; D3Q19: 1/6, 1/12).
+template <class L>
 struct EfsForceOp {
     SCFields c;
     LBM_HD void operator()(int64_t i) const {
@@ -338,92 +390,128 @@ struct EfsForceOp {
         const int64_t id = g.at(x, y, z), V = g.vol;
         if (!(c.cls[id] & CLS_FLUID)) return;
         const int nc = c.p.nc;
-        int64_t nb[9]; bool fl[9];
-        for (int q = 1; q < 9; ++q) {
-            nb[q] = g.nb(x, y, z, D2Q9::d0(q), 0, D2Q9::d2(q));
+        int64_t nb[L::Q]; bool fl[L::Q];
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            nb[q] = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
             fl[q] = c.cls[nb[q]] & CLS_FLUID;
         }
-        double mx = 0.0, my = 0.0, rt = 0.0;
+        double mt[3] = {0.0, 0.0, 0.0}, rt = 0.0;
         for (int k = 0; k < nc; ++k) {
             const double psi = c.rho[k * V + id];
-            double gx = 0.0, gy = 0.0, sx = 0.0, sy = 0.0;
-            for (int q = 1; q < 9; ++q) {
-                const double wI = q < 5 ? 1.0 / 3.0 : 1.0 / 12.0;
+            double gr[3] = {0.0, 0.0, 0.0}, sl[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                const double wI = L::D == 2 ? (q < 5 ? 1.0 / 3.0 : 1.0 / 12.0) : (q < 7 ? 1.0 / 6.0 : 1.0 / 12.0);
                 if (fl[q]) {
                     for (int j = 0; j < nc; ++j) {
                         const double t = wI * (c.rho[j * V + nb[q]] - c.rho[j * V + id]);
-                        if (D2Q9::cx(q) != 0) gx += t * D2Q9::cx(q) * c.p.G[k * SC_MAXC + j];
-                        if (D2Q9::cy(q) != 0) gy += t * D2Q9::cy(q) * c.p.G[k * SC_MAXC + j];
+#pragma unroll
+                        for (int a = 0; a < L::D; ++a)
+                            if (L::c(q, a) != 0) gr[a] += t * L::c(q, a) * c.p.G[k * SC_MAXC + j];
                     }
                 } else {
                     const double t = -wI * c.p.Gs[k] * psi;
-                    if (D2Q9::cx(q) != 0) sx += t * D2Q9::cx(q);
-                    if (D2Q9::cy(q) != 0) sy += t * D2Q9::cy(q);
+#pragma unroll
+                    for (int a = 0; a < L::D; ++a)
+                        if (L::c(q, a) != 0) sl[a] += t * L::c(q, a);
                 }
             }
-            double fx = -6.0 * psi * gx + sx, fy = -6.0 * psi * gy + sy;
-            if (c.p.scheme != 4) efs_force_iso(c, x, y, z, id, k, &fx, &fy);
-            c.F[(k * 2) * V + id] = fx; c.F[(k * 2 + 1) * V + id] = fy;
-            double ex = 0.0, ey = 0.0;
-            for (int q = 0; q < 9; ++q) {
-                const double v = c.f(c.fS, k, q)[id];
-                ex += v * D2Q9::cx(q); ey += v * D2Q9::cy(q);
-            }
-            ex += 1.0 / 2.0 * fx; ey += 1.0 / 2.0 * fy;
+            double F[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int a = 0; a < L::D; ++a) F[a] = -6.0 * psi * gr[a] + sl[a];
+            if (L::D == 2 && c.p.scheme != 4) efs_force_iso(c, x, y, z, id, k, &F[0], &F[1]);
+            double f[L::Q], e[3];
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) f[q] = c.f(c.fS, k, q)[id];
+            sc_momentum<L>(f, e);
             const double wgt = c.p.relax == 0 ? 1.0 / c.p.tau[k] : 1.0;
-            if (c.p.relax == 0) { mx += ex / c.p.tau[k]; my += ey / c.p.tau[k]; rt = rt + psi / c.p.tau[k]; }
-            else { mx += ex * wgt; my += ey * wgt; rt += psi * wgt; }
+#pragma unroll
+            for (int a = 0; a < L::D; ++a) {
+                c.Fc(k, a, id) = F[a];
+                const double ea = e[a] + 1.0 / 2.0 * F[a];
+                if (c.p.relax == 0) mt[a] += ea / c.p.tau[k]; else mt[a] += ea * wgt;
+            }
+            if (c.p.relax == 0) rt = rt + psi / c.p.tau[k]; else rt += psi * wgt;
         }
-        c.ueq[id] = mx / rt; c.ueq[V + id] = my / rt;
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) c.ueq[a * V + id] = mt[a] / rt;
     }
 };
 
 // equilibrium and force distributions of component k at a node (calEquilibriumFuncEFGPU 227-248,
 // calForceDistrGPU 255-272)
+template <class L>
 LBM_HD void efs_feq_ff(const SCFields& c, int k, int64_t id, double* feq, double* ff) {
     const int64_t V = c.g.vol;
-    const double r = c.rho[k * V + id], ux = c.ueq[id], uy = c.ueq[V + id];
-    const double fx = c.F[(k * 2) * V + id], fy = c.F[(k * 2 + 1) * V + id];
-    for (int q = 0; q < 9; ++q) {
-        feq[q] = sc_feq(q, r, ux, uy);
-        ff[q] = ((fx * (D2Q9::cx(q) - ux)) + (fy * (D2Q9::cy(q) - uy))) * feq[q] / (1.0 / 3.0 * r);
+    const double r = c.rho[k * V + id];
+    double u[3] = {0.0, 0.0, 0.0}, F[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < L::D; ++a) { u[a] = c.ueq[a * V + id]; F[a] = c.Fc(k, a, id); }
+#pragma unroll
+    for (int q = 0; q < L::Q; ++q) {
+        feq[q] = sc_feq<L>(q, r, u);
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) s += F[a] * (L::c(q, a) - u[a]);
+        ff[q] = s * feq[q] / (1.0 / 3.0 * r);
     }
 }
 // transformPDFGPU (ExplicitD2Q9GPU.py:278-287), once before the first iteration: f <- f - fF / 2
+template <class L>
 struct EfsTransformOp {
     SCFields c;
     LBM_HD void operator()(int64_t i) const {
         const int64_t id = (int64_t)NG * c.g.plane + i;
         if (!(c.cls[id] & CLS_FLUID)) return;
         for (int k = 0; k < c.p.nc; ++k) {
-            double feq[9], ff[9];
-            efs_feq_ff(c, k, id, feq, ff);
-            for (int q = 0; q < 9; ++q) c.f(c.fS, k, q)[id] = c.f(c.fS, k, q)[id] - 1.0 / 2.0 * ff[q];
+            double feq[L::Q], ff[L::Q];
+            efs_feq_ff<L>(c, k, id, feq, ff);
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) c.f(c.fS, k, q)[id] = c.f(c.fS, k, q)[id] - 1.0 / 2.0 * ff[q];
         }
     }
 };
+// relaxation rates of the non-conserved moments: D2Q9 s = [1, 0.6, 1.5, 1, 1.2, 1, 1.2, 1/tau, 1/tau] for the first
+// two components, 1 (and 1/tau on the stress moments) for further ones (ShanChenD2Q9.py:99-106, 484-496); D3Q19:
+// the d'Humieres rates of the colour-gradient specification (1.19, 1.4, 1.2, 1.4, 1.98), 1/tau on the five
+// stress moments (oracle/sc_dense.py)
+template <class L>
+LBM_HD void efs_scale_moments(double* m, double st, bool tuned) {
+    if (L::Q == 9) {
+        if (tuned) { m[1] *= 0.6; m[2] *= 1.5; m[4] *= 1.2; m[6] *= 1.2; }
+        m[7] *= st; m[8] *= st;
+    } else {
+        if (tuned) {
+            m[1] *= 1.19; m[2] *= 1.4; m[4] *= 1.2; m[6] *= 1.2; m[8] *= 1.2; m[10] *= 1.4; m[12] *= 1.4;
+            m[16] *= 1.98; m[17] *= 1.98; m[18] *= 1.98;
+        }
+        m[9] *= st; m[11] *= st; m[13] *= st; m[14] *= st; m[15] *= st;
+    }
+}
 // calCollisionEXGPU (294-304) / transfromForceTerm + transformPDFandEquil + calAfterCollisionMRT
-// (1379-1469): f <- f + C (feq - f - fF/2) + fF with C = 1/tau (SRT) or M^-1 diag(s) M (MRT),
-// s = [1, 0.6, 1.5, 1, 1.2, 1, 1.2, 1/tau, 1/tau] for the first two components (ShanChenD2Q9.py:99-106)
+// (1379-1469): f <- f + C (feq - f - fF/2) + fF with C = 1/tau (SRT) or M^-1 diag(s) M (MRT)
+template <class L>
 struct EfsCollideOp {
     SCFields c;
     LBM_HD void operator()(int64_t i) const {
         const int64_t id = (int64_t)NG * c.g.plane + i;
         if (!(c.cls[id] & CLS_FLUID)) return;
         for (int k = 0; k < c.p.nc; ++k) {
-            double feq[9], ff[9], f[9], d[9];
-            efs_feq_ff(c, k, id, feq, ff);
-            for (int q = 0; q < 9; ++q) { f[q] = c.f(c.fS, k, q)[id]; d[q] = feq[q] - f[q] - 1.0 / 2.0 * ff[q]; }
+            double feq[L::Q], ff[L::Q], f[L::Q], d[L::Q];
+            efs_feq_ff<L>(c, k, id, feq, ff);
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) { f[q] = c.f(c.fS, k, q)[id]; d[q] = feq[q] - f[q] - 1.0 / 2.0 * ff[q]; }
             if (c.p.relax == 0) {
-                for (int q = 0; q < 9; ++q) c.f(c.fC, k, q)[id] = f[q] + 1.0 / c.p.tau[k] * d[q] + 1.0 * ff[q];
+#pragma unroll
+                for (int q = 0; q < L::Q; ++q) c.f(c.fC, k, q)[id] = f[q] + 1.0 / c.p.tau[k] * d[q] + 1.0 * ff[q];
             } else {
-                double m[9], cd[9];
-                D2Q9::to_moments(d, m);
-                const double st = 1.0 / c.p.tau[k];
-                if (k < 2) { m[1] *= 0.6; m[2] *= 1.5; m[4] *= 1.2; m[6] *= 1.2; }
-                m[7] *= st; m[8] *= st;
-                D2Q9::from_moments(m, cd);
-                for (int q = 0; q < 9; ++q) c.f(c.fC, k, q)[id] = f[q] + cd[q] + 1.0 * ff[q];
+                double m[L::Q], cd[L::Q];
+                L::to_moments(d, m);
+                efs_scale_moments<L>(m, 1.0 / c.p.tau[k], k < 2);
+                L::from_moments(m, cd);
+#pragma unroll
+                for (int q = 0; q < L::Q; ++q) c.f(c.fC, k, q)[id] = f[q] + cd[q] + 1.0 * ff[q];
             }
         }
     }

@@ -259,3 +259,49 @@ def case_d3q19_open_boundaries(lib_path, inlet="Neumann", outlet="Convective", n
     bc = dict(inlet=inlet, outlet=outlet, v_inlet=-2.0e-3, dBH=5e-8, dRH=1.004, dBL=1.0, dRL=5e-8)
     return run_dense_case(19, dom, np.where(red, 1.0, 5e-8), np.where(red, 5e-8, 1.0), steps, lib_path, atol=1e-9,
                           relax=relax, chunk=[1, 3, steps - 4], bc=bc, contact_angle_deg=65.0, **par)
+
+
+# ---------------------------------------------------------------------------------------------------
+# D3Q19 Shan-Chen (original and explicit forcing) against the lattice-generic dense oracle
+# ---------------------------------------------------------------------------------------------------
+def run_sc_dense_case(lattice, dom, rho, steps, lib_path, model="EFS", relax="SRT", tau=(1.0, 0.9), G=0.2,
+                      Gs=(-0.14, 0.14), atol=1e-10, chunk=None, **extra):
+    """CUDA path vs oracle/sc_dense.py on the same input: densities, velocities and populations of every chunk"""
+    from oracle import sc_dense
+    L = sc_dense.d2q9() if lattice == 9 else sc_dense.d3q19()
+    sim = sc_dense.SCDense(L, dom, model=model, relax=relax, tau=tau, G=G, Gs=Gs)
+    sim.set_densities(rho)
+    eng = _lib.Engine(lattice, dom.shape, model=_lib.MODEL_SC if model == "ShanChen" else _lib.MODEL_EFS,
+                      relax=RELAX[relax], lib_path=lib_path, n_components=2, sc_tau=list(tau),
+                      sc_G=[0.0, G, 0.0, 0.0, G, 0.0], sc_Gsolid=list(Gs), **extra)
+    eng.set_geometry(dom)
+    eng.init_equilibrium(*[np.where(dom, r, 0.0) for r in rho])
+    shp = dom.shape
+    done = 0
+    for n in (chunk or [steps]):
+        eng.step(n)
+        sim.step(n)
+        done += n
+        r, u = eng.download_macros()
+        for k in range(2):
+            np.testing.assert_allclose(r[k], sim.rho[k].reshape(shp), rtol=0, atol=atol, err_msg="rho%d after %d" % (k, done))
+        for a in range(L.D):
+            np.testing.assert_allclose(u[a], sim.uph[a].reshape(shp), rtol=0, atol=atol, err_msg="u%d after %d" % (a, done))
+    pdf = eng.download_pdfs()
+    for k in range(2):
+        np.testing.assert_allclose(pdf[k], np.moveaxis(sim.f[k], 0, -1).reshape(shp + (L.Q,)), rtol=0, atol=atol)
+    m = eng.total_mass()
+    eng.close()
+    return m, sim.rho.sum(axis=(1, 2, 3))
+
+
+def case_sc_d3q19(lib_path, model="EFS", relax="SRT", n=(10, 12, 14), steps=8, solid=True, **extra):
+    rng = np.random.default_rng(23)
+    dom = np.ones(n, bool)
+    if solid:
+        dom &= sphere_geometry(n, 2.6)
+        dom[0:2, 0:3, :] = False           # a bar through the periodic x faces, touching the z = 0 face
+    r0 = 0.6 + 0.3 * (rng.random(n) - 0.5)
+    G = 3.0 if model == "ShanChen" else 0.2
+    return run_sc_dense_case(19, dom, [r0, 1.1 - r0], steps, lib_path, model=model, relax=relax, G=G,
+                             chunk=[1, 2, steps - 3], **extra)

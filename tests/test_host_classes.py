@@ -73,9 +73,24 @@ def test_cg3d_class_and_main(hostlib, monkeypatch):
     monkeypatch.chdir(os.path.join(REF_INI, "cg3d"))
     assert main.main(["3D", "flow", "CG", "--ini", os.path.join(REF_INI, "cg3d")]) == 0
     assert main.main(["2D", "transport", "CG"]) == 2
+
+
+def test_sc3d_class_and_main(hostlib):
+    """`ShanChenD3Q19(ini).runEFS4LBM3DGPU()` (main.py:73-77): the class the reference names but does not ship"""
+    import main
     from openlbmpm_b200.ShanChenD3Q19 import ShanChenD3Q19
-    with pytest.raises(NotImplementedError):
-        ShanChenD3Q19("x").runEFS4LBM3DGPU()
+    from oracle import sc_dense
+    sim = ShanChenD3Q19(os.path.join(REF_INI, "efs3d"), verbose=False)
+    sim.runEFS4LBM3DGPU()
+    assert sim.fluidsDensity.shape == (2, 24, 10, 12) and sim.fluidPDF.shape == (2, 24, 10, 12, 19)
+    assert sim.neighboringNodes.size == 18 * sim.fluidNodes.size and sim.physicalVZ.shape == (24, 10, 12)
+    ref = sc_dense.SCDense(sc_dense.d3q19(), sim.isDomain, model="EFS", relax="MRT", tau=(1., 1.), G=0.2, Gs=(-0.14, 0.14))
+    reg = np.indices((24, 10, 12))[0] < 14
+    ref.set_densities(np.stack([np.where(reg, 1.0, 0.02), np.where(reg, 0.02, 1.0)]))
+    ref.step(sim.numTimeStep + 1)               # the reference's loops run numTimeStep + 1 iterations
+    np.testing.assert_allclose(sim.fluidsDensity, ref.rho, atol=1e-10)
+    np.testing.assert_allclose(sim.physicalVZ, ref.uph[2], atol=1e-10)
+    assert main.main(["3D", "flow", "SC", "--ini", os.path.join(REF_INI, "efs3d")]) == 0
 
 
 def test_missing_key_exits_like_the_reference(hostlib, tmp_path):
