@@ -133,17 +133,29 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             __pipeline_memcpy_async(&sphi[slot][ly][lx], src + (int64_t)wrapy(y0 + ly - 2) * g.n0 + wrapx(x0 + lx - 2), 8);
         }
     };
-    auto normal_plane = [&](int zp) {
+    // elements of the normal tile this thread fills (NE per plane) and their in-plane offsets; with solids the
+    // node classes of the NEXT plane are requested together with the populations, before the tile synchronises
+    constexpr int NE = (NH * NW + NT - 1) / NT;
+    int noff[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int e = tid + k * NT, ly = e / NW, lx = e - ly * NW;
+        noff[k] = e < NH * NW ? wrapy(y0 + ly - 1) * g.n0 + wrapx(x0 + lx - 1) : -1;
+    }
+    auto class_plane = [&](int zp, uint8_t* cl) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) cl[k] = (SOLIDS && noff[k] >= 0) ? c.cls[(int64_t)(zp + NG) * g.plane + noff[k]] : (uint8_t)CLS_FLUID;
+    };
+    auto normal_plane = [&](int zp, const uint8_t* cl) {
         const int slot = (zp + 9) % 3;
-        for (int e = tid; e < NH * NW; e += NT) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const int e = tid + k * NT;
+            if (e >= NH * NW) break;
             const int ly = e / NW, lx = e - ly * NW;
             double G[3] = {0.0, 0.0, 0.0}, n[3] = {0.0, 0.0, 0.0}, gn = 0.0;
-            bool fluid = true;
-            int64_t id = 0;
-            if (SOLIDS) {
-                id = (int64_t)(zp + NG) * g.plane + (int64_t)wrapy(y0 + ly - 1) * g.n0 + wrapx(x0 + lx - 1);
-                fluid = c.cls[id] & CLS_FLUID;
-            }
+            const bool fluid = cl[k] & CLS_FLUID;
+            const int64_t id = (int64_t)(zp + NG) * g.plane + noff[k];
             if (fluid) {
                 // G = 3 sum_q w_q e_q phi(x + e_q) grouped as (1/6) * face differences + (1/12) * edge differences.
                 // (3-D runs WettingType 2 only, whose 1e-8 threshold on |G| makes the exact-cancellation care of the
@@ -158,9 +170,9 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
                        (1.0 / 12.0) * (((pxy - mxy) - (pmxy - mpxy)) + ((pyz - myz) + (pmyz - mpyz)));
                 G[2] = (1.0 / 6.0) * (P(0, 0, 1) - P(0, 0, -1)) +
                        (1.0 / 12.0) * (((pxz - mxz) - (pmxz - mpxz)) + ((pyz - myz) - (pmyz - mpyz)));
-                if (SOLIDS && (c.cls[id] & CLS_NEAR)) {
+                if (SOLIDS && (cl[k] & CLS_NEAR)) {
                     const double ns[3] = {c.ns[id], c.ns[V + id], c.ns[2 * V + id]};
-                    cg_wetting<3>(G, ns, c.p.cosT, c.p.sinT, c.p.wetting_type);
+                    cg_wetting<3>(G, ns, c.p.cosT, c.p.sinT, c.p.wetting_type, c.p.exact_trig != 0);
                 }
                 const double g2 = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
                 const double inv = g2 > 0.0 ? rsqrt(g2) : 0.0;
@@ -195,20 +207,30 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     __pipeline_wait_prior(1);
     for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) wait_phi_plane(zp);
     __syncthreads();
-    normal_plane(z_begin - 1);
-    normal_plane(z_begin);
+    uint8_t ncl[NE];
+    class_plane(z_begin - 1, ncl);
+    normal_plane(z_begin - 1, ncl);
+    class_plane(z_begin, ncl);
+    normal_plane(z_begin, ncl);
     // the first asynchronous copy of the loop lands in the slot of plane z_begin - 2, which normal_plane(z_begin - 1)
     // has just read: every thread must be done with it first (found as a run-to-run difference at 256^3)
     __syncthreads();
 
     const double sgn = c.p.wetting_type == 1 ? 1.0 : -1.0;
+    uint32_t pm_next = 1u;
+    if (SOLIDS) pm_next = c.pull[(int64_t)(z_begin + NG) * g.plane + yo[1] + xo[1]];
     for (int z = z_begin; z < z_end; ++z) {
         if (z + 1 < z_end) load_phi_plane(z + 3);       // needed by the NEXT plane step
         __pipeline_commit();
         // ---- requests to HBM first: pulled populations, densities, lagged force ----
         const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
-        bool fluid = true;
-        if (SOLIDS) fluid = c.cls[id] & CLS_FLUID;
+        // pull mask (grid.cuh::PullMaskOp): arrived one plane step ago, the next one is requested now
+        uint32_t pm = 0xFFFFFFFFu;
+        if (SOLIDS) {
+            pm = pm_next;
+            if (z + 1 < z_end) pm_next = c.pull[id + g.plane];
+        }
+        const bool fluid = pm & 1u;
         double fT[L::Q];
         double rR = 1.0, rB = 1.0, Fl[3] = {0.0, 0.0, 0.0}, phi0 = 0.0;
         if (fluid) {
@@ -217,17 +239,18 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             for (int q = 1; q < L::Q; ++q) {
                 const int64_t src = (int64_t)(z - L::d2(q) + NG) * g.plane + yo[1 - L::d1(q)] + xo[1 - L::d0(q)];
                 int64_t addr = q * V + src;
-                if (SOLIDS && !(c.cls[src] & CLS_FLUID)) addr = L::opp(q) * V + id;
+                if (SOLIDS && !(pm & (1u << q))) addr = L::opp(q) * V + id;      // half-way bounce back
                 fT[q] = __ldcs(s.gT + addr);
             }
             rR = c.rho[0][id]; rB = c.rho[1][id];
 #pragma unroll
             for (int d = 0; d < 3; ++d) Fl[d] = c.F[d * V + id];
         }
+        class_plane(z + 1, ncl);
         __pipeline_wait_prior(1);                       // plane z + 2 (requested one step ago) has landed
         wait_phi_plane(z + 2);
         __syncthreads();
-        normal_plane(z + 1);
+        normal_plane(z + 1, ncl);
         __syncthreads();
         if (!fluid) continue;
         phi0 = sphi[(z + 10) % 5][ty + 2][tx + 2];
@@ -358,19 +381,23 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
     const int64_t yo[3] = {(int64_t)wrapy(y - 1) * g.n0, (int64_t)y * g.n0, (int64_t)wrapy(y + 1) * g.n0};
 
     // request the pulled populations of plane z: values + bit mask of the directions whose upstream node is fluid
-    auto request = [&](int z, double* f, unsigned& mask, bool& fluid) {
+    // `pm` = the node's pull mask (grid.cuh::PullMaskOp), requested one plane step before the populations it steers
+    auto request = [&](int z, uint32_t pm, double* f, unsigned& mask, bool& fluid) {
         const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
-        fluid = true; mask = 0xFFFFFFFFu;
-        if (SOLIDS) fluid = c.cls[id] & CLS_FLUID;
+        mask = SOLIDS ? pm : 0xFFFFFFFFu;
+        fluid = mask & 1u;
         if (!fluid) return;
         f[0] = __ldcs(s.gT + id);
 #pragma unroll
         for (int q = 1; q < L::Q; ++q) {
             const int64_t src = (int64_t)(z - L::d2(q) + NG) * g.plane + yo[1 - L::d1(q)] + xo[1 - L::d0(q)];
             int64_t addr = q * V + src;
-            if (SOLIDS && !(c.cls[src] & CLS_FLUID)) { addr = L::opp(q) * V + id; mask &= ~(1u << q); }
+            if (SOLIDS && !(mask & (1u << q))) addr = L::opp(q) * V + id;        // half-way bounce back
             f[q] = __ldcs(s.gT + addr);
         }
+    };
+    auto pull_mask = [&](int z) -> uint32_t {
+        return (SOLIDS && z < z_end) ? c.pull[(int64_t)(z + NG) * g.plane + yo[1] + xo[1]] : 0u;
     };
 
     if (TMA) {
@@ -390,11 +417,14 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
     double cur[L::Q], nxt[L::Q];
     unsigned mcur = 0, mnxt = 0;
     bool fcur = true, fnxt = true;
-    request(z_begin, cur, mcur, fcur);
+    uint32_t pm1 = pull_mask(z_begin + 1), pm2 = 0u;
+    request(z_begin, pull_mask(z_begin), cur, mcur, fcur);
     for (int z = z_begin; z < z_end; ++z) {
         if (z + 1 < z_end) load_scalar_plane(z + 2);    // cp.async, needed by the next plane step
         __pipeline_commit();
-        if (z + 1 < z_end) request(z + 1, nxt, mnxt, fnxt);
+        pm2 = pull_mask(z + 2);
+        if (z + 1 < z_end) request(z + 1, pm1, nxt, mnxt, fnxt);
+        pm1 = pm2;
         __pipeline_wait_prior(1);                       // plane z + 1 has landed
         wait_scalar_plane(z + 1, z_begin - 1);
         __syncthreads();

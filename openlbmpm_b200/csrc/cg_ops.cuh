@@ -20,6 +20,7 @@ struct CGFields {
     double* F;          // [3][vol] CSF force (lagged by one step when the velocity is evaluated)
     double* K;          // curvature
     const uint8_t* cls;
+    const uint32_t* pull;   // [vol] pull masks (tiled kernels, lattices with solids)
     const double* ns;   // [3][vol] solid normals
     // open boundaries (global plane numbers along axis 2; -1000 = not on this slab)
     int inlet, outlet;

@@ -111,6 +111,28 @@ struct SolidNormalOp {
     }
 };
 
+// Pull mask of an owned node for the tiled kernels: bit 0 = the node is fluid, bit q (1..Q-1) = the upstream node
+// x - e_q is fluid (the population is pulled; otherwise it bounces back from the node's own opposite direction),
+// bit 31 = fluid node next to solid.  One coalesced 4-byte load per node replaces Q byte gathers of the class
+// array, and -- unlike those -- it can be requested one plane ahead of the populations it steers.
+constexpr uint32_t PULL_NEAR = 0x80000000u;
+template <class L>
+struct PullMaskOp {
+    Grid g; const uint8_t* cls; uint32_t* pull;
+    LBM_HD void operator()(int64_t i) const {
+        int x, y, z; g.decode(i, 0, x, y, z);
+        const int64_t id = g.at(x, y, z);
+        uint32_t m = 0;
+        if (cls[id] & CLS_FLUID) {
+            m = 1u | ((cls[id] & CLS_NEAR) ? PULL_NEAR : 0u);
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q)
+                if (cls[g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q))] & CLS_FLUID) m |= 1u << q;
+        }
+        pull[id] = m;
+    }
+};
+
 // ---- export of the reference's compact index structures (single slab; bit-exact contract) -------
 struct FlagOp {          // flag[i] = 1 where the owned node has all bits of `mask` set, row-major order
     Grid g; const uint8_t* cls; uint8_t mask; int64_t* flag;

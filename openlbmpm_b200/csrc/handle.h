@@ -19,6 +19,7 @@ struct lbm_handle {
     uint8_t* dom = nullptr;     // [vol] 1 = void
     uint8_t* cls = nullptr;     // [vol] node classes
     double* ns = nullptr;       // [3][vol]
+    uint32_t* pull = nullptr;   // [vol] pull masks of the tiled kernels (grid.cuh::PullMaskOp; D3Q19 with solids only)
     int64_t n_fluid = 0, n_wet = 0, n_near = 0;
     bool has_geometry = false;
     bool has_solid = false;     // any solid node in the slab or its ghost planes

@@ -41,12 +41,14 @@ CGFields lbm_handle::fields() const {
     c.p.sigma = cfg.sigma; c.p.cosT = cos(th); c.p.sinT = sin(th);
     c.p.beta = cfg.beta; c.p.delta = cfg.delta; c.p.tauR = cfg.tauR; c.p.tauB = cfg.tauB;
     c.p.tau_type = cfg.tau_type; c.p.wetting_type = cfg.wetting_type; c.p.relax = cfg.relax;
+    static const int exact_trig = getenv("LBM_WETTING_EXACT_TRIG") ? atoi(getenv("LBM_WETTING_EXACT_TRIG")) : 0;
+    c.p.exact_trig = exact_trig;
     const int64_t cv = (int64_t)Q * g.vol;
     c.fS[0] = fS; c.fS[1] = fS + cv;
     c.fC[0] = fC; c.fC[1] = fC ? fC + cv : nullptr;
     c.rho[0] = rho; c.rho[1] = rho + g.vol;
     c.u = u; c.phi = phi; c.G = G; c.nrm = nrm; c.F = F; c.K = K;
-    c.cls = cls; c.ns = ns;
+    c.cls = cls; c.ns = ns; c.pull = pull;
     c.inlet = cfg.inlet; c.outlet = cfg.outlet;
     // open-boundary rows in local plane numbers; the top rows live on the last rank, the bottom rows on rank 0
     const int off = -100000;
@@ -151,7 +153,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
 #endif
     graph_release(&h->graph, h->stream);
     free_state(h);
-    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns);
+    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull);
     comm_destroy(h);
 #ifndef LBM_HOSTCHECK
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -180,7 +182,8 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
     const Grid& g = h->g;
     const int64_t owned = g.plane * g.n2;
     free_state(h);
-    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns);
+    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull);
+    h->pull = nullptr;
     h->dom = (uint8_t*)dev_alloc(g.vol); h->cls = (uint8_t*)dev_alloc(g.vol);
     h->ns = (double*)dev_alloc(3 * g.vol * sizeof(double));
     dev_zero(h->dom, g.vol, h->stream); dev_zero(h->cls, g.vol, h->stream);
@@ -206,6 +209,11 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
     } else {
         launch(ClassifyOp<3>{g, h->dom, h->cls}, g.count(NG), h->stream);
         launch(SolidNormalOp<3>{g, h->dom, h->cls, h->ns}, g.count(1), h->stream);
+        if (h->has_solid) {
+            h->pull = (uint32_t*)dev_alloc((size_t)g.vol * sizeof(uint32_t));
+            dev_zero(h->pull, (size_t)g.vol * sizeof(uint32_t), h->stream);
+            launch(PullMaskOp<D3Q19>{g, h->cls, h->pull}, g.count(0), h->stream);
+        }
     }
     dev_sync(h->stream);
     h->n_wet = h->n_near = -1;
