@@ -231,6 +231,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             if (z + 1 < z_end) pm_next = c.pull[id + g.plane];
         }
         const bool fluid = pm & 1u;
+        class_plane(z + 1, ncl);                        // node classes of the normal tile of the next plane
         double fT[L::Q];
         double rR = 1.0, rB = 1.0, Fl[3] = {0.0, 0.0, 0.0}, phi0 = 0.0;
         if (fluid) {
@@ -246,13 +247,23 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 #pragma unroll
             for (int d = 0; d < 3; ++d) Fl[d] = c.F[d * V + id];
         }
-        class_plane(z + 1, ncl);
         __pipeline_wait_prior(1);                       // plane z + 2 (requested one step ago) has landed
         wait_phi_plane(z + 2);
         __syncthreads();
         normal_plane(z + 1, ncl);
         __syncthreads();
         if (!fluid) continue;
+        if (SOLIDS) {
+            // The requests above sit in a conditional block; without this fence the compiler sinks the first
+            // arithmetic on the loaded values (0.5 * F, the first moment sums) into that block, i.e. in FRONT of the
+            // two barriers, and every warp then waits for HBM before the shared-memory phase instead of during it
+            // (ncu, porous 256 x 256 x 192: 19.5 % of all stall samples on that one DMUL).  The empty asm makes the
+            // values opaque until here.
+            asm volatile("" : "+d"(fT[0]), "+d"(fT[1]), "+d"(fT[2]), "+d"(fT[3]), "+d"(fT[4]), "+d"(fT[5]), "+d"(fT[6]),
+                              "+d"(fT[7]), "+d"(fT[8]), "+d"(fT[9]), "+d"(fT[10]), "+d"(fT[11]), "+d"(fT[12]), "+d"(fT[13]),
+                              "+d"(fT[14]), "+d"(fT[15]), "+d"(fT[16]), "+d"(fT[17]), "+d"(fT[18]), "+d"(rR), "+d"(rB),
+                              "+d"(Fl[0]), "+d"(Fl[1]), "+d"(Fl[2]));
+        }
         phi0 = sphi[(z + 10) % 5][ty + 2][tx + 2];
         // ---- curvature and force from the normals in shared memory ----
         const int sl = (z + 9) % 3;

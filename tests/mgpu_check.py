@@ -28,6 +28,9 @@ def run(shape_global, dom, rhoR, steps, rank, world, **kw):
     return np.stack(rho + u)
 
 
+OPEN = dict(inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_CONVECTIVE, inlet_velocity=-2.0e-3)
+
+
 def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -39,12 +42,16 @@ def main():
     for name, shape, solid, kw in (("periodic tiled", (16 * world, 16, 32), False, {}),
                                    ("sphere wetting tiled", (16 * world, 16, 32), True, dict(contact_angle_deg=70.0)),
                                    ("general kernels", (8 * world, 10, 12), True, dict(flags=1, contact_angle_deg=50.0)),
-                                   ("untiled fast path", (8 * world, 10, 12), True, dict(flags=2))):
+                                   ("untiled fast path", (8 * world, 10, 12), True, dict(flags=2)),
+                                   # cfg 5 layout: outlet planes on rank 0, inlet planes on the last rank, solids in between
+                                   ("open channel tiled", (16 * world, 16, 32), True, dict(OPEN, contact_angle_deg=60.0)),
+                                   ("open channel general", (16 * world, 16, 32), True, dict(OPEN, flags=1))):
         dom = np.ones(shape, bool)
         if solid:
             z, y, x = np.mgrid[0:shape[0], 0:shape[1], 0:shape[2]]
             dom = ((x - shape[2] / 2) ** 2 + (y - shape[1] / 2) ** 2 + (z - shape[0] / 2 + 0.5) ** 2) > 9.0
-            dom &= ((x - 3) ** 2 + (y - 3) ** 2 + (z - 1) ** 2) > 4.0        # a second solid straddling the slab seam
+            if "inlet" not in kw:      # a second solid straddling the periodic seam (open channels keep their end planes void)
+                dom &= ((x - 3) ** 2 + (y - 3) ** 2 + (z - 1) ** 2) > 4.0
         rhoR = 0.5 + 0.3 * (rng.random(shape) - 0.5)
         kw = dict(kw); kw["flags"] = kw.get("flags", 0) | extra
         mine = run(shape, dom, rhoR, 7, rank, world, **kw)
