@@ -172,7 +172,8 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
                        (1.0 / 12.0) * (((pxz - mxz) - (pmxz - mpxz)) + ((pyz - myz) - (pmyz - mpyz)));
                 if (SOLIDS && (cl[k] & CLS_NEAR)) {
                     const double ns[3] = {c.ns[id], c.ns[V + id], c.ns[2 * V + id]};
-                    cg_wetting<3>(G, ns, c.p.cosT, c.p.sinT, c.p.wetting_type, c.p.exact_trig != 0);
+                    if (c.p.exact_trig || c.p.wetting_type != 2) cg_wetting<3>(G, ns, c.p.cosT, c.p.sinT, c.p.wetting_type);
+                    else cg_wetting_akai3_fast(G, ns, c.p.cosT, c.p.sinT);
                 }
                 const double g2 = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
                 const double inv = g2 > 0.0 ? rsqrt(g2) : 0.0;

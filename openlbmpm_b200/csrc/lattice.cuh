@@ -247,7 +247,7 @@ struct D3Q19 {
 struct CGParams {
     double sigma, cosT, sinT, beta, delta, tauR, tauB;
     int tau_type, wetting_type, relax;
-    int exact_trig;     // tiled kernels: 1 = acos / sin / cos like the reference's wetting kernel, 0 = sin(acos d) as sqrt(1 - d^2)
+    int exact_trig;     // tiled 3-D kernels: 1 = the reference-ordered wetting arithmetic (cg_wetting), 0 = cg_wetting_akai3_fast
 };
 
 // tau(phi) -- AcceleratedRKGPU2D.py:1820-1834 (identical in the four collision/forcing kernels)
@@ -316,7 +316,7 @@ LBM_HD void cg_recolour(const double* fT, double rhoR, double rhoB, const double
 //   type 1: updateColorGradientOnWetting    (1637-1679, Xu et al. 2017; 2-D rotation)
 //   type 2: updateColorGradientOnWettingNew (2428-2492, Akai et al. 2018; any D)
 template <int D>
-LBM_HD void cg_wetting(double* G, const double* ns, double cosT, double sinT, int type, bool exact_trig = true) {
+LBM_HD void cg_wetting(double* G, const double* ns, double cosT, double sinT, int type) {
     // Every product and sum below is rounded separately (mul_rn / add_rn, no FMA contraction): which of the
     // two candidate normals is "closer" is decided by comparing two distances that are EQUAL by symmetry at
     // corner and axis nodes; the reference's tie rule (d1 == d2) only reproduces with its own rounding.
@@ -348,13 +348,8 @@ LBM_HD void cg_wetting(double* G, const double* ns, double cosT, double sinT, in
     // acos outside [-1,1] is NaN on the GPU and ends in "no update" (2451-2460); clamping gives
     // sin(theta') = 0 (or 1.2e-16) and therefore the same outcome without the NaN.
     dot = fmin(1.0, fmax(-1.0, dot));
-    // theta' = acos(dot) only enters through its sine and cosine.  The reference evaluates acos, sin and cos
-    // (2451-2456); the tiled 3-D kernels, whose parity target is the oracle at 1e-10, may take cos(theta') = dot and
-    // sin(theta') = sqrt(1 - dot^2) instead: ~300 FP64 instructions less on the critical path of every tile that
-    // touches a solid surface.  Same outcome at the guards: dot = +-1 gives sin = 0 (exact: 0 or 1.2e-16 < 1e-9).
-    double sth, cth;
-    if (exact_trig) { const double th = acos(dot); sth = sin(th); cth = cos(th); }
-    else { cth = dot; sth = sqrt(fmax(0.0, 1.0 - dot * dot)); }
+    const double th = acos(dot);
+    const double sth = sin(th), cth = cos(th);
     double c1 = 0.0, c2 = 0.0;
     if (fabs(sth) > 1.0e-9) { c1 = M(sinT, cth) / sth; c2 = sinT / sth; }
     double d1 = 0.0, d2 = 0.0, n1[3], n2[3];
@@ -372,6 +367,44 @@ LBM_HD void cg_wetting(double* G, const double* ns, double cosT, double sinT, in
     } else if (d1 > d2) {
 #pragma unroll
         for (int a = 0; a < D; ++a) G[a] = M(-gn, n2[a]);
+    }
+}
+
+// The same Akai-2018 correction for the tiled 3-D kernels, whose parity target is the oracle at 1e-10 (no golden
+// vector hangs on its last bit): one rsqrt instead of three divisions, cos(theta') = dot and sin(theta') =
+// sqrt(1 - dot^2) instead of acos / sin / cos, one reciprocal, and the two candidate distances compared squared.
+// ~80 FP64 instructions instead of ~450 on the critical path of every tile that touches a solid surface.  The
+// guards are those of cg_wetting: |G| <= 1e-8 gives u = 0 and two identical candidates (no update), sin(theta')
+// <= 1e-9 gives c1 = c2 = 0 and two identical candidates (no update).
+LBM_HD void cg_wetting_akai3_fast(double* G, const double* ns, double cosT, double sinT) {
+    const double g2 = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
+    if (!(g2 > 1.0e-16)) return;
+#ifdef __CUDA_ARCH__
+    const double inv = rsqrt(g2);
+#else
+    const double inv = 1.0 / sqrt(g2);
+#endif
+    const double gn = g2 * inv;
+    const double un[3] = {-G[0] * inv, -G[1] * inv, -G[2] * inv};
+    double dot = un[0] * ns[0] + un[1] * ns[1] + un[2] * ns[2];
+    dot = fmin(1.0, fmax(-1.0, dot));
+    const double sth = sqrt(fmax(0.0, 1.0 - dot * dot));
+    if (!(sth > 1.0e-9)) return;
+    const double r = 1.0 / sth, c1 = sinT * dot * r, c2 = sinT * r;
+    double d1 = 0.0, d2 = 0.0, n1[3], n2[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        n1[a] = (cosT - c1) * ns[a] + c2 * un[a];
+        n2[a] = (cosT + c1) * ns[a] - c2 * un[a];
+        d1 += (n1[a] - un[a]) * (n1[a] - un[a]);
+        d2 += (n2[a] - un[a]) * (n2[a] - un[a]);
+    }
+    if (d1 < d2) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) G[a] = -gn * n1[a];
+    } else if (d1 > d2) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) G[a] = -gn * n2[a];
     }
 }
 

@@ -100,3 +100,34 @@ def test_open_boundary_fast_path_equals_general_kernels(lib):
         out.append(np.stack(rho + u))
         eng.close()
     np.testing.assert_allclose(out[0], out[1], rtol=0, atol=cases.ATOL_GOLD)
+
+
+def test_fast_wetting_form_of_the_tiled_kernels_equals_the_reference_ordered_form(lib):
+    """cg_wetting_akai3_fast (rsqrt, sqrt(1 - dot^2), squared distances) vs cg_wetting<3> (acos / sin / cos, the
+    reference's order of operations) on random gradients and solid normals, away from the degenerate alignment
+    G || n_s where the reference's own choice between the two candidates is rounding noise"""
+    import ctypes
+    import numpy as np
+    h = ctypes.CDLL(lib)
+    rng = np.random.default_rng(12)
+    n = 200000
+    G = rng.uniform(-1, 1, (n, 3)) * rng.choice([1.0, 1e-3, 1e-6], (n, 1))
+    ns = rng.uniform(-1, 1, (n, 3)); ns /= np.linalg.norm(ns, axis=1, keepdims=True)
+    dot = -(G * ns).sum(1) / np.linalg.norm(G, axis=1)
+    keep = np.abs(dot) < 1 - 1e-6
+    G, ns = np.ascontiguousarray(G[keep]), np.ascontiguousarray(ns[keep])
+    p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    h.hostcheck_wetting3.argtypes = [ctypes.POINTER(ctypes.c_double)] * 2 + [ctypes.c_double] * 2 + [ctypes.c_int, ctypes.c_int64,
+                                                                                                  ctypes.POINTER(ctypes.c_double)]
+    for theta in (20.0, 60.0, 90.0, 135.0):
+        out = [np.empty_like(G), np.empty_like(G)]
+        for fast in (0, 1):
+            h.hostcheck_wetting3(p(G), p(ns), np.cos(np.radians(theta)), np.sin(np.radians(theta)), fast, len(G), p(out[fast]))
+        rel = np.abs(out[0] - out[1]).max(axis=1) / np.linalg.norm(G, axis=1)
+        assert rel.max() < 1e-10, (theta, rel.max())
+        assert np.abs(np.linalg.norm(out[1], axis=1) / np.linalg.norm(G, axis=1) - 1).max() < 1e-9      # |G| is preserved
+    # tiny gradients (|G| <= 1e-8) and exact alignment: no update
+    Gs = np.array([[1e-9, 0, 0], [0.0, 0.0, 0.3], [0.0, 0.0, -0.3]]); nz = np.array([[0, 0, 1.0]] * 3)
+    o = np.empty_like(Gs)
+    h.hostcheck_wetting3(p(Gs), p(np.ascontiguousarray(nz)), 0.5, np.sqrt(0.75), 1, 3, p(o))
+    assert np.array_equal(o, Gs)
