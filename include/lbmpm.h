@@ -46,6 +46,11 @@ extern "C" {
 #define LBM_MODEL_SC    1   /* original Shan-Chen                    (ShanChen2D/Optimized...)  */
 #define LBM_MODEL_EFS   2   /* explicit-forcing Shan-Chen SRT/MRT    (ShanChen2D/Explicit...)   */
 
+/* lbm_config.surface_tension_type (LBM_MODEL_CG) */
+#define LBM_ST_CSF           0   /* continuum surface force: runRKColorGradient2DCSF (RKD2Q9.py:1225-1490)          */
+#define LBM_ST_PERTURBATION  1   /* perturbation operator, MRT, closed boxes: runRKColorGradient2DPerturbation
+                                    (RKD2Q9.py:979-1219; kernels calRKCollision1GPU2DMRTNew, calRKCollision23GPUNew) */
+
 /* lbm_config.relax */
 #define LBM_RELAX_SRT   0
 #define LBM_RELAX_MRT   1
@@ -83,7 +88,8 @@ typedef struct lbm_config {
     uint32_t flags;
     int32_t n_components;      /* SC/EFS: number of fluids (1..4); CG: ignored (2 colours)  */
     int32_t sc_isotropy;       /* EFS: [ForceScheme] ExplicitScheme 4 | 8 | 10 (0 = 4)      */
-    int32_t reserved_i[2];
+    int32_t surface_tension_type; /* CG: [SurfaceTension] SurfaceTensionType, LBM_ST_*      */
+    int32_t reserved_i[1];
     /* colour gradient */
     double sigma;              /* [SurfaceTension] SurfaceTension(Value)                    */
     double contact_angle_deg;  /* [SurfaceTension] ContactAngle                             */
@@ -99,7 +105,11 @@ typedef struct lbm_config {
     double sc_Gsolid[4];       /* fluid-solid interaction strengths                         */
     double sc_inlet_velocity[4];
     double sc_rho_in[4], sc_rho_out[4];
-    double reserved_d[8];
+    /* colour gradient with the perturbation operator (LBM_ST_PERTURBATION) */
+    double AkR, AkB;           /* [RKParameters] AkR, AkB                                   */
+    double solid_phi;          /* [SolidBoundarySetup] SolidColorDiff: phi seen on solid neighbours */
+    double body_force[3];      /* [BodyForce] bodyForceX, bodyForceY (, Z)                  */
+    double reserved_d[2];
 } lbm_config;
 
 /* ---- lifetime -------------------------------------------------------------------------- */

@@ -35,9 +35,8 @@ class RKColorGradientLBM:
         self._read_domain(ini)
         # surface tension / recolouring (RKD2Q9.py:60-140)
         self.surfaceTensionType = ini.quoted("SurfaceTension", "SurfaceTensionType", default="CSF")
-        if self.surfaceTensionType != "'CSF'":
-            raise IniError("Only SurfaceTensionType 'CSF' is a live path of the reference "
-                           "(runRKColorGradient2DPerturbation is unfinished upstream: RKD2Q9.py:1218-1223).")
+        if self.surfaceTensionType not in ("'CSF'", "'Perturbation'"):
+            raise IniError("SurfaceTensionType must be 'CSF' or 'Perturbation'")
         self.surfaceTension = ini.number("SurfaceTension", "SurfaceTensionValue", "SurfaceTension", default=0.1)
         self.contactAngle = ini.number("SurfaceTension", "ContactAngle", default=90.0)
         self.cosTheta = np.cos(self.contactAngle / 180. * np.pi)
@@ -47,13 +46,20 @@ class RKColorGradientLBM:
         self.deltaValue = ini.number("RKParameters", "DeltaValue", default=0.98)
         self.alphaR = ini.number("RKParameters", "AlphaR", default=4. / 9.)
         self.alphaB = ini.number("RKParameters", "AlphaB", default=4. / 9.)
+        # perturbation operator (RKD2Q9.py:107-133, 182): surface strengths and the colour seen on solid neighbours
+        self.AkR = ini.number("RKParameters", "AkR", default=0.0)
+        self.AkB = ini.number("RKParameters", "AkB", default=0.0)
+        self.solidPhi = ini.number("SolidBoundarySetup", "SolidColorDiff", default=0.0)
         self.tauR = ini.number("FluidParameters", "TauR")
         self.tauB = ini.number("FluidParameters", "TauB")
         self.initialRhoR = ini.number("FluidParameters", "InitialRhoR")
         self.initialRhoB = ini.number("FluidParameters", "InitialRhoB")
         self.tauCalculation = ini.integer("FluidParameters", "TauType", default=2)
         self.isBodyForce = ini.quoted("BodyForce", "isBodyForce", default="no")
-        if self.isBodyForce == "'yes'":
+        self.bodyFX = ini.number("BodyForce", "bodyForceX", default=0.0)
+        self.bodyFY = ini.number("BodyForce", "bodyForceY", default=0.0)
+        self.bodyFZ = ini.number("BodyForce", "bodyForceZ", default=0.0)
+        if self.isBodyForce == "'yes'" and self.surfaceTensionType == "'CSF'":
             raise IniError("A body force is read but never applied by the reference's CSF loop (RKD2Q9.py:1225-1490).")
         self._read_time(ini)
         self.Parallel = ini.quoted("Parallelism", "Parallel", default="yes")
@@ -62,6 +68,15 @@ class RKColorGradientLBM:
         self.numGPUs = ini.integer("Parallelism", "NumGPUs", default=1)
         self.relaxationType = ini.quoted("RelaxationType", "Type", default="MRT")
         self._read_boundaries(ini)
+        if self.surfaceTensionType == "'Perturbation'":
+            # the one combination under which the reference's work-in-progress driver is self-consistent
+            # (RKD2Q9.py:979-1223; tests/golden/gen_goldens_cgp2d.py)
+            if self.relaxationType != "'MRT'":
+                raise IniError("SurfaceTensionType 'Perturbation' runs with RelaxationType 'MRT' (the reference's SRT branch "
+                               "is discarded by its own recolouring step, RKD2Q9.py:1158-1219)")
+            if self.boundaryTypeInlet != "'Periodic'" or self.boundaryTypeOutlet != "'Periodic'":
+                raise IniError("SurfaceTensionType 'Perturbation' runs on closed boxes (the reference treats the open rows "
+                               "after the total population was formed, RKD2Q9.py:1063-1118)")
         self.isCycles = ini.quoted("CyclesSetup", "IsCycle", default="no")
         if self.isCycles == "'yes'":
             self.lastStep = ini.integer("CyclesSetup", "LastStep")
@@ -181,7 +196,11 @@ class RKColorGradientLBM:
                                   tauR=self.tauR, tauB=self.tauB, tau_type=self.tauCalculation,
                                   inlet=INLET[inlet], outlet=OUTLET[outlet], inlet_velocity=self._inlet_velocity(),
                                   rhoBH=self.densityRhoBH, rhoRH=self.densityRhoRH, rhoBL=self.densityRhoBL,
-                                  rhoRL=self.densityRhoRL)
+                                  rhoRL=self.densityRhoRL,
+                                  surface_tension_type=_lib.ST_PERTURBATION if self.surfaceTensionType == "'Perturbation'" else _lib.ST_CSF,
+                                  AkR=self.AkR, AkB=self.AkB, solid_phi=self.solidPhi,
+                                  body_force=[self.bodyFX, self.bodyFY, self.bodyFZ if self.LATTICE == 19 else 0.0]
+                                  if self.isBodyForce == "'yes'" else [0.0, 0.0, 0.0])
         self.engine.set_geometry(self.isDomain)
 
     def _inlet_velocity(self):
@@ -275,9 +294,18 @@ class RKColorGradientLBM:
         self.convertOptTo2D()
         self._say("%d steps, %.3f s, %.1f MLUPS (output included)" % (self.timeSteps, dt, self.voidSpace * self.timeSteps / dt / 1e6))
 
+    def runRKColorGradient2DPerturbation(self):
+        """RKD2Q9.py:979-1223: same host loop, the engine runs the perturbation operator (LBM_ST_PERTURBATION).  The first
+        record is the state after the streaming the reference's loop starts with (:1048-1059)."""
+        if self.surfaceTensionType != "'Perturbation'":
+            raise IniError("SurfaceTensionType is not 'Perturbation'")
+        self.runRKColorGradient2DCSF()
+
     def runRKColorGradient2D(self):
         """RKD2Q9.py:1495-1498"""
         if self.surfaceTensionType == "'CSF'":
             self.runRKColorGradient2DCSF()
+        elif self.surfaceTensionType == "'Perturbation'":
+            self.runRKColorGradient2DPerturbation()
 
     runModifiedRKColorGradient2D = runRKColorGradient2D     # the name main.py:53 calls

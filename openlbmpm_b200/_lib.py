@@ -13,6 +13,7 @@ RELAX_SRT, RELAX_MRT = 0, 1
 BC_PERIODIC, INLET_VELOCITY, INLET_PRESSURE = 0, 1, 2
 OUTLET_CONVECTIVE, OUTLET_PRESSURE = 1, 2
 FLAG_GENERIC_KERNELS = 1
+ST_CSF, ST_PERTURBATION = 0, 1
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)
@@ -27,14 +28,16 @@ class LbmConfig(ctypes.Structure):
         ("relax", ctypes.c_int32), ("tau_type", ctypes.c_int32), ("wetting_type", ctypes.c_int32),
         ("inlet", ctypes.c_int32), ("outlet", ctypes.c_int32), ("device", ctypes.c_int32),
         ("flags", ctypes.c_uint32), ("n_components", ctypes.c_int32), ("sc_isotropy", ctypes.c_int32),
-        ("reserved_i", ctypes.c_int32 * 2),
+        ("surface_tension_type", ctypes.c_int32), ("reserved_i", ctypes.c_int32 * 1),
         ("sigma", ctypes.c_double), ("contact_angle_deg", ctypes.c_double), ("beta", ctypes.c_double),
         ("delta", ctypes.c_double), ("tauR", ctypes.c_double), ("tauB", ctypes.c_double),
         ("inlet_velocity", ctypes.c_double),
         ("rhoBH", ctypes.c_double), ("rhoRH", ctypes.c_double), ("rhoBL", ctypes.c_double), ("rhoRL", ctypes.c_double),
         ("sc_tau", ctypes.c_double * 4), ("sc_G", ctypes.c_double * 16), ("sc_Gsolid", ctypes.c_double * 4),
         ("sc_inlet_velocity", ctypes.c_double * 4), ("sc_rho_in", ctypes.c_double * 4),
-        ("sc_rho_out", ctypes.c_double * 4), ("reserved_d", ctypes.c_double * 8),
+        ("sc_rho_out", ctypes.c_double * 4),
+        ("AkR", ctypes.c_double), ("AkB", ctypes.c_double), ("solid_phi", ctypes.c_double),
+        ("body_force", ctypes.c_double * 3), ("reserved_d", ctypes.c_double * 2),
     ]
 
 

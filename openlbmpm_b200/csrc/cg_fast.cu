@@ -33,7 +33,7 @@ bool cg_fast_eligible(const lbm_handle* h) {
     // (AcceleratedRKGPU2D.py:1700-1706), so its trajectories hang on the exact cancellation of phi between the copied
     // outlet rows; the factored arithmetic rounds differently there, and that combination stays on the
     // reference-ordered kernels.
-    if (h->cfg.model != LBM_MODEL_CG || (h->cfg.flags & LBM_FLAG_GENERIC_KERNELS)) return false;
+    if (h->cfg.model != LBM_MODEL_CG || (h->cfg.flags & LBM_FLAG_GENERIC_KERNELS) || h->cfg.surface_tension_type != LBM_ST_CSF) return false;
     return !open_box(h) || (h->g.n2 >= 8 && h->cfg.wetting_type != 1);
 }
 

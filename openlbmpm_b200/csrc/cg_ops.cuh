@@ -413,6 +413,95 @@ struct StreamOp {
     }
 };
 
+// ---- colour gradient with the PERTURBATION surface-tension operator (LBM_ST_PERTURBATION) -------------------------
+// One operator for the collision side of runRKColorGradient2DPerturbation's MRT branch (RKD2Q9.py:1157-1219):
+//   calRKCollision1GPU2DMRTNew (AcceleratedRKGPU2D.py:1272-1343): fT <- fT - M^-1 S M (fT - feq(rho, u)) + w_F e.F_body,
+//       tau(phi) = 1/2 + 1 / ((1 + phi) / (2 (tauR - 1/2)) + (1 - phi) / (2 (tauB - 1/2))), w_F = 3 w_i;
+//   calRKCollision23GPUNew (1169-1266): G = 3 sum_k w_k e_k phi(x + e_k), SolidColorDiff on solid neighbours;
+//       fT_i += (A_R + A_B)/2 |G| (w_i (e_i.G)^2 / |G|^2 - B_i)   (exactly zero gradient: nothing);
+//       fR_i = rho_R/rho fT_i + beta rho_R rho_B / rho^2 w_i cos(theta_i),  fB_i = rho_B/rho fT_i - ...
+// B = (w_0 - 2/3, w_i): (-2/9, 1/9, 1/36) for D2Q9 (RKD2Q9.py:131-133), (-1/3, 1/18, 1/36) for D3Q19 (Liu et al. 2012).
+// The gradient products are rounded one by one in the reference's order (mul_rn / add_rn): the kernel tests
+// `G.G == 0` exactly and normalises any other G, however small, in the recolouring term.
+// fS (streamed populations), rho, u, phi -> fC; also leaves G for lbm_download_fields.
+template <class L>
+struct PerturbCollideOp {
+    CGFields c;
+    LBM_HD static void scale_moments(double* m, double s_nu) {
+        if (L::Q == 9) {      // S = (0, 1.64, 1.54, 0, 1.9, 0, 1.9, 1/tau, 1/tau), RKD2Q9.py:338-340
+            m[0] = 0.0; m[1] *= 1.64; m[2] *= 1.54; m[3] = 0.0; m[4] *= 1.9; m[5] = 0.0; m[6] *= 1.9; m[7] *= s_nu; m[8] *= s_nu;
+        } else {              // the rates of the D3Q19 specification (lattice.cuh::D3Q19::relax_moments)
+            m[0] = 0.0; m[1] *= 1.19; m[2] *= 1.4; m[3] = 0.0; m[4] *= 1.2; m[5] = 0.0; m[6] *= 1.2; m[7] = 0.0; m[8] *= 1.2;
+            m[9] *= s_nu; m[10] *= 1.4; m[11] *= s_nu; m[12] *= 1.4; m[13] *= s_nu; m[14] *= s_nu; m[15] *= s_nu;
+            m[16] *= 1.98; m[17] *= 1.98; m[18] *= 1.98;
+        }
+    }
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        int x, y, z; g.decode(i, 0, x, y, z);
+        const int64_t id = g.at(x, y, z), V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        const double rR = c.rho[0][id], rB = c.rho[1][id], rho = rB + rR, phi = c.phi[id];
+        double u[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) u[a] = c.u[a * V + id];
+        double fT[L::Q], d[L::Q], m[L::NMOM];
+        double uu = 0.0;
+#pragma unroll
+        for (int a = 0; a < L::D; ++a) uu += u[a] * u[a];
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) {
+            fT[q] = c.fS[0][q * V + id] + c.fS[1][q * V + id];
+            double eu = 0.0;
+#pragma unroll
+            for (int a = 0; a < L::D; ++a)
+                if (L::c(q, a) != 0) eu += L::c(q, a) * u[a];
+            d[q] = fT[q] - rho * L::w(q) * (1.0 + (3.0 * eu + 4.5 * eu * eu - 1.5 * uu));
+        }
+        const double tau = 0.5 + 1.0 / ((1.0 + phi) / (2.0 * (c.p.tauR - 0.5)) + (1.0 - phi) / (2.0 * (c.p.tauB - 0.5)));
+        L::to_moments(d, m);
+        scale_moments(m, 1.0 / tau);
+        L::from_moments(m, d);
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) {
+            double eF = 0.0;
+#pragma unroll
+            for (int a = 0; a < L::D; ++a)
+                if (L::c(q, a) != 0) eF += L::c(q, a) * c.p.bf[a];
+            fT[q] = -d[q] + (q == 0 ? 0.0 : 3.0 * L::w(q)) * eF + fT[q];
+        }
+        double G[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            const int64_t n = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
+            const double pk = (c.cls[n] & CLS_FLUID) ? c.phi[n] : c.p.solid_phi;
+#pragma unroll
+            for (int a = 0; a < L::D; ++a)
+                if (L::c(q, a) != 0) G[a] = add_rn(G[a], mul_rn(3.0 * L::w(q) * L::c(q, a), pk));
+        }
+        double g2 = mul_rn(G[0], G[0]);
+#pragma unroll
+        for (int a = 1; a < L::D; ++a) g2 = add_rn(g2, mul_rn(G[a], G[a]));
+        const double gn = sqrt(g2);
+        const double A = c.p.Ak, kR = rR / rho, kB = rB / rho, amp = c.p.beta * (rR * rB) / (rho * rho);
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) {
+            double eg = 0.0;
+#pragma unroll
+            for (int a = 0; a < L::D; ++a)
+                if (L::c(q, a) != 0) eg += L::c(q, a) * G[a];
+            double f = fT[q];
+            if (g2 != 0.0) f += A * gn * (L::w(q) * (eg * eg) / g2 - (q == 0 ? L::w(0) - 2.0 / 3.0 : L::w(q)));
+            const double cosT = (q != 0 && gn != 0.0) ? eg / (L::enorm(q) * gn) : 0.0;
+            const double a_ = amp * L::w(q) * cosT;
+            c.fC[0][q * V + id] = kR * f + a_;
+            c.fC[1][q * V + id] = kB * f - a_;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) c.G[a * V + id] = G[a];
+    }
+};
+
 // sum of a density over the owned void nodes is done on the host side of the ABI from a download
 // (mass check only; never on the timed path)
 

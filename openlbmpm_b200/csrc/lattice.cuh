@@ -247,6 +247,8 @@ struct D3Q19 {
 struct CGParams {
     double sigma, cosT, sinT, beta, delta, tauR, tauB;
     int tau_type, wetting_type, relax;
+    int st_type;        // LBM_ST_*: 0 = continuum surface force, 1 = perturbation operator
+    double Ak, solid_phi, bf[3];   // perturbation operator: (AkR + AkB) / 2, phi on solid neighbours, body force
     int exact_trig;     // tiled 3-D kernels: 1 = the reference-ordered wetting arithmetic (cg_wetting), 0 = cg_wetting_akai3_fast
 };
 

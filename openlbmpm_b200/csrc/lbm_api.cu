@@ -43,6 +43,8 @@ CGFields lbm_handle::fields() const {
     c.p.tau_type = cfg.tau_type; c.p.wetting_type = cfg.wetting_type; c.p.relax = cfg.relax;
     static const int exact_trig = getenv("LBM_WETTING_EXACT_TRIG") ? atoi(getenv("LBM_WETTING_EXACT_TRIG")) : 0;
     c.p.exact_trig = exact_trig;
+    c.p.st_type = cfg.surface_tension_type; c.p.Ak = 0.5 * (cfg.AkR + cfg.AkB); c.p.solid_phi = cfg.solid_phi;
+    for (int a = 0; a < 3; ++a) c.p.bf[a] = cfg.body_force[a];
     const int64_t cv = (int64_t)Q * g.vol;
     c.fS[0] = fS; c.fS[1] = fS + cv;
     c.fC[0] = fC; c.fC[1] = fC ? fC + cv : nullptr;
@@ -106,6 +108,20 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
         if (cfg->wetting_type == 1 && cfg->lattice == 19) { g_create_error = "WettingType 1 is a 2-D rotation; use 2 for D3Q19"; return LBM_EINVAL; }
         if (cfg->inlet < 0 || cfg->inlet > LBM_INLET_PRESSURE || cfg->outlet < 0 || cfg->outlet > LBM_OUTLET_PRESSURE) {
             g_create_error = "unknown inlet / outlet type"; return LBM_EINVAL;
+        }
+        if (cfg->surface_tension_type != LBM_ST_CSF && cfg->surface_tension_type != LBM_ST_PERTURBATION) {
+            g_create_error = "surface_tension_type must be LBM_ST_CSF or LBM_ST_PERTURBATION"; return LBM_EINVAL;
+        }
+        if (cfg->surface_tension_type == LBM_ST_PERTURBATION) {
+            // the reference's driver is only self-consistent for this combination (tests/golden/gen_goldens_cgp2d.py)
+            if (cfg->relax != LBM_RELAX_MRT) {
+                g_create_error = "perturbation operator: MRT only (the reference's SRT branch is discarded by its own recolouring, RKD2Q9.py:1158-1219)";
+                return LBM_EINVAL;
+            }
+            if (cfg->inlet != LBM_BC_PERIODIC || cfg->outlet != LBM_BC_PERIODIC) {
+                g_create_error = "perturbation operator: closed boxes only (the reference treats the open rows after the total population was formed, RKD2Q9.py:1063-1118)";
+                return LBM_EINVAL;
+            }
         }
     }
     lbm_handle* h = new (std::nothrow) lbm_handle();
@@ -338,6 +354,8 @@ void lbm::cg_alloc_postcollision(lbm_handle* h) {
     dev_zero(h->fC, bytes, h->stream);
 }
 
+static void cgp_initial_stream(lbm_handle* h);
+
 extern "C" int lbm_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp) {
     API_BEGIN(h)
     if (!h->has_geometry) return fail(h, LBM_ESTATE, "lbm_set_geometry has not been called");
@@ -358,6 +376,7 @@ extern "C" int lbm_init_equilibrium(lbm_handle* h, const double* const* rho, int
     } catch (...) { dev_free(tmp); throw; }
     dev_free(tmp);
     h->has_state = true; h->head_done = false; h->fast_pending_stream = false;
+    cgp_initial_stream(h);
     API_END(h)
 }
 
@@ -387,6 +406,7 @@ extern "C" int lbm_upload_state(lbm_handle* h, const double* const* pdf, const d
     } catch (...) { dev_free(tmp); throw; }
     dev_free(tmp);
     h->has_state = true; h->head_done = false; h->fast_pending_stream = false;
+    cgp_initial_stream(h);
     API_END(h)
 }
 
@@ -442,6 +462,31 @@ static void cg_body(lbm_handle* h) {
     h->head_done = false;
 }
 
+// perturbation operator: collision side of one iteration, then the streaming the NEXT iteration starts with
+template <class L>
+static void cgp_body(lbm_handle* h) {
+    cg_alloc_postcollision(h);
+    CGFields c = h->fields();
+    const Grid& g = h->g;
+    exchange_f64(h, c.phi, 0, 1, 1);
+    launch(PerturbCollideOp<L>{c}, g.count(0), h->stream);
+    exchange_f64(h, h->fC, g.vol, 2 * L::Q, 1);
+    launch(StreamOp<L>{c}, g.count(0), h->stream);
+    h->head_done = false;
+}
+// the reference's loop STARTS with the streaming (RKD2Q9.py:1048-1059): a freshly set state is streamed once, so that
+// a download after k steps is what the reference writes at iteration k of its loop
+static void cgp_initial_stream(lbm_handle* h) {
+    if (h->cfg.surface_tension_type != LBM_ST_PERTURBATION) return;
+    cg_alloc_postcollision(h);
+    CGFields c = h->fields();
+    const Grid& g = h->g;
+    dev_d2d(h->fC, h->fS, 2 * (size_t)h->Q * g.vol * sizeof(double), h->stream);
+    exchange_f64(h, h->fC, g.vol, 2 * h->Q, 1);
+    if (h->Q == 9) launch(StreamOp<D2Q9>{c}, g.count(0), h->stream); else launch(StreamOp<D3Q19>{c}, g.count(0), h->stream);
+    dev_sync(h->stream);
+}
+
 void lbm::cg_ensure_head(lbm_handle* h) {
     if (h->head_done) return;
     if (h->Q == 9) cg_head<D2Q9>(h); else cg_head<D3Q19>(h);
@@ -451,6 +496,10 @@ void lbm::cg_apply_open_rows(lbm_handle* h) {
     if (h->Q == 9) cg_open_rows<D2Q9>(h, c); else cg_open_rows<D3Q19>(h, c);
 }
 void lbm::cg_generic_body(lbm_handle* h) {
+    if (h->cfg.surface_tension_type == LBM_ST_PERTURBATION) {
+        if (h->Q == 9) cgp_body<D2Q9>(h); else cgp_body<D3Q19>(h);
+        return;
+    }
     if (h->Q == 9) cg_body<D2Q9>(h); else cg_body<D3Q19>(h);
 }
 void lbm::cg_generic_forces(lbm_handle* h) {
@@ -642,6 +691,7 @@ extern "C" int lbm_init_spinodal_device(lbm_handle* h, double amplitude, uint64_
     else launch(SpinodalInitOp<D3Q19>{c, amplitude, seed, node0}, owned, h->stream);
     dev_sync(h->stream);
     h->has_state = true; h->head_done = false; h->fast_pending_stream = false;
+    cgp_initial_stream(h);
     API_END(h)
 }
 

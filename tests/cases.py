@@ -305,3 +305,110 @@ def case_sc_d3q19(lib_path, model="EFS", relax="SRT", n=(10, 12, 14), steps=8, s
     G = 3.0 if model == "ShanChen" else 0.2
     return run_sc_dense_case(19, dom, [r0, 1.1 - r0], steps, lib_path, model=model, relax=relax, G=G,
                              chunk=[1, 2, steps - 3], **extra)
+
+
+# ---------------------------------------------------------------------------------------------------
+# colour gradient with the perturbation surface-tension operator
+# ---------------------------------------------------------------------------------------------------
+GOLD_CGP2D = sorted(glob.glob(os.path.join(HERE, "golden", "cgp2d_*.npz")))
+
+
+def cgp_engine(lattice, dom, lib_path, beta, AkR, AkB, tauR, tauB, solid_phi, body_force=(0., 0., 0.), **extra):
+    bf = list(body_force) + [0.0] * (3 - len(body_force))
+    if lattice == 9:
+        bf = [bf[0], bf[1], 0.0]
+    eng = _lib.Engine(lattice, dom.shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, lib_path=lib_path,
+                      surface_tension_type=_lib.ST_PERTURBATION, beta=beta, AkR=AkR, AkB=AkB, tauR=tauR, tauB=tauB,
+                      solid_phi=solid_phi, body_force=bf, **extra)
+    eng.set_geometry(dom)
+    return eng
+
+
+def cgp_clean_snapshots(g, p):
+    """The reference's kernel tests `G.G == 0` exactly and otherwise normalises G (AcceleratedRKGPU2D.py:1222-1255), so
+    a gradient that is pure rounding noise -- where the true one vanishes by symmetry, e.g. at the antipode of a
+    centred droplet in a periodic box once both colours have arrived there -- becomes a unit vector of random
+    direction and feeds beta rho_R rho_B / rho^2 w_i cos(theta_i) into the recolouring: from that step on the
+    reference's own trajectory hangs on the last bit of its arithmetic (its mirror symmetry breaks at 1e-5 in
+    cgp2d_droplet, snapshot 4).  Parity is only defined before that; the oracle, which shares the reference's order of
+    operations, tells when it happens."""
+    from oracle import cgp_dense
+    dom, red, minor = g["is_domain"], g["red_mask"], float(g["minor"])
+    sim = cgp_dense.CGPDense(cgp_dense.d2q9(), dom, beta=float(p["beta"]), AkR=float(p["akr"]), AkB=float(p["akb"]),
+                             tauR=float(p["tauR"]), tauB=float(p["tauB"]), solid_phi=float(p["solidphi"]),
+                             body_force=(float(p["bfx"]), float(p["bfy"])))
+    sim.set_densities(np.where(dom, np.where(red, float(p["rhoR"]), minor), 0.0),
+                      np.where(dom, np.where(red, minor, float(p["rhoB"])), 0.0))
+    nsnap = g["rhoR"].shape[0]
+    for s in range(nsnap - 1):
+        rho = sim.rhoR + sim.rhoB
+        with np.errstate(invalid="ignore", divide="ignore"):
+            amp = np.where(sim.dom, float(p["beta"]) * sim.rhoR * sim.rhoB / (rho * rho), 0.0)
+        sim.step(1)
+        g2 = (sim.G * sim.G).sum(0)
+        if ((g2 > 0) & (g2 < 1e-22) & (amp > 1e-13)).any():
+            return s + 1          # snapshots 0..s are clean
+    return nsnap
+
+
+def check_cgp_vs_gold(path, lib_path, chunk=1):
+    """snapshot k of the golden file = what the reference's kernels hold at the output point of loop iteration k"""
+    g, p = load_gold(path)
+    clean = cgp_clean_snapshots(g, p)
+    dom, red, minor = g["is_domain"], g["red_mask"], float(g["minor"])
+    eng = cgp_engine(9, dom, lib_path, float(p["beta"]), float(p["akr"]), float(p["akb"]), float(p["tauR"]), float(p["tauB"]),
+                     float(p["solidphi"]), (float(p["bfx"]), float(p["bfy"])))
+    eng.init_equilibrium(np.where(dom, np.where(red, float(p["rhoR"]), minor), 0.0),
+                         np.where(dom, np.where(red, minor, float(p["rhoB"])), 0.0))
+    nsnap = g["rhoR"].shape[0]
+    s = 0
+    while s < clean:
+        rho, u = eng.download_macros()
+        for k, a in (("rhoR", rho[0]), ("rhoB", rho[1]), ("ux", u[0]), ("uy", u[1])):
+            np.testing.assert_allclose(a, g[k][s], rtol=0, atol=ATOL_GOLD, err_msg="%s snapshot %d" % (k, s))
+        if s == 0 or s == nsnap - 1:
+            pdf = eng.download_pdfs()
+            np.testing.assert_allclose(pdf[0], g["pdfR_first" if s == 0 else "pdfR_last"], rtol=0, atol=ATOL_GOLD)
+            np.testing.assert_allclose(pdf[1], g["pdfB_first" if s == 0 else "pdfB_last"], rtol=0, atol=ATOL_GOLD)
+        if s == nsnap - 1:
+            break
+        n = min(chunk, nsnap - 1 - s)
+        eng.step(n)
+        s += n
+    eng.close()
+    return clean
+
+
+def case_cgp_dense(lib_path, lattice=19, n=(10, 12, 14), steps=8, solid=True, atol=1e-10, **extra):
+    """CUDA path vs oracle/cgp_dense.py (D3Q19: the generalisation the reference's 3-D ini parameterises)"""
+    from oracle import cgp_dense
+    rng = np.random.default_rng(31)
+    dom = np.ones(n, bool)
+    if solid:
+        if lattice == 19:
+            dom &= sphere_geometry(n, 2.6)
+            dom[0:2, 0:3, :] = False
+        else:
+            dom[4:7, 3:9] = False
+    rhoR = 0.5 + 0.4 * (rng.random(n) - 0.5)
+    par = dict(beta=0.8, AkR=1.0e-2, AkB=1.6e-2, tauR=1.0, tauB=0.85, solid_phi=0.3,
+               body_force=(1.0e-5, -2.0e-5, 3.0e-5)[:3 if lattice == 19 else 2])
+    L = cgp_dense.d3q19() if lattice == 19 else cgp_dense.d2q9()
+    sim = cgp_dense.CGPDense(L, dom, **par)
+    sim.set_densities(rhoR, 1.0 - rhoR)
+    eng = cgp_engine(lattice, dom, lib_path, **par, **extra)
+    eng.init_equilibrium(np.where(dom, rhoR, 0.0), np.where(dom, 1.0 - rhoR, 0.0))
+    done = 0
+    for k in (0, 1, 2, steps - 3):
+        eng.step(k); sim.step(k); done += k
+        rho, u = eng.download_macros()
+        np.testing.assert_allclose(rho[0], sim.rhoR.reshape(n), rtol=0, atol=atol, err_msg="rhoR after %d" % done)
+        np.testing.assert_allclose(rho[1], sim.rhoB.reshape(n), rtol=0, atol=atol, err_msg="rhoB after %d" % done)
+        for a in range(L.D):
+            np.testing.assert_allclose(u[a], sim.u[a].reshape(n), rtol=0, atol=atol, err_msg="u%d after %d" % (a, done))
+    pdf = eng.download_pdfs()
+    np.testing.assert_allclose(pdf[0], np.moveaxis(sim.fR, 0, -1).reshape(n + (L.Q,)), rtol=0, atol=atol)
+    np.testing.assert_allclose(pdf[1], np.moveaxis(sim.fB, 0, -1).reshape(n + (L.Q,)), rtol=0, atol=atol)
+    m = eng.total_mass()
+    eng.close()
+    return m, (sim.rhoR.sum(), sim.rhoB.sum())

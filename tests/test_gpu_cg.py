@@ -152,3 +152,17 @@ def test_d3q19_open_boundaries_tiled_equals_untiled_and_general(inlet, outlet):
 @pytest.mark.parametrize("flags", [0, 1, 8])
 def test_trajectory_vs_reference_graph_replay(path, flags):
     cases.check_trajectory_vs_gold(path, None, chunk=19, flags=flags)
+
+
+# ---- perturbation surface-tension operator: reference kernels' vectors + dense oracle ----
+@pytest.mark.parametrize("path", cases.GOLD_CGP2D, ids=[cases.os.path.basename(p)[6:-4] for p in cases.GOLD_CGP2D])
+@pytest.mark.parametrize("chunk", [1, 13])
+def test_perturbation_trajectory_vs_reference_kernels(path, chunk):
+    cases.check_cgp_vs_gold(path, None, chunk=chunk)
+
+
+@pytest.mark.parametrize("lattice,n", [(19, (10, 12, 14)), (9, (14, 18)), (19, (24, 20, 36))])
+@pytest.mark.parametrize("solid", [False, True])
+def test_perturbation_vs_dense_oracle(lattice, n, solid):
+    m, m_ref = cases.case_cgp_dense(None, lattice, n, steps=8 if n[0] < 20 else 14, solid=solid)
+    assert abs(m[0] - m_ref[0]) < 1e-9 and abs(m[1] - m_ref[1]) < 1e-9

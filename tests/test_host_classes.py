@@ -99,3 +99,37 @@ def test_missing_key_exits_like_the_reference(hostlib, tmp_path):
     (d / "RKtwophasesetup2D.ini").write_text("[DomainSize]\nxDomain = 8\n")
     with pytest.raises(SystemExit):
         RKColorGradientLBM(str(d))
+
+
+def test_perturbation_classes(hostlib):
+    """SurfaceTensionType 'Perturbation' (RKD2Q9.py:979-1223; the flavour the reference's 3-D ini parameterises): the
+    classes drive the engine's perturbation operator; trajectories equal the oracle run with the ini's numbers"""
+    from openlbmpm_b200.RKD2Q9 import RKColorGradientLBM
+    from openlbmpm_b200.RKColorGradientD3Q19 import RKColorGradient3D
+    from oracle import cgp_dense
+    sim = RKColorGradientLBM(os.path.join(REF_INI, "cgp2d"), verbose=False)
+    yy, xx = np.indices((22, 18))
+    sim.initialRedRegion = np.sqrt((yy - 12.3) ** 2 + (xx - 8.6) ** 2) <= 5.
+    sim.runRKColorGradient2D()
+    ref = cgp_dense.CGPDense(cgp_dense.d2q9(), sim.isDomain, beta=0.7, AkR=1.4e-2, AkB=1.0e-2, tauR=1.0, tauB=0.8,
+                             solid_phi=0.4, body_force=(1.0e-5, -2.0e-5))
+    red = sim.initialRedRegion & sim.isDomain
+    ref.set_densities(np.where(red, 1.0, 0.0) * sim.isDomain, np.where(red, 0.0, 1.0) * sim.isDomain)
+    ref.step(sim.timeSteps)
+    assert 0.05 < sim.fluidsRhoR.mean() < 0.5
+    np.testing.assert_allclose(sim.fluidsRhoR, ref.rhoR[0], atol=1e-9)
+    np.testing.assert_allclose(sim.physicalVX, ref.u[0, 0], atol=1e-9)
+    sim3 = RKColorGradient3D(os.path.join(REF_INI, "cgp3d"), verbose=False)
+    zz = np.indices((40, 10, 12))[0]
+    sim3.initialRedRegion = zz < 20
+    sim3.runRKColorGradient3D()
+    ref3 = cgp_dense.CGPDense(cgp_dense.d3q19(), sim3.isDomain, beta=1.0, AkR=7e-3, AkB=7e-3, solid_phi=0.7)
+    ref3.set_densities(np.where(zz < 20, 1.0, 0.0), np.where(zz < 20, 0.0, 1.0))
+    ref3.step(sim3.timeSteps)
+    np.testing.assert_allclose(sim3.fluidsRhoR, ref3.rhoR, atol=1e-9)
+    np.testing.assert_allclose(sim3.physicalVZ, ref3.u[2], atol=1e-9)
+    with pytest.raises(SystemExit):       # the open-boundary 3-D ini of the reference stays on the CSF operator
+        bad = os.path.join(str(hostlib), "bad3d"); os.makedirs(bad)
+        txt = open(os.path.join(REF_INI, "cgp3d", "RKtwophasesetup3D.ini")).read().replace("BoundaryTypeInlet = 'Periodic'", "BoundaryTypeInlet = 'Neumann'")
+        open(os.path.join(bad, "RKtwophasesetup3D.ini"), "w").write(txt)
+        RKColorGradient3D(bad, verbose=False)
