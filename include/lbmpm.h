@@ -178,6 +178,20 @@ int lbm_synchronize(lbm_handle* h);
  * rho: n_comp pointers; u: up to 3 pointers (x, y, z); any pointer may be NULL.            */
 int lbm_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u);
 
+/* Asynchronous form of lbm_download_macros for output that must not stall the step loop (SURVEY.md section 8, row f-4;
+ * the reference blocks in copy_to_host every TimeInterval steps, RKD2Q9.py:1382-1393): the fields of the output point
+ * are snapshot into a device staging buffer on the compute stream and copied to the host arrays on a second stream.
+ * Returns at once; lbm_step may be called right away.  The host arrays must stay valid until lbm_output_wait returns
+ * and should come from lbm_host_alloc (page-locked), otherwise the copy degenerates to a synchronous one.
+ * One download in flight per handle: a second call waits (on the device) for the previous copy.              */
+int lbm_download_macros_async(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u);
+/* Blocks the calling host thread until the copies of the last lbm_download_macros_async have landed.  The only entry
+ * point that may be called from a second host thread (an output writer) while the owner thread keeps stepping.  */
+int lbm_output_wait(lbm_handle* h);
+/* Page-locked host memory for the asynchronous output (cudaHostAlloc / cudaFreeHost).                          */
+int lbm_host_alloc(void** ptr, int64_t bytes);
+int lbm_host_free(void* ptr);
+
 /* Populations in the reference's dense AoS layout [nz][ny][nx][Q] per component
  * (fluidPDFR/B at the same output point).                                                  */
 int lbm_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp);

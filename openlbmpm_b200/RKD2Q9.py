@@ -80,8 +80,6 @@ class RKColorGradientLBM:
         self.isCycles = ini.quoted("CyclesSetup", "IsCycle", default="no")
         if self.isCycles == "'yes'":
             self.lastStep = ini.integer("CyclesSetup", "LastStep")
-            raise IniError("[CyclesSetup] IsCycle = 'yes' (restart from ~/LBMInitial/*.h5, RKD2Q9.py:491-559) is not built: "
-                           "assign fluidsRhoR/B and call engine.upload_state instead (SURVEY.md section 8, f-4)")
         # lattice constants (RKD2Q9.py:299-303)
         self.weightsCoeff = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
         self.unitEX = np.array([0., 1., 0., -1., 0., 1., -1., -1., 1.])
@@ -141,45 +139,87 @@ class RKColorGradientLBM:
         self._say('The porosity of the layout is %f.' % (self.voidSpace / self.isDomain.size))
 
     def _process_image(self):
-        """RKD2Q9.py:373-414: 0 = solid, 255 = void, buffering layers of void rows above and below"""
-        path = os.path.expanduser("~/StructureImage/structure.png")
-        img = None
-        for loader in ("imageio", "PIL.Image", "matplotlib.image"):
-            try:
-                mod = __import__(loader, fromlist=["x"])
-                img = np.asarray(mod.imread(path) if hasattr(mod, "imread") else mod.open(path))
-                break
-            except Exception:
-                continue
-        if img is None:
-            raise IniError("Cannot read %s (needs imageio, Pillow or matplotlib)" % path)
-        if img.ndim == 3:
-            img = img[..., 0]
-        void = img > (0.5 * img.max())
-        nb = self.numBufferingLayers
-        top = int(round(nb * self.ratioTopToBottom * 2)) if nb else 0
-        bottom = 2 * nb - top if nb else 0
-        void = np.vstack([np.ones((bottom, void.shape[1]), bool), void, np.ones((top, void.shape[1]), bool)])
-        self.isDomain = void
-        self.yDomain, self.xDomain = void.shape
+        """RKD2Q9.py:373-414: crop to the solid pixels (== 0), solid side columns, `int(2 n ratioTopToBottom)` void
+        buffer rows in front of the image (low row indices, the outlet side) and the rest of the `2 n` behind it"""
+        from . import imagegeo
+        try:
+            img = imagegeo.crop_to_solid(imagegeo.load_gray())
+        except (FileNotFoundError, ValueError) as e:
+            raise IniError(str(e))
+        low = int(2 * self.numBufferingLayers * self.ratioTopToBottom)
+        self.effectiveDomain = imagegeo.close_and_pad(img, low, 2 * self.numBufferingLayers - low)
+        self.isDomain = imagegeo.to_domain(self.effectiveDomain)
+        self.yDomain, self.xDomain = self.isDomain.shape
+        self.originalXdim = self.xDomain
+        self._say('Now the size of domain is %g and %g' % (self.yDomain, self.xDomain))
+
+    def _equilibrium(self, rho, vel):
+        """RKD2Q9.py:577-601: f_i = rho w_i (1 + 3 e.u + 4.5 (e.u)^2 - 1.5 u.u), dense `[..., Q]`"""
+        e = [self.unitEX, self.unitEY] + ([self.unitEZ] if hasattr(self, "unitEZ") else [])
+        eu = sum(e[a] * vel[a][..., None] for a in range(len(vel)))
+        uu = sum(v * v for v in vel)[..., None]
+        return rho[..., None] * self._weights() * (1. + (3. * eu + 4.5 * eu * eu - 1.5 * uu))
 
     def initializeDomainCondition(self):
-        """RKD2Q9.py:445-490: droplet of R with radius 16 around the centre, B elsewhere, at rest; assign
-        `self.initialRedRegion` (boolean array) beforehand for another layout."""
+        """RKD2Q9.py:445-559.  No image: droplet of R with radius 16 around the centre, B elsewhere, at rest (assign
+        `self.initialRedRegion`, a boolean array, beforehand for another layout); image: R below the inlet buffer
+        rows, B in them; `[CyclesSetup] IsCycle = 'yes'`: drainage-imbibition restart from the previous run's results
+        in ~/LBMInitial (LBM_INITIAL_DIR)."""
         shape = self._shape()
+        self.physicalVX = np.zeros(shape); self.physicalVY = np.zeros(shape)
+        if len(shape) == 3:
+            self.physicalVZ = np.zeros(shape)
+        if self.isCycles == "'yes'":
+            return self._initialize_from_previous_run()
         red = getattr(self, "initialRedRegion", None)
         if red is None:
             idx = np.indices(shape)
-            centre = [int(n / 2) for n in shape]
-            red = np.sqrt(sum((idx[a] - centre[a]) ** 2 for a in range(len(shape)))) <= 16.
+            if self.imageExist == "'yes'":
+                red = idx[0] < shape[0] - self.numBufferingLayers
+            else:
+                centre = [int(n / 2) for n in shape]
+                red = np.sqrt(sum((idx[a] - centre[a]) ** 2 for a in range(len(shape)))) <= 16.
         red = np.asarray(red, bool) & self.isDomain
         self.fluidsRhoR = np.where(red, self.initialRhoR, 0.0) * self.isDomain
         self.fluidsRhoB = np.where(red, 0.0, self.initialRhoB) * self.isDomain
         self.fluidPDFR = self.fluidsRhoR[..., None] * self._weights()
         self.fluidPDFB = self.fluidsRhoB[..., None] * self._weights()
-        self.physicalVX = np.zeros(shape); self.physicalVY = np.zeros(shape)
-        if len(shape) == 3:
-            self.physicalVZ = np.zeros(shape)
+
+    def _initialize_from_previous_run(self):
+        """RKD2Q9.py:491-559"""
+        from .results import initial_dir, read_arrays
+        shape = self._shape()
+        if len(shape) != 2:
+            raise IniError("[CyclesSetup] IsCycle = 'yes' is a 2-D feature of the reference")
+        try:
+            if self.imageExist == "'no'":
+                # :491-508 -- densities and velocity of record LastStep, fresh B in the top 20 rows, equilibrium populations
+                n = self.lastStep
+                names = ["/FluidMacro/FluidDensityRin%d" % n, "/FluidMacro/FluidDensityBin%d" % n,
+                         "/FluidVelocity/FluidVelocityXAt%d" % n, "/FluidVelocity/FluidVelocityYAt%d" % n]
+                d = read_arrays(initial_dir(), "SimulationResultsRK.h5", names)
+                self.fluidsRhoR, self.fluidsRhoB, self.physicalVX, self.physicalVY = (np.array(d[k], float) for k in names)
+                self.fluidsRhoR[-20:, :] = 0.; self.fluidsRhoB[-20:, :] = self.initialRhoB
+                self.fluidsRhoR *= self.isDomain; self.fluidsRhoB *= self.isDomain
+                vel = [self.physicalVX, self.physicalVY]
+                self.fluidPDFR = self._equilibrium(self.fluidsRhoR, vel) * self.isDomain[..., None]
+                self.fluidPDFB = self._equilibrium(self.fluidsRhoB, vel) * self.isDomain[..., None]
+            else:
+                # :533-559 -- cycleInitialRK.h5: state of the previous half cycle, the colours swapped in the inlet buffer rows
+                names = ["/FluidMacro/FluidDensityR", "/FluidMacro/FluidDensityB", "/FluidPDF/FluidPDFR", "/FluidPDF/FluidPDFB",
+                         "/FluidVelocity/FluidVelocityX", "/FluidVelocity/FluidVelocityY"]
+                d = read_arrays(initial_dir(), "cycleInitialRK.h5", names)
+                rR, rB, fR, fB, vx, vy = (np.array(d[k], float) for k in names)
+                nb = self.numBufferingLayers
+                self.fluidsRhoR, self.fluidsRhoB, self.fluidPDFR, self.fluidPDFB = rR.copy(), rB.copy(), fR.copy(), fB.copy()
+                if nb > 0:
+                    self.fluidsRhoR[-nb:], self.fluidsRhoB[-nb:] = rB[-nb:], rR[-nb:]
+                    self.fluidPDFR[-nb:], self.fluidPDFB[-nb:] = fB[-nb:], fR[-nb:]
+                self.physicalVX, self.physicalVY = vx, vy
+        except FileNotFoundError as e:
+            raise IniError("There is no file for initializing the domain: %s" % e)
+        if self.fluidsRhoR.shape != shape:
+            raise IniError("the restart file holds arrays of shape %s, the domain is %s" % (self.fluidsRhoR.shape, shape))
 
     def _weights(self):
         return self.weightsCoeff
@@ -253,6 +293,26 @@ class RKColorGradientLBM:
             arrays["/FluidVelocity/FluidVelocityZAt%g" % iStep] = self.physicalVZ
         self._results.write(iStep, arrays)
 
+    def _write_macro_record(self, iStep, rho, u):
+        """record of the asynchronous output: the reference's dataset names, densities and velocities only"""
+        if self._results is None:
+            self._results = ResultFile("SimulationResultsRK.h5")
+        arrays = {"/FluidMacro/FluidDensityRin%g" % iStep: rho[0], "/FluidMacro/FluidDensityBin%g" % iStep: rho[1]}
+        for name, a in zip("XYZ", u):
+            arrays["/FluidVelocity/FluidVelocity%sAt%g" % (name, iStep)] = a
+        self._results.write(iStep, arrays)
+
+    def saveCycleInitial(self):
+        """Writes the current state as `cycleInitialRK.h5` into ~/LBMInitial (LBM_INITIAL_DIR): the file the image-based
+        drainage-imbibition restart reads (RKD2Q9.py:533-559; upstream it is prepared by hand from a result file)."""
+        from .results import initial_dir
+        os.makedirs(initial_dir(), exist_ok=True)
+        f = ResultFile("cycleInitialRK.h5", directory=initial_dir())
+        f.write(0, {"/FluidMacro/FluidDensityR": self.fluidsRhoR, "/FluidMacro/FluidDensityB": self.fluidsRhoB,
+                    "/FluidPDF/FluidPDFR": self.fluidPDFR, "/FluidPDF/FluidPDFB": self.fluidPDFB,
+                    "/FluidVelocity/FluidVelocityX": self.physicalVX, "/FluidVelocity/FluidVelocityY": self.physicalVY},
+                single_file=True)
+
     def plotDensityDistributionOPT(self, iStep):
         """RKD2Q9.py:959-975 (PNG snapshots; skipped when matplotlib is absent)"""
         try:
@@ -278,18 +338,29 @@ class RKColorGradientLBM:
         iStep = 0
         recordStep = 0
         t0 = time.perf_counter()
+        # `asyncOutput` (attribute, or LBM_ASYNC_OUTPUT=1): records of densities + velocities are copied and written
+        # behind the step loop (results.AsyncMacroOutput) instead of the reference's blocking copy + append
+        out = None
+        if getattr(self, "asyncOutput", os.environ.get("LBM_ASYNC_OUTPUT") == "1"):
+            from .results import AsyncMacroOutput
+            out = AsyncMacroOutput(self.engine, self._write_macro_record)
         while iStep < self.timeSteps:
             if iStep % self.timeInterval == 0:                       # RKD2Q9.py:1382-1393
-                self.convertOptTo2D()
-                self.resultInHDF5(recordStep)
-                self.plotDensityDistributionOPT(recordStep)
+                if out is not None:
+                    out.snapshot()
+                else:
+                    self.convertOptTo2D()
+                    self.resultInHDF5(recordStep)
+                    self.plotDensityDistributionOPT(recordStep)
+                    m = self.engine.total_mass()
+                    self._say("step %d: mass R %.12g, mass B %.12g" % (iStep, m[0], m[1]))
                 recordStep += 1
-                m = self.engine.total_mass()
-                self._say("step %d: mass R %.12g, mass B %.12g" % (iStep, m[0], m[1]))
             n = min(self.timeInterval - iStep % self.timeInterval, self.timeSteps - iStep)
             self.engine.step(n)
             iStep += n
         self.engine.synchronize()
+        if out is not None:
+            out.close()
         dt = time.perf_counter() - t0
         self.convertOptTo2D()
         self._say("%d steps, %.3f s, %.1f MLUPS (output included)" % (self.timeSteps, dt, self.voidSpace * self.timeSteps / dt / 1e6))

@@ -5,6 +5,7 @@ which the reference demands but does not ship, is optional); entry points `runTy
 `runOptimizedLBM`, `runOptimizedEFLBM`; public arrays `isDomain`, `isSolid`, `fluidsDensity[nf, ny, nx]`,
 `fluidPDF[nf, ny, nx, 9]`, `physicalVX/VY`, `fluidNodes`, `neighboringNodes`, `optFluidRho`, `optFluidPDF`.
 The per-step loops (ShanChenD2Q9.py:1492-1629, 1852-2087; 15-20 kernel launches each) run inside liblbmpm.so."""
+import os
 import time
 
 import numpy as np
@@ -22,8 +23,6 @@ class ShanChenD2Q9:
         self.verbose = verbose
         ini = Ini(pathIniFile, "twophasesetup.ini")
         self.PictureExistance = ini.quoted("PictureSetup", "Exist", default="no")
-        if self.PictureExistance == "'yes'":
-            raise IniError("image input for the Shan-Chen class: provide the geometry through SimpleGeometry.defineGeometry")
         self.nx = self.borderX = ini.integer("SeparationBorder", "xGrid")
         self.ny = self.borderY = ini.integer("SeparationBorder", "yGrid")
         self._read_extra_dimensions(ini)
@@ -39,6 +38,8 @@ class ShanChenD2Q9:
             raise IniError("TRT is read by the reference but never launched by a live driver")
         self.duplicateDomain = ini.quoted("DuplicateDomain", "Option", default="no")
         self.isCycles = ini.quoted("DICycles", "Option", default="no")
+        if self.isCycles == "'yes'":
+            self.lastStep = ini.integer("DICycles", "LastStep")
         self._set_lattice()
         efs = self.interactionType == "'EFS'"
         self._read_model(self._model_ini(pathIniFile, efs), "EFSParameters" if efs else "ShanChenParameters")
@@ -111,8 +112,33 @@ class ShanChenD2Q9:
         self.numTimeStep = ini.integer("Time", "numberTimeStep")
 
     # -- geometry / initial condition --------------------------------------------------------------
+    def _process_image(self):
+        """ShanChenD2Q9.py:542-585: crop to the solid pixels, optional mirror tiling ([DuplicateDomain] Option = 'yes'; the
+        two counts the reference asks for with input() come from `self.duplicateX / duplicateY`, LBM_DUPLICATE_X / _Y or
+        the prompt), solid side columns, 20 void buffer rows at either end"""
+        import os
+        from . import imagegeo
+        if self.LATTICE != 9:
+            raise IniError("image input is a 2-D feature of the reference")
+        try:
+            img = imagegeo.crop_to_solid(imagegeo.load_gray())
+        except (FileNotFoundError, ValueError) as e:
+            raise IniError(str(e))
+        if self.duplicateDomain == "'yes'":
+            def count(attr, env, prompt):
+                v = getattr(self, attr, None) or os.environ.get(env)
+                return int(v if v else input(prompt))
+            img = imagegeo.expand_image_domain(img, count("duplicateX", "LBM_DUPLICATE_X", "Number of duplication in x direction: "),
+                                               count("duplicateY", "LBM_DUPLICATE_Y", "Number of duplication in y direction: "))
+        self.effectiveDomain = imagegeo.close_and_pad(img, 20, 20)
+        self.ny, self.nx = self.effectiveDomain.shape
+        self.originalXdim = self.nx
+        self._say('Now the size of domain is %g and %g' % (self.ny, self.nx))
+        dom = imagegeo.to_domain(self.effectiveDomain)
+        return dom, ~dom
+
     def initializeDomainBorder(self):
-        self.isDomain, self.isSolid = self._define_geometry()
+        self.isDomain, self.isSolid = self._process_image() if self.PictureExistance == "'yes'" else self._define_geometry()
         self.isDomain = np.ascontiguousarray(self.isDomain, dtype=bool)
         self.isSolid = ~self.isDomain
         self.voidSpace = int(np.count_nonzero(self.isDomain))
@@ -123,10 +149,13 @@ class ShanChenD2Q9:
         (boolean [ny, nx]) beforehand for another layout"""
         reg = getattr(self, "initialRegion0", None)
         shape = self._shape()
+        image = self.PictureExistance == "'yes'"
         if reg is None:
-            reg = np.indices(shape)[0] < shape[0] - 10
+            reg = np.indices(shape)[0] < shape[0] - (20 if image else 10)      # :757 / :771
         nf = self.typesFluids
         self.fluidsDensity = np.zeros((nf,) + shape)
+        if image and self.isCycles == "'yes'":
+            return self._initialize_from_previous_run()
         for k in range(nf):
             inside = self.initialDensities[k] if k == 0 else self.backgroundDensities[k]
             outside = self.backgroundDensities[k] if k == 0 else self.initialDensities[k]
@@ -135,6 +164,28 @@ class ShanChenD2Q9:
         self.physicalVX = np.zeros(shape); self.physicalVY = np.zeros(shape)
         if self.LATTICE == 19:
             self.physicalVZ = np.zeros(shape)
+
+    def _initialize_from_previous_run(self):
+        """ShanChenD2Q9.py:788-817: the fluids of the previous run keep their densities of record LastStep (background
+        in the 30 inlet rows), the NEW fluid enters through those rows; populations at rest"""
+        from .results import initial_dir, read_arrays
+        nf, shape = self.typesFluids, self._shape()
+        names = ["/FluidMacro/FluidDensityType%gin%d" % (k, self.lastStep) for k in range(nf - 1)]
+        try:
+            d = read_arrays(initial_dir(), "SimulationResults.h5", names)
+        except FileNotFoundError as e:
+            raise IniError("There is no file for initializing the domain: %s" % e)
+        for k in range(nf - 1):
+            old = np.array(d[names[k]], float)
+            if old.shape != shape:
+                raise IniError("the restart file holds arrays of shape %s, the domain is %s" % (old.shape, shape))
+            self.fluidsDensity[k, :-30] = old[:-30]
+            self.fluidsDensity[k, -30:] = self.backgroundDensities[k]
+        rows = np.indices(shape)[0]
+        self.fluidsDensity[-1] = np.where(rows < shape[0] - 30, self.backgroundDensities[-1], self.initialDensities[-1])
+        self.fluidsDensity *= self.isDomain
+        self.fluidPDF = self.fluidsDensity[..., None] * self.weightsCoeff
+        self.physicalVX = np.zeros(shape); self.physicalVY = np.zeros(shape)
 
     def _make_engine(self, model):
         inlet = {"'Periodic'": _lib.BC_PERIODIC, "'Neumann'": _lib.INLET_VELOCITY}.get(self.boundaryTypeInlet)
@@ -182,6 +233,14 @@ class ShanChenD2Q9:
             arrays["/FluidVelocity/FluidVelocityZAt%g" % iStep] = self.physicalVZ
         self._results.write(iStep, arrays)
 
+    def _write_macro_record(self, iStep, rho, u):
+        if self._results is None:
+            self._results = ResultFile("SimulationResults.h5", groups=("FluidMacro", "FluidVelocity"))
+        arrays = {"/FluidMacro/FluidDensityType%gin%g" % (k, iStep): rho[k] for k in range(self.typesFluids)}
+        for name, a in zip("XYZ", u):
+            arrays["/FluidVelocity/FluidVelocity%sAt%g" % (name, iStep)] = a
+        self._results.write(iStep, arrays)
+
     def _run(self, model, interval):
         self.initializeDomainBorder()
         self.initializeDomainCondition()
@@ -191,16 +250,25 @@ class ShanChenD2Q9:
         step = record = 0
         total = self.numTimeStep + 1                 # both loops run numTimeStep + 1 iterations
         t0 = time.perf_counter()
+        out = None          # `asyncOutput` / LBM_ASYNC_OUTPUT=1: records are copied and written behind the step loop
+        if getattr(self, "asyncOutput", os.environ.get("LBM_ASYNC_OUTPUT") == "1"):
+            from .results import AsyncMacroOutput
+            out = AsyncMacroOutput(self.engine, self._write_macro_record)
         while step < total:
             if step % interval == 0:
-                self.convertOptTo2D()
-                self.resultInHDF5(record)
+                if out is not None:
+                    out.snapshot()
+                else:
+                    self.convertOptTo2D()
+                    self.resultInHDF5(record)
+                    self._say("step %d: masses %s" % (step, self.engine.total_mass()))
                 record += 1
-                self._say("step %d: masses %s" % (step, self.engine.total_mass()))
             n = min(interval - step % interval, total - step)
             self.engine.step(n)
             step += n
         self.engine.synchronize()
+        if out is not None:
+            out.close()
         dt = time.perf_counter() - t0
         self.convertOptTo2D()
         self._say("%d steps, %.3f s, %.1f MLUPS (output included)" % (total, dt, self.voidSpace * total / dt / 1e6))

@@ -58,6 +58,11 @@ PROTOTYPES = {
     "lbm_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "lbm_download_macros": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_double_p), ctypes.c_int32,
                                            ctypes.POINTER(c_double_p)]),
+    "lbm_download_macros_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_double_p), ctypes.c_int32,
+                                                 ctypes.POINTER(c_double_p)]),
+    "lbm_output_wait": (ctypes.c_int, [ctypes.c_void_p]),
+    "lbm_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64]),
+    "lbm_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "lbm_download_pdfs": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_double_p), ctypes.c_int32]),
     "lbm_download_fields": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.POINTER(c_double_p),
                                            ctypes.POINTER(c_double_p), c_double_p]),
@@ -156,8 +161,12 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.lbm_output_wait(self._h)
             self.lib.lbm_destroy(self._h)
             self._h = ctypes.c_void_p()
+        for p in getattr(self, "_pinned", []):
+            self.lib.lbm_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -238,6 +247,33 @@ class Engine:
         self._check(self.lib.lbm_download_macros(self._h, _ptr_array(rho), len(rho), _ptr_array(u + [None] * (3 - len(u)))),
                     "lbm_download_macros")
         return rho, u
+
+    # -- asynchronous output (include/lbmpm.h: lbm_download_macros_async) ----------------------
+    def host_alloc(self, shape=None):
+        """float64 array of `shape` (default: the lattice) in page-locked host memory, owned by the engine"""
+        shape = tuple(shape or self.shape)
+        n = int(np.prod(shape))
+        p = ctypes.c_void_p()
+        rc = self.lib.lbm_host_alloc(ctypes.byref(p), n * 8)
+        if rc != OK:
+            raise LbmError("lbm_host_alloc of %d bytes failed (%d)" % (n * 8, rc))
+        if not hasattr(self, "_pinned"):
+            self._pinned = []
+        self._pinned.append(p)
+        return np.ctypeslib.as_array(ctypes.cast(p, c_double_p), shape=(n,)).reshape(shape)
+
+    def download_macros_async(self, out_rho, out_u):
+        """enqueue the copy of the output point's densities and velocity into the given (page-locked) arrays and return;
+        `output_wait()` blocks until they have landed"""
+        for a in list(out_rho) + list(out_u):
+            if a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != self.shape:
+                raise LbmError("C-contiguous float64 arrays of shape %s expected" % (self.shape,))
+        u = list(out_u) + [None] * (3 - len(out_u))
+        self._check(self.lib.lbm_download_macros_async(self._h, _ptr_array(list(out_rho)), len(out_rho), _ptr_array(u)),
+                    "lbm_download_macros_async")
+
+    def output_wait(self):
+        self._check(self.lib.lbm_output_wait(self._h), "lbm_output_wait")
 
     def download_pdfs(self):
         pdf = [np.empty(self.shape + (self.Q,)) for _ in range(self.ncomp)]

@@ -48,6 +48,10 @@ struct lbm_handle {
     lbm::GraphKeep graph;
     bool graph_ok() const { return nranks == 1 && g.plane * (int64_t)g.n2 <= (int64_t)1 << 22 && !(cfg.flags & 8u); }
 
+    // asynchronous output (lbm_download_macros_async): device staging buffer [n_comp + D][owned]
+    double* out_stage = nullptr;
+    size_t out_stage_bytes = 0;
+
     // measurement
     double last_ms = 0.0;
     int64_t last_launches = 0;
@@ -57,6 +61,8 @@ struct lbm_handle {
     // slab decomposition: ghost-plane exchanges run on their own stream, overlapped with the interior planes
     cudaStream_t comm_stream = nullptr, xstream = nullptr;   // xstream: where exchange_* currently enqueues (null = stream)
     cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+    cudaStream_t out_stream = nullptr;                       // device -> host copies of the asynchronous output
+    cudaEvent_t ev_out_ready = nullptr, ev_out_done = nullptr;
     double *stage_send = nullptr, *stage_recv = nullptr;     // packed boundary planes (comm.cu)
     size_t stage_bytes = 0;
 #endif

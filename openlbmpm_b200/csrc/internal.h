@@ -33,6 +33,7 @@ void sc_step(lbm_handle* h, int nsteps);
 int sc_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u);
 int sc_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp);
 int sc_total_mass(lbm_handle* h, double* mass, int32_t n_comp);
+void sc_output_pointers(lbm_handle* h, const double** rho, const double** u);   // device arrays [n_comp][vol], [D][vol] at the output point
 void sc_free(lbm_handle* h);
 
 }  // namespace lbm

@@ -169,9 +169,12 @@ extern "C" int lbm_destroy(lbm_handle* h) {
 #endif
     graph_release(&h->graph, h->stream);
     free_state(h);
-    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull);
+    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull); dev_free(h->out_stage);
     comm_destroy(h);
 #ifndef LBM_HOSTCHECK
+    if (h->out_stream) { cudaStreamSynchronize(h->out_stream); cudaStreamDestroy(h->out_stream); }
+    if (h->ev_out_ready) cudaEventDestroy(h->ev_out_ready);
+    if (h->ev_out_done) cudaEventDestroy(h->ev_out_done);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -564,6 +567,85 @@ extern "C" int lbm_download_macros(lbm_handle* h, double* const* rho, int32_t n_
             if (u[a]) dev_d2h(u[a], h->u + a * g.vol + off, owned * 8, h->stream);
     dev_sync(h->stream);
     API_END(h)
+}
+
+extern "C" int lbm_download_macros_async(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u) {
+    API_BEGIN(h)
+    if (!h->has_state) return fail(h, LBM_ESTATE, "no state");
+    set_device(h);
+    const bool cg = h->cfg.model == LBM_MODEL_CG;
+    const int nc = cg ? 2 : h->cfg.n_components;
+    if (rho && n_comp != nc) return fail(h, LBM_EINVAL, "one density array per component expected");
+    const double* d_rho = nullptr; const double* d_u = nullptr;
+    if (cg) { to_output_point(h); d_rho = h->rho; d_u = h->u; }
+    else sc_output_pointers(h, &d_rho, &d_u);
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2, off = NG * g.plane;
+    const size_t need = (size_t)(nc + h->D) * owned * sizeof(double);
+#ifndef LBM_HOSTCHECK
+    if (!h->out_stream) {
+        LBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+        LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_out_ready, cudaEventDisableTiming));
+        LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_out_done, cudaEventDisableTiming));
+        LBM_CUDA_CHECK(cudaEventRecord(h->ev_out_done, h->out_stream));
+    }
+    // the staging buffer is free again once the previous copy has left it (device-side wait, the host does not block)
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));
+#endif
+    if (h->out_stage_bytes < need) {
+        dev_sync(h->stream);
+        dev_free(h->out_stage);
+        h->out_stage = (double*)dev_alloc(need); h->out_stage_bytes = need;
+    }
+    for (int k = 0; k < nc; ++k) dev_d2d(h->out_stage + (int64_t)k * owned, d_rho + k * g.vol + off, owned * 8, h->stream);
+    for (int a = 0; a < h->D; ++a) dev_d2d(h->out_stage + (int64_t)(nc + a) * owned, d_u + a * g.vol + off, owned * 8, h->stream);
+#ifndef LBM_HOSTCHECK
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_out_ready, h->stream));
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->out_stream, h->ev_out_ready, 0));
+    auto copy_out = [&](double* dst, const double* src) {
+        LBM_CUDA_CHECK(cudaMemcpyAsync(dst, src, owned * 8, cudaMemcpyDeviceToHost, h->out_stream));
+    };
+#else
+    auto copy_out = [&](double* dst, const double* src) { memcpy(dst, src, owned * 8); };
+#endif
+    if (rho)
+        for (int k = 0; k < nc; ++k)
+            if (rho[k]) copy_out(rho[k], h->out_stage + (int64_t)k * owned);
+    if (u)
+        for (int a = 0; a < h->D; ++a)
+            if (u[a]) copy_out(u[a], h->out_stage + (int64_t)(nc + a) * owned);
+#ifndef LBM_HOSTCHECK
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_out_done, h->out_stream));
+#endif
+    API_END(h)
+}
+
+extern "C" int lbm_output_wait(lbm_handle* h) {
+    if (!h) return LBM_EINVAL;
+#ifndef LBM_HOSTCHECK
+    // no handle state is touched: this entry point may run on a writer thread while the owner thread keeps stepping
+    if (h->ev_out_done && cudaEventSynchronize(h->ev_out_done) != cudaSuccess) return LBM_ECUDA;
+#endif
+    return LBM_OK;
+}
+
+extern "C" int lbm_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return LBM_EINVAL;
+#ifndef LBM_HOSTCHECK
+    if (cudaHostAlloc(ptr, bytes ? (size_t)bytes : 8, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return LBM_ENOMEM; }
+#else
+    *ptr = malloc(bytes ? (size_t)bytes : 8);
+    if (!*ptr) return LBM_ENOMEM;
+#endif
+    return LBM_OK;
+}
+extern "C" int lbm_host_free(void* ptr) {
+#ifndef LBM_HOSTCHECK
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) return LBM_ECUDA;
+#else
+    free(ptr);
+#endif
+    return LBM_OK;
 }
 
 extern "C" int lbm_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp) {

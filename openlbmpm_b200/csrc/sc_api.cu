@@ -220,6 +220,13 @@ int sc_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double
     return LBM_OK;
 }
 
+void sc_output_pointers(lbm_handle* h, const double** rho, const double** u) {
+    if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
+    sc_ensure_head(h);
+    SCFields c = sc_fields(h);
+    *rho = c.rho; *u = c.uph;
+}
+
 int sc_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp) {
     if (!pdf || n_comp != h->cfg.n_components) { h->err = "one population array per component expected"; return LBM_EINVAL; }
     if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);

@@ -412,3 +412,36 @@ def case_cgp_dense(lib_path, lattice=19, n=(10, 12, 14), steps=8, solid=True, at
     m = eng.total_mass()
     eng.close()
     return m, (sim.rhoR.sum(), sim.rhoB.sum())
+
+
+def check_async_output(lib_path, n=(10, 12, 16)):
+    """two engines in lock step: one records through lbm_download_macros_async into two alternating page-locked buffer
+    sets while it keeps stepping, the other through the blocking download"""
+    rng = np.random.default_rng(8)
+    r = 0.5 + 0.3 * (rng.random(n) - 0.5)
+
+    def engine():
+        e = _lib.Engine(19, n, lib_path=lib_path, sigma=0.1, beta=0.7)
+        e.set_geometry(np.ones(n, np.uint8))
+        e.init_equilibrium(r, 1.0 - r)
+        return e
+    a, b = engine(), engine()
+    bufs = [[a.host_alloc() for _ in range(5)] for _ in range(2)]
+    want = []
+    for k in range(5):
+        a.step(7); b.step(7)
+        cur = bufs[k % 2]
+        if k >= 2:                                  # the set about to be reused holds record k - 2
+            a.output_wait()
+            for x, y in zip(cur, want[k - 2]):
+                assert np.array_equal(x, y)
+        a.download_macros_async(cur[:2], cur[2:])
+        a.step(3)                                   # the owner keeps stepping while the copy is in flight
+        rho, u = b.download_macros()
+        want.append([x.copy() for x in rho + u])
+        b.step(3)
+    a.output_wait()
+    for k in (3, 4):
+        for x, y in zip(bufs[k % 2], want[k]):
+            assert np.array_equal(x, y)
+    a.close(); b.close()

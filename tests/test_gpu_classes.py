@@ -27,3 +27,10 @@ def test_shanchen_class(results, which):
 
 def test_cg3d_class_and_main(results, monkeypatch):
     T.test_cg3d_class_and_main(results, monkeypatch)
+
+
+def test_asynchronous_output_equals_blocking_download():
+    """lbm_download_macros_async (device snapshot + copy on a second stream into page-locked buffers) while the next steps
+    are already queued: same numbers as the blocking lbm_download_macros at the same step"""
+    import cases
+    cases.check_async_output(None, (40, 48, 64))
