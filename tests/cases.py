@@ -445,3 +445,67 @@ def check_async_output(lib_path, n=(10, 12, 16)):
         for x, y in zip(bufs[k % 2], want[k]):
             assert np.array_equal(x, y)
     a.close(); b.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases: degenerate lattices and geometries
+# ---------------------------------------------------------------------------------------------------
+def check_edge_cases(lib_path):
+    # smallest lattices (3 planes along the flow axis; 1 or 2 nodes across wrap onto themselves) against the oracle
+    for lattice, shapes in ((9, ((3, 1), (3, 2), (4, 1), (3, 3))), (19, ((3, 1, 1), (3, 2, 2), (3, 1, 4), (4, 3, 2)))):
+        L = cg_dense.d2q9() if lattice == 9 else cg_dense.d3q19()
+        for shp in shapes:
+            rng = np.random.default_rng(2)
+            r = 0.5 + 0.3 * (rng.random(shp) - 0.5)
+            eng = _lib.Engine(lattice, shp, lib_path=lib_path)
+            eng.set_geometry(np.ones(shp, bool)); eng.init_equilibrium(r, 1 - r); eng.step(4)
+            rho, u = eng.download_macros(); eng.close()
+            sim = cg_dense.CGDense(L, np.ones(shp, bool), theta_deg=90.0)
+            sim.set_densities(r, 1 - r); sim.step(4); sim.head()
+            np.testing.assert_allclose(rho[0], sim.rhoR.reshape(shp), rtol=0, atol=1e-12, err_msg=str(shp))
+            np.testing.assert_allclose(u[0], sim.u[0].reshape(shp), rtol=0, atol=1e-12, err_msg=str(shp))
+    # fewer than 3 planes: refused at creation
+    for lattice, shp in ((9, (2, 8)), (19, (1, 4, 4))):
+        try:
+            _lib.Engine(lattice, shp, lib_path=lib_path)
+            raise AssertionError("a lattice with %s planes was accepted" % shp[0])
+        except _lib.LbmError as e:
+            assert "at least 3 planes" in str(e)
+    # no void node at all: every call succeeds, nothing to compute, empty index structures
+    eng = _lib.Engine(9, (6, 8), lib_path=lib_path)
+    eng.set_geometry(np.zeros((6, 8), bool)); eng.init_equilibrium(np.zeros((6, 8)), np.zeros((6, 8))); eng.step(3)
+    rho, u = eng.download_macros()
+    idx = eng.export_indexing()
+    assert (rho[0] == 0).all() and (u[1] == 0).all() and idx["fluidNodes"].size == 0 and idx["neighboringNodes"].size == 0
+    eng.close()
+    # one void node enclosed by solid: all 8 populations bounce back, the node keeps its masses and stays at rest
+    dom = np.zeros((5, 5), bool); dom[2, 2] = True
+    eng = _lib.Engine(9, (5, 5), lib_path=lib_path, sigma=0.1)
+    eng.set_geometry(dom); eng.init_equilibrium(0.7 * dom, 0.3 * dom); eng.step(9)
+    rho, u = eng.download_macros()
+    assert abs(rho[0][2, 2] - 0.7) < 1e-14 and abs(rho[1][2, 2] - 0.3) < 1e-14 and abs(u[0][2, 2]) < 1e-14
+    idx = eng.export_indexing()
+    assert idx["fluidNodes"].tolist() == [12] and (idx["neighboringNodes"] <= -2).all() and idx["wettingSolidNodes"].size == 8
+    eng.close()
+    # Shan-Chen with 1, 3 and 4 components: component masses conserved
+    for nc in (1, 3, 4):
+        shp = (8, 10)
+        G = np.zeros((4, 4)); G[:nc, :nc] = 0.1 * (1 - np.eye(nc))
+        eng = _lib.Engine(9, shp, model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, lib_path=lib_path, n_components=nc,
+                          sc_tau=[1.0] * nc + [0.0] * (4 - nc), sc_G=G.ravel(), sc_Gsolid=[0.05, -0.05, 0.0, 0.0])
+        dom = np.ones(shp, bool); dom[3:5, 4:6] = False
+        eng.set_geometry(dom)
+        rng = np.random.default_rng(1)
+        eng.init_equilibrium(*[(0.5 + 0.2 * rng.random(shp)) * dom for _ in range(nc)])
+        m0 = eng.total_mass(); eng.step(10); m1 = eng.total_mass()
+        rho, u = eng.download_macros()
+        assert len(rho) == nc and np.allclose(m0, m1, rtol=1e-12) and np.isfinite(rho[0]).all()
+        eng.close()
+    # wrong number of density arrays
+    eng = _lib.Engine(9, (4, 4), lib_path=lib_path); eng.set_geometry(np.ones((4, 4), bool))
+    try:
+        eng.init_equilibrium(np.ones((4, 4)))
+        raise AssertionError("one density array was accepted for two colours")
+    except _lib.LbmError:
+        pass
+    eng.close()

@@ -166,3 +166,8 @@ def test_perturbation_trajectory_vs_reference_kernels(path, chunk):
 def test_perturbation_vs_dense_oracle(lattice, n, solid):
     m, m_ref = cases.case_cgp_dense(None, lattice, n, steps=8 if n[0] < 20 else 14, solid=solid)
     assert abs(m[0] - m_ref[0]) < 1e-9 and abs(m[1] - m_ref[1]) < 1e-9
+
+
+def test_edge_cases():
+    """smallest lattices, no void node, one enclosed void node, 1 / 3 / 4 Shan-Chen components, wrong argument counts"""
+    cases.check_edge_cases(None)

@@ -155,3 +155,7 @@ def test_perturbation_rejects_what_the_reference_cannot_run(lib):
     for bad in (dict(relax=_lib.RELAX_SRT), dict(inlet=_lib.INLET_VELOCITY)):
         with pytest.raises(_lib.LbmError):
             _lib.Engine(9, (8, 8), lib_path=lib, surface_tension_type=_lib.ST_PERTURBATION, **bad)
+
+
+def test_edge_cases(lib):
+    cases.check_edge_cases(lib)
