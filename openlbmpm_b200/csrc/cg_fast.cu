@@ -506,11 +506,11 @@ static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2) + 8);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};          // per device: the attribute belongs to the function on ONE device
+    if (!configured[h->cfg.device & 63]) {
         LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[h->cfg.device & 63] = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tiled_d3q19<solids>" : "cg_collide_tiled_d3q19<all-fluid>", h->stream);
     cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi);
@@ -537,11 +537,11 @@ static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastF
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * 4 * (TILE_Y + 2) * (TILE_X + (TMA ? 4 : 2)) + 8);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (!configured[h->cfg.device & 63]) {
         LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[h->cfg.device & 63] = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_density_tiled_d3q19<solids>" : "cg_density_tiled_d3q19<all-fluid>", h->stream);
     cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA><<<grid, block, smem, h->stream>>>(c, s, zchunk, z_lo, z_hi);
