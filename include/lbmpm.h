@@ -198,7 +198,8 @@ int lbm_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp);
 
 /* Auxiliary per-node fields at the output point, dense [nz][ny][nx] (NULL = skip): phi (colour field incl.
  * wetting-solid values), G (D arrays, after the wetting correction) and curvature K of the current time level,
- * F (D arrays) = the CSF force of the PREVIOUS step (the lagged force the velocity is evaluated with).        */
+ * F (D arrays) = the CSF force of the PREVIOUS step (the lagged force the velocity is evaluated with).
+ * LBM_ST_PERTURBATION: phi of the output point, G of the last collision, K = F = 0 (the model has neither).    */
 int lbm_download_fields(lbm_handle* h, double* phi, double* const* G, double* const* F, double* K);
 
 /* Sum of each component's density over the void nodes (mass check).                        */

@@ -677,8 +677,10 @@ extern "C" int lbm_download_fields(lbm_handle* h, double* phi, double* const* G,
     if (h->cfg.model != LBM_MODEL_CG) return fail(h, LBM_EINVAL, "colour-gradient fields only");
     set_device(h);
     to_output_point(h);
-    cg_generic_forces(h);           // phi on the wetting solids, G, unit normals of the current time level
-    {
+    // perturbation operator: phi of the output point, G as evaluated by the last collision (phi = SolidColorDiff on solid
+    // neighbours); the model has neither a curvature nor a force field (K and F stay zero)
+    if (h->cfg.surface_tension_type != LBM_ST_PERTURBATION) {
+        cg_generic_forces(h);       // phi on the wetting solids, G, unit normals of the current time level
         CGFields c = h->fields();
         if (h->Q == 9) launch(CurvatureOp<D2Q9>{c}, h->g.count(0), h->stream);
         else launch(CurvatureOp<D3Q19>{c}, h->g.count(0), h->stream);

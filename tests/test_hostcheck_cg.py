@@ -159,3 +159,24 @@ def test_perturbation_rejects_what_the_reference_cannot_run(lib):
 
 def test_edge_cases(lib):
     cases.check_edge_cases(lib)
+
+
+def test_perturbation_fields_download(lib):
+    """lbm_download_fields with the perturbation operator: phi of the output point, G of the last collision, no K / F"""
+    import numpy as np
+    from oracle import cgp_dense
+    dom = np.ones((12, 14), bool); dom[4:6, 5:8] = False
+    rng = np.random.default_rng(0)
+    r = 0.5 + 0.3 * (rng.random(dom.shape) - 0.5)
+    par = dict(beta=0.8, AkR=1e-2, AkB=1e-2, tauR=1.0, tauB=0.9, solid_phi=0.3)
+    eng = cases.cgp_engine(9, dom, lib, **par)
+    eng.init_equilibrium(r * dom, (1 - r) * dom); eng.step(3)
+    sim = cgp_dense.CGPDense(cgp_dense.d2q9(), dom, **par)
+    sim.set_densities(r, 1 - r); sim.step(3)
+    f = eng.download_fields()
+    np.testing.assert_allclose(f["phi"], sim.phi[0], atol=1e-13)
+    np.testing.assert_allclose(f["G"][0], sim.G[0, 0], atol=1e-13); np.testing.assert_allclose(f["G"][1], sim.G[1, 0], atol=1e-13)
+    assert not f["K"].any() and not f["F"][0].any()
+    eng.step(2); sim.step(2)                       # the download did not disturb the run
+    np.testing.assert_allclose(eng.download_macros()[0][0], sim.rhoR[0], atol=1e-13)
+    eng.close()
