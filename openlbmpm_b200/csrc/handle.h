@@ -52,12 +52,13 @@ struct lbm_handle {
     double* out_stage = nullptr;
     size_t out_stage_bytes = 0;
 
+    void* nccl = nullptr;       // ncclComm_t (host test hook: the in-process ring of host_stubs.cu)
+
     // measurement
     double last_ms = 0.0;
     int64_t last_launches = 0;
 #ifndef LBM_HOSTCHECK
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    void* nccl = nullptr;       // ncclComm_t
     // slab decomposition: ghost-plane exchanges run on their own stream, overlapped with the interior planes
     cudaStream_t comm_stream = nullptr, xstream = nullptr;   // xstream: where exchange_* currently enqueues (null = stream)
     cudaEvent_t ev_main = nullptr, ev_comm = nullptr;

@@ -1,13 +1,100 @@
-// host_stubs.cu -- compiled ONLY into the host test hook (tests/hostcheck): the pieces that exist
-// solely as CUDA code (tiled collision kernel, NCCL halo exchange) are absent there.
+// host_stubs.cu -- compiled ONLY into the host test hook (tests/hostcheck): stand-ins for the pieces that exist solely
+// as CUDA code.  The tiled kernels are simply absent; the NCCL halo exchange is replaced by an in-process ring.
 #ifdef LBM_HOSTCHECK
+#include <pthread.h>
+
+#include <map>
+#include <mutex>
+
 #include "internal.h"
+
+// ---- slab decomposition inside ONE process (test hook) ---------------------------------------------------------
+// The CUDA build exchanges ghost planes with ncclSend / ncclRecv between one process per GPU (comm.cu).  Here the
+// "ranks" are host threads of the test process, one handle each, and an exchange is: publish my array, barrier, copy
+// the neighbours' boundary planes into my ghost planes, barrier.  Same ring, same planes, same `dirs` filter as
+// comm.cu::ring_exchange -- so the CPU tier can demand that P slabs reproduce the single-slab run bit for bit for
+// every model and kernel path (tests/test_hostcheck_slabs.py), i.e. it checks WHICH planes the step loops exchange
+// and WHEN, everything about the decomposition except NCCL itself.
+namespace {
+struct HostRing {
+    int n = 0;
+    std::vector<lbm_handle*> members;
+    std::vector<void*> pub;
+    std::vector<int> ival;
+    pthread_barrier_t bar;
+};
+std::mutex g_ring_mutex;
+std::map<std::string, HostRing*> g_rings;
+uint64_t g_ring_counter = 0;
+
+template <class T>
+void host_ring_exchange(lbm_handle* h, T* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+    HostRing* r = (HostRing*)h->nccl;
+    const lbm::Grid& g = h->g;
+    r->pub[h->rank] = base;
+    pthread_barrier_wait(&r->bar);                      // every slab has written its own planes and published its array
+    const int up = (h->rank + 1) % r->n, down = (h->rank + r->n - 1) % r->n;
+    const T* bup = (const T*)r->pub[up];
+    const T* bdown = (const T*)r->pub[down];
+    const size_t bytes = (size_t)gp * g.plane * sizeof(T);
+    for (int a = 0; a < narr; ++a) {
+        T* f = base + a * stride;
+        const int dir = dirs ? dirs[a] : 0;
+        if (dir == 0 || dir == 1)           // my low ghost <- top planes of the rank below
+            memcpy(f + (int64_t)(lbm::NG - gp) * g.plane, bdown + a * stride + (int64_t)(lbm::NG + g.n2 - gp) * g.plane, bytes);
+        if (dir == 0 || dir == -1)          // my high ghost <- bottom planes of the rank above
+            memcpy(f + (int64_t)(lbm::NG + g.n2) * g.plane, bup + a * stride + (int64_t)lbm::NG * g.plane, bytes);
+    }
+    pthread_barrier_wait(&r->bar);                      // nobody overwrites its planes before the neighbours have read them
+    ++lbm::g_launch_counter;
+}
+}  // namespace
+
 namespace lbm {
-void comm_exchange_f64(lbm_handle*, double*, int64_t, int, int, const int8_t*) { throw BackendError{"multi-rank needs the CUDA build"}; }
-void comm_exchange_u8(lbm_handle*, uint8_t*, int) { throw BackendError{"multi-rank needs the CUDA build"}; }
+void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+    host_ring_exchange(h, base, stride, narr, gp, dirs);
+}
+void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp) { host_ring_exchange(h, base, 0, 1, gp, nullptr); }
 void comm_destroy(lbm_handle*) {}
-int comm_allreduce_max(lbm_handle*, int v) { return v; }
+int comm_allreduce_max(lbm_handle* h, int v) {
+    if (h->nranks <= 1) return v;
+    HostRing* r = (HostRing*)h->nccl;
+    r->ival[h->rank] = v;
+    pthread_barrier_wait(&r->bar);
+    int m = v;
+    for (int k = 0; k < r->n; ++k) m = r->ival[k] > m ? r->ival[k] : m;
+    pthread_barrier_wait(&r->bar);
+    return m;
+}
 }  // namespace lbm
+extern "C" int lbm_nccl_unique_id(uint8_t* id_out) {
+    if (!id_out) return LBM_EINVAL;
+    std::lock_guard<std::mutex> lock(g_ring_mutex);
+    memset(id_out, 0, 128);
+    const uint64_t c = ++g_ring_counter;
+    memcpy(id_out, &c, sizeof(c));
+    memcpy(id_out + 8, "hostring", 8);
+    return LBM_OK;
+}
+extern "C" int lbm_comm_init(lbm_handle* h, int32_t rank, int32_t nranks, const uint8_t* id) {
+    if (!h) return LBM_EINVAL;
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id) { h->err = "bad rank / nranks / id"; return LBM_EINVAL; }
+    if (h->has_geometry) { h->err = "lbm_comm_init must precede lbm_set_geometry"; return LBM_ESTATE; }
+    if (nranks > 1) {
+        std::lock_guard<std::mutex> lock(g_ring_mutex);
+        HostRing*& r = g_rings[std::string((const char*)id, 128)];
+        if (!r) {
+            r = new HostRing();
+            r->n = nranks; r->members.assign(nranks, nullptr); r->pub.assign(nranks, nullptr); r->ival.assign(nranks, 0);
+            pthread_barrier_init(&r->bar, nullptr, (unsigned)nranks);
+        }
+        if (r->n != nranks) { h->err = "nranks differs between the members of one ring"; return LBM_EINVAL; }
+        r->members[rank] = h;
+        h->nccl = r;
+    }
+    h->rank = rank; h->nranks = nranks;
+    return LBM_OK;
+}
 // test hook: the two forms of the 3-D Akai wetting correction (reference-ordered / the tiled kernels' fast form)
 extern "C" void hostcheck_wetting3(const double* G, const double* ns, double cosT, double sinT, int fast, int64_t n, double* out) {
     for (int64_t i = 0; i < n; ++i) {
@@ -17,6 +104,4 @@ extern "C" void hostcheck_wetting3(const double* G, const double* ns, double cos
         for (int a = 0; a < 3; ++a) out[3 * i + a] = g[a];
     }
 }
-extern "C" int lbm_nccl_unique_id(uint8_t*) { return LBM_ENCCL; }
-extern "C" int lbm_comm_init(lbm_handle*, int32_t, int32_t, const uint8_t*) { return LBM_ENCCL; }
 #endif

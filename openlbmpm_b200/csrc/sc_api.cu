@@ -53,7 +53,6 @@ void sc_free(lbm_handle* h) {
 
 static void sc_alloc(lbm_handle* h) {
     if (h->sc) return;
-    if (h->nranks > 1) throw BackendError{"the Shan-Chen models run on one slab"};
     SCState* s = new SCState();
     h->sc = s;
     const int nc = h->cfg.n_components;
@@ -109,14 +108,19 @@ int sc_upload_state(lbm_handle* h, const double* const* pdf, const double* const
 }
 
 // inlet rows: Zou-He velocity per component + ghost row (OptimizedD2Q9GPU.py:839-861, 710-736)
+// slab decomposition: the inlet rows live on the last slab, the outlet rows on the first one
+static bool owns_inlet(const lbm_handle* h) { return h->rank == h->nranks - 1; }
+static bool owns_outlet(const lbm_handle* h) { return h->rank == 0; }
+
 static void sc_inlet(lbm_handle* h, const SCFields& c) {
-    if (c.p.inlet == LBM_INLET_VELOCITY) {
+    if (c.p.inlet == LBM_INLET_VELOCITY && owns_inlet(h)) {
         launch(ScInletVelocityOp{c}, h->g.n0, h->stream);
         for (int zr = c.z_in; zr < c.z_in_ghost; ++zr)         // ghost rows, one after the other (ghostPointsConstantVelocity8/82)
             launch(ScRowCopyOp{c, zr + 1, zr}, h->g.plane, h->stream);
     }
 }
 static void sc_outlet_pressure(lbm_handle* h, const SCFields& c) {
+    if (!owns_outlet(h)) return;
     launch(ScOutletPressureOp{c}, h->g.n0, h->stream);
     for (int zr = c.z_out; zr > 0; --zr)                        // ghostPointsConstantPressureOutlet8/82
         launch(ScRowCopyOp{c, zr - 1, zr}, h->g.plane, h->stream);
@@ -140,7 +144,7 @@ static void sc_iteration(lbm_handle* h) {
     SC_LAUNCH(g.count(0), ScCollideOp, c);                  // interactionCollisionProcess
     exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
     SC_LAUNCH(g.count(0), ScStreamOp, c);                   // calStreaming1GPU/2GPU (+ densities)
-    if (c.p.outlet == LBM_OUTLET_CONVECTIVE) {                  // convectiveOutletGPU / Ghost2 / Ghost3
+    if (c.p.outlet == LBM_OUTLET_CONVECTIVE && owns_outlet(h)) {   // convectiveOutletGPU / Ghost2 / Ghost3
         launch(ScRowCopyOp{c, 2, 3}, g.plane, h->stream);
         launch(ScRowCopyOp{c, 1, 2}, g.plane, h->stream);
         launch(ScRowCopyOp{c, 0, 1}, g.plane, h->stream);
@@ -176,15 +180,18 @@ static void efs_prepare(lbm_handle* h) {
 static void efs_iteration(lbm_handle* h) {
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
-    if (c.p.outlet == LBM_OUTLET_CONVECTIVE) launch(ScSaveRowsOp{c}, 3 * g.plane, h->stream);   // savePDFLastStep
+    const bool convective = c.p.outlet == LBM_OUTLET_CONVECTIVE;
+    if (convective && owns_outlet(h)) launch(ScSaveRowsOp{c}, 3 * g.plane, h->stream);   // savePDFLastStep
     SC_LAUNCH(g.count(0), EfsCollideOp, c);
     exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
     SC_LAUNCH(g.count(0), ScStreamOp, c);
-    if (c.p.outlet == LBM_OUTLET_CONVECTIVE) {
+    if (convective) {
         SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);
-        launch(ScConvectiveEachOp{c, 2}, g.plane, h->stream);
-        launch(ScConvectiveEachOp{c, 1}, g.plane, h->stream);
-        launch(ScConvectiveEachOp{c, 0}, g.plane, h->stream);
+        if (owns_outlet(h)) {
+            launch(ScConvectiveEachOp{c, 2}, g.plane, h->stream);
+            launch(ScConvectiveEachOp{c, 1}, g.plane, h->stream);
+            launch(ScConvectiveEachOp{c, 0}, g.plane, h->stream);
+        }
     } else if (c.p.outlet == LBM_OUTLET_PRESSURE) {
         sc_outlet_pressure(h, c);
     }

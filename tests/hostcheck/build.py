@@ -17,7 +17,7 @@ def build(force=False):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) > os.path.getmtime(d) for d in deps):
         return OUT
-    cmd = ["g++", "-O2", "-std=c++17", "-DLBM_HOSTCHECK", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++"] + srcs + ["-o", OUT]
+    cmd = ["g++", "-O2", "-std=c++17", "-DLBM_HOSTCHECK", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-x", "c++"] + srcs + ["-o", OUT]
     subprocess.check_call(cmd)
     return OUT
 

@@ -1,0 +1,145 @@
+"""Slab decomposition on the CPU tier.  The host test hook replaces NCCL by an in-process ring (host_stubs.cu): the
+"ranks" are threads of this process, one handle each.  P slabs must reproduce the single-slab run BIT FOR BIT (pull
+streaming makes halo arithmetic identical to interior arithmetic), for every model and kernel path -- this checks which
+ghost planes the step loops exchange and when, and who owns the open-boundary rows; NCCL itself and the tiled kernels are
+checked on the GPUs by tests/mgpu_check.py."""
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "hostcheck"))
+import build as hostcheck_build
+from openlbmpm_b200 import _lib
+
+pytestmark = pytest.mark.timeout(300)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return hostcheck_build.build()
+
+
+def run(lib, lattice, dom, rho, steps, world, **kw):
+    """-> stacked [densities..., velocity components...] of the whole lattice after sum(steps) steps"""
+    n_flow = dom.shape[0]
+    assert n_flow % world == 0
+    t = n_flow // world
+    engines = [_lib.Engine(lattice, (t,) + dom.shape[1:], lib_path=lib, **kw) for _ in range(world)]
+    if world > 1:
+        uid = engines[0].nccl_unique_id()
+        for r, e in enumerate(engines):
+            e.comm_init(r, world, uid)
+    out, errors = [None] * world, []
+
+    def work(r):
+        try:
+            sl = slice(r * t, (r + 1) * t)
+            e = engines[r]
+            e.set_geometry(dom[sl])
+            e.init_equilibrium(*[np.where(dom[sl], a[sl], 0.0) for a in rho])
+            parts = []
+            for n in steps:
+                e.step(n)
+                d, u = e.download_macros()
+                parts.append(np.stack(d + u))
+            pdf = e.download_pdfs()
+            out[r] = (parts, np.stack(pdf), e.total_mass())
+        except Exception as ex:       # a rank that dies would leave the others in the barrier: report and bail out
+            errors.append(ex)
+            os._exit(3) if world > 1 else None
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errors:
+        raise errors[0]
+    for e in engines:
+        e.close()
+    macros = [np.concatenate([out[r][0][k] for r in range(world)], axis=1) for k in range(len(steps))]
+    return macros, np.concatenate([out[r][1] for r in range(world)], axis=1), sum(out[r][2] for r in range(world))
+
+
+def geometry(shape, solid, open_ends):
+    dom = np.ones(shape, bool)
+    if solid:
+        idx = np.indices(shape)
+        c = [s / 2 for s in shape]
+        dom = sum((idx[a] - c[a] + (0.5 if a == 0 else 0.0)) ** 2 for a in range(len(shape))) > 6.0     # straddles the seam at n/2
+        if not open_ends:
+            dom &= sum((idx[a] - (1 if a == 0 else 3)) ** 2 for a in range(len(shape))) > 3.0           # and the periodic seam
+    return dom
+
+
+def compare(lib, lattice, shape, steps, solid=True, worlds=(2, 3), ncomp=2, **kw):
+    open_ends = kw.get("inlet", 0) != 0 or kw.get("outlet", 0) != 0
+    dom = geometry(shape, solid, open_ends)
+    rng = np.random.default_rng(3)
+    base = 0.5 + 0.3 * (rng.random(shape) - 0.5)
+    rho = [base, 1.0 - base] + [0.3 + 0.1 * rng.random(shape) for _ in range(ncomp - 2)]
+    ref = run(lib, lattice, dom, rho[:ncomp], steps, 1, **kw)
+    for P in worlds:
+        if shape[0] % P or shape[0] // P < 4:
+            continue
+        got = run(lib, lattice, dom, rho[:ncomp], steps, P, **kw)
+        for k in range(len(steps)):
+            assert np.array_equal(got[0][k], ref[0][k]), "P = %d differs after chunk %d (max %.3e)" % (
+                P, k, np.abs(got[0][k] - ref[0][k]).max())
+        assert np.array_equal(got[1], ref[1]), "populations differ for P = %d" % P
+        np.testing.assert_allclose(got[2], ref[2], rtol=1e-13)
+
+
+OPEN = dict(inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_CONVECTIVE, inlet_velocity=-2.0e-3)
+OPEN_P = dict(inlet=_lib.INLET_PRESSURE, outlet=_lib.OUTLET_PRESSURE, rhoRH=1.004, rhoBH=5e-8, rhoRL=5e-8, rhoBL=1.0)
+
+
+@pytest.mark.parametrize("lattice,shape", [(19, (24, 6, 8)), (9, (24, 10))])
+@pytest.mark.parametrize("name,kw", [
+    ("fast path", dict(contact_angle_deg=70.0)),
+    ("reference-ordered kernels", dict(flags=1, contact_angle_deg=50.0)),
+    ("SRT, unequal viscosities", dict(relax=_lib.RELAX_SRT, tauR=1.0, tauB=0.8, tau_type=1)),
+    ("open channel, velocity inlet + convective outlet, fast path", dict(OPEN, contact_angle_deg=60.0)),
+    ("open channel, reference-ordered kernels", dict(OPEN, flags=1)),
+    ("open channel, pressure inlet + pressure outlet", dict(OPEN_P, contact_angle_deg=110.0)),
+    ("perturbation operator", dict(surface_tension_type=_lib.ST_PERTURBATION, AkR=8e-3, AkB=1e-2, solid_phi=0.4, tauB=0.85)),
+])
+def test_colour_gradient_slabs_bit_equal(lattice, shape, name, kw, lib):
+    compare(lib, lattice, shape, [1, 2, 6], **kw)
+
+
+def test_all_fluid_box_slabs_bit_equal(lib):
+    compare(lib, 19, (24, 6, 8), [3, 5], solid=False, worlds=(2, 3, 6))
+
+
+SC_OPEN = dict(inlet=_lib.INLET_VELOCITY, sc_inlet_velocity=[0.0, -5.0e-4], sc_rho_out=[1.0, 0.02])
+
+
+@pytest.mark.parametrize("lattice,shape", [(9, (24, 12)), (19, (24, 6, 8))])
+@pytest.mark.parametrize("name,kw", [
+    ("original Shan-Chen", dict(model=_lib.MODEL_SC, relax=_lib.RELAX_SRT, sc_G=[0, 0.9, 0, 0, 0.9, 0])),
+    ("explicit forcing SRT", dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_SRT, sc_G=[0, 0.15, 0, 0, 0.15, 0])),
+    ("explicit forcing MRT", dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, sc_G=[0, 0.15, 0, 0, 0.15, 0])),
+])
+def test_shan_chen_slabs_bit_equal(lattice, shape, name, kw, lib):
+    compare(lib, lattice, shape, [1, 2, 6], n_components=2, sc_tau=[1.0, 0.9], sc_Gsolid=[-0.1, 0.1], **kw)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("isotropy 8", dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_SRT, sc_isotropy=8)),
+    ("isotropy 10", dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, sc_isotropy=10)),
+    ("original Shan-Chen, velocity inlet + convective outlet", dict(SC_OPEN, model=_lib.MODEL_SC, relax=_lib.RELAX_SRT, outlet=_lib.OUTLET_CONVECTIVE,
+                                                                     sc_G=[0, 0.9, 0, 0, 0.9, 0])),
+    ("explicit forcing, velocity inlet + pressure outlet", dict(SC_OPEN, model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, outlet=_lib.OUTLET_PRESSURE)),
+    ("explicit forcing, velocity inlet + convective outlet", dict(SC_OPEN, model=_lib.MODEL_EFS, relax=_lib.RELAX_SRT, outlet=_lib.OUTLET_CONVECTIVE)),
+    ("explicit forcing isotropy 8, deep boundary rows", dict(SC_OPEN, model=_lib.MODEL_EFS, relax=_lib.RELAX_SRT, outlet=_lib.OUTLET_PRESSURE, sc_isotropy=8)),
+    ("three components", dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, n_components=3, sc_tau=[1.0, 0.9, 1.1],
+                              sc_G=[0, 0.1, 0.12, 0, 0.1, 0, 0.08, 0, 0.12, 0.08, 0, 0], sc_Gsolid=[-0.1, 0.1, 0.0])),
+])
+def test_shan_chen_d2q9_variants_slabs_bit_equal(name, kw, lib):
+    par = dict(n_components=2, sc_tau=[1.0, 0.9], sc_G=[0, 0.15, 0, 0, 0.15, 0], sc_Gsolid=[-0.1, 0.1])
+    par.update(kw)
+    compare(lib, 9, (24, 12), [1, 2, 6], ncomp=par["n_components"], **par)
