@@ -3,6 +3,7 @@
 methods, but the three `input()` answers can also come from argv or the environment, e.g.
     python main.py 2D flow CG            (or LBM_DIMENSION=2D LBM_MODEL=flow LBM_METHOD=CG python main.py)
     python main.py 3D flow CG --ini IniFiles
+    torchrun --nproc-per-node 8 main.py 3D flow CG --ini IniFiles      (slab decomposition along the flow axis, one GPU per rank)
 The .ini directory defaults to ./IniFiles (the reference hard-codes the same relative path)."""
 import os
 import sys
@@ -51,6 +52,10 @@ def main(argv):
     else:
         print("The chosen type does not exist in current version. Stop here.")
         return 2
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # launched as `torchrun --nproc-per-node P main.py ...`: one slab per GPU
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
     return 0
 
 

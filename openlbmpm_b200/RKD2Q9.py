@@ -86,6 +86,9 @@ class RKColorGradientLBM:
         self.unitEY = np.array([0., 0., 1., 0., -1., 1., 1., -1., -1.])
         self.engine = None
         self._results = None
+        # slab decomposition along the flow axis: one process per GPU under `torchrun` (slab.from_environment), every
+        # rank holds the whole host-side arrays, runs its own slab on its GPU and gathers the results
+        self.slabs = None
 
     # -- ini pieces (overridden by the 3-D class) ---------------------------------------------------
     def _read_domain(self, ini):
@@ -115,7 +118,7 @@ class RKColorGradientLBM:
             self.densityRhoRL = ini.number("BoundaryCondition", "densityRL")
 
     def _say(self, *a):
-        if self.verbose:
+        if self.verbose and (self.slabs is None or self.slabs.rank == 0):
             print(*a)
 
     # -- geometry and initial condition ---------------------------------------------------------------
@@ -230,7 +233,19 @@ class RKColorGradientLBM:
         if inlet not in INLET or outlet not in OUTLET:
             raise IniError("Unknown boundary type %s / %s" % (self.boundaryTypeInlet, self.boundaryTypeOutlet))
         relax = _lib.RELAX_MRT if self.relaxationType == "'MRT'" else _lib.RELAX_SRT
-        self.engine = _lib.Engine(self.LATTICE, self._shape(), model=_lib.MODEL_CG, relax=relax,
+        if self.slabs is None:
+            from . import slab
+            self.slabs = slab.from_environment()
+        shape = self._shape()
+        if self.slabs is not None:
+            from . import slab
+            lo, hi = slab.slab_bounds(shape[0], self.slabs.rank, self.slabs.world)
+            self._slab = slice(lo, hi)
+            shape = (hi - lo,) + tuple(shape[1:])
+        else:
+            self._slab = slice(None)
+        self.engine = _lib.Engine(self.LATTICE, shape, model=_lib.MODEL_CG, relax=relax,
+                                  device=self.slabs.device_index if self.slabs is not None else 0,
                                   sigma=self.surfaceTension, contact_angle_deg=self.contactAngle,
                                   wetting_type=self.wettingType, beta=self.betaThickness, delta=self.deltaValue,
                                   tauR=self.tauR, tauB=self.tauB, tau_type=self.tauCalculation,
@@ -241,7 +256,9 @@ class RKColorGradientLBM:
                                   AkR=self.AkR, AkB=self.AkB, solid_phi=self.solidPhi,
                                   body_force=[self.bodyFX, self.bodyFY, self.bodyFZ if self.LATTICE == 19 else 0.0]
                                   if self.isBodyForce == "'yes'" else [0.0, 0.0, 0.0])
-        self.engine.set_geometry(self.isDomain)
+        if self.slabs is not None:
+            self.engine.comm_init(self.slabs.rank, self.slabs.world, self.slabs.unique_id(self.engine))
+        self.engine.set_geometry(self.isDomain[self._slab])
 
     def _inlet_velocity(self):
         return self.velocityYB + self.velocityYR            # RKD2Q9.py:1300
@@ -251,6 +268,10 @@ class RKColorGradientLBM:
         compact index structures, built on the device and exported bit-exactly."""
         if self.engine is None:
             self._make_engine()
+        if self.slabs is not None:
+            # the compact node numbering of the reference is a property of the whole lattice; a slab only knows its own
+            self._say("slab decomposition: the reference's compact index arrays are not exported")
+            return
         idx = self.engine.export_indexing()
         self.fluidNodes = idx["fluidNodes"]
         self.neighboringNodes = idx["neighboringNodes"]
@@ -273,14 +294,20 @@ class RKColorGradientLBM:
     def convertOptTo2D(self):
         """RKD2Q9.py:902-911: refresh the dense host arrays from the device state (output point of the loop)"""
         rho, u = self.engine.download_macros()
+        pdf = self.engine.download_pdfs()
+        if self.slabs is not None:          # every rank receives the whole lattice
+            rho = [self.slabs.gather(a) for a in rho]; u = [self.slabs.gather(a) for a in u]
+            pdf = [self.slabs.gather(a) for a in pdf]
         self.fluidsRhoR, self.fluidsRhoB = rho
         self.physicalVX, self.physicalVY = u[0], u[1]
         if len(u) == 3:
             self.physicalVZ = u[2]
-        self.fluidPDFR, self.fluidPDFB = self.engine.download_pdfs()
+        self.fluidPDFR, self.fluidPDFB = pdf
 
     def resultInHDF5(self, iStep):
         """RKD2Q9.py:938-957, same group / dataset names"""
+        if self.slabs is not None and self.slabs.rank != 0:
+            return                                  # rank 0 writes the gathered arrays
         if self._results is None:
             self._results = ResultFile("SimulationResultsRK.h5")
         arrays = {"/FluidMacro/FluidDensityRin%g" % iStep: self.fluidsRhoR,
@@ -315,6 +342,8 @@ class RKColorGradientLBM:
 
     def plotDensityDistributionOPT(self, iStep):
         """RKD2Q9.py:959-975 (PNG snapshots; skipped when matplotlib is absent)"""
+        if self.slabs is not None and self.slabs.rank != 0:
+            return
         try:
             import matplotlib
             matplotlib.use("Agg")
@@ -334,14 +363,15 @@ class RKColorGradientLBM:
         self.initializeDomainCondition()
         self._make_engine()
         self.optimizeFluidandSolidArray()
-        self.engine.upload_state([self.fluidPDFR, self.fluidPDFB], [self.fluidsRhoR, self.fluidsRhoB])
+        sl = self._slab
+        self.engine.upload_state([self.fluidPDFR[sl], self.fluidPDFB[sl]], [self.fluidsRhoR[sl], self.fluidsRhoB[sl]])
         iStep = 0
         recordStep = 0
         t0 = time.perf_counter()
         # `asyncOutput` (attribute, or LBM_ASYNC_OUTPUT=1): records of densities + velocities are copied and written
         # behind the step loop (results.AsyncMacroOutput) instead of the reference's blocking copy + append
         out = None
-        if getattr(self, "asyncOutput", os.environ.get("LBM_ASYNC_OUTPUT") == "1"):
+        if getattr(self, "asyncOutput", os.environ.get("LBM_ASYNC_OUTPUT") == "1") and self.slabs is None:
             from .results import AsyncMacroOutput
             out = AsyncMacroOutput(self.engine, self._write_macro_record)
         while iStep < self.timeSteps:
@@ -353,6 +383,8 @@ class RKColorGradientLBM:
                     self.resultInHDF5(recordStep)
                     self.plotDensityDistributionOPT(recordStep)
                     m = self.engine.total_mass()
+                    if self.slabs is not None:
+                        m = self.slabs.sum(m)
                     self._say("step %d: mass R %.12g, mass B %.12g" % (iStep, m[0], m[1]))
                 recordStep += 1
             n = min(self.timeInterval - iStep % self.timeInterval, self.timeSteps - iStep)

@@ -45,6 +45,7 @@ class ShanChenD2Q9:
         self._read_model(self._model_ini(pathIniFile, efs), "EFSParameters" if efs else "ShanChenParameters")
         self.engine = None
         self._results = None
+        self.slabs = None        # slab decomposition under `torchrun` (slab.from_environment), see RKD2Q9.py
 
     # -- lattice-specific pieces (ShanChenD3Q19 overrides them) ------------------------------------
     def _read_extra_dimensions(self, ini):
@@ -69,7 +70,7 @@ class ShanChenD2Q9:
         return defineGeometry(self.nx, self.ny)
 
     def _say(self, *a):
-        if self.verbose:
+        if self.verbose and (self.slabs is None or self.slabs.rank == 0):
             print(*a)
 
     def _read_model(self, ini, section):
@@ -196,16 +197,30 @@ class ShanChenD2Q9:
         if model == _lib.MODEL_SC and outlet == _lib.OUTLET_PRESSURE:
             raise IniError("the original Shan-Chen loop has no pressure outlet (ShanChenD2Q9.py:1603-1621)")
         G = np.zeros((4, 4)); G[:self.typesFluids, :self.typesFluids] = self.interCoeff
-        self.engine = _lib.Engine(self.LATTICE, self._shape(), model=model,
+        from . import slab
+        if self.slabs is None:
+            self.slabs = slab.from_environment()
+        shape = self._shape()
+        self._slab = slice(None)
+        if self.slabs is not None:
+            lo, hi = slab.slab_bounds(shape[0], self.slabs.rank, self.slabs.world)
+            self._slab = slice(lo, hi)
+            shape = (hi - lo,) + tuple(shape[1:])
+        self.engine = _lib.Engine(self.LATTICE, shape, model=model,
+                                  device=self.slabs.device_index if self.slabs is not None else 0,
                                   relax=_lib.RELAX_MRT if self.relaxationType == "'MRT'" else _lib.RELAX_SRT,
                                   n_components=self.typesFluids, inlet=inlet, outlet=outlet, sc_tau=self.tau,
                                   sc_G=G.ravel(), sc_Gsolid=self.interactionSolid, sc_inlet_velocity=self.velocityYInlet,
                                   sc_rho_out=[1.0, 0.02],      # hard-coded upstream: OptimizedD2Q9GPU.py:560-561
                                   sc_isotropy=self.explicitScheme if model == _lib.MODEL_EFS else 4)
-        self.engine.set_geometry(self.isDomain)
+        if self.slabs is not None:
+            self.engine.comm_init(self.slabs.rank, self.slabs.world, self.slabs.unique_id(self.engine))
+        self.engine.set_geometry(self.isDomain[self._slab])
 
     def optimizeFluidArray(self):
         """ShanChenD2Q9.py:587-659: compact node list and neighbour table (solids are -1 in this class)"""
+        if self.slabs is not None:
+            return          # the compact numbering belongs to the whole lattice; a slab only knows its own nodes
         idx = self.engine.export_indexing()
         self.fluidNodes = idx["fluidNodes"]
         nb = idx["neighboringNodes"].copy()
@@ -216,14 +231,20 @@ class ShanChenD2Q9:
 
     def convertOptTo2D(self):
         rho, u = self.engine.download_macros()
+        pdf = self.engine.download_pdfs()
+        if self.slabs is not None:          # every rank receives the whole lattice
+            rho = [self.slabs.gather(a) for a in rho]; u = [self.slabs.gather(a) for a in u]
+            pdf = [self.slabs.gather(a) for a in pdf]
         self.fluidsDensity = np.stack(rho)
         self.physicalVX, self.physicalVY = u[0], u[1]
         if self.LATTICE == 19:
             self.physicalVZ = u[2]
-        self.fluidPDF = np.stack(self.engine.download_pdfs())
+        self.fluidPDF = np.stack(pdf)
 
     def resultInHDF5(self, iStep):
         """ShanChenD2Q9.py:940-955"""
+        if self.slabs is not None and self.slabs.rank != 0:
+            return                                  # rank 0 writes the gathered arrays
         if self._results is None:
             self._results = ResultFile("SimulationResults.h5", groups=("FluidMacro", "FluidVelocity"))
         arrays = {"/FluidMacro/FluidDensityType%gin%g" % (k, iStep): self.fluidsDensity[k] for k in range(self.typesFluids)}
@@ -246,12 +267,13 @@ class ShanChenD2Q9:
         self.initializeDomainCondition()
         self._make_engine(model)
         self.optimizeFluidArray()
-        self.engine.upload_state(list(self.fluidPDF), list(self.fluidsDensity))
+        sl = self._slab
+        self.engine.upload_state([f[sl] for f in self.fluidPDF], [r[sl] for r in self.fluidsDensity])
         step = record = 0
         total = self.numTimeStep + 1                 # both loops run numTimeStep + 1 iterations
         t0 = time.perf_counter()
         out = None          # `asyncOutput` / LBM_ASYNC_OUTPUT=1: records are copied and written behind the step loop
-        if getattr(self, "asyncOutput", os.environ.get("LBM_ASYNC_OUTPUT") == "1"):
+        if getattr(self, "asyncOutput", os.environ.get("LBM_ASYNC_OUTPUT") == "1") and self.slabs is None:
             from .results import AsyncMacroOutput
             out = AsyncMacroOutput(self.engine, self._write_macro_record)
         while step < total:
@@ -261,7 +283,8 @@ class ShanChenD2Q9:
                 else:
                     self.convertOptTo2D()
                     self.resultInHDF5(record)
-                    self._say("step %d: masses %s" % (step, self.engine.total_mass()))
+                    m = self.engine.total_mass()
+                    self._say("step %d: masses %s" % (step, self.slabs.sum(m) if self.slabs is not None else m))
                 record += 1
             n = min(interval - step % interval, total - step)
             self.engine.step(n)

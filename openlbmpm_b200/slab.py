@@ -65,3 +65,70 @@ def ring_exchange_reference(dist, padded, ng, gp, rank, world):
     padded[ng - gp:ng] = lo
     padded[ng + n:ng + n + gp] = hi
     return padded
+
+
+# ---------------------------------------------------------------------------------------------------
+# what a host class needs from "the other ranks": the NCCL id, gathers of result slabs, small sums
+# ---------------------------------------------------------------------------------------------------
+class TorchSlabs:
+    """one process per GPU, launched by `torchrun` (RANK / LOCAL_RANK / WORLD_SIZE in the environment)"""
+
+    def __init__(self, dist, rank, world, local_rank):
+        self.dist, self.rank, self.world, self.local_rank = dist, rank, world, local_rank
+        self.device_index = local_rank
+
+    def unique_id(self, engine):
+        return share_unique_id(self.dist, engine, self.rank, device="cuda")
+
+    def gather(self, local):
+        return gather_slabs(self.dist, local, self.world, device="cuda")
+
+    def sum(self, values):
+        import torch
+        t = torch.as_tensor(np.asarray(values, dtype=np.float64), device="cuda")
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+
+def from_environment():
+    """-> TorchSlabs when the process was launched as one rank of several (`torchrun`), else None"""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return TorchSlabs(dist, int(os.environ.get("RANK", "0")), world, local)
+
+
+class ThreadSlabs:
+    """the ranks are threads of one process (CPU test tier, with the host test hook's in-process ring)"""
+
+    class Shared:
+        def __init__(self, world):
+            import threading
+            self.world, self.barrier, self.slots = world, threading.Barrier(world), [None] * world
+
+    def __init__(self, shared, rank):
+        self.shared, self.rank, self.world, self.device_index = shared, rank, shared.world, 0
+
+    def _exchange(self, value):
+        s = self.shared
+        s.slots[self.rank] = value
+        s.barrier.wait()
+        got = list(s.slots)
+        s.barrier.wait()
+        return got
+
+    def unique_id(self, engine):
+        return self._exchange(engine.nccl_unique_id() if self.rank == 0 else None)[0]
+
+    def gather(self, local):
+        return np.concatenate(self._exchange(np.ascontiguousarray(local)), axis=0)
+
+    def sum(self, values):
+        return np.sum(self._exchange(np.asarray(values, dtype=np.float64)), axis=0)

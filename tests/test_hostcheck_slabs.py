@@ -143,3 +143,71 @@ def test_shan_chen_d2q9_variants_slabs_bit_equal(name, kw, lib):
     par = dict(n_components=2, sc_tau=[1.0, 0.9], sc_G=[0, 0.15, 0, 0, 0.15, 0], sc_Gsolid=[-0.1, 0.1])
     par.update(kw)
     compare(lib, 9, (24, 12), [1, 2, 6], ncomp=par["n_components"], **par)
+
+
+# ---- the host classes on slabs: `torchrun --nproc-per-node P main.py 3D flow CG` (slab.from_environment); here the ranks
+# are threads (slab.ThreadSlabs) over the in-process ring ----
+def run_class(cls, ini_dir, world, monkeypatch, tmp_path, edit=None):
+    from openlbmpm_b200 import slab
+    monkeypatch.setattr(_lib, "LIB_PATH", hostcheck_build.build())
+    monkeypatch.setenv("LBM_RESULTS_DIR", str(tmp_path / ("results%d" % world)))
+    shared = slab.ThreadSlabs.Shared(world)
+    sims, errors = [None] * world, []
+
+    def work(r):
+        try:
+            sim = cls(ini_dir, verbose=False)
+            if world > 1:
+                sim.slabs = slab.ThreadSlabs(shared, r)
+            if edit:
+                edit(sim)
+            getattr(sim, "runRKColorGradient2D", None) and sim.runRKColorGradient2D()
+            getattr(sim, "runTypeSCmodel", None) and sim.runTypeSCmodel()
+            sims[r] = sim
+        except BaseException as ex:
+            errors.append(ex)
+            if world > 1:
+                os._exit(3)
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errors:
+        raise errors[0]
+    return sims
+
+
+@pytest.mark.parametrize("which", ["cg3d", "cg2d", "cgp3d"])
+def test_host_classes_on_slabs(which, monkeypatch, tmp_path):
+    from openlbmpm_b200.RKD2Q9 import RKColorGradientLBM
+    from openlbmpm_b200.RKColorGradientD3Q19 import RKColorGradient3D
+    ini = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ini", which)
+    cls = RKColorGradientLBM if which == "cg2d" else RKColorGradient3D
+
+    def edit(sim):
+        shape = sim._shape()
+        idx = np.indices(shape)
+        sim.initialRedRegion = sum((idx[a] - shape[a] / 2 + 0.5) ** 2 for a in range(len(shape))) < (min(shape) / 3.0) ** 2
+    one = run_class(cls, ini, 1, monkeypatch, tmp_path, edit)[0]
+    two = run_class(cls, ini, 2, monkeypatch, tmp_path, edit)
+    for sim in two:                                   # every rank ends with the whole lattice
+        assert np.array_equal(sim.fluidsRhoR, one.fluidsRhoR) and np.array_equal(sim.fluidsRhoB, one.fluidsRhoB)
+        assert np.array_equal(sim.physicalVX, one.physicalVX) and np.array_equal(sim.fluidPDFB, one.fluidPDFB)
+    import glob
+    assert len(glob.glob(str(tmp_path / "results2" / "*"))) == len(glob.glob(str(tmp_path / "results1" / "*"))) > 0   # rank 0 wrote
+
+
+@pytest.mark.parametrize("which", ["sc", "efs", "efs3d"])
+def test_shan_chen_classes_on_slabs(which, monkeypatch, tmp_path):
+    from openlbmpm_b200.ShanChenD2Q9 import ShanChenD2Q9
+    from openlbmpm_b200.ShanChenD3Q19 import ShanChenD3Q19
+    ini = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ini", which)
+    cls = ShanChenD3Q19 if which == "efs3d" else ShanChenD2Q9
+    if which == "efs3d":
+        monkeypatch.setattr(ShanChenD3Q19, "runTypeSCmodel", ShanChenD3Q19.runEFS4LBM3DGPU, raising=False)
+    one = run_class(cls, ini, 1, monkeypatch, tmp_path)[0]
+    two = run_class(cls, ini, 2, monkeypatch, tmp_path)
+    for sim in two:
+        assert np.array_equal(sim.fluidsDensity, one.fluidsDensity) and np.array_equal(sim.physicalVY, one.physicalVY)
+        assert np.array_equal(sim.fluidPDF, one.fluidPDF)
