@@ -2,7 +2,8 @@
 (`from ShanChenD3Q19 import ShanChenD3Q19`, main.py:17,73-77: `.runEFS4LBM3DGPU()`, `.runOriginalSC3DGPU()`)
 but never shipped.  It is the D3Q19 instantiation of the SAME lattice-generic operators that reproduce the
 reference's D2Q9 Shan-Chen vectors (sc_ops.cuh; specification in oracle/sc_dense.py: interaction weights w_q
-(original) / 3 w_q (explicit forcing), solid weights w_q, d'Humieres MRT basis, closed boxes, isotropy 4).
+(original) / 3 w_q (explicit forcing), solid weights w_q, d'Humieres MRT basis, isotropy 4; open boundaries along z:
+per-component Zou-He velocity inlet, Zou-He pressure / convective outlet in their Hecht-Harting form).
 Input contract, mirroring the 2-D class: twophasesetup.ini ([SeparationBorder] xGrid, yGrid, zGrid) plus
 efs3D.ini | shanchen3D.ini (falling back to efs2D.ini | shanchen2D.ini, same sections); geometry from
 `SimpleGeometry.defineGeometry3D(x, y, z)`.  Arrays are `[zGrid, yGrid, xGrid]`, populations `[nf, z, y, x, 19]`."""
@@ -44,11 +45,15 @@ class ShanChenD3Q19(ShanChenD2Q9):
             from .SimpleGeometry import defineGeometry3D
         return defineGeometry3D(self.nx, self.ny, self.nz)
 
+    def _read_model(self, ini, section):
+        super()._read_model(ini, section)
+        if self.boundaryTypeInlet == "'Neumann'":       # the flow axis is z: [VelocityBoundary] velocityZ (velocityY accepted)
+            self.velocityZInlet = np.array(ini.numbers("VelocityBoundary", "velocityZ", "velocityY"))
+            self.velocityYInlet = self.velocityZInlet   # what the engine receives as the inlet velocity per component
+
     def _make_engine(self, model):
-        if self.boundaryTypeInlet != "'Periodic'" or self.boundaryTypeOutlet != "'Periodic'":
-            raise IniError("D3Q19 Shan-Chen runs on closed boxes (periodic faces + bounce-back solids)")
         if model == _lib.MODEL_EFS and self.explicitScheme != 4:
-            raise IniError("D3Q19 explicit forcing: ExplicitScheme 4")
+            raise IniError("D3Q19 explicit forcing: ExplicitScheme 4 (the higher-isotropy neighbour tables of the reference are 2-D)")
         super()._make_engine(model)
 
     def runEFS4LBM3DGPU(self):

@@ -91,9 +91,8 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 1) { g_create_error = "domain sizes must be positive"; return LBM_EINVAL; }
     if (cfg->lattice == 9 && cfg->nz != 1) { g_create_error = "D2Q9 needs nz = 1"; return LBM_EINVAL; }
     if (cfg->model < LBM_MODEL_CG || cfg->model > LBM_MODEL_EFS) { g_create_error = "unknown model"; return LBM_EINVAL; }
-    if (cfg->model != LBM_MODEL_CG && cfg->lattice == 19 &&
-        (cfg->inlet != LBM_BC_PERIODIC || cfg->outlet != LBM_BC_PERIODIC || (cfg->sc_isotropy != 0 && cfg->sc_isotropy != 4))) {
-        g_create_error = "D3Q19 Shan-Chen: closed boxes (periodic + bounce back) and ExplicitScheme 4 only"; return LBM_EINVAL;
+    if (cfg->model != LBM_MODEL_CG && cfg->lattice == 19 && cfg->sc_isotropy != 0 && cfg->sc_isotropy != 4) {
+        g_create_error = "D3Q19 Shan-Chen: ExplicitScheme 4 only (the higher-isotropy neighbour tables of the reference are 2-D)"; return LBM_EINVAL;
     }
     if (cfg->model != LBM_MODEL_CG && (cfg->n_components < 1 || cfg->n_components > 4)) {
         g_create_error = "n_components must be 1..4"; return LBM_EINVAL;

@@ -1,7 +1,7 @@
 // sc_api.cu -- state and step loops of the Shan-Chen models behind the C ABI
 // (original Shan-Chen: ShanChenD2Q9.py:1492-1629; explicit forcing SRT/MRT: ShanChenD2Q9.py:1714-2087).
 // D2Q9 follows the reference; D3Q19 (`ShanChenD3Q19.runOriginalSC3DGPU / runEFS4LBM3DGPU`, named by main.py:73-77
-// but absent upstream) runs the same lattice-generic operators on closed boxes (oracle/sc_dense.py).
+// but absent upstream) runs the same lattice-generic operators, open boundaries included (oracle/sc_dense.py).
 #include "internal.h"
 #include "sc_ops.cuh"
 
@@ -61,7 +61,7 @@ static void sc_alloc(lbm_handle* h) {
     const int Q = h->Q, D = h->D;
     s->fS = alloc0(nc * Q * V); s->fC = alloc0(nc * Q * V); s->rho = alloc0(nc * V); s->F = alloc0(nc * D * V);
     s->ueq = alloc0(D * V); s->uph = alloc0(D * V);
-    s->fold = alloc0((size_t)nc * 9 * 3 * h->g.plane * sizeof(double));
+    s->fold = alloc0((size_t)nc * Q * 3 * h->g.plane * sizeof(double));
 }
 
 int sc_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp) {
@@ -114,16 +114,16 @@ static bool owns_outlet(const lbm_handle* h) { return h->rank == 0; }
 
 static void sc_inlet(lbm_handle* h, const SCFields& c) {
     if (c.p.inlet == LBM_INLET_VELOCITY && owns_inlet(h)) {
-        launch(ScInletVelocityOp{c}, h->g.n0, h->stream);
+        SC_LAUNCH(h->g.plane, ScInletVelocityOp, c);
         for (int zr = c.z_in; zr < c.z_in_ghost; ++zr)         // ghost rows, one after the other (ghostPointsConstantVelocity8/82)
-            launch(ScRowCopyOp{c, zr + 1, zr}, h->g.plane, h->stream);
+            SC_LAUNCH(h->g.plane, ScRowCopyOp, c, zr + 1, zr);
     }
 }
 static void sc_outlet_pressure(lbm_handle* h, const SCFields& c) {
     if (!owns_outlet(h)) return;
-    launch(ScOutletPressureOp{c}, h->g.n0, h->stream);
+    SC_LAUNCH(h->g.plane, ScOutletPressureOp, c);
     for (int zr = c.z_out; zr > 0; --zr)                        // ghostPointsConstantPressureOutlet8/82
-        launch(ScRowCopyOp{c, zr - 1, zr}, h->g.plane, h->stream);
+        SC_LAUNCH(h->g.plane, ScRowCopyOp, c, zr - 1, zr);
 }
 
 static void sc_ensure_head(lbm_handle* h) {
@@ -145,9 +145,9 @@ static void sc_iteration(lbm_handle* h) {
     exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
     SC_LAUNCH(g.count(0), ScStreamOp, c);                   // calStreaming1GPU/2GPU (+ densities)
     if (c.p.outlet == LBM_OUTLET_CONVECTIVE && owns_outlet(h)) {   // convectiveOutletGPU / Ghost2 / Ghost3
-        launch(ScRowCopyOp{c, 2, 3}, g.plane, h->stream);
-        launch(ScRowCopyOp{c, 1, 2}, g.plane, h->stream);
-        launch(ScRowCopyOp{c, 0, 1}, g.plane, h->stream);
+        SC_LAUNCH(g.plane, ScRowCopyOp, c, 2, 3);
+        SC_LAUNCH(g.plane, ScRowCopyOp, c, 1, 2);
+        SC_LAUNCH(g.plane, ScRowCopyOp, c, 0, 1);
     }
     SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);
     s->head_done = false;
@@ -181,16 +181,16 @@ static void efs_iteration(lbm_handle* h) {
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
     const bool convective = c.p.outlet == LBM_OUTLET_CONVECTIVE;
-    if (convective && owns_outlet(h)) launch(ScSaveRowsOp{c}, 3 * g.plane, h->stream);   // savePDFLastStep
+    if (convective && owns_outlet(h)) SC_LAUNCH(3 * g.plane, ScSaveRowsOp, c);   // savePDFLastStep
     SC_LAUNCH(g.count(0), EfsCollideOp, c);
     exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
     SC_LAUNCH(g.count(0), ScStreamOp, c);
     if (convective) {
         SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);
         if (owns_outlet(h)) {
-            launch(ScConvectiveEachOp{c, 2}, g.plane, h->stream);
-            launch(ScConvectiveEachOp{c, 1}, g.plane, h->stream);
-            launch(ScConvectiveEachOp{c, 0}, g.plane, h->stream);
+            SC_LAUNCH(g.plane, ScConvectiveEachOp, c, 2);
+            SC_LAUNCH(g.plane, ScConvectiveEachOp, c, 1);
+            SC_LAUNCH(g.plane, ScConvectiveEachOp, c, 0);
         }
     } else if (c.p.outlet == LBM_OUTLET_PRESSURE) {
         sc_outlet_pressure(h, c);

@@ -1,6 +1,6 @@
 // sc_ops.cuh -- multi-component Shan-Chen models on the dense grid, one thread per node, written once for any
 // lattice (D2Q9: the reference's; D3Q19: `ShanChenD3Q19`, which main.py:17,73-77 names but the reference does not
-// ship -- the direct generalisation fixed in oracle/sc_dense.py, closed boxes, isotropy 4):
+// ship -- the direct generalisation fixed in oracle/sc_dense.py, isotropy 4):
 //   * original Shan-Chen      (ShanChenD2Q9.runOptimizedLBM,   ShanChenD2Q9.py:1433-1629; kernels in
 //                              ShanChen2D/OptimizedD2Q9GPU.py)
 //   * explicit forcing SRT/MRT (ShanChenD2Q9.runOptimizedEFLBM, ShanChenD2Q9.py:1631-2087; kernels in
@@ -32,7 +32,7 @@ struct SCFields {
     double* F;       // [nc][D][vol]
     double* ueq;     // [D][vol]   common equilibrium velocity (EFS)
     double* uph;     // [D][vol]   physical velocity
-    double* fold;    // [nc][9][3 planes] populations of rows 0..2 before the collision (convective outlet, D2Q9)
+    double* fold;    // [nc][Q][3 planes] populations of planes 0..2 before the collision (convective outlet)
     const uint8_t* cls;
     int z_in, z_in_ghost, z_out;
     LBM_HD double* f(double* base, int c, int q) const { return base + ((int64_t)c * Q + q) * g.vol; }
@@ -137,45 +137,74 @@ struct ScPhysicalVelocityOp {
     }
 };
 
-// constantVelocityZouHeBoundaryHigher (OptimizedD2Q9GPU.py:839-861): per-component Zou-He velocity on row z_in
+// ---- open boundaries: planes along the flow axis (y in 2-D, z in 3-D; inlet on top, outlet at the bottom) -------
+// Written for any lattice: the unknown populations of a plane are those pointing into the domain, s0 / s1 the sums of
+// the in-plane / outward populations, N_t the in-plane transverse momentum that Zou-He redistributes over the diagonal
+// unknowns.  For D2Q9 these are the reference's formulas term by term (f4 = f2 - 2/3 rho v, f7 = f5 + (f1 - f3)/2 -
+// rho v / 6, ...); for D3Q19 (no reference code) their Hecht-Harting generalisation, as for the colour gradient.
+// Items: the n0 * n1 nodes of one plane.
+template <class L>
+LBM_HD void sc_plane_sums(const SCFields& c, int k, int64_t id, int sign, double* fl, double* s0, double* s1, double* N) {
+    bool first0 = true, first1 = true;
+    N[0] = N[1] = 0.0; *s0 = *s1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < L::Q; ++q) {
+        fl[q] = c.f(c.fS, k, q)[id];
+        if (L::d2(q) == 0) {
+            *s0 = first0 ? fl[q] : *s0 + fl[q]; first0 = false;
+            if (L::d0(q) != 0) N[0] += L::d0(q) * fl[q];
+            if (L::d1(q) != 0) N[1] += L::d1(q) * fl[q];
+        } else if (L::d2(q) == sign) {
+            *s1 = first1 ? fl[q] : *s1 + fl[q]; first1 = false;
+        }
+    }
+}
+// constantVelocityZouHeBoundaryHigher (OptimizedD2Q9GPU.py:839-861): per-component Zou-He velocity on plane z_in
+template <class L>
 struct ScInletVelocityOp {
     SCFields c;
-    LBM_HD void operator()(int64_t x) const {
-        const Grid& g = c.g; const int64_t id = g.at((int)x, 0, c.z_in);
+    LBM_HD void operator()(int64_t r) const {
+        const Grid& g = c.g; const int64_t id = (int64_t)(c.z_in + NG) * g.plane + r;
         if (!(c.cls[id] & CLS_FLUID)) return;
         for (int k = 0; k < c.p.nc; ++k) {
             const double v = c.p.vin[k];
-            const double f0 = c.f(c.fS, k, 0)[id], f1 = c.f(c.fS, k, 1)[id], f2 = c.f(c.fS, k, 2)[id], f3 = c.f(c.fS, k, 3)[id];
-            const double f5 = c.f(c.fS, k, 5)[id], f6 = c.f(c.fS, k, 6)[id];
-            const double r = (f0 + f1 + f3 + 2.0 * (f2 + f5 + f6)) / (1.0 + v);
-            c.rho[k * g.vol + id] = r;
-            c.f(c.fS, k, 4)[id] = f2 - 2.0 / 3.0 * r * v;
-            c.f(c.fS, k, 7)[id] = f5 + (f1 - f3) / 2.0 - 1.0 / 6.0 * r * v;
-            c.f(c.fS, k, 8)[id] = f6 - (f1 - f3) / 2.0 - 1.0 / 6.0 * r * v;
+            double fl[L::Q], s0, sp, N[2];
+            sc_plane_sums<L>(c, k, id, +1, fl, &s0, &sp, N);
+            const double rho = (s0 + 2.0 * sp) / (1.0 + v);
+            c.rho[k * g.vol + id] = rho;
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                if (L::d2(q) != -1) continue;
+                c.f(c.fS, k, q)[id] = fl[L::opp(q)] + 1.0 / 2.0 * (-(L::d0(q) * N[0] + L::d1(q) * N[1])) - 6.0 * L::w(q) * rho * v;
+            }
         }
     }
 };
-// constantPressureZouHeBoundaryLower (OptimizedD2Q9GPU.py:555-584) on row 1.  The reference ignores its
+// constantPressureZouHeBoundaryLower (OptimizedD2Q9GPU.py:555-584) on plane z_out.  The reference ignores its
 // densityL argument and uses the hard-coded densities [1.0, 0.02]; they arrive here as p.rho_out.
+template <class L>
 struct ScOutletPressureOp {
     SCFields c;
-    LBM_HD void operator()(int64_t x) const {
-        const Grid& g = c.g; const int64_t id = g.at((int)x, 0, c.z_out);
+    LBM_HD void operator()(int64_t r) const {
+        const Grid& g = c.g; const int64_t id = (int64_t)(c.z_out + NG) * g.plane + r;
         if (!(c.cls[id] & CLS_FLUID)) return;
         for (int k = 0; k < c.p.nc; ++k) {
             const double d = c.p.rho_out[k];
-            const double f0 = c.f(c.fS, k, 0)[id], f1 = c.f(c.fS, k, 1)[id], f3 = c.f(c.fS, k, 3)[id], f4 = c.f(c.fS, k, 4)[id];
-            const double f7 = c.f(c.fS, k, 7)[id], f8 = c.f(c.fS, k, 8)[id];
-            const double vy = 1.0 - (f0 + f1 + f3 + 2.0 * (f4 + f7 + f8)) / d;
-            c.f(c.fS, k, 2)[id] = f4 + 2.0 / 3.0 * vy * d;
-            c.f(c.fS, k, 5)[id] = f7 + 1.0 / 2.0 * (f3 - f1) + 1.0 / 6.0 * d * vy;
-            c.f(c.fS, k, 6)[id] = f8 - 1.0 / 2.0 * (f3 - f1) + 1.0 / 6.0 * d * vy;
+            double fl[L::Q], s0, sm, N[2];
+            sc_plane_sums<L>(c, k, id, -1, fl, &s0, &sm, N);
+            const double vy = 1.0 - (s0 + 2.0 * sm) / d;
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                if (L::d2(q) != 1) continue;
+                c.f(c.fS, k, q)[id] = fl[L::opp(q)] + 1.0 / 2.0 * (-(L::d0(q) * N[0] + L::d1(q) * N[1])) + 6.0 * L::w(q) * d * vy;
+            }
             c.rho[k * g.vol + id] = d;
         }
     }
 };
-// row copies with rho = sum: ghostPointsConstantVelocityInlet (710-736), ghostPointsConstantPressureOutlet
+// plane copies with rho = sum: ghostPointsConstantVelocityInlet (710-736), ghostPointsConstantPressureOutlet
 // (743-768), convectiveOutletGPU / Ghost2 / Ghost3 (960-1036)
+template <class L>
 struct ScRowCopyOp {
     SCFields c; int z_dst, z_src;
     LBM_HD void operator()(int64_t r) const {
@@ -184,7 +213,7 @@ struct ScRowCopyOp {
         if (!(c.cls[d] & CLS_FLUID) || !(c.cls[s] & CLS_FLUID)) return;
         for (int k = 0; k < c.p.nc; ++k) {
             double acc = 0.0;
-            for (int q = 0; q < 9; ++q) {
+            for (int q = 0; q < L::Q; ++q) {
                 const double v = c.f(c.fS, k, q)[s];
                 c.f(c.fS, k, q)[d] = v;
                 acc = q == 0 ? v : acc + v;
@@ -193,16 +222,18 @@ struct ScRowCopyOp {
         }
     }
 };
-// savePDFLastStep (OptimizedD2Q9GPU.py:70-78), restricted to the rows the convective outlet reads (0..2)
+// savePDFLastStep (OptimizedD2Q9GPU.py:70-78), restricted to the planes the convective outlet reads (0..2)
+template <class L>
 struct ScSaveRowsOp {
     SCFields c;
     LBM_HD void operator()(int64_t i) const {      // i over 3 planes
         const Grid& g = c.g; const int64_t id = (int64_t)NG * g.plane + i;
         for (int k = 0; k < c.p.nc; ++k)
-            for (int q = 0; q < 9; ++q) c.fold[((int64_t)k * 9 + q) * 3 * g.plane + i] = c.f(c.fS, k, q)[id];
+            for (int q = 0; q < L::Q; ++q) c.fold[((int64_t)k * L::Q + q) * 3 * g.plane + i] = c.f(c.fS, k, q)[id];
     }
 };
-// convectiveOutletEachGPU / Each2 / Each3 (OptimizedD2Q9GPU.py:1044-1119): row z <- (f_old + |u_y(row 3)| f(row z+1)) / (1 + |u_y|)
+// convectiveOutletEachGPU / Each2 / Each3 (OptimizedD2Q9GPU.py:1044-1119): plane z <- (f_old + |u_up(plane 3)| f(plane z+1)) / (1 + |u_up|)
+template <class L>
 struct ScConvectiveEachOp {
     SCFields c; int z;
     LBM_HD void operator()(int64_t r) const {
@@ -210,11 +241,11 @@ struct ScConvectiveEachOp {
         const int64_t d = (int64_t)(z + NG) * g.plane + r, s = (int64_t)(z + 1 + NG) * g.plane + r;
         const int64_t r3 = (int64_t)(3 + NG) * g.plane + r;
         if (!(c.cls[d] & CLS_FLUID)) return;
-        const double v = fabs(c.uph[g.vol + r3]);
+        const double v = fabs(c.uph[(int64_t)(L::D - 1) * g.vol + r3]);
         for (int k = 0; k < c.p.nc; ++k) {
             double acc = 0.0;
-            for (int q = 0; q < 9; ++q) {
-                const double fo = c.fold[((int64_t)k * 9 + q) * 3 * g.plane + (int64_t)z * g.plane + r];
+            for (int q = 0; q < L::Q; ++q) {
+                const double fo = c.fold[((int64_t)k * L::Q + q) * 3 * g.plane + (int64_t)z * g.plane + r];
                 const double val = (fo + v * c.f(c.fS, k, q)[s]) / (1.0 + v);
                 c.f(c.fS, k, q)[d] = val;
                 acc += val;

@@ -2,8 +2,11 @@
 
 Second restatement of the two live Shan-Chen loops of openLBMPM (ShanChen2D/ShanChenD2Q9.py:1492-1629 original
 Shan-Chen; :1714-2087 explicit forcing SRT/MRT, isotropy 4; kernels in OptimizedD2Q9GPU.py / ExplicitD2Q9GPU.py),
-written once for any lattice on `[z, y, x]` arrays (closed boxes: periodic + half-way bounce back), so that the
-SAME code runs
+written once for any lattice on `[z, y, x]` arrays (periodic + half-way bounce back; open boundaries along the flow
+axis: per-component Zou-He velocity inlet on top, Zou-He pressure or convective outlet at the bottom -- for D2Q9 the
+reference's row kernels term by term, OptimizedD2Q9GPU.py:555-584, 710-768, 839-861, 960-1119; for D3Q19 their
+Hecht-Harting generalisation: unknown = the populations pointing into the domain, N_t = the in-plane transverse
+momentum), so that the SAME code runs
   * D2Q9  -- pinned against the reference's golden vectors (tests/golden/sc2d_*.npz, periodic and solid cases) in
              tests/test_oracle_sc_dense.py, and
   * D3Q19 -- for which the reference ships no code (`ShanChenD3Q19` is imported by main.py:17 but absent).  The 3-D
@@ -23,7 +26,8 @@ def shift(a, e):
 
 
 class SCDense:
-    def __init__(self, lattice, is_domain, model="EFS", relax="SRT", tau=(1., 1.), G=0.2, Gs=(-0.14, 0.14)):
+    def __init__(self, lattice, is_domain, model="EFS", relax="SRT", tau=(1., 1.), G=0.2, Gs=(-0.14, 0.14),
+                 inlet="Periodic", outlet="Periodic", v_in=(0., 0.), rho_out=(1.0, 0.02)):
         L = self.L = lattice
         dom = np.asarray(is_domain, bool)
         self.dom = dom[None] if dom.ndim == 2 else dom
@@ -33,6 +37,11 @@ class SCDense:
         self.G = np.zeros((self.nc, self.nc)); self.G[0, 1] = self.G[1, 0] = G
         self.Gs = np.asarray(Gs, float)
         self.ef = L.e.astype(float)
+        self.inlet, self.outlet = inlet, outlet
+        self.v_in = np.asarray(v_in, float); self.rho_out = np.asarray(rho_out, float)
+        self.nflow = self.shape[0] if L.D == 3 else self.shape[1]
+        self.z_in, self.z_out = self.nflow - 2, 1
+        self.up = L.e[:, L.D - 1]                       # component along the flow axis (y in 2-D, z in 3-D)
         if relax == "MRT":
             if L.Q == 9:      # ShanChenD2Q9.py:99-106
                 base = np.array([1., 0.6, 1.5, 1., 1.2, 1., 1.2, np.nan, np.nan])
@@ -78,9 +87,76 @@ class SCDense:
                 v = sum(self._momentum(k)[a] + 0.5 * self.F[k, a] for k in range(self.nc))
                 self.uph[a] = np.where(self.dom, v / r, 0.)
 
+    # -- open boundaries: planes along the flow axis ----------------------------------------------------------
+    def _ix(self, r):
+        return (r, slice(None), slice(None)) if self.L.D == 3 else (0, r, slice(None))
+
+    def _row_copy(self, dst, src):
+        """ghostPointsConstantVelocityInlet / ...PressureOutlet / convectiveOutletGPU...: plane dst <- plane src, rho = sum"""
+        d, s_ = self._ix(dst), self._ix(src)
+        m = self.dom[d] & self.dom[s_]
+        for k in range(self.nc):
+            acc = None
+            for q in range(self.L.Q):
+                v = np.where(m, self.f[k, q][s_], self.f[k, q][d])
+                self.f[k, q][d] = v
+                acc = v.copy() if acc is None else acc + v
+            self.rho[k][d] = np.where(m, acc, self.rho[k][d])
+
+    def _plane_sums(self, k, ix, sign):
+        """s0 = sum of the in-plane populations, s1 = sum of those with e_up = sign, N_t = in-plane transverse momentum"""
+        L = self.L
+        s0 = s1 = None
+        N = [0., 0.]
+        for q in range(L.Q):
+            fq = self.f[k, q][ix]
+            if self.up[q] == 0:
+                s0 = fq.copy() if s0 is None else s0 + fq
+                for a in range(L.D - 1):
+                    if L.e[q, a] != 0:
+                        N[a] = N[a] + self.ef[q, a] * fq
+            elif self.up[q] == sign:
+                s1 = fq.copy() if s1 is None else s1 + fq
+        return s0, s1, N
+
+    def _inlet(self):
+        """constantVelocityZouHeBoundaryHigher (OptimizedD2Q9GPU.py:839-861) + ghost plane (710-736)"""
+        if self.inlet != "Neumann":
+            return
+        L = self.L; ix = self._ix(self.z_in); m = self.dom[ix]
+        for k in range(self.nc):
+            v = self.v_in[k]
+            s0, sp, N = self._plane_sums(k, ix, +1)
+            rho = (s0 + 2. * sp) / (1. + v)
+            self.rho[k][ix] = np.where(m, rho, 0.)
+            old = [self.f[k, q][ix].copy() for q in range(L.Q)]
+            for q in range(1, L.Q):
+                if self.up[q] != -1:
+                    continue
+                val = old[L.opp[q]] - 0.5 * sum(self.ef[q, a] * N[a] for a in range(L.D - 1)) - 6. * L.w[q] * rho * v
+                self.f[k, q][ix] = np.where(m, val, old[q])
+        self._row_copy(self.z_in + 1, self.z_in)
+
+    def _outlet_pressure(self):
+        """constantPressureZouHeBoundaryLower (555-584, the hard-coded densities arrive as rho_out) + ghost plane (743-768)"""
+        L = self.L; ix = self._ix(self.z_out); m = self.dom[ix]
+        for k in range(self.nc):
+            d = self.rho_out[k]
+            s0, sm, N = self._plane_sums(k, ix, -1)
+            vy = 1. - (s0 + 2. * sm) / d
+            old = [self.f[k, q][ix].copy() for q in range(L.Q)]
+            for q in range(1, L.Q):
+                if self.up[q] != 1:
+                    continue
+                val = old[L.opp[q]] - 0.5 * sum(self.ef[q, a] * N[a] for a in range(L.D - 1)) + 6. * L.w[q] * d * vy
+                self.f[k, q][ix] = np.where(m, val, old[q])
+            self.rho[k][ix] = np.where(m, d, 0.)
+        self._row_copy(self.z_out - 1, self.z_out)
+
     # -- original Shan-Chen: interactionCollisionProcess (OptimizedD2Q9GPU.py:1274-1446) ----------------------
     def _sc_iteration(self):
         L = self.L
+        self._inlet()
         self._rho()
         psi = self.rho
         with np.errstate(invalid="ignore", divide="ignore"):
@@ -106,6 +182,8 @@ class SCDense:
         self.f = np.where(self.dom, self.f, 0.)
         self._stream()
         self._rho()
+        if self.outlet == "Convective":                  # convectiveOutletGPU / Ghost2 / Ghost3 (960-1036)
+            self._row_copy(2, 3); self._row_copy(1, 2); self._row_copy(0, 1)
         self._uphys()
 
     # -- explicit forcing (ExplicitD2Q9GPU.py:51-363, 1379-1469) ---------------------------------------------
@@ -144,10 +222,16 @@ class SCDense:
         self.fF = np.where(self.dom, self.fF, 0.)
 
     def _efs_iteration(self):
-        if not self.prepared:
+        if not self.prepared:                            # pre-loop, ShanChenD2Q9.py:1714-1849
             self._efs_force_ueq()
             self.f = self.f - 0.5 * self.fF
+            keep = self.rho.copy()
+            self._inlet()
+            if self.outlet == "Dirichlet":
+                self._outlet_pressure()
+            self.rho = keep          # boundary densities set here are overwritten by calFluidRhoGPU before any use
             self.prepared = True
+        f_old = self.f.copy()                            # savePDFLastStep
         d = self.feq - self.f - 0.5 * self.fF
         if self.relax == "SRT":
             self.f = self.f + d / self.tau[:, None, None, None, None] + self.fF
@@ -156,6 +240,21 @@ class SCDense:
         self.f = np.where(self.dom, self.f, 0.)
         self._stream()
         self._rho()
+        self._uphys()
+        if self.outlet == "Convective":                  # convectiveOutletEach{,2,3}GPU (OptimizedD2Q9GPU.py:1044-1119)
+            v = np.abs(self.uph[self.L.D - 1][self._ix(3)])
+            for row in (2, 1, 0):
+                ix, ixn = self._ix(row), self._ix(row + 1)
+                m = self.dom[ix]
+                for k in range(self.nc):
+                    for q in range(self.L.Q):
+                        new = (f_old[k, q][ix] + v * self.f[k, q][ixn]) / (1. + v)
+                        self.f[k, q][ix] = np.where(m, new, self.f[k, q][ix])
+        elif self.outlet == "Dirichlet":
+            self._outlet_pressure()
+        self._inlet()
+        if self.inlet != "Periodic" or self.outlet != "Periodic":
+            self._rho()
         self._uphys()
         self._efs_force_ueq()
 

@@ -265,11 +265,16 @@ def case_d3q19_open_boundaries(lib_path, inlet="Neumann", outlet="Convective", n
 # D3Q19 Shan-Chen (original and explicit forcing) against the lattice-generic dense oracle
 # ---------------------------------------------------------------------------------------------------
 def run_sc_dense_case(lattice, dom, rho, steps, lib_path, model="EFS", relax="SRT", tau=(1.0, 0.9), G=0.2,
-                      Gs=(-0.14, 0.14), atol=1e-10, chunk=None, **extra):
+                      Gs=(-0.14, 0.14), atol=1e-10, chunk=None, bc=None, rows=slice(None), **extra):
     """CUDA path vs oracle/sc_dense.py on the same input: densities, velocities and populations of every chunk"""
     from oracle import sc_dense
     L = sc_dense.d2q9() if lattice == 9 else sc_dense.d3q19()
-    sim = sc_dense.SCDense(L, dom, model=model, relax=relax, tau=tau, G=G, Gs=Gs)
+    opar = {}
+    if bc:      # open boundaries: dict(inlet=, outlet=, v_in=(v0, v1), rho_out=(r0, r1))
+        opar = dict(bc)
+        extra.update(inlet=INLET[bc.get("inlet", "Periodic")], outlet=OUTLET[bc.get("outlet", "Periodic")],
+                     sc_inlet_velocity=list(bc.get("v_in", (0., 0.))), sc_rho_out=list(bc.get("rho_out", (1.0, 0.02))))
+    sim = sc_dense.SCDense(L, dom, model=model, relax=relax, tau=tau, G=G, Gs=Gs, **opar)
     sim.set_densities(rho)
     eng = _lib.Engine(lattice, dom.shape, model=_lib.MODEL_SC if model == "ShanChen" else _lib.MODEL_EFS,
                       relax=RELAX[relax], lib_path=lib_path, n_components=2, sc_tau=list(tau),
@@ -284,12 +289,12 @@ def run_sc_dense_case(lattice, dom, rho, steps, lib_path, model="EFS", relax="SR
         done += n
         r, u = eng.download_macros()
         for k in range(2):
-            np.testing.assert_allclose(r[k], sim.rho[k].reshape(shp), rtol=0, atol=atol, err_msg="rho%d after %d" % (k, done))
+            np.testing.assert_allclose(r[k][rows], sim.rho[k].reshape(shp)[rows], rtol=0, atol=atol, err_msg="rho%d after %d" % (k, done))
         for a in range(L.D):
-            np.testing.assert_allclose(u[a], sim.uph[a].reshape(shp), rtol=0, atol=atol, err_msg="u%d after %d" % (a, done))
+            np.testing.assert_allclose(u[a][rows], sim.uph[a].reshape(shp)[rows], rtol=0, atol=atol, err_msg="u%d after %d" % (a, done))
     pdf = eng.download_pdfs()
     for k in range(2):
-        np.testing.assert_allclose(pdf[k], np.moveaxis(sim.f[k], 0, -1).reshape(shp + (L.Q,)), rtol=0, atol=atol)
+        np.testing.assert_allclose(pdf[k][rows], np.moveaxis(sim.f[k], 0, -1).reshape(shp + (L.Q,))[rows], rtol=0, atol=atol)
     m = eng.total_mass()
     eng.close()
     return m, sim.rho.sum(axis=(1, 2, 3))
@@ -509,3 +514,20 @@ def check_edge_cases(lib_path):
     except _lib.LbmError:
         pass
     eng.close()
+
+
+def case_sc_d3q19_open(lib_path, model="EFS", relax="MRT", outlet="Dirichlet", n=(22, 8, 10), steps=10, **extra):
+    """D3Q19 Shan-Chen channel along z with a solid obstacle: per-component Zou-He velocity inlet on top, pressure or
+    convective outlet at the bottom (oracle: the lattice-generic rows whose D2Q9 form matches the reference's vectors)"""
+    dom = np.ones(n, bool)
+    dom[9:13, 2:5, 3:7] = False
+    z = np.mgrid[0:n[0], 0:n[1], 0:n[2]][0]
+    top = z >= n[0] - 8
+    rho = [np.where(top, 0.02, 1.0), np.where(top, 1.0, 0.02)]
+    G = 3.0 if model == "ShanChen" else 0.2
+    bc = dict(inlet="Neumann", outlet=outlet, v_in=(0.0, -5.03e-4), rho_out=(1.0, 0.02))
+    # the original Shan-Chen loop treats the inlet at the TOP of the next iteration: a download shows the inlet planes after
+    # that treatment, the oracle before it -- compare the planes below them, like the D2Q9 goldens do (cases.check_sc_vs_gold)
+    rows = slice(0, n[0] - 2) if model == "ShanChen" else slice(None)
+    return run_sc_dense_case(19, dom, rho, steps, lib_path, model=model, relax=relax, tau=(1.0, 1.0), G=G, atol=1e-9,
+                             chunk=[1, 3, steps - 4], bc=bc, rows=rows, **extra)

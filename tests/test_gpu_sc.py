@@ -33,3 +33,9 @@ def test_d3q19_larger_box_graph_replay():
     """24 x 20 x 36 nodes, 30 steps in chunks of 1 / 2 / 27 (the last one replays the captured CUDA graph)"""
     m, m_ref = cases.case_sc_d3q19(None, "EFS", "MRT", n=(24, 20, 36), steps=30)
     assert abs(m - m_ref).max() < 1e-8
+
+
+@pytest.mark.parametrize("model,relax,outlet", [("ShanChen", "SRT", "Convective"), ("EFS", "MRT", "Dirichlet"), ("EFS", "SRT", "Convective")])
+def test_d3q19_open_boundaries_vs_dense_oracle(model, relax, outlet):
+    cases.case_sc_d3q19_open(None, model, relax, outlet)
+    cases.case_sc_d3q19_open(None, model, relax, outlet, n=(30, 12, 16), steps=14)

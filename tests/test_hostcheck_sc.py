@@ -40,3 +40,9 @@ def test_d2q9_dense_case_through_the_generic_operators(lib):
     r0 = 0.6 + 0.3 * (rng.random(dom.shape) - 0.5)
     for model, relax in (("ShanChen", "SRT"), ("EFS", "MRT")):
         cases.run_sc_dense_case(9, dom, [r0, 1.1 - r0], 10, lib, model=model, relax=relax, G=3.0 if model == "ShanChen" else 0.2)
+
+
+@pytest.mark.parametrize("model,relax,outlet", [("ShanChen", "SRT", "Convective"), ("EFS", "MRT", "Dirichlet"), ("EFS", "SRT", "Convective"),
+                                                ("EFS", "SRT", "Dirichlet")])
+def test_d3q19_open_boundaries_vs_dense_oracle(model, relax, outlet, lib):
+    cases.case_sc_d3q19_open(lib, model, relax, outlet)

@@ -128,6 +128,15 @@ def test_shan_chen_slabs_bit_equal(lattice, shape, name, kw, lib):
     compare(lib, lattice, shape, [1, 2, 6], n_components=2, sc_tau=[1.0, 0.9], sc_Gsolid=[-0.1, 0.1], **kw)
 
 
+def test_shan_chen_d3q19_open_channel_slabs_bit_equal(lib):
+    for kw in (dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, outlet=_lib.OUTLET_PRESSURE),
+               dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_SRT, outlet=_lib.OUTLET_CONVECTIVE),
+               dict(model=_lib.MODEL_SC, relax=_lib.RELAX_SRT, outlet=_lib.OUTLET_CONVECTIVE, sc_G=[0, 0.9, 0, 0, 0.9, 0])):
+        par = dict(SC_OPEN, n_components=2, sc_tau=[1.0, 0.9], sc_G=[0, 0.15, 0, 0, 0.15, 0], sc_Gsolid=[-0.1, 0.1])
+        par.update(kw)
+        compare(lib, 19, (24, 6, 8), [1, 2, 6], **par)
+
+
 @pytest.mark.parametrize("name,kw", [
     ("isotropy 8", dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_SRT, sc_isotropy=8)),
     ("isotropy 10", dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, sc_isotropy=10)),
