@@ -124,6 +124,8 @@ def run_reference(args):
 
 
 def workload_name(args):
+    if args.workload.startswith("cfg"):
+        return getattr(args, "cfg_description", "BASELINE configuration %s" % args.workload[3:])
     if args.workload == "porous":
         return ("D3Q19 colour-gradient CSF MRT, %d x %d x %d sphere pack (seed 7, porosity ~0.6, half-way bounce back, contact "
                 "angle 60), velocity inlet along -z, convective outlet (BASELINE config 5 geometry)" % (args.size, args.size, args.nz or args.size))
@@ -149,8 +151,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="lbm_config.flags (LBM_FLAG_*), for A/B measurements")
-    ap.add_argument("--workload", default="box", choices=["box", "porous"],
-                    help="box: the metric's periodic spinodal box; porous: sphere pack with velocity inlet + convective outlet (cfg 5)")
+    ap.add_argument("--workload", default="box", choices=["box", "porous", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="box: the metric's periodic spinodal box; porous: sphere pack with velocity inlet + convective outlet (cfg 5 "
+                         "geometry, any size, slab-decomposable); cfgN: BASELINE.json configuration N at its own size on one GPU "
+                         "(--scale shrinks it)")
+    ap.add_argument("--scale", type=float, default=1.0, help="cfgN: factor on the lattice extents")
     ap.add_argument("--nz", type=int, default=0, help="porous: planes along the flow axis (default: --size)")
     args = ap.parse_args()
     if args.workload == "porous":
@@ -172,8 +177,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    cfg = int(args.workload[3:]) if args.workload.startswith("cfg") else 0
+    if cfg and world > 1:
+        raise SystemExit("--workload cfgN runs on one GPU; the slab-decomposed workloads are box and porous")
+    if cfg:
+        args.lattice = 9 if cfg <= 3 else 19
     Q, n = args.lattice, args.size
-    porous = args.workload == "porous"
+    porous = args.workload == "porous" or cfg > 0        # no host-buffer round trip / CPU arm for these lines
     nz = (args.nz or n) if porous else n
     if nz % world:
         raise SystemExit("size must be divisible by the number of GPUs")
@@ -181,12 +191,19 @@ def main():
     shape = (nloc, n, n) if Q == 19 else (nloc, n)
     flags = (_lib.FLAG_GENERIC_KERNELS if args.general else 0) | args.flags
     bc = dict(inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_CONVECTIVE, inlet_velocity=-5.0e-4, contact_angle_deg=60.0) if porous else {}
-    eng = _lib.Engine(Q, shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, device=local, flags=flags,
-                      sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2, **bc)
+    if cfg:
+        from openlbmpm_b200 import synthetic
+        eng, nodes_total, args.cfg_description = synthetic.baseline_config(cfg, scale=args.scale, device=local, flags=flags)
+        shape = eng.shape
+    else:
+        eng = _lib.Engine(Q, shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, device=local, flags=flags,
+                          sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2, **bc)
     if world > 1:
         from openlbmpm_b200 import slab
         eng.comm_init(rank, world, slab.share_unique_id(dist, eng, rank, device="cuda"))
-    if porous:
+    if cfg:
+        pass
+    elif porous:
         from openlbmpm_b200 import synthetic
         sl = slice(rank * nloc, (rank + 1) * nloc)
         dom = synthetic.sphere_pack((nz, n, n))[sl]
@@ -299,13 +316,16 @@ def main():
         except Exception as e:       # the oracle is a checker; its absence must not hide the GPU number
             cpu = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port", "sample": "unavailable: %r" % (e,)}
 
-    line = {"metric": "MLUPS D3Q19 CG-MRT 512^3" if (Q == 19 and n == 512 and not porous) else "MLUPS (void nodes) D3Q19 CG-MRT porous" if porous else "MLUPS %s CG-MRT %d" % ("D3Q19" if Q == 19 else "D2Q9", n),
+    ws_gb = 2 * 2 * Q * 8 * nodes_total / world / 1e9
+    line = {"metric": "MLUPS (void nodes) BASELINE config %d" % cfg if cfg else "MLUPS D3Q19 CG-MRT 512^3" if (Q == 19 and n == 512 and not porous) else "MLUPS (void nodes) D3Q19 CG-MRT porous" if porous else "MLUPS %s CG-MRT %d" % ("D3Q19" if Q == 19 else "D2Q9", n),
             "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "l2": "working set (%.1f GB) far larger than the 126 MB L2" % (
-                           2 * 2 * Q * 8 * nodes_total / 1e9),
-                       "path": "general kernels" if args.general else "fused fast path", "slab": list(shape),
+            "config": {"workload": workload_name(args),
+                       "l2": ("working set (%.2f GB) far larger than the 126 MB L2" if ws_gb > 0.5 else
+                              "working set (%.3f GB) is of the order of the 126 MB L2: this configuration is cache-resident by its "
+                              "own size, consecutive steps are timed without a flush") % ws_gb,
+                       "path": "general kernels" if args.general else ("Shan-Chen operators" if cfg in (1, 3) else "fused fast path"), "slab": list(shape),
                        "void_nodes": nodes_total},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": tm["launches"],
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,

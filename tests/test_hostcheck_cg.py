@@ -180,3 +180,20 @@ def test_perturbation_fields_download(lib):
     eng.step(2); sim.step(2)                       # the download did not disturb the run
     np.testing.assert_allclose(eng.download_macros()[0][0], sim.rhoR[0], atol=1e-13)
     eng.close()
+
+
+@pytest.mark.parametrize("k,scale", [(1, 0.25), (2, 0.0625), (3, 0.0625), (4, 0.046875), (5, 0.03125)])
+def test_baseline_configurations_run_small(k, scale, lib):
+    """synthetic.baseline_config: the five BASELINE.json configurations (what `bench.py --workload cfgN` times), shrunk"""
+    from openlbmpm_b200 import synthetic
+    import numpy as np
+    eng, nodes, what = synthetic.baseline_config(k, scale=scale, lib_path=lib)
+    m0 = eng.total_mass()
+    eng.step(12)
+    rho, u = eng.download_macros()
+    m1 = eng.total_mass()
+    assert nodes > 0 and ("cfg %d" % k) in what
+    assert all(np.isfinite(a).all() for a in rho + u)
+    if k in (1, 4):                       # closed boxes conserve every component
+        np.testing.assert_allclose(m1, m0, rtol=1e-12)
+    eng.close()
