@@ -205,6 +205,30 @@ int lbm_download_fields(lbm_handle* h, double* phi, double* const* G, double* co
 /* Sum of each component's density over the void nodes (mass check).                        */
 int lbm_total_mass(lbm_handle* h, double* mass, int32_t n_comp);
 
+/* ---- solute tracers riding on the colour-gradient CSF flow ------------------ */
+
+/* The numbers the reference reads from transportsetup.ini (Transport2DRK.py:96-391), NumberSchemes = 9.        */
+typedef struct lbm_tracer_config {
+    int32_t n_tracers;         /* [TransportParameters] NumberTracers (1..4)                                    */
+    int32_t relax;             /* [RelaxationType] Relaxation: LBM_RELAX_SRT | LBM_RELAX_MRT (MRT: D2Q9 only)   */
+    double tau[4];             /* [TransportParameters] Tau                      (SRT)                          */
+    double dxx[4], dyy[4];     /* [TransportMRT] DiffusionX, DiffusionY          (MRT)                          */
+    double dxy[4], dyx[4];     /* [TransportMRT] DiffusionXY, DiffusionYX        (MRT)                          */
+    double beta[4];            /* [TransportParameters] BetaInterface                                           */
+    double criterion;          /* rho_R above which a node is outside the transport domain (0.5, :1167)         */
+} lbm_tracer_config;
+
+/* Attaches tracers to a colour-gradient CSF handle on a closed box.  Must precede lbm_init_equilibrium /
+ * lbm_upload_state: the reference's transport loop STARTS with the streaming of the flow (Transport2DRK.py:1180-1200),
+ * so a freshly set flow state is streamed once.  From then on every lbm_step iteration runs, between the colour
+ * gradient and the flow collision, the tracer collision + interface term + streaming + concentration
+ * (Transport2DRK.py:1341-1425 with the kernels of AccelerateTransport2DRK.py).                                  */
+int lbm_tracer_setup(lbm_handle* h, const lbm_tracer_config* cfg);
+/* g = w_j C at rest (Transport2DRK.py:461-470); conc: n pointers to dense [nz][ny][nx]; after the flow state.  */
+int lbm_tracer_init(lbm_handle* h, const double* const* conc, int32_t n);
+/* Concentrations at the output point of the current iteration (Transport2DRK.py:1427-1437), zero on solids.    */
+int lbm_tracer_download(lbm_handle* h, double* const* conc, int32_t n);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 
 /* CUDA-event time of the last lbm_step call (ms, on the handle's stream), number of kernel

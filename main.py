@@ -38,8 +38,11 @@ def main(argv):
     dim = ask(0, "LBM_DIMENSION", "Please choose 2D/3D model (enter 2D or 3D):", argv)
     kind = ask(1, "LBM_MODEL", "Please choose the type of the simulation (enter flow or transport): ", argv)
     method = ask(2, "LBM_METHOD", "Please choose ShanChen(SC) or Color Gradient(CG) methods for flow: ", argv)
+    if kind == "transport" and dim == "2D" and method == "CG":
+        Transport2DRK(ini).runTransport2DMPMCRK()               # main.py:66-68
+        return 0
     if kind != "flow":
-        print("Solute transport is outside this build's scope (collision + streaming of the flow). Stop here.")
+        print("Solute transport on the Shan-Chen flow is outside this build's scope. Stop here.")
         return 2
     if dim == "2D" and method == "SC":
         ShanChenD2Q9(ini).runTypeSCmodel()

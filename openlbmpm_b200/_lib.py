@@ -41,6 +41,13 @@ class LbmConfig(ctypes.Structure):
     ]
 
 
+class LbmTracerConfig(ctypes.Structure):
+    """Mirror of `struct lbm_tracer_config` (include/lbmpm.h)."""
+    _fields_ = [("n_tracers", ctypes.c_int32), ("relax", ctypes.c_int32), ("tau", ctypes.c_double * 4),
+                ("dxx", ctypes.c_double * 4), ("dyy", ctypes.c_double * 4), ("dxy", ctypes.c_double * 4),
+                ("dyx", ctypes.c_double * 4), ("beta", ctypes.c_double * 4), ("criterion", ctypes.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/lbmpm.h declares
 PROTOTYPES = {
     "lbm_abi_version": (ctypes.c_int, []),
@@ -66,6 +73,9 @@ PROTOTYPES = {
     "lbm_download_pdfs": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_double_p), ctypes.c_int32]),
     "lbm_download_fields": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.POINTER(c_double_p),
                                            ctypes.POINTER(c_double_p), c_double_p]),
+    "lbm_tracer_setup": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(LbmTracerConfig)]),
+    "lbm_tracer_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_double_p), ctypes.c_int32]),
+    "lbm_tracer_download": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_double_p), ctypes.c_int32]),
     "lbm_total_mass": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int32]),
     "lbm_get_timing": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_int64_p, c_int64_p]),
     "lbm_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
@@ -247,6 +257,29 @@ class Engine:
         self._check(self.lib.lbm_download_macros(self._h, _ptr_array(rho), len(rho), _ptr_array(u + [None] * (3 - len(u)))),
                     "lbm_download_macros")
         return rho, u
+
+    # -- solute tracers riding on the colour-gradient CSF flow ------------------------------------
+    def tracer_setup(self, n_tracers=1, relax=RELAX_SRT, tau=(1.0,), dxx=(0.0,), dyy=(0.0,), dxy=(0.0,), dyx=(0.0,),
+                     beta=(0.0,), criterion=0.5):
+        """before init_equilibrium / upload_state (the transport loop starts with the flow's streaming)"""
+        cfg = LbmTracerConfig()
+        cfg.n_tracers, cfg.relax, cfg.criterion = int(n_tracers), int(relax), float(criterion)
+        for name, vals in (("tau", tau), ("dxx", dxx), ("dyy", dyy), ("dxy", dxy), ("dyx", dyx), ("beta", beta)):
+            arr = getattr(cfg, name)
+            vals = list(np.asarray(vals, float).ravel())
+            for i in range(4):
+                arr[i] = vals[i] if i < len(vals) else vals[-1]
+        self._check(self.lib.lbm_tracer_setup(self._h, ctypes.byref(cfg)), "lbm_tracer_setup")
+        self.n_tracers = int(n_tracers)
+
+    def tracer_init(self, *conc):
+        arrs = [self._dense(c) for c in conc]
+        self._check(self.lib.lbm_tracer_init(self._h, _ptr_array(arrs), len(arrs)), "lbm_tracer_init")
+
+    def tracer_download(self):
+        out = [np.empty(self.shape) for _ in range(self.n_tracers)]
+        self._check(self.lib.lbm_tracer_download(self._h, _ptr_array(out), len(out)), "lbm_tracer_download")
+        return out
 
     # -- asynchronous output (include/lbmpm.h: lbm_download_macros_async) ----------------------
     def host_alloc(self, shape=None):

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblbmpm.so")
-SOURCES = ["lbm_api.cu", "sc_api.cu", "cg_fast.cu", "comm.cu"]
+SOURCES = ["lbm_api.cu", "sc_api.cu", "tr_api.cu", "cg_fast.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
 

@@ -34,6 +34,7 @@ bool cg_fast_eligible(const lbm_handle* h) {
     // outlet rows; the factored arithmetic rounds differently there, and that combination stays on the
     // reference-ordered kernels.
     if (h->cfg.model != LBM_MODEL_CG || (h->cfg.flags & LBM_FLAG_GENERIC_KERNELS) || h->cfg.surface_tension_type != LBM_ST_CSF) return false;
+    if (h->tracer) return false;      // tracers need G and u in memory between the two halves of the step: reference-ordered kernels
     return !open_box(h) || (h->g.n2 >= 8 && h->cfg.wetting_type != 1);
 }
 

@@ -44,6 +44,9 @@ struct lbm_handle {
     // Shan-Chen / explicit forcing state (sc_ops)
     void* sc = nullptr;
 
+    // solute tracers riding on the colour-gradient flow (tr_api.cu)
+    void* tracer = nullptr;
+
     // launch-bound lattices replay a captured CUDA graph of the step (backend.h::replay)
     lbm::GraphKeep graph;
     bool graph_ok() const { return nranks == 1 && g.plane * (int64_t)g.n2 <= (int64_t)1 << 22 && !(cfg.flags & 8u); }

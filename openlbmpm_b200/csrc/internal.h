@@ -36,4 +36,9 @@ int sc_total_mass(lbm_handle* h, double* mass, int32_t n_comp);
 void sc_output_pointers(lbm_handle* h, const double** rho, const double** u);   // device arrays [n_comp][vol], [D][vol] at the output point
 void sc_free(lbm_handle* h);
 
+// solute tracers (tr_api.cu)
+void tracer_phase(lbm_handle* h);                 // no-op without tracers or when already run for this iteration
+void tracer_iteration_finished(lbm_handle* h);
+void tracer_free(lbm_handle* h);
+
 }  // namespace lbm

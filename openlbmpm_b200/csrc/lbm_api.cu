@@ -157,6 +157,7 @@ static void free_state(lbm_handle* h) {
     for (double** p : arrs) { dev_free(*p); *p = nullptr; }
     cg_fast_free(h);
     sc_free(h);
+    if (h->tracer) tracer_iteration_finished(h);
     h->has_state = false;
 }
 
@@ -169,6 +170,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     graph_release(&h->graph, h->stream);
     free_state(h);
     dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull); dev_free(h->out_stage);
+    tracer_free(h);
     comm_destroy(h);
 #ifndef LBM_HOSTCHECK
     if (h->out_stream) { cudaStreamSynchronize(h->out_stream); cudaStreamDestroy(h->out_stream); }
@@ -458,10 +460,12 @@ static void cg_body(lbm_handle* h) {
     CGFields c = h->fields();
     const Grid& g = h->g;
     cg_forces<L>(h, c);
+    tracer_phase(h);                // solute tracers: between the colour gradient and the flow collision
     launch(CollideOp<L>{c}, g.count(0), h->stream);
     exchange_f64(h, h->fC, g.vol, 2 * L::Q, 1);
     launch(StreamOp<L>{c}, g.count(0), h->stream);
     h->head_done = false;
+    tracer_iteration_finished(h);
 }
 
 // perturbation operator: collision side of one iteration, then the streaming the NEXT iteration starts with
@@ -479,7 +483,8 @@ static void cgp_body(lbm_handle* h) {
 // the reference's loop STARTS with the streaming (RKD2Q9.py:1048-1059): a freshly set state is streamed once, so that
 // a download after k steps is what the reference writes at iteration k of its loop
 static void cgp_initial_stream(lbm_handle* h) {
-    if (h->cfg.surface_tension_type != LBM_ST_PERTURBATION) return;
+    // the perturbation-operator loop and the transport loop (Transport2DRK.py:1180-1200) both start with the streaming
+    if (h->cfg.surface_tension_type != LBM_ST_PERTURBATION && !h->tracer) return;
     cg_alloc_postcollision(h);
     CGFields c = h->fields();
     const Grid& g = h->g;

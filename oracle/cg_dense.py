@@ -253,6 +253,45 @@ class CGDense:
         tau[mid] = t[mid]
         return tau
 
+    def gradient(self):
+        """colour value on the wetting solids, G = 3 sum w_k e_k phi(x + e_k), wetting correction -> self.G (what body()
+        evaluates first; a function of phi only, so callers that need G between head() and body() may ask for it)"""
+        L = self.L; dom = self.dom; Q = L.Q
+        ef = L.e.astype(float)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            num = np.zeros(self.shape); den = np.zeros(self.shape)
+            for k in range(1, Q):
+                fl = shift(dom, L.e[k])
+                num += np.where(fl, L.w[k] * shift(self.phi, L.e[k]), 0.); den += np.where(fl, L.w[k], 0.)
+            phi_ext = np.where(dom, self.phi, np.where(self.wet_solid, num / den, 0.))
+            G = np.zeros((3,) + self.shape)
+            for k in range(1, Q):
+                pk = shift(phi_ext, L.e[k])
+                for a in range(L.D):
+                    if L.e[k, a] != 0:
+                        G[a] += L.w[k] * pk * ef[k, a]
+            G *= 3.
+            G = np.where(dom, G, 0.)
+            if self.wet_solid.any():
+                G = self._wetting(G)
+        self.G = G
+        return G
+
+    def stream_only(self):
+        """one streaming step with half-way bounce back + densities, no collision (drivers whose loop STARTS with the
+        streaming: runTransport2DMPMCRKNew, Transport2DRK.py:1180-1200)"""
+        L = self.L; dom = self.dom
+        for name in ("fR", "fB"):
+            f = getattr(self, name)
+            new = np.empty_like(f)
+            new[0] = f[0]
+            for i in range(1, L.Q):
+                src_fluid = shift(dom, -L.e[i])
+                new[i] = np.where(src_fluid, shift(f[i], -L.e[i]), f[L.opp[i]])
+            setattr(self, name, np.where(dom, new, 0.))
+        self.fT = self.fR + self.fB
+        self.rhoR = _qsum(self.fR); self.rhoB = _qsum(self.fB)
+
     def body(self):
         L = self.L; dom = self.dom; Q = L.Q
         ef = L.e.astype(float)

@@ -531,3 +531,100 @@ def case_sc_d3q19_open(lib_path, model="EFS", relax="MRT", outlet="Dirichlet", n
     rows = slice(0, n[0] - 2) if model == "ShanChen" else slice(None)
     return run_sc_dense_case(19, dom, rho, steps, lib_path, model=model, relax=relax, tau=(1.0, 1.0), G=G, atol=1e-9,
                              chunk=[1, 3, steps - 4], bc=bc, rows=rows, **extra)
+
+
+# ---------------------------------------------------------------------------------------------------
+# solute tracers riding on the colour-gradient CSF flow
+# ---------------------------------------------------------------------------------------------------
+GOLD_TR2D = sorted(glob.glob(os.path.join(HERE, "golden", "tr2d_*.npz")))
+
+
+def tracer_pair(lattice, dom, rhoR, rhoB, conc, lib_path, flow=None, tr=None, **extra):
+    """-> (engine, oracle) with the same flow and tracer parameters, both holding the initial state"""
+    from oracle import tr_dense
+    flow = dict(dict(sigma=0.1, contact_angle_deg=60.0, wetting_type=2, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2), **(flow or {}))
+    tr = dict(dict(relax="SRT", tau=(0.8,), dxx=(0.05,), dyy=(0.08,), dxy=(0.01,), dyx=(0.02,), beta=(0.6,), criterion=0.5), **(tr or {}))
+    L = cg_dense.d2q9() if lattice == 9 else cg_dense.d3q19()
+    sim = cg_dense.CGDense(L, dom, sigma=flow["sigma"], theta_deg=flow["contact_angle_deg"], wetting=flow["wetting_type"],
+                           beta=flow["beta"], delta=flow["delta"], tauR=flow["tauR"], tauB=flow["tauB"], tautype=flow["tau_type"], relax="MRT")
+    sim.set_densities(rhoR, rhoB)
+    trs = tr_dense.TracerDense(sim, **tr)
+    trs.set_concentrations(conc)
+    eng = _lib.Engine(lattice, dom.shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, lib_path=lib_path, **flow, **extra)
+    eng.tracer_setup(n_tracers=len(tr["tau"]), relax=RELAX[tr["relax"]], tau=tr["tau"], dxx=tr["dxx"], dyy=tr["dyy"],
+                     dxy=tr["dxy"], dyx=tr["dyx"], beta=tr["beta"], criterion=tr["criterion"])
+    eng.set_geometry(dom)
+    eng.init_equilibrium(np.where(dom, rhoR, 0.0), np.where(dom, rhoB, 0.0))
+    nt = len(tr["tau"])
+    eng.tracer_init(*[np.where(dom, c, 0.0) for c in np.asarray(conc).reshape((nt,) + dom.shape)])
+    return eng, trs
+
+
+def case_tracer_dense(lib_path, lattice=9, n=(14, 18), steps=9, solid=True, relax="SRT", atol=1e-10, **extra):
+    """CUDA path vs oracle/tr_dense.py: flow densities / velocity and tracer concentrations after every chunk"""
+    rng = np.random.default_rng(41)
+    dom = np.ones(n, bool)
+    if solid:
+        if lattice == 19:
+            dom &= sphere_geometry(n, 2.6)
+        else:
+            dom[4:7, 3:9] = False
+    rhoR = 0.5 + 0.4 * (rng.random(n) - 0.5)
+    nt = 2
+    conc = 0.2 + rng.random((nt,) + n)
+    tr = dict(relax=relax, tau=(0.8, 1.1), dxx=(0.05, 0.1), dyy=(0.08, 0.1), dxy=(0.01, 0.0), dyx=(0.02, 0.0), beta=(0.6, 0.3))
+    eng, trs = tracer_pair(lattice, dom, rhoR, 1.0 - rhoR, conc, lib_path, flow=dict(tauB=0.85, tau_type=1), tr=tr, **extra)
+    sim = trs.flow
+    m0 = [c.sum() for c in eng.tracer_download()]           # iteration 0's tracer phase has run: compare it right away
+    done = 0
+    for k in (0, 1, 2, steps - 3):
+        eng.step(k)
+        for _ in range(k):
+            trs.step(1)
+        done += k
+        # the engine's downloads show iteration `done`: flow head + tracer phase; bring the oracle there without colliding
+        sim.head(); G = sim.gradient()
+        rho, u = eng.download_macros()
+        np.testing.assert_allclose(rho[0], sim.rhoR.reshape(n), rtol=0, atol=atol, err_msg="rhoR after %d" % done)
+        np.testing.assert_allclose(u[0], sim.u[0].reshape(n), rtol=0, atol=atol, err_msg="ux after %d" % done)
+    # tracer: one more oracle iteration's tracer phase = what the engine's download triggers
+    conc_e = eng.tracer_download()
+    import copy
+    probe = copy.deepcopy(trs); probe.step(1)
+    for i in range(nt):
+        np.testing.assert_allclose(conc_e[i], probe.conc[i].reshape(n), rtol=0, atol=atol, err_msg="tracer %d after %d" % (i, done))
+    eng.step(2); trs.step(2)
+    probe = copy.deepcopy(trs); probe.step(1)
+    conc_e = eng.tracer_download()
+    for i in range(nt):
+        np.testing.assert_allclose(conc_e[i], probe.conc[i].reshape(n), rtol=0, atol=atol, err_msg="tracer %d at the end" % i)
+    m1 = [c.sum() for c in conc_e]
+    eng.close()
+    return m0, m1
+
+
+def check_tracer_vs_gold(path, lib_path, chunk=1):
+    """flow snapshot k / tracer snapshot k of the golden file = what the reference's kernels hold at the two output
+    points of loop iteration k (Transport2DRK.py:1300-1312 and :1427-1437)"""
+    g, p = load_gold(path)
+    dom, red, minor = g["is_domain"], g["red_mask"], float(g["minor"])
+    flow = dict(sigma=float(p["sigma"]), contact_angle_deg=float(p["theta"]), wetting_type=int(p["wetting"]), beta=float(p["beta"]),
+                delta=float(p["delta"]), tauR=float(p["tauR"]), tauB=float(p["tauB"]), tau_type=int(p["tautype"]))
+    tr = dict(relax=p["tr_relax"], tau=(float(p["tr_tau"]),), dxx=(float(p["dxx"]),), dyy=(float(p["dyy"]),),
+              dxy=(float(p["dxy"]),), dyx=(float(p["dyx"]),), beta=(float(p["beta_tr"]),), criterion=0.5)
+    eng, trs = tracer_pair(9, dom, np.where(red, float(p["rhoR"]), minor), np.where(red, minor, float(p["rhoB"])), g["tracer0"], lib_path,
+                           flow=flow, tr=tr)
+    nsnap = g["rhoR"].shape[0]
+    s = 0
+    while True:
+        rho, u = eng.download_macros()
+        for k, a in (("rhoR", rho[0]), ("rhoB", rho[1]), ("ux", u[0]), ("uy", u[1])):
+            np.testing.assert_allclose(a, g[k][s], rtol=0, atol=ATOL_GOLD, err_msg="%s snapshot %d" % (k, s))
+        conc = eng.tracer_download()
+        np.testing.assert_allclose(conc[0], g["conc"][s][0], rtol=0, atol=ATOL_GOLD, err_msg="tracer snapshot %d" % s)
+        if s == nsnap - 1:
+            break
+        n = min(chunk, nsnap - 1 - s)
+        eng.step(n)
+        s += n
+    eng.close()

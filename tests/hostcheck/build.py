@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "openlbmpm_b200", "csrc")
 OUT = os.path.join(HERE, "libhostcheck.so")
-SOURCES = ["lbm_api.cu", "sc_api.cu", "cg_fast.cu", "host_stubs.cu"]
+SOURCES = ["lbm_api.cu", "sc_api.cu", "tr_api.cu", "cg_fast.cu", "host_stubs.cu"]
 
 
 def build(force=False):

@@ -171,3 +171,16 @@ def test_perturbation_vs_dense_oracle(lattice, n, solid):
 def test_edge_cases():
     """smallest lattices, no void node, one enclosed void node, 1 / 3 / 4 Shan-Chen components, wrong argument counts"""
     cases.check_edge_cases(None)
+
+
+# ---- solute tracers riding on the colour-gradient CSF flow (SURVEY section 8, row f-3) ----
+@pytest.mark.parametrize("path", cases.GOLD_TR2D, ids=[cases.os.path.basename(p)[5:-4] for p in cases.GOLD_TR2D])
+@pytest.mark.parametrize("chunk", [1, 13])
+def test_tracer_trajectory_vs_reference_kernels(path, chunk):
+    cases.check_tracer_vs_gold(path, None, chunk=chunk)
+
+
+@pytest.mark.parametrize("lattice,n,relax", [(9, (14, 18), "SRT"), (9, (14, 18), "MRT"), (19, (8, 10, 12), "SRT"), (19, (20, 16, 32), "SRT")])
+def test_tracers_vs_dense_oracle(lattice, n, relax):
+    m0, m1 = cases.case_tracer_dense(None, lattice, n, relax=relax, solid=True, steps=9 if n[0] < 20 else 14)
+    np.testing.assert_allclose(m1, m0, rtol=1e-12)

@@ -72,7 +72,7 @@ def test_cg3d_class_and_main(hostlib, monkeypatch):
     import main
     monkeypatch.chdir(os.path.join(REF_INI, "cg3d"))
     assert main.main(["3D", "flow", "CG", "--ini", os.path.join(REF_INI, "cg3d")]) == 0
-    assert main.main(["2D", "transport", "CG"]) == 2
+    assert main.main(["2D", "transport", "SC"]) == 2
 
 
 def test_sc3d_class_and_main(hostlib):
@@ -133,3 +133,31 @@ def test_perturbation_classes(hostlib):
         txt = open(os.path.join(REF_INI, "cgp3d", "RKtwophasesetup3D.ini")).read().replace("BoundaryTypeInlet = 'Periodic'", "BoundaryTypeInlet = 'Neumann'")
         open(os.path.join(bad, "RKtwophasesetup3D.ini"), "w").write(txt)
         RKColorGradient3D(bad, verbose=False)
+
+
+def test_transport_class_and_main(hostlib):
+    """`Transport2DRK(ini).runTransport2DMPMCRK()` (main.py:66-68): flow + 2 tracers, MRT tracers; equals the oracle"""
+    import main
+    from openlbmpm_b200.Transport2DRK import Transport2DRK
+    from oracle import cg_dense, tr_dense
+    from openlbmpm_b200 import results
+    ini = os.path.join(REF_INI, "tr2d")
+    sim = Transport2DRK(ini, verbose=False)
+    yy, xx = np.indices((sim.yDomain, sim.xDomain))
+    sim.initialRedRegion = np.sqrt((yy - 20.3) ** 2 + (xx - 9.6) ** 2) <= 6.
+    sim.runTransport2DMPMCRK()
+    assert sim.tracerConc.shape == (2, sim.yDomain, sim.xDomain) and np.isfinite(sim.tracerConc).all()
+    flow = cg_dense.CGDense(cg_dense.d2q9(), sim.isDomain, sigma=0.1, theta_deg=60.0, wetting=2, beta=0.7, delta=0.98, tauR=1.0,
+                            tauB=1.0, tautype=2, relax="MRT")
+    red = sim.initialRedRegion & sim.isDomain
+    flow.set_densities(np.where(red, 1.0, 0.0) * sim.isDomain, np.where(red, 0.0, 1.0) * sim.isDomain)
+    tr = tr_dense.TracerDense(flow, relax="MRT", tau=(0.8, 1.1), dxx=(0.05, 0.1), dyy=(0.08, 0.1), dxy=(0.01, 0.0), dyx=(0.02, 0.0),
+                              beta=(0.6, 0.2))
+    reg = yy <= sim.yDomain - sim.numBufferingLayers
+    tr.set_concentrations(np.stack([np.where(reg, 1.0, 0.0), np.where(reg, 0.5, 0.0)]))
+    tr.step(sim.timeSteps + 1)          # the class's last download shows iteration timeSteps, tracer phase included
+    np.testing.assert_allclose(sim.tracerConc, tr.conc[:, 0], atol=1e-9)
+    rec = results.read_arrays(str(hostlib / "results"), "ConcentrationResults.h5", ["/TransportMacro/TracerConcType1in0"])
+    assert rec["/TransportMacro/TracerConcType1in0"].shape == (sim.yDomain, sim.xDomain)
+    assert main.main(["2D", "transport", "CG", "--ini", ini]) == 0
+    assert main.main(["2D", "transport", "SC", "--ini", ini]) == 2

@@ -197,3 +197,36 @@ def test_baseline_configurations_run_small(k, scale, lib):
     if k in (1, 4):                       # closed boxes conserve every component
         np.testing.assert_allclose(m1, m0, rtol=1e-12)
     eng.close()
+
+
+# ---- solute tracers riding on the colour-gradient CSF flow ----
+@pytest.mark.parametrize("path", cases.GOLD_TR2D, ids=[os.path.basename(p)[5:-4] for p in cases.GOLD_TR2D])
+@pytest.mark.parametrize("chunk", [1, 9])
+def test_tracer_trajectory_vs_reference_kernels(path, chunk, lib):
+    cases.check_tracer_vs_gold(path, lib, chunk=chunk)
+
+
+@pytest.mark.parametrize("lattice,n,relax", [(9, (14, 18), "SRT"), (9, (14, 18), "MRT"), (19, (8, 10, 12), "SRT")])
+@pytest.mark.parametrize("solid", [False, True])
+def test_tracers_vs_dense_oracle(lattice, n, relax, solid, lib):
+    m0, m1 = cases.case_tracer_dense(lib, lattice, n, relax=relax, solid=solid)
+    import numpy as np
+    np.testing.assert_allclose(m1, m0, rtol=1e-12)          # the tracer is conserved (half-way bounce back at the solids)
+
+
+def test_tracer_setup_rejects_what_is_not_built(lib):
+    from openlbmpm_b200 import _lib
+    import numpy as np
+    eng = _lib.Engine(19, (6, 6, 6), lib_path=lib)
+    with pytest.raises(_lib.LbmError):
+        eng.tracer_setup(relax=_lib.RELAX_MRT)                      # tracer MRT is D2Q9
+    eng.close()
+    eng = _lib.Engine(9, (8, 8), lib_path=lib, inlet=_lib.INLET_VELOCITY)
+    with pytest.raises(_lib.LbmError):
+        eng.tracer_setup()                                          # closed boxes only
+    eng.close()
+    eng = _lib.Engine(9, (8, 8), lib_path=lib)
+    eng.set_geometry(np.ones((8, 8), bool)); eng.init_equilibrium(np.full((8, 8), 0.5), np.full((8, 8), 0.5))
+    with pytest.raises(_lib.LbmError):
+        eng.tracer_setup()                                          # must precede the flow state
+    eng.close()
