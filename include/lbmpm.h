@@ -73,7 +73,7 @@ extern "C" {
 
 typedef struct lbm_handle lbm_handle;
 
-/* Plain-old-data configuration: the numbers the reference reads from IniFiles/*.ini
+/* Plain-old-data configuration: the numbers the reference reads from the .ini files of IniFiles/
  * (RKD2Q9.py:24-297, ShanChenD2Q9.py:39-496).  Zero-initialise, then fill.        */
 typedef struct lbm_config {
     int32_t abi_version;       /* = LBM_ABI_VERSION                                         */

@@ -58,3 +58,17 @@ def test_bad_config_rejected(lib):
     h = ctypes.c_void_p()
     assert lib.lbm_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"abi_version" in lib.lbm_last_error(None)
+
+
+def test_c_program_against_the_abi(tmp_path):
+    """examples/abi_minimal.c: the header is plain C (gcc -std=c99) and a C caller can drive the whole path; linked here
+    against the host test hook (same entry points), on a GPU box against liblbmpm.so"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "hostcheck"))
+    import build as hostcheck_build
+    so = hostcheck_build.build()
+    exe = tmp_path / "abi_minimal"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "abi_minimal.c"), so, "-Wl,-rpath," + os.path.dirname(so), "-lm", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "abi_minimal ok" in out.stdout, out.stdout + out.stderr
