@@ -9,6 +9,8 @@
 #include "internal.h"
 #ifndef LBM_HOSTCHECK
 #include <cuda_pipeline.h>
+#else
+#include "cta_emu.h"      // test hook: the tiled kernels below on host threads (one per CUDA thread of a CTA)
 #endif
 
 namespace lbm {
@@ -53,7 +55,17 @@ static void fast_alloc(lbm_handle* h) {
     for (int k = 0; k < 2; ++k) { f->buf[k] = (double*)dev_alloc(bytes); dev_zero(f->buf[k], bytes, h->stream); }
 }
 
-#ifndef LBM_HOSTCHECK
+#ifdef LBM_HOSTCHECK
+// the TMA variants are never instantiated on the host (cta_emu.h); their calls sit in `if (TMA)` branches and must compile
+inline void mbar_init(uint64_t*, int) {}
+inline void mbar_fence_init() {}
+inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+inline void bulk_g2s(void*, const void*, uint32_t, uint64_t*) {}
+inline void mbar_wait(uint64_t*, uint32_t) {}
+#define LBM_DYN_SMEM(name) double* name = cta_emu::tls().shared
+#define LBM_OPAQUE(...) ((void)0)
+#else
+#define LBM_DYN_SMEM(name) extern __shared__ __align__(128) double name[]
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -75,6 +87,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Tiled collision pass for D3Q19.  One CTA owns a TX x TY column of the lattice and marches along z.
@@ -93,7 +107,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     constexpr int NT = TX * TY;
     constexpr int PW = TX + 4, PH = TY + 4;     // phi tile
     constexpr int NW = TX + 2, NH = TY + 2;     // normal tile
-    extern __shared__ __align__(128) double smem_dyn[];
+    LBM_DYN_SMEM(smem_dyn);
     double (*sphi)[PH][PW] = reinterpret_cast<double (*)[PH][PW]>(smem_dyn);                    // [5]
     double (*sn)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn + 5 * PH * PW);  // [3][nx, ny, nz, |G|]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + 5 * PH * PW + 3 * 4 * NH * NW);     // [5] one mbarrier per phi slot
@@ -198,7 +212,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     if (TMA) {
         if (tid == 0) {
             for (int k = 0; k < 5; ++k) mbar_init(&bars[k], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_fence_init();
         }
         __syncthreads();
     }
@@ -261,10 +275,12 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             // two barriers, and every warp then waits for HBM before the shared-memory phase instead of during it
             // (ncu, porous 256 x 256 x 192: 19.5 % of all stall samples on that one DMUL).  The empty asm makes the
             // values opaque until here.
+#ifndef LBM_HOSTCHECK
             asm volatile("" : "+d"(fT[0]), "+d"(fT[1]), "+d"(fT[2]), "+d"(fT[3]), "+d"(fT[4]), "+d"(fT[5]), "+d"(fT[6]),
                               "+d"(fT[7]), "+d"(fT[8]), "+d"(fT[9]), "+d"(fT[10]), "+d"(fT[11]), "+d"(fT[12]), "+d"(fT[13]),
                               "+d"(fT[14]), "+d"(fT[15]), "+d"(fT[16]), "+d"(fT[17]), "+d"(fT[18]), "+d"(rR), "+d"(rB),
                               "+d"(Fl[0]), "+d"(Fl[1]), "+d"(Fl[2]));
+#endif
         }
         phi0 = sphi[(z + 10) % 5][ty + 2][tx + 2];
         // ---- curvature and force from the normals in shared memory ----
@@ -346,7 +362,7 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
     constexpr int NT = TX * TY;
     constexpr int XH = TMA ? 2 : 1;                 // halo columns kept in shared memory
     constexpr int NW = TX + 2 * XH, NH = TY + 2;
-    extern __shared__ __align__(128) double smem_dyn[];
+    LBM_DYN_SMEM(smem_dyn);
     double (*ss)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn);   // [5 slots][kR, ax, ay, az]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + 5 * 4 * NH * NW);      // [5] one mbarrier per slot
     const Grid& g = c.g;
@@ -416,7 +432,7 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
     if (TMA) {
         if (tid == 0) {
             for (int k = 0; k < 5; ++k) mbar_init(&bars[k], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_fence_init();
         }
         __syncthreads();
     }
@@ -507,6 +523,9 @@ static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2) + 8);
+#ifdef LBM_HOSTCHECK
+    cta_emu::launch(grid, block, smem, [&] { cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>(c, s, o, zchunk, z_lo, z_hi); });
+#else
     static bool configured[64] = {};          // per device: the attribute belongs to the function on ONE device
     if (!configured[h->cfg.device & 63]) {
         LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
@@ -517,12 +536,17 @@ static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s
     cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
+#endif
     ++g_launch_counter;
 }
 
 template <bool SOLIDS>
 static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo = 0, int z_hi = -1) {
+#ifdef LBM_HOSTCHECK
+    static const bool tma = false;                               // host emulation: the copies are plain memcpy
+#else
     static const bool tma = env_int("LBM_PHI_TMA", 1) != 0;      // 0: 8-byte cp.async copies instead of TMA bulk copies
+#endif
     switch (tile_y_collide()) {
         case 4: if (tma) launch_tiled_t<SOLIDS, 4, true>(h, c, s, o, z_lo, z_hi); else launch_tiled_t<SOLIDS, 4, false>(h, c, s, o, z_lo, z_hi); break;
         case 16: launch_tiled_t<SOLIDS, 16, false>(h, c, s, o, z_lo, z_hi); break;
@@ -538,6 +562,9 @@ static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastF
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * 4 * (TILE_Y + 2) * (TILE_X + (TMA ? 4 : 2)) + 8);
+#ifdef LBM_HOSTCHECK
+    cta_emu::launch(grid, block, smem, [&] { cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>(c, s, zchunk, z_lo, z_hi); });
+#else
     static bool configured[64] = {};
     if (!configured[h->cfg.device & 63]) {
         LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
@@ -548,20 +575,24 @@ static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastF
     cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA><<<grid, block, smem, h->stream>>>(c, s, zchunk, z_lo, z_hi);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
+#endif
     ++g_launch_counter;
 }
 template <bool SOLIDS>
 static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo = 0, int z_hi = -1) {
     // TMA bulk copies for the scalar planes exist (LBM_SCALAR_TMA=1) but measured 7.2 ms vs 4.7 ms per 512^3 launch:
     // 40 row copies per plane step issued by four threads sit on the critical path of this short loop; cp.async stays
+#ifdef LBM_HOSTCHECK
+    static const bool tma = false;
+#else
     static const bool tma = env_int("LBM_SCALAR_TMA", 0) != 0;
+#endif
     switch (tile_y_density()) {
         case 4: launch_density_tiled_t<SOLIDS, 4, false>(h, c, s, z_lo, z_hi); break;
         case 16: launch_density_tiled_t<SOLIDS, 16, false>(h, c, s, z_lo, z_hi); break;
         default: if (tma) launch_density_tiled_t<SOLIDS, 8, true>(h, c, s, z_lo, z_hi); else launch_density_tiled_t<SOLIDS, 8, false>(h, c, s, z_lo, z_hi);
     }
 }
-#endif
 
 // which ghost planes of the factored state are ever read: population q is pulled from z - c_z(q), so it has
 // to travel upwards (c_z = +1) or downwards (c_z = -1) only, in-plane directions never cross a slab face
@@ -687,12 +718,10 @@ static void fast_one_step(lbm_handle* h) {
     const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
     exchange_f64(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
     bool dens_done = false;
-#ifndef LBM_HOSTCHECK
-    if (tiled_ok(h) && !(h->cfg.flags & 4u)) {
+    if (tiled_ok(h) && !(h->cfg.flags & 4u)) {       // host test hook: the same kernels on host threads (cta_emu.h)
         if (h->has_solid) launch_density_tiled<true>(h, c, s); else launch_density_tiled<false>(h, c, s);
         dens_done = true;
     }
-#endif
     if (!dens_done) {
         if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
         else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
@@ -702,12 +731,10 @@ static void fast_one_step(lbm_handle* h) {
     exchange_f64(h, c.phi, 0, 1, h->has_solid ? NG : 2);
     if (h->has_solid) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
     bool done = false;
-#ifndef LBM_HOSTCHECK
     if (tiled_ok(h)) {
         if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);
         done = true;
     }
-#endif
     if (!done) {
         launch(GradientOp<L>{c}, g.count(1), h->stream);
         if (h->has_solid) launch(PullCollideOp<L, true>{c, s, o}, g.count(0), h->stream);
