@@ -69,6 +69,7 @@ extern "C" {
 #define LBM_FLAG_NO_TILED_DENSITY 4u /* keep the tiled collision pass, use the one-thread-per-node density pass */
 #define LBM_FLAG_OVERLAP 16u         /* slab decomposition: overlap the ghost-plane exchanges with the interior planes */
 #define LBM_FLAG_PACKED_EXCHANGE 32u /* slab decomposition: pack the boundary planes into one message per direction (experimental) */
+#define LBM_FLAG_GHOST_PLANES 64u     /* single slab: keep copying the periodic ghost planes every step instead of wrapping the flow axis by index arithmetic */
 #define LBM_FLAG_NO_CUDA_GRAPH 8u    /* small lattices: launch every kernel instead of replaying a captured graph */
 
 typedef struct lbm_handle lbm_handle;

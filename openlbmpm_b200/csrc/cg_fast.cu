@@ -515,6 +515,8 @@ static bool tiled_ok(const lbm_handle* h) {
     return h->Q == 19 && h->g.n0 % TILE_X == 0 && h->g.n1 % tile_y_collide() == 0 && h->g.n1 % tile_y_density() == 0 && !(h->cfg.flags & 2u);
 }
 
+bool cg_tiled_possible(const lbm_handle* h) { return h->cfg.model == LBM_MODEL_CG && tiled_ok(h); }
+
 template <bool SOLIDS, int TILE_Y, bool TMA>
 static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi) {
     const Grid& g = h->g;

@@ -19,13 +19,16 @@ struct Grid {
     int n0, n1, n2;
     int64_t plane;   // n0 * n1
     int64_t vol;     // plane * (n2 + 2 NG)
+    int wrap2;       // 1: a single slab whose one-thread-per-node operators wrap axis 2 by index arithmetic, so that the
+                     //    per-step ghost-plane copies (2 launches of a launch-bound 2-D step) are not needed at all
     LBM_HD int64_t at(int x, int y, int z) const { return (int64_t)(z + NG) * plane + (int64_t)y * n0 + x; }
-    // neighbour (x+dx, y+dy, z+dz): periodic in axes 0 and 1, ghost planes along axis 2
+    // neighbour (x+dx, y+dy, z+dz): periodic in axes 0 and 1; along axis 2 the ghost planes, or the periodic image itself
     LBM_HD int64_t nb(int x, int y, int z, int dx, int dy, int dz) const {
-        int xn = x + dx, yn = y + dy;
+        int xn = x + dx, yn = y + dy, zn = z + dz;
         if (xn < 0) xn += n0; else if (xn >= n0) xn -= n0;
         if (yn < 0) yn += n1; else if (yn >= n1) yn -= n1;
-        return at(xn, yn, z + dz);
+        if (wrap2) { if (zn < 0) zn += n2; else if (zn >= n2) zn -= n2; }
+        return at(xn, yn, zn);
     }
     // item i of a launch over planes [-ext, n2 + ext)
     LBM_HD void decode(int64_t i, int ext, int& x, int& y, int& z) const {

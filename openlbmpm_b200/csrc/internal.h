@@ -22,6 +22,7 @@ void cg_generic_forces(lbm_handle* h);
 
 // fused fast path for closed boxes (cg_fast.cu)
 bool cg_fast_eligible(const lbm_handle* h);
+bool cg_tiled_possible(const lbm_handle* h);     // lattice extents and flags admit the tiled kernels (they read ghost planes)
 void cg_fast_step(lbm_handle* h, int nsteps);
 void cg_fast_materialise(lbm_handle* h);
 void cg_fast_free(lbm_handle* h);

@@ -67,6 +67,7 @@ CGFields lbm_handle::fields() const {
 // ------------------------------------------------------------------------------------------------
 void lbm::exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
     if (h->nranks > 1) { comm_exchange_f64(h, base, stride, narr, gp, dirs); return; }
+    if (h->g.wrap2) return;       // the operators wrap the flow axis themselves (grid.cuh::Grid::nb)
     GhostWrapOp<double> op{h->g, base, stride, narr, gp};
     launch(op, op.items(), h->stream);
 }
@@ -132,6 +133,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
     else { g.n0 = cfg->nx; g.n1 = cfg->ny; g.n2 = cfg->nz; }
     g.plane = (int64_t)g.n0 * g.n1;
     g.vol = g.plane * (g.n2 + 2 * NG);
+    g.wrap2 = 0;
     if (g.n2 < NG) { g_create_error = "the flow axis needs at least 3 planes"; delete h; return LBM_EINVAL; }
     try {
 #ifndef LBM_HOSTCHECK
@@ -199,6 +201,7 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
     API_BEGIN(h)
     if (!is_domain) return fail(h, LBM_EINVAL, "is_domain is NULL");
     set_device(h);
+    h->g.wrap2 = 0;               // the geometry operators read the ghost planes of the mask (filled below)
     const Grid& g = h->g;
     const int64_t owned = g.plane * g.n2;
     free_state(h);
@@ -238,6 +241,10 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
     dev_sync(h->stream);
     h->n_wet = h->n_near = -1;
     h->has_geometry = true;
+    // One slab, no tiled kernels (every 2-D lattice, 3-D extents that are no multiple of the tile): the per-step copies of the
+    // periodic ghost planes are replaced by index arithmetic in Grid::nb.  The tiled kernels stage whole planes with bulk
+    // copies and keep reading the ghost planes.
+    h->g.wrap2 = (h->nranks == 1 && !cg_tiled_possible(h) && !(h->cfg.flags & LBM_FLAG_GHOST_PLANES)) ? 1 : 0;
     API_END(h)
 }
 

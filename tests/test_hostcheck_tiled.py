@@ -35,8 +35,11 @@ def launches_per_step(lib, shape, dom=None, **kw):
 
 def test_the_tiled_kernels_are_the_ones_that_run(lib):
     assert launches_per_step(lib, (10, 16, 32)) == 4                 # ghost wrap, tiled density, ghost wrap, tiled collision
-    assert launches_per_step(lib, (10, 16, 32), flags=2) == 5        # ... untiled: + the gradient operator
-    assert launches_per_step(lib, (10, 12, 30)) == 5                 # extents that are no multiple of the tile: untiled
+    # untiled (flag, or extents that are no multiple of the tile): density, gradient, collision -- a single slab wraps the
+    # flow axis by index arithmetic, the two ghost-plane copies only come back with LBM_FLAG_GHOST_PLANES
+    assert launches_per_step(lib, (10, 16, 32), flags=2) == 3
+    assert launches_per_step(lib, (10, 12, 30)) == 3
+    assert launches_per_step(lib, (10, 12, 30), flags=_lib.FLAG_GHOST_PLANES) == 5
 
 
 @pytest.mark.parametrize("relax", ["MRT", "SRT"])
@@ -68,3 +71,26 @@ def test_tiled_slabs_bit_equal(lib):
     S.compare(lib, 19, (24, 8, 32), [1, 2, 4], contact_angle_deg=70.0)
     S.compare(lib, 19, (24, 8, 32), [2, 4], solid=False)
     S.compare(lib, 19, (48, 8, 32), [1, 3], worlds=(2, 3), **dict(S.OPEN, contact_angle_deg=60.0))
+
+
+def test_index_wrap_equals_ghost_plane_copies(lib):
+    """one slab: wrapping the flow axis by index arithmetic (default when the tiled kernels are not in play) is bit-equal
+    to copying the periodic ghost planes every step, for every model"""
+    rng = np.random.default_rng(6)
+    for lattice, shape in ((9, (14, 18)), (19, (9, 6, 10))):
+        dom = np.ones(shape, bool); dom[(slice(4, 6),) + (slice(2, 5),) * (len(shape) - 1)] = False
+        dom[(0,) + (slice(0, 2),) * (len(shape) - 1)] = False                    # a solid on the periodic seam
+        r = 0.5 + 0.3 * (rng.random(shape) - 0.5)
+        for kw in (dict(), dict(flags=1), dict(surface_tension_type=_lib.ST_PERTURBATION, AkR=8e-3, AkB=1e-2, solid_phi=0.3),
+                   dict(model=_lib.MODEL_SC, relax=_lib.RELAX_SRT, n_components=2, sc_tau=[1.0, 0.9], sc_G=[0, 0.9, 0, 0, 0.9, 0], sc_Gsolid=[-0.1, 0.1]),
+                   dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, n_components=2, sc_tau=[1.0, 0.9], sc_G=[0, 0.15, 0, 0, 0.15, 0], sc_Gsolid=[-0.1, 0.1],
+                        sc_isotropy=10 if lattice == 9 else 4)):
+            out = []
+            for extra in (0, _lib.FLAG_GHOST_PLANES):
+                par = dict(kw); par["flags"] = par.get("flags", 0) | extra
+                eng = _lib.Engine(lattice, shape, lib_path=lib, **par)
+                eng.set_geometry(dom); eng.init_equilibrium(r * dom, (1 - r) * dom); eng.step(7)
+                rho, u = eng.download_macros()
+                out.append(np.stack(rho + u))
+                eng.close()
+            assert np.array_equal(out[0], out[1]), (lattice, kw)
