@@ -613,15 +613,16 @@ static const int8_t* factored_dirs() {
 // operators run on them, and velocity + phi are re-evaluated there; after the collision pass the same planes are
 // collided again from the treated populations (general-path arithmetic) and overwrite the fast pass's result.
 // Everything else of the lattice stays on the two fused passes.
+// planes [lo[k], hi[k]) (k < n <= 2) of an operator whose item 0 is the first node of plane -ext, in one launch
 template <class Op>
-struct PlaneRangeOp {
-    Op op; int64_t off;
-    LBM_HD void operator()(int64_t i) const { op(i + off); }
-};
-// planes [z_lo, z_hi) of an operator whose item 0 is the first node of plane -ext
-template <class Op>
-static void launch_planes(lbm_handle* h, const Op& op, int ext, int z_lo, int z_hi) {
-    launch(PlaneRangeOp<Op>{op, (int64_t)(z_lo + ext) * h->g.plane}, (int64_t)(z_hi - z_lo) * h->g.plane, h->stream);
+static void launch_plane_ranges(lbm_handle* h, const Op& op, int ext, int n, const int* lo, const int* hi) {
+    const int64_t plane = h->g.plane;
+    if (n == 1) {
+        launch(PlaneRangeOp<Op>{op, (int64_t)(lo[0] + ext) * plane}, (int64_t)(hi[0] - lo[0]) * plane, h->stream);
+    } else if (n == 2) {
+        const int64_t cnt0 = (int64_t)(hi[0] - lo[0]) * plane, cnt1 = (int64_t)(hi[1] - lo[1]) * plane;
+        launch(TwoRangeOp<Op>{op, (int64_t)(lo[0] + ext) * plane, cnt0, (int64_t)(lo[1] + ext) * plane}, cnt0 + cnt1, h->stream);
+    }
 }
 struct OpenRows {
     int n = 0;
@@ -643,20 +644,24 @@ template <class L>
 static void fast_open_rows_pre(lbm_handle* h, const CGFields& c, const FastFields& s) {
     const OpenRows r = open_rows(c);
     if (!r.n) return;
-    for (int k = 0; k < r.n; ++k) launch_planes(h, PullMaterialiseOp<L>{c, s}, 0, r.mat_lo[k], r.mat_hi[k]);
+    launch_plane_ranges(h, PullMaterialiseOp<L>{c, s}, 0, r.n, r.mat_lo, r.mat_hi);
     cg_apply_open_rows(h);
-    for (int k = 0; k < r.n; ++k) launch_planes(h, HeadOp<L>{c}, 0, r.mod_lo[k], r.mod_hi[k]);   // u with the lagged force, phi
+    launch_plane_ranges(h, HeadOp<L>{c}, 0, r.n, r.mod_lo, r.mod_hi);      // u with the lagged force, phi
 }
 template <class L>
 static void fast_open_rows_post(lbm_handle* h, const CGFields& c, const FastFields& o, bool need_gradient) {
     const OpenRows r = open_rows(c);
-    for (int k = 0; k < r.n; ++k) {
-        // the tiled collision pass keeps G and the normals in shared memory: evaluate them around the patched planes
-        if (need_gradient)
-            launch_planes(h, GradientOp<L>{c}, 1, r.mod_lo[k] - 1 < -1 ? -1 : r.mod_lo[k] - 1,
-                          r.mod_hi[k] + 1 > h->g.n2 + 1 ? h->g.n2 + 1 : r.mod_hi[k] + 1);
-        launch_planes(h, CollideFactoredOp<L>{c, o}, 0, r.mod_lo[k], r.mod_hi[k]);
+    if (!r.n) return;
+    if (need_gradient) {      // the tiled collision pass keeps G and the normals in shared memory: evaluate them around the patched planes
+        int lo[2], hi[2];
+        for (int k = 0; k < r.n; ++k) {
+            lo[k] = r.mod_lo[k] - 1 < -1 ? -1 : r.mod_lo[k] - 1;
+            hi[k] = r.mod_hi[k] + 1 > h->g.n2 + 1 ? h->g.n2 + 1 : r.mod_hi[k] + 1;
+        }
+        if (r.n == 2 && hi[0] > lo[1]) { hi[0] = hi[1]; launch_plane_ranges(h, GradientOp<L>{c}, 1, 1, lo, hi); }   // thin slab: the two ranges touch
+        else launch_plane_ranges(h, GradientOp<L>{c}, 1, r.n, lo, hi);
     }
+    launch_plane_ranges(h, CollideFactoredOp<L>{c, o}, 0, r.n, r.mod_lo, r.mod_hi);
 }
 
 template <class L>

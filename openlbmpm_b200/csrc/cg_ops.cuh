@@ -3,6 +3,7 @@
 // wetting, open boundaries, SRT/MRT, D2Q9/D3Q19.  Populations are structure-of-arrays [Q][vol].
 // The fused fast path for closed (periodic / bounce-back) boxes lives in cg_fast.cu.
 #pragma once
+#include "../../include/lbmpm.h"
 #include "grid.cuh"
 
 namespace lbm {
@@ -219,6 +220,35 @@ struct RowCopyOp {
                 acc = q == 0 ? v : acc + v;
             }
             c.rho[k][d] = sum_rho ? acc : c.rho[k][s];
+        }
+    }
+};
+
+// All open-boundary rows of one iteration in ONE launch (RKD2Q9.py:1299-1352 launches 2 + 2..3 kernels over every node;
+// the operators above, one launch each, were 4-5 launches of a launch-bound 2-D step).  Items: 2 planes' worth of
+// columns -- the first `plane` items walk the outlet rows of their column, the others its inlet rows.  The rows of one
+// column only depend on each other (treated row -> ghost row, row 3 -> 2 -> 1 -> 0), so running them back to back in one
+// thread is the same arithmetic in the same order.
+template <class L>
+struct OpenRowsOp {
+    CGFields c;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t plane = c.g.plane;
+        if (i < plane) {
+            if (c.z_out < 0) return;
+            if (c.outlet == LBM_OUTLET_CONVECTIVE) {
+                RowCopyOp<L>{c, 2, 3, 1}(i); RowCopyOp<L>{c, 1, 2, 1}(i); RowCopyOp<L>{c, 0, 1, 1}(i);
+            } else if (c.outlet == LBM_OUTLET_PRESSURE) {
+                OutletPressureOp<L>{c}(i); RowCopyOp<L>{c, 0, 1, 0}(i);
+            }
+        } else {
+            const int64_t r = i - plane;
+            if (c.z_in < 0) return;
+            if (c.inlet == LBM_INLET_VELOCITY) {
+                InletVelocityOp<L>{c}(r); RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 1}(r);
+            } else if (c.inlet == LBM_INLET_PRESSURE) {
+                InletPressureOp<L>{c}(r); RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 0}(r);
+            }
         }
     }
 };

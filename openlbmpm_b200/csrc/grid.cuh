@@ -40,6 +40,20 @@ struct Grid {
     int64_t count(int ext) const { return plane * (int64_t)(n2 + 2 * ext); }
 };
 
+// an operator restricted to a range of planes: item i of the launch is item i + off of the operator
+template <class Op>
+struct PlaneRangeOp {
+    Op op; int64_t off;
+    LBM_HD void operator()(int64_t i) const { op(i + off); }
+};
+
+// ... and to two disjoint ranges in one launch (the outlet planes and the inlet planes of an open box)
+template <class Op>
+struct TwoRangeOp {
+    Op op; int64_t off0, cnt0, off1;
+    LBM_HD void operator()(int64_t i) const { op(i < cnt0 ? i + off0 : i - cnt0 + off1); }
+};
+
 // Fill the ghost planes of `narr` arrays (stride `stride` elements apart) from the slab's own opposite
 // planes: periodic wrap on one GPU.  item = (array, side, ghost plane j, node in plane)
 template <class T>

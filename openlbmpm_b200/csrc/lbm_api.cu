@@ -427,22 +427,8 @@ extern "C" int lbm_upload_state(lbm_handle* h, const double* const* pdf, const d
 // boundary treatment of the streamed populations at the top of an iteration (RKD2Q9.py:1299-1352)
 template <class L>
 static void cg_open_rows(lbm_handle* h, const CGFields& c) {
-    const Grid& g = h->g;
-    if (c.inlet == LBM_INLET_VELOCITY && c.z_in >= 0) {
-        launch(InletVelocityOp<L>{c}, g.plane, h->stream);
-        launch(RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 1}, g.plane, h->stream);
-    } else if (c.inlet == LBM_INLET_PRESSURE && c.z_in >= 0) {
-        launch(InletPressureOp<L>{c}, g.plane, h->stream);
-        launch(RowCopyOp<L>{c, c.z_in_ghost, c.z_in, 0}, g.plane, h->stream);
-    }
-    if (c.outlet == LBM_OUTLET_CONVECTIVE && c.z_out >= 0) {
-        launch(RowCopyOp<L>{c, 2, 3, 1}, g.plane, h->stream);
-        launch(RowCopyOp<L>{c, 1, 2, 1}, g.plane, h->stream);
-        launch(RowCopyOp<L>{c, 0, 1, 1}, g.plane, h->stream);
-    } else if (c.outlet == LBM_OUTLET_PRESSURE && c.z_out >= 0) {
-        launch(OutletPressureOp<L>{c}, g.plane, h->stream);
-        launch(RowCopyOp<L>{c, 0, 1, 0}, g.plane, h->stream);
-    }
+    const bool in = c.inlet != LBM_BC_PERIODIC && c.z_in >= 0, out = c.outlet != LBM_BC_PERIODIC && c.z_out >= 0;
+    if (in || out) launch(OpenRowsOp<L>{c}, 2 * h->g.plane, h->stream);
 }
 
 template <class L>

@@ -18,7 +18,17 @@ struct SCState {
     double *fS = nullptr, *fC = nullptr, *rho = nullptr, *F = nullptr, *ueq = nullptr, *uph = nullptr, *fold = nullptr;
     bool efs_prepared = false;    // EFS pre-loop (force, u_eq, f <- f - fF/2, boundary rows) done
     bool head_done = false;       // SC: inlet treatment of the current iteration already applied
+    bool rho_is_sum = false;      // SC: rho == sum_q f_q on every node (the streaming leaves it so; a fresh state may not)
+    bool uph_valid = true;        // SC: the physical velocity of the last finished iteration has been evaluated
 };
+
+// planes [z_lo, z_hi) of a lattice-generic operator whose item 0 is the first node of plane 0
+#define SC_LAUNCH_PLANES(z_lo, z_hi, OP, ...)                                                                      \
+    do {                                                                                                           \
+        const int64_t off_ = (int64_t)(z_lo) * h->g.plane, cnt_ = (int64_t)((z_hi) - (z_lo)) * h->g.plane;         \
+        if (h->Q == 9) launch(PlaneRangeOp<OP<D2Q9>>{OP<D2Q9>{__VA_ARGS__}, off_}, cnt_, h->stream);              \
+        else launch(PlaneRangeOp<OP<D3Q19>>{OP<D3Q19>{__VA_ARGS__}, off_}, cnt_, h->stream);                     \
+    } while (0)
 
 static SCFields sc_fields(const lbm_handle* h) {
     const SCState* s = (const SCState*)h->sc;
@@ -77,7 +87,7 @@ int sc_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp)
     } catch (...) { dev_free(tmp); throw; }
     dev_free(tmp);
     SCState* s = (SCState*)h->sc;
-    s->efs_prepared = false; s->head_done = false;
+    s->efs_prepared = false; s->head_done = false; s->rho_is_sum = false; s->uph_valid = true;
     h->has_state = true;
     return LBM_OK;
 }
@@ -100,7 +110,7 @@ int sc_upload_state(lbm_handle* h, const double* const* pdf, const double* const
         }
         SCState* s = (SCState*)h->sc;
         dev_zero(s->F, (size_t)n_comp * h->D * h->g.vol * 8, h->stream);
-        s->efs_prepared = false; s->head_done = false;
+        s->efs_prepared = false; s->head_done = false; s->rho_is_sum = false; s->uph_valid = true;
     } catch (...) { dev_free(tmp); throw; }
     dev_free(tmp);
     h->has_state = true;
@@ -138,19 +148,37 @@ static void sc_iteration(lbm_handle* h) {
     SCState* s = (SCState*)h->sc;
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
-    sc_ensure_head(h);
-    SC_LAUNCH(g.count(0), ScRhoOp, c);                      // calFluidRhoGPU; psi = rho
+    // Inlet rows, then calFluidRhoGPU (psi = rho).  The streaming of the previous iteration left rho = sum_q f_q (same order
+    // of summation) on every node and so do the copied rows; only the Zou-He plane of the inlet carries another value, and
+    // the thread that treated the column re-sums it: no pass over the lattice.  A fresh state is summed once.
+    const bool inlet_here = c.p.inlet == LBM_INLET_VELOCITY && owns_inlet(h);
+    if (!s->rho_is_sum) {
+        sc_ensure_head(h);
+        SC_LAUNCH(g.count(0), ScRhoOp, c); s->rho_is_sum = true;
+    } else if (inlet_here) {
+        if (s->head_done) SC_LAUNCH_PLANES(c.z_in, c.z_in + 1, ScRhoOp, c);      // a download already treated the inlet rows
+        else SC_LAUNCH(2 * g.plane, ScOpenRowsOp, c, 0, 1, 1, 0, 1);
+        s->head_done = true;
+    }
     exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
     SC_LAUNCH(g.count(0), ScCollideOp, c);                  // interactionCollisionProcess
     exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
     SC_LAUNCH(g.count(0), ScStreamOp, c);                   // calStreaming1GPU/2GPU (+ densities)
-    if (c.p.outlet == LBM_OUTLET_CONVECTIVE && owns_outlet(h)) {   // convectiveOutletGPU / Ghost2 / Ghost3
-        SC_LAUNCH(g.plane, ScRowCopyOp, c, 2, 3);
-        SC_LAUNCH(g.plane, ScRowCopyOp, c, 1, 2);
-        SC_LAUNCH(g.plane, ScRowCopyOp, c, 0, 1);
-    }
-    SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);
+    if (c.p.outlet == LBM_OUTLET_CONVECTIVE && owns_outlet(h))      // convectiveOutletGPU / Ghost2 / Ghost3
+        SC_LAUNCH(2 * g.plane, ScOpenRowsOp, c, 0, 2, 0, 1, 0);
+    // calPhysicalVelocity: an output, nothing in the loop reads it -> evaluated when somebody asks (sc_ensure_velocity)
+    s->uph_valid = false;
     s->head_done = false;
+}
+
+// the physical velocity of the last finished iteration of the original Shan-Chen loop (ShanChenD2Q9.py:1561-1573); must
+// run BEFORE the inlet treatment of the next iteration touches the inlet rows
+static void sc_ensure_velocity(lbm_handle* h) {
+    SCState* s = (SCState*)h->sc;
+    if (h->cfg.model != LBM_MODEL_SC || s->uph_valid) return;
+    SCFields c = sc_fields(h);
+    SC_LAUNCH(h->g.count(0), ScPhysicalVelocityOp, c);
+    s->uph_valid = true;
 }
 
 // pre-loop of runOptimizedEFLBM (ShanChenD2Q9.py:1714-1849)
@@ -185,21 +213,16 @@ static void efs_iteration(lbm_handle* h) {
     SC_LAUNCH(g.count(0), EfsCollideOp, c);
     exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
     SC_LAUNCH(g.count(0), ScStreamOp, c);
-    if (convective) {
-        SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);
-        if (owns_outlet(h)) {
-            SC_LAUNCH(g.plane, ScConvectiveEachOp, c, 2);
-            SC_LAUNCH(g.plane, ScConvectiveEachOp, c, 1);
-            SC_LAUNCH(g.plane, ScConvectiveEachOp, c, 0);
-        }
-    } else if (c.p.outlet == LBM_OUTLET_PRESSURE) {
-        sc_outlet_pressure(h, c);
+    // boundary rows (convective-each | pressure outlet, velocity inlet) and calFluidRhoGPU after them: the streaming and the
+    // copied rows already hold rho = sum_q f_q, only the two Zou-He planes carry the imposed values and are re-summed by the
+    // thread that treated the column (ShanChenD2Q9.py:1933-2014)
+    {
+        const int do_out = (c.p.outlet != LBM_BC_PERIODIC && owns_outlet(h)) ? 1 : 0;
+        const int do_in = (c.p.inlet == LBM_INLET_VELOCITY && owns_inlet(h)) ? 1 : 0;
+        if (do_out || do_in) SC_LAUNCH(2 * g.plane, ScOpenRowsOp, c, 1, 0, do_in, do_out, 1);
     }
-    sc_inlet(h, c);
-    if (c.p.inlet != LBM_BC_PERIODIC || c.p.outlet != LBM_BC_PERIODIC) SC_LAUNCH(g.count(0), ScRhoOp, c);
-    SC_LAUNCH(g.count(0), ScPhysicalVelocityOp, c);     // output point (:2016-2027)
     exchange_f64(h, c.rho, g.vol, c.p.nc, c.p.scheme == 4 ? 1 : NG);
-    SC_LAUNCH(g.count(0), EfsForceOp, c);
+    SC_LAUNCH(g.count(0), EfsForceOp, c);               // also the physical velocity of the output point (:2016-2027)
 }
 
 void sc_step(lbm_handle* h, int nsteps) {
@@ -213,6 +236,7 @@ void sc_step(lbm_handle* h, int nsteps) {
 int sc_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double* const* u) {
     if (rho && n_comp != h->cfg.n_components) { h->err = "one density array per component expected"; return LBM_EINVAL; }
     if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
+    sc_ensure_velocity(h);
     sc_ensure_head(h);
     SCFields c = sc_fields(h);
     const Grid& g = h->g;
@@ -229,6 +253,7 @@ int sc_download_macros(lbm_handle* h, double* const* rho, int32_t n_comp, double
 
 void sc_output_pointers(lbm_handle* h, const double** rho, const double** u) {
     if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
+    sc_ensure_velocity(h);
     sc_ensure_head(h);
     SCFields c = sc_fields(h);
     *rho = c.rho; *u = c.uph;
@@ -237,6 +262,7 @@ void sc_output_pointers(lbm_handle* h, const double** rho, const double** u) {
 int sc_download_pdfs(lbm_handle* h, double* const* pdf, int32_t n_comp) {
     if (!pdf || n_comp != h->cfg.n_components) { h->err = "one population array per component expected"; return LBM_EINVAL; }
     if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
+    sc_ensure_velocity(h);
     sc_ensure_head(h);
     SCFields c = sc_fields(h);
     const int64_t owned = h->g.plane * h->g.n2;

@@ -10,6 +10,7 @@
 // the equilibrium / force distributions live in registers inside the collision operator.  The MRT
 // relaxation is applied in moment space (M, diag(S), M^-1 hand-factored) instead of a dense 9x9 product.
 #pragma once
+#include "../../include/lbmpm.h"
 #include "grid.cuh"
 
 namespace lbm {
@@ -255,6 +256,44 @@ struct ScConvectiveEachOp {
     }
 };
 
+// All boundary rows of one iteration in ONE launch (the reference: 3-6 kernels over every node; one launch per row
+// operator here was 5-7 launches of a launch-bound 2-D step).  Items: 2 planes' worth of columns -- the first `plane`
+// items walk the outlet rows of their column, the others its inlet rows.  Rows of one column only depend on each other,
+// so one thread runs them back to back: same arithmetic, same order.  `efs`: the explicit-forcing loop
+// (ShanChenD2Q9.py:1933-2014: convective-each / pressure outlet, inlet, then calFluidRhoGPU -- of which only the two
+// Zou-He planes are not already sums); otherwise the original loop's pieces selected by `part`:
+// 1 = inlet at the top of an iteration (+ calFluidRhoGPU on its plane), 2 = convective outlet copies after the streaming.
+template <class L>
+struct ScOpenRowsOp {
+    SCFields c; int efs, part, do_in, do_out, rho_after_inlet;
+    LBM_HD void inlet_column(int64_t r) const {
+        ScInletVelocityOp<L>{c}(r);
+        for (int zr = c.z_in; zr < c.z_in_ghost; ++zr) ScRowCopyOp<L>{c, zr + 1, zr}(r);
+        if (rho_after_inlet) ScRhoOp<L>{c}((int64_t)c.z_in * c.g.plane + r);
+    }
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t plane = c.g.plane;
+        if (i < plane) {
+            if (!do_out) return;
+            if (efs) {
+                if (c.p.outlet == LBM_OUTLET_CONVECTIVE) {
+                    ScPhysicalVelocityOp<L>{c}(3 * plane + i);          // |u_up| of plane 3 is all the convective rows read
+                    ScConvectiveEachOp<L>{c, 2}(i); ScConvectiveEachOp<L>{c, 1}(i); ScConvectiveEachOp<L>{c, 0}(i);
+                } else if (c.p.outlet == LBM_OUTLET_PRESSURE) {
+                    ScOutletPressureOp<L>{c}(i);
+                    for (int zr = c.z_out; zr > 0; --zr) ScRowCopyOp<L>{c, zr - 1, zr}(i);
+                    ScRhoOp<L>{c}((int64_t)c.z_out * plane + i);
+                }
+            } else if (part == 2 && c.p.outlet == LBM_OUTLET_CONVECTIVE) {
+                ScRowCopyOp<L>{c, 2, 3}(i); ScRowCopyOp<L>{c, 1, 2}(i); ScRowCopyOp<L>{c, 0, 1}(i);
+            }
+        } else {
+            if (!do_in || c.p.inlet != LBM_INLET_VELOCITY) return;
+            if (efs || part == 1) inlet_column(i - plane);
+        }
+    }
+};
+
 // pull streaming with half-way bounce back + densities (calStreaming1GPU/2GPU 450-548, calFluidRhoGPU)
 template <class L>
 struct ScStreamOp {
@@ -426,6 +465,23 @@ struct EfsForceOp {
         for (int q = 1; q < L::Q; ++q) {
             nb[q] = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
             fl[q] = c.cls[nb[q]] & CLS_FLUID;
+        }
+        // physical velocity of the output point, u = sum_k (sum_q e_q f_k,q + F_k / 2) / sum_k rho_k with the force of the
+        // PREVIOUS evaluation (calPhysicalVelocity, OptimizedD2Q9GPU.py:156-175, launched by the reference right before
+        // this kernel, ShanChenD2Q9.py:2016-2027): same inputs, so it rides along instead of costing a pass of its own
+        {
+            double v[3] = {0.0, 0.0, 0.0}, r = 0.0;
+            for (int k = 0; k < nc; ++k) {
+                double f[L::Q], m[3];
+#pragma unroll
+                for (int q = 1; q < L::Q; ++q) f[q] = c.f(c.fS, k, q)[id];
+                sc_momentum<L>(f, m);
+#pragma unroll
+                for (int a = 0; a < L::D; ++a) v[a] += (m[a] + 1.0 / 2.0 * c.Fc(k, a, id));
+                r += c.rho[k * V + id];
+            }
+#pragma unroll
+            for (int a = 0; a < L::D; ++a) c.uph[a * V + id] = v[a] / r;
         }
         double mt[3] = {0.0, 0.0, 0.0}, rt = 0.0;
         for (int k = 0; k < nc; ++k) {
