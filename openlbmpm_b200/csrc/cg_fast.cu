@@ -640,13 +640,29 @@ static OpenRows open_rows(const CGFields& c) {
     }
     return r;
 }
+// One thread per column and side: materialise the streamed populations of the column's open rows from the factored state
+// (read-only neighbours), run the row operators on them, re-evaluate velocity (lagged force) and phi there.  Every step of
+// that chain only reads what the same thread wrote, so the three launches it used to be are one.
+template <class L>
+struct FastOpenPreOp {
+    CGFields c; FastFields s; OpenRows rows;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t plane = c.g.plane;
+        const bool outlet_side = i < plane;
+        const int64_t r = outlet_side ? i : i - plane;
+        const bool has_out = c.outlet != LBM_BC_PERIODIC && c.z_out >= 0, has_in = c.inlet != LBM_BC_PERIODIC && c.z_in >= 0;
+        if (outlet_side ? !has_out : !has_in) return;
+        const int k = outlet_side ? 0 : (has_out ? 1 : 0);
+        for (int z = rows.mat_lo[k]; z < rows.mat_hi[k]; ++z) PullMaterialiseOp<L>{c, s}((int64_t)z * plane + r);
+        OpenRowsOp<L>{c}(i);
+        for (int z = rows.mod_lo[k]; z < rows.mod_hi[k]; ++z) HeadOp<L>{c}((int64_t)z * plane + r);
+    }
+};
 template <class L>
 static void fast_open_rows_pre(lbm_handle* h, const CGFields& c, const FastFields& s) {
     const OpenRows r = open_rows(c);
     if (!r.n) return;
-    launch_plane_ranges(h, PullMaterialiseOp<L>{c, s}, 0, r.n, r.mat_lo, r.mat_hi);
-    cg_apply_open_rows(h);
-    launch_plane_ranges(h, HeadOp<L>{c}, 0, r.n, r.mod_lo, r.mod_hi);      // u with the lagged force, phi
+    launch(FastOpenPreOp<L>{c, s, r}, 2 * h->g.plane, h->stream);
 }
 template <class L>
 static void fast_open_rows_post(lbm_handle* h, const CGFields& c, const FastFields& o, bool need_gradient) {
