@@ -752,7 +752,7 @@ static void fast_one_step(lbm_handle* h) {
     const bool open = open_box(h);
     if (open) fast_open_rows_pre<L>(h, c, s);
     exchange_f64(h, c.phi, 0, 1, h->has_solid ? NG : 2);
-    if (h->has_solid) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
+    if (h->has_solid && tiled_ok(h)) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);     // the tiled kernel stages phi, solids included
     bool done = false;
     if (tiled_ok(h)) {
         if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);

@@ -281,7 +281,20 @@ struct HeadOp {
     }
 };
 
-// calColorValueOnSolid (1559-1580): phi_s = sum_{fluid nb} w phi / sum w, planes [-2, n2+2)
+// calColorValueOnSolid (1559-1580): phi_s = sum_{fluid nb} w phi / sum w of the wetting solid at (x, y, z)
+template <class L>
+LBM_HD double cg_phi_on_solid(const CGFields& c, int x, int y, int z) {
+    const Grid& g = c.g;
+    double num = 0.0, den = 0.0;
+#pragma unroll
+    for (int q = 1; q < L::Q; ++q) {
+        const int64_t n = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
+        if (c.cls[n] & CLS_FLUID) { num = add_rn(num, mul_rn(L::w(q), c.phi[n])); den += L::w(q); }
+    }
+    return den > 0.0 ? num / den : 0.0;
+}
+// ... stored into the phi array, planes [-2, n2+2): what the tiled collision kernel stages in shared memory and what
+// lbm_download_fields returns.  The one-thread-per-node gradient evaluates it in place (GradientOp) and needs no such pass.
 template <class L>
 struct PhiSolidOp {
     CGFields c;
@@ -290,13 +303,7 @@ struct PhiSolidOp {
         int x, y, z; g.decode(i, 2, x, y, z);
         const int64_t id = g.at(x, y, z);
         if (!(c.cls[id] & CLS_WET)) return;
-        double num = 0.0, den = 0.0;
-#pragma unroll
-        for (int q = 1; q < L::Q; ++q) {
-            const int64_t n = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
-            if (c.cls[n] & CLS_FLUID) { num = add_rn(num, mul_rn(L::w(q), c.phi[n])); den += L::w(q); }
-        }
-        c.phi[id] = den > 0.0 ? num / den : 0.0;
+        c.phi[id] = cg_phi_on_solid<L>(c, x, y, z);
     }
 };
 
@@ -311,9 +318,16 @@ struct GradientOp {
         const int64_t id = g.at(x, y, z), V = g.vol;
         if (!(c.cls[id] & CLS_FLUID)) return;
         double G[3] = {0.0, 0.0, 0.0};
+        const bool near_solid = c.cls[id] & CLS_NEAR;
 #pragma unroll
         for (int q = 1; q < L::Q; ++q) {
-            const double v = mul_rn(L::w(q), c.phi[g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q))]);
+            int xn, yn, zn;
+            g.nb_coords(x, y, z, L::d0(q), L::d1(q), L::d2(q), xn, yn, zn);
+            const int64_t nbid = g.at(xn, yn, zn);
+            // the colour a wetting solid shows is a function of its fluid neighbours' phi: evaluated here instead of in a
+            // pass of its own over the lattice (calColorValueOnSolid + calRKInitialGradient, 1559-1632)
+            const double pv = (near_solid && (c.cls[nbid] & CLS_WET)) ? cg_phi_on_solid<L>(c, xn, yn, zn) : c.phi[nbid];
+            const double v = mul_rn(L::w(q), pv);
 #pragma unroll
             for (int a = 0; a < L::D; ++a)
                 if (L::c(q, a) != 0) G[a] = add_rn(G[a], L::c(q, a) > 0 ? v : -v);

@@ -30,6 +30,13 @@ struct Grid {
         if (wrap2) { if (zn < 0) zn += n2; else if (zn >= n2) zn -= n2; }
         return at(xn, yn, zn);
     }
+    // the coordinates nb() addresses
+    LBM_HD void nb_coords(int x, int y, int z, int dx, int dy, int dz, int& xn, int& yn, int& zn) const {
+        xn = x + dx; yn = y + dy; zn = z + dz;
+        if (xn < 0) xn += n0; else if (xn >= n0) xn -= n0;
+        if (yn < 0) yn += n1; else if (yn >= n1) yn -= n1;
+        if (wrap2) { if (zn < 0) zn += n2; else if (zn >= n2) zn -= n2; }
+    }
     // item i of a launch over planes [-ext, n2 + ext)
     LBM_HD void decode(int64_t i, int ext, int& x, int& y, int& z) const {
         z = (int)(i / plane) - ext;

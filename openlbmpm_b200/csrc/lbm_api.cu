@@ -443,8 +443,7 @@ template <class L>
 static void cg_forces(lbm_handle* h, const CGFields& c) {
     const Grid& g = h->g;
     exchange_f64(h, c.phi, 0, 1, NG);
-    if (h->has_solid) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
-    launch(GradientOp<L>{c}, g.count(1), h->stream);
+    launch(GradientOp<L>{c}, g.count(1), h->stream);     // evaluates the colour of the wetting solids in place
 }
 
 template <class L>
@@ -677,8 +676,12 @@ extern "C" int lbm_download_fields(lbm_handle* h, double* phi, double* const* G,
     // perturbation operator: phi of the output point, G as evaluated by the last collision (phi = SolidColorDiff on solid
     // neighbours); the model has neither a curvature nor a force field (K and F stay zero)
     if (h->cfg.surface_tension_type != LBM_ST_PERTURBATION) {
-        cg_generic_forces(h);       // phi on the wetting solids, G, unit normals of the current time level
+        cg_generic_forces(h);       // G (with the colour of the wetting solids), unit normals of the current time level
         CGFields c = h->fields();
+        if (h->has_solid) {         // the phi array itself only carries the solids' colour when somebody asks for it
+            if (h->Q == 9) launch(PhiSolidOp<D2Q9>{c}, h->g.count(2), h->stream);
+            else launch(PhiSolidOp<D3Q19>{c}, h->g.count(2), h->stream);
+        }
         if (h->Q == 9) launch(CurvatureOp<D2Q9>{c}, h->g.count(0), h->stream);
         else launch(CurvatureOp<D3Q19>{c}, h->g.count(0), h->stream);
     }
