@@ -70,6 +70,8 @@ extern "C" {
 #define LBM_FLAG_OVERLAP 16u         /* slab decomposition: overlap the ghost-plane exchanges with the interior planes */
 #define LBM_FLAG_PACKED_EXCHANGE 32u /* slab decomposition: pack the boundary planes into one message per direction (experimental) */
 #define LBM_FLAG_GHOST_PLANES 64u     /* single slab: keep copying the periodic ghost planes every step instead of wrapping the flow axis by index arithmetic */
+#define LBM_FLAG_PERSISTENT 128u      /* single slab, one-thread-per-node fast path: all steps of an lbm_step call in ONE cooperative
+                                        kernel (one grid-wide barrier between the phases of a step instead of a launch); opt-in */
 #define LBM_FLAG_NO_CUDA_GRAPH 8u    /* small lattices: launch every kernel instead of replaying a captured graph */
 
 typedef struct lbm_handle lbm_handle;

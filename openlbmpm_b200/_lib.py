@@ -14,6 +14,7 @@ BC_PERIODIC, INLET_VELOCITY, INLET_PRESSURE = 0, 1, 2
 OUTLET_CONVECTIVE, OUTLET_PRESSURE = 1, 2
 FLAG_GENERIC_KERNELS = 1
 FLAG_GHOST_PLANES = 64
+FLAG_PERSISTENT = 128
 ST_CSF, ST_PERTURBATION = 0, 1
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

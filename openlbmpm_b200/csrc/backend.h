@@ -89,6 +89,7 @@ struct Profiler {
     }
 };
 extern thread_local Profiler g_prof;
+inline bool g_prof_active() { return g_prof.on; }
 
 template <class Op>
 inline void launch(const Op& op, int64_t n, stream_t s) {
@@ -172,6 +173,7 @@ inline void launch(const Op& op, int64_t n, stream_t) {
     for (int64_t i = 0; i < n; ++i) op(i);
     ++g_launch_counter;
 }
+inline bool g_prof_active() { return false; }
 struct GraphKeep { int unused = 0; };
 inline void graph_release(GraphKeep*, stream_t) {}
 template <class F>

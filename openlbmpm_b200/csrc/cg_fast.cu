@@ -8,7 +8,9 @@
 #include "cg_fast_ops.cuh"
 #include "internal.h"
 #ifndef LBM_HOSTCHECK
+#include <cooperative_groups.h>
 #include <cuda_pipeline.h>
+#define LBM_GRID_SYNC() cooperative_groups::this_grid().sync()
 #else
 #include "cta_emu.h"      // test hook: the tiled kernels below on host threads (one per CUDA thread of a CTA)
 #endif
@@ -767,6 +769,79 @@ static void fast_one_step(lbm_handle* h) {
     f->cur = 1 - f->cur;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent form of the one-thread-per-node fast path (LBM_FLAG_PERSISTENT, opt-in).  The 2-D configurations are a few
+// hundred thousand nodes: their lattice lives in the L2 and a step is bounded by its launches, not by bandwidth.  Here every
+// step of an lbm_step call runs inside ONE cooperative kernel -- as many CTAs as are co-resident, grid-stride loops over the
+// nodes, and a grid-wide barrier where the launch boundaries used to be (the phases of a step read what other threads wrote in
+// the phase before).  Same operators, same order: bit-equal to the launched form (tests/test_hostcheck_tiled.py runs it on
+// host threads).  Needs one slab with index wrap (no ghost-plane copies between the phases).
+// ------------------------------------------------------------------------------------------------
+template <class L, bool SOLIDS>
+__global__ void __launch_bounds__(256)
+cg_fast_persistent(const CGFields c, const FastFields b0, const FastFields b1, const OpenRows rows, const int open,
+                   const int nsteps, const int cur0) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const Grid& g = c.g;
+    const int64_t n_owned = g.count(0), n_grad = g.count(1), n_rows = 2 * g.plane;
+    for (int step = 0; step < nsteps; ++step) {
+        const bool odd = (cur0 + step) & 1;
+        const FastFields& s = odd ? b1 : b0;
+        const FastFields& o = odd ? b0 : b1;
+        for (int64_t i = tid; i < n_owned; i += nth) PullDensityOp<L, SOLIDS>{c, s}(i);
+        LBM_GRID_SYNC();
+        if (open) {
+            for (int64_t i = tid; i < n_rows; i += nth) FastOpenPreOp<L>{c, s, rows}(i);
+            LBM_GRID_SYNC();
+        }
+        for (int64_t i = tid; i < n_grad; i += nth) GradientOp<L>{c}(i);
+        LBM_GRID_SYNC();
+        for (int64_t i = tid; i < n_owned; i += nth) PullCollideOp<L, SOLIDS>{c, s, o}(i);
+        if (open) {
+            LBM_GRID_SYNC();
+            for (int k = 0; k < rows.n; ++k) {
+                const int64_t off = (int64_t)rows.mod_lo[k] * g.plane, cnt = (int64_t)(rows.mod_hi[k] - rows.mod_lo[k]) * g.plane;
+                for (int64_t i = tid; i < cnt; i += nth) CollideFactoredOp<L>{c, o}(i + off);
+            }
+        }
+        LBM_GRID_SYNC();
+    }
+}
+
+static bool persistent_ok(const lbm_handle* h) {
+    return (h->cfg.flags & LBM_FLAG_PERSISTENT) && h->nranks == 1 && h->g.wrap2 && !tiled_ok(h) && !g_prof_active();
+}
+
+template <class L, bool SOLIDS>
+static void launch_persistent_t(lbm_handle* h, int nsteps) {
+    FastState* f = (FastState*)h->fast;
+    CGFields c = h->fields();
+    FastFields b0 = fast_fields(h, 0), b1 = fast_fields(h, 1);
+    OpenRows rows = open_rows(c);
+    int open = open_box(h) ? 1 : 0, cur0 = f->cur;
+#ifdef LBM_HOSTCHECK
+    cta_emu::launch_cooperative(dim3(3), dim3(32), [&] { cg_fast_persistent<L, SOLIDS>(c, b0, b1, rows, open, nsteps, cur0); });
+#else
+    static int grid_for_device[64] = {};
+    int& grid = grid_for_device[h->cfg.device & 63];
+    if (!grid) {
+        int per_sm = 0, sms = 0;
+        LBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_fast_persistent<L, SOLIDS>, 256, 0));
+        LBM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        if (per_sm < 1) throw BackendError{"the persistent kernel does not fit on an SM"};
+        grid = per_sm * sms;
+    }
+    void* args[] = {&c, &b0, &b1, &rows, &open, &nsteps, &cur0};
+    LBM_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_fast_persistent<L, SOLIDS>, dim3(grid), dim3(256), args, 0, h->stream));
+#endif
+    ++g_launch_counter;
+    f->cur = (f->cur + nsteps) & 1;
+}
+static void launch_persistent(lbm_handle* h, int nsteps) {
+    if (h->Q == 9) { if (h->has_solid) launch_persistent_t<D2Q9, true>(h, nsteps); else launch_persistent_t<D2Q9, false>(h, nsteps); }
+    else { if (h->has_solid) launch_persistent_t<D3Q19, true>(h, nsteps); else launch_persistent_t<D3Q19, false>(h, nsteps); }
+}
+
 void cg_fast_step(lbm_handle* h, int nsteps) {
     if (nsteps <= 0) return;
     fast_alloc(h);
@@ -775,6 +850,7 @@ void cg_fast_step(lbm_handle* h, int nsteps) {
         if (h->Q == 9) fast_enter<D2Q9>(h); else fast_enter<D3Q19>(h);
         --left;
     }
+    if (left > 0 && persistent_ok(h)) { launch_persistent(h, left); return; }
     auto one = [&] { if (h->Q == 9) fast_one_step<D2Q9>(h); else fast_one_step<D3Q19>(h); };
     if (left > 0) { one(); --left; }          // outside the graph: configures the tiled kernels on first use
     // the double buffer flips every step, so the replayed unit is a pair of steps

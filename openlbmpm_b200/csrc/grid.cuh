@@ -44,7 +44,7 @@ struct Grid {
         y = r / n0;
         x = r - y * n0;
     }
-    int64_t count(int ext) const { return plane * (int64_t)(n2 + 2 * ext); }
+    LBM_HD int64_t count(int ext) const { return plane * (int64_t)(n2 + 2 * ext); }
 };
 
 // an operator restricted to a range of planes: item i of the launch is item i + off of the operator

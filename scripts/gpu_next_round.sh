@@ -7,6 +7,7 @@ O=gpurun_out
 ( timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/n_smoke.log 2>&1; echo "rc=$?" >> $O/n_smoke.log ); tail -2 $O/n_smoke.log
 for w in cfg1 cfg2 cfg3; do
   ( timeout 120 python bench.py --workload $w --steps 2000 --warmup 50 > $O/n_bench_$w.json 2> $O/n_bench_$w.err ); python scripts/bench_brief.py $O/n_bench_$w.json || tail -3 $O/n_bench_$w.err
+  ( timeout 120 python bench.py --workload $w --steps 2000 --warmup 50 --flags 128 > $O/n_bench_${w}_persistent.json 2>> $O/n_bench_$w.err ); python scripts/bench_brief.py $O/n_bench_${w}_persistent.json | head -1
   ( timeout 120 python bench.py --workload $w --steps 2000 --warmup 50 --flags 64 > $O/n_bench_${w}_ghostplanes.json 2>> $O/n_bench_$w.err ); python scripts/bench_brief.py $O/n_bench_${w}_ghostplanes.json | head -1
 done
 ( timeout 150 python bench.py --workload cfg4 --steps 100 --warmup 10 > $O/n_bench_cfg4.json 2> $O/n_bench_cfg4.err ); python scripts/bench_brief.py $O/n_bench_cfg4.json

@@ -628,3 +628,37 @@ def check_tracer_vs_gold(path, lib_path, chunk=1):
         eng.step(n)
         s += n
     eng.close()
+
+
+def check_persistent_kernel(lib_path):
+    """LBM_FLAG_PERSISTENT (all steps of an lbm_step call in one cooperative kernel, grid-wide barriers between the phases) is
+    bit-equal to one launch per phase: closed and open boxes, with and without solids, D2Q9 and untiled D3Q19, several calls"""
+    rng = np.random.default_rng(13)
+    cases_ = []
+    for lattice, shape in ((9, (26, 18)), (19, (12, 6, 10))):
+        dom = np.ones(shape, bool)
+        dom[(slice(10, 13),) + (slice(2, 5),) * (len(shape) - 1)] = False
+        r = 0.5 + 0.3 * (rng.random(shape) - 0.5)
+        cases_.append((lattice, shape, np.ones(shape, bool), r, dict()))
+        cases_.append((lattice, shape, dom, r, dict(contact_angle_deg=65.0)))
+        top = np.indices(shape)[0] >= shape[0] - 6
+        cases_.append((lattice, shape, dom, np.where(top, 1.0, 5e-8), dict(inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_CONVECTIVE,
+                                                                          inlet_velocity=-2e-3, contact_angle_deg=60.0)))
+        cases_.append((lattice, shape, dom, np.where(top, 1.0, 5e-8), dict(inlet=_lib.INLET_PRESSURE, outlet=_lib.OUTLET_PRESSURE, rhoRH=1.004,
+                                                                          rhoBH=5e-8, rhoRL=5e-8, rhoBL=1.0)))
+    for lattice, shape, dom, r, kw in cases_:
+        out = []
+        for flags in (0, _lib.FLAG_PERSISTENT):
+            eng = _lib.Engine(lattice, shape, lib_path=lib_path, flags=flags, **kw)
+            eng.set_geometry(dom)
+            eng.init_equilibrium(np.where(dom, r, 0.0), np.where(dom, 1.0 - r if r.max() < 0.99 else np.where(r > 0.5, 5e-8, 1.0), 0.0))
+            got = []
+            for n in (1, 2, 5, 4):
+                eng.step(n)
+                got.append(eng.timing()["launches"])
+                rho, u = eng.download_macros() if n == 5 else (None, None)
+            rho, u = eng.download_macros()
+            out.append((np.stack(rho + u + [p.sum(-1) for p in eng.download_pdfs()]), got))
+            eng.close()
+        assert np.array_equal(out[0][0], out[1][0]), (lattice, kw, np.abs(out[0][0] - out[1][0]).max())
+        assert out[1][1][2] == 1 and out[0][1][2] >= 15, (out[0][1], out[1][1])      # 5 steps from the factored state: ONE launch

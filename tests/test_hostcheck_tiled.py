@@ -94,3 +94,9 @@ def test_index_wrap_equals_ghost_plane_copies(lib):
                 out.append(np.stack(rho + u))
                 eng.close()
             assert np.array_equal(out[0], out[1]), (lattice, kw)
+
+
+def test_persistent_kernel_equals_launched_form(lib):
+    """LBM_FLAG_PERSISTENT: all steps of an lbm_step call in one cooperative kernel with grid-wide barriers between the
+    phases (here: 3 CTAs x 32 host threads, csrc/cta_emu.h) -- bit-equal to one launch per phase"""
+    cases.check_persistent_kernel(lib)
