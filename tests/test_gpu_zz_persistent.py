@@ -5,7 +5,7 @@ import pytest
 
 import cases
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]      # a cooperative kernel that cannot make progress must not hang the tier
 
 
 def test_persistent_kernel_equals_launched_form():
