@@ -7,12 +7,9 @@
 // consecutive lbm_step calls stay in factored form.
 #include "cg_fast_ops.cuh"
 #include "internal.h"
+#include "coop.h"         // grid-wide barrier; on the host (test hook) also the CUDA vocabulary of the kernels below, cta_emu.h
 #ifndef LBM_HOSTCHECK
-#include <cooperative_groups.h>
 #include <cuda_pipeline.h>
-#define LBM_GRID_SYNC() cooperative_groups::this_grid().sync()
-#else
-#include "cta_emu.h"      // test hook: the tiled kernels below on host threads (one per CUDA thread of a CTA)
 #endif
 
 namespace lbm {

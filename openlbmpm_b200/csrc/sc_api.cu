@@ -2,6 +2,7 @@
 // (original Shan-Chen: ShanChenD2Q9.py:1492-1629; explicit forcing SRT/MRT: ShanChenD2Q9.py:1714-2087).
 // D2Q9 follows the reference; D3Q19 (`ShanChenD3Q19.runOriginalSC3DGPU / runEFS4LBM3DGPU`, named by main.py:73-77
 // but absent upstream) runs the same lattice-generic operators, open boundaries included (oracle/sc_dense.py).
+#include "coop.h"
 #include "internal.h"
 #include "sc_ops.cuh"
 
@@ -225,11 +226,83 @@ static void efs_iteration(lbm_handle* h) {
     SC_LAUNCH(g.count(0), EfsForceOp, c);               // also the physical velocity of the output point (:2016-2027)
 }
 
+// Persistent form of both loops (LBM_FLAG_PERSISTENT, opt-in; see cg_fast.cu::cg_fast_persistent): every iteration of an
+// lbm_step call inside ONE cooperative kernel, a grid-wide barrier where the launch boundaries of sc_iteration /
+// efs_iteration are.  128 x 128 nodes (BASELINE configuration 1) are sixteen thousand threads: two launches per step cost
+// more than the step.  Same operators, same order.
+template <class L>
+__global__ void __launch_bounds__(256)
+sc_persistent(const SCFields c, const int efs, const int nsteps, const int do_in, const int do_out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const Grid& g = c.g;
+    const int64_t n_owned = g.count(0), n_rows = 2 * g.plane;
+    const bool convective = c.p.outlet == LBM_OUTLET_CONVECTIVE && do_out;
+    for (int step = 0; step < nsteps; ++step) {
+        if (!efs) {
+            if (do_in) {
+                for (int64_t i = tid; i < n_rows; i += nth) ScOpenRowsOp<L>{c, 0, 1, 1, 0, 1}(i);
+                LBM_GRID_SYNC();
+            }
+            for (int64_t i = tid; i < n_owned; i += nth) ScCollideOp<L>{c}(i);
+            LBM_GRID_SYNC();
+            for (int64_t i = tid; i < n_owned; i += nth) ScStreamOp<L>{c}(i);
+            if (convective) {
+                LBM_GRID_SYNC();
+                for (int64_t i = tid; i < n_rows; i += nth) ScOpenRowsOp<L>{c, 0, 2, 0, 1, 0}(i);
+            }
+            LBM_GRID_SYNC();
+        } else {
+            if (convective)
+                for (int64_t i = tid; i < 3 * g.plane; i += nth) ScSaveRowsOp<L>{c}(i);      // reads what the collision reads
+            for (int64_t i = tid; i < n_owned; i += nth) EfsCollideOp<L>{c}(i);
+            LBM_GRID_SYNC();
+            for (int64_t i = tid; i < n_owned; i += nth) ScStreamOp<L>{c}(i);
+            LBM_GRID_SYNC();
+            if (do_in || do_out) {
+                for (int64_t i = tid; i < n_rows; i += nth) ScOpenRowsOp<L>{c, 1, 0, do_in, do_out, 1}(i);
+                LBM_GRID_SYNC();
+            }
+            for (int64_t i = tid; i < n_owned; i += nth) EfsForceOp<L>{c}(i);
+            LBM_GRID_SYNC();
+        }
+    }
+}
+
+template <class L>
+static void sc_launch_persistent(lbm_handle* h, int nsteps) {
+    SCState* s = (SCState*)h->sc;
+    SCFields c = sc_fields(h);
+    int efs = h->cfg.model == LBM_MODEL_EFS ? 1 : 0;
+    int do_in = (c.p.inlet == LBM_INLET_VELOCITY && owns_inlet(h)) ? 1 : 0;
+    int do_out = (c.p.outlet != LBM_BC_PERIODIC && owns_outlet(h)) ? 1 : 0;
+#ifdef LBM_HOSTCHECK
+    cta_emu::launch_cooperative(dim3(3), dim3(32), [&] { sc_persistent<L>(c, efs, nsteps, do_in, do_out); });
+#else
+    static int grid_for_device[64] = {};
+    int& grid = grid_for_device[h->cfg.device & 63];
+    if (!grid) {
+        int per_sm = 0, sms = 0;
+        LBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc_persistent<L>, 256, 0));
+        LBM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        if (per_sm < 1) throw BackendError{"the persistent kernel does not fit on an SM"};
+        grid = per_sm * sms;
+    }
+    void* args[] = {&c, &efs, &nsteps, &do_in, &do_out};
+    LBM_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)sc_persistent<L>, dim3(grid), dim3(256), args, 0, h->stream));
+#endif
+    ++g_launch_counter;
+    s->head_done = false; s->uph_valid = efs ? s->uph_valid : false;
+}
+
 void sc_step(lbm_handle* h, int nsteps) {
     if (h->cfg.model == LBM_MODEL_EFS) efs_prepare(h);
     auto one = [&] { if (h->cfg.model == LBM_MODEL_SC) sc_iteration(h); else efs_iteration(h); };
     if (nsteps <= 0) return;
     one();      // outside the graph: whether the inlet treatment of this iteration is still due depends on the host state
+    if (nsteps > 1 && (h->cfg.flags & LBM_FLAG_PERSISTENT) && h->nranks == 1 && h->g.wrap2 && !g_prof_active()) {
+        if (h->Q == 9) sc_launch_persistent<D2Q9>(h, nsteps - 1); else sc_launch_persistent<D3Q19>(h, nsteps - 1);
+        return;
+    }
     replay(nsteps - 1, h->graph_ok(), &h->graph, h->stream, one);
 }
 

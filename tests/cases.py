@@ -222,10 +222,10 @@ def sc_engine_for_gold(g, p, lib_path, **extra):
     return eng
 
 
-def check_sc_vs_gold(path, lib_path, chunk=1):
+def check_sc_vs_gold(path, lib_path, chunk=1, **extra):
     """snapshot k of the golden file = state at the end of loop iteration k of the reference driver"""
     g, p = load_gold(path)
-    eng = sc_engine_for_gold(g, p, lib_path)
+    eng = sc_engine_for_gold(g, p, lib_path, **extra)
     nsnap = g["rho"].shape[0]
     ny = g["is_domain"].shape[0]
     # original SC + velocity inlet: a download shows the inlet rows after the NEXT iteration's inlet treatment

@@ -46,3 +46,10 @@ def test_d2q9_dense_case_through_the_generic_operators(lib):
                                                 ("EFS", "SRT", "Dirichlet")])
 def test_d3q19_open_boundaries_vs_dense_oracle(model, relax, outlet, lib):
     cases.case_sc_d3q19_open(lib, model, relax, outlet)
+
+
+@pytest.mark.parametrize("path", cases.GOLD_SC2D, ids=[cases.gold_id(p) for p in cases.GOLD_SC2D])
+def test_trajectory_vs_reference_persistent_kernel(path, lib):
+    """LBM_FLAG_PERSISTENT: the iterations of a call inside one cooperative kernel (host threads here, csrc/cta_emu.h)"""
+    from openlbmpm_b200 import _lib
+    cases.check_sc_vs_gold(path, lib, chunk=13, flags=_lib.FLAG_PERSISTENT)

@@ -100,3 +100,9 @@ def test_persistent_kernel_equals_launched_form(lib):
     """LBM_FLAG_PERSISTENT: all steps of an lbm_step call in one cooperative kernel with grid-wide barriers between the
     phases (here: 3 CTAs x 32 host threads, csrc/cta_emu.h) -- bit-equal to one launch per phase"""
     cases.check_persistent_kernel(lib)
+
+
+@pytest.mark.parametrize("path", cases.GOLD_CG2D, ids=[cases.gold_id(p) for p in cases.GOLD_CG2D])
+def test_colour_gradient_trajectories_persistent_kernel(path, lib):
+    """the reference's own vectors through the persistent kernel (19 steps per call)"""
+    cases.check_trajectory_vs_gold(path, lib, chunk=19, flags=_lib.FLAG_PERSISTENT)
