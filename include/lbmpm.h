@@ -48,8 +48,9 @@ extern "C" {
 
 /* lbm_config.surface_tension_type (LBM_MODEL_CG) */
 #define LBM_ST_CSF           0   /* continuum surface force: runRKColorGradient2DCSF (RKD2Q9.py:1225-1490)          */
-#define LBM_ST_PERTURBATION  1   /* perturbation operator, MRT, closed boxes: runRKColorGradient2DPerturbation
-                                    (RKD2Q9.py:979-1219; kernels calRKCollision1GPU2DMRTNew, calRKCollision23GPUNew) */
+#define LBM_ST_PERTURBATION  1   /* perturbation operator: runRKColorGradient2DPerturbation (RKD2Q9.py:979-1219; kernels
+                                    calRKCollision1GPU2D{MRT,SRT}New, calRKCollision23GPUNew).  Open boundaries as in the
+                                    CSF loop; SRT has no body-force term (the reference's SRT kernel has none)          */
 
 /* lbm_config.relax */
 #define LBM_RELAX_SRT   0

@@ -20,6 +20,18 @@ class RKColorGradient3D(RKColorGradientLBM):
         self.numBufferingLayers = ini.integer("DomainSize", "numBufferingLayers", default=0)
         self.ratioTopToBottom = ini.number("DomainSize", "ratioTopToBottom", default=0.5)
 
+    def _default_surface_tension(self, ini):
+        """The reference's 3-D ini has no [SurfaceTension] section: it parameterises the perturbation operator
+        ([RKParameters] AkR / AkB, [BoundariesSetup] SolidRhoR / SolidRhoB; RKtwophasesetup3D.ini:9-25)."""
+        if not ini.has_section("SurfaceTension") and ini.number("RKParameters", "AkR", default=0.0) > 0.0:
+            return "Perturbation"
+        return "CSF"
+
+    def _default_solid_phi(self, ini):
+        """fictitious colour densities on the solid -> the colour its neighbours see"""
+        r = ini.number("BoundariesSetup", "SolidRhoR", default=0.0); b = ini.number("BoundariesSetup", "SolidRhoB", default=0.0)
+        return (r - b) / (r + b) if r + b > 0.0 else 0.0
+
     def _read_time(self, ini):
         sec = "TimeSteps" if ini.has_section("TimeSteps") else "TimeSetup"
         self.timeSteps = ini.integer(sec, "TimeSteps")

@@ -34,7 +34,7 @@ class RKColorGradientLBM:
         self.imageExist = ini.quoted("ImageSetup", "Existance", default="no")
         self._read_domain(ini)
         # surface tension / recolouring (RKD2Q9.py:60-140)
-        self.surfaceTensionType = ini.quoted("SurfaceTension", "SurfaceTensionType", default="CSF")
+        self.surfaceTensionType = ini.quoted("SurfaceTension", "SurfaceTensionType", default=self._default_surface_tension(ini))
         if self.surfaceTensionType not in ("'CSF'", "'Perturbation'"):
             raise IniError("SurfaceTensionType must be 'CSF' or 'Perturbation'")
         self.surfaceTension = ini.number("SurfaceTension", "SurfaceTensionValue", "SurfaceTension", default=0.1)
@@ -49,7 +49,7 @@ class RKColorGradientLBM:
         # perturbation operator (RKD2Q9.py:107-133, 182): surface strengths and the colour seen on solid neighbours
         self.AkR = ini.number("RKParameters", "AkR", default=0.0)
         self.AkB = ini.number("RKParameters", "AkB", default=0.0)
-        self.solidPhi = ini.number("SolidBoundarySetup", "SolidColorDiff", default=0.0)
+        self.solidPhi = ini.number("SolidBoundarySetup", "SolidColorDiff", default=self._default_solid_phi(ini))
         self.tauR = ini.number("FluidParameters", "TauR")
         self.tauB = ini.number("FluidParameters", "TauB")
         self.initialRhoR = ini.number("FluidParameters", "InitialRhoR")
@@ -68,15 +68,6 @@ class RKColorGradientLBM:
         self.numGPUs = ini.integer("Parallelism", "NumGPUs", default=1)
         self.relaxationType = ini.quoted("RelaxationType", "Type", default="MRT")
         self._read_boundaries(ini)
-        if self.surfaceTensionType == "'Perturbation'":
-            # the one combination under which the reference's work-in-progress driver is self-consistent
-            # (RKD2Q9.py:979-1223; tests/golden/gen_goldens_cgp2d.py)
-            if self.relaxationType != "'MRT'":
-                raise IniError("SurfaceTensionType 'Perturbation' runs with RelaxationType 'MRT' (the reference's SRT branch "
-                               "is discarded by its own recolouring step, RKD2Q9.py:1158-1219)")
-            if self.boundaryTypeInlet != "'Periodic'" or self.boundaryTypeOutlet != "'Periodic'":
-                raise IniError("SurfaceTensionType 'Perturbation' runs on closed boxes (the reference treats the open rows "
-                               "after the total population was formed, RKD2Q9.py:1063-1118)")
         self.isCycles = ini.quoted("CyclesSetup", "IsCycle", default="no")
         if self.isCycles == "'yes'":
             self.lastStep = ini.integer("CyclesSetup", "LastStep")
@@ -89,6 +80,12 @@ class RKColorGradientLBM:
         # slab decomposition along the flow axis: one process per GPU under `torchrun` (slab.from_environment), every
         # rank holds the whole host-side arrays, runs its own slab on its GPU and gathers the results
         self.slabs = None
+
+    def _default_surface_tension(self, ini):
+        return "CSF"
+
+    def _default_solid_phi(self, ini):
+        return 0.0
 
     # -- ini pieces (overridden by the 3-D class) ---------------------------------------------------
     def _read_domain(self, ini):

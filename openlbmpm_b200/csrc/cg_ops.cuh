@@ -503,9 +503,16 @@ struct PerturbCollideOp {
             d[q] = fT[q] - rho * L::w(q) * (1.0 + (3.0 * eu + 4.5 * eu * eu - 1.5 * uu));
         }
         const double tau = 0.5 + 1.0 / ((1.0 + phi) / (2.0 * (c.p.tauR - 0.5)) + (1.0 - phi) / (2.0 * (c.p.tauB - 0.5)));
-        L::to_moments(d, m);
-        scale_moments(m, 1.0 / tau);
-        L::from_moments(m, d);
+        if (c.p.relax == 0) {
+            // SRT: the reference collides the two colours separately with the same tau (calRKCollision1GPU2DSRTNew,
+            // 1125-1163); their sum is this relaxation of the total population (f_eq is linear in rho)
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) d[q] = 1.0 / tau * d[q];
+        } else {
+            L::to_moments(d, m);
+            scale_moments(m, 1.0 / tau);
+            L::from_moments(m, d);
+        }
 #pragma unroll
         for (int q = 0; q < L::Q; ++q) {
             double eF = 0.0;

@@ -36,7 +36,7 @@ def constant_B(L):
 
 class CGPDense:
     def __init__(self, lattice, is_domain, beta=0.7, AkR=1.4e-2, AkB=1.4e-2, tauR=1.0, tauB=1.0, solid_phi=0.5,
-                 body_force=(0., 0., 0.)):
+                 body_force=(0., 0., 0.), relax="MRT", **open_boundaries):
         L = self.L = lattice
         dom = np.asarray(is_domain, bool)
         self.dom = dom[None] if dom.ndim == 2 else dom
@@ -45,6 +45,15 @@ class CGPDense:
         self.bf = np.zeros(3); self.bf[:len(body_force)] = body_force
         self.B = constant_B(L)
         self.ef = L.e.astype(float)
+        self.relax = relax      # "SRT": relaxation of the total population with tau(phi) = the sum of the reference's two per-colour
+                                # SRT collisions (calRKCollision1GPU2DSRTNew), whose result its driver drops
+        # Open boundaries (inlet=, outlet=, v_inlet=, dBH=, dRH=, dBL=, dRL= as for cg_dense.CGDense).  The reference's driver
+        # treats the open rows AFTER forming the total population (RKD2Q9.py:1063 vs :1065-1118), so their effect never
+        # reaches its collision; the consistent order -- the one of its CSF loop -- is taken here: streaming, densities, the
+        # row operators of the CSF loop (cg_dense.CGDense.boundaries), velocity, phi, collision.  This is what the
+        # reference's 3-D ini asks for (perturbation parameters + velocity inlet + pressure outlet); no reference vector
+        # exists for it.
+        self.bc = cg_dense.CGDense(L, self.dom, **open_boundaries) if open_boundaries else None
 
     def set_densities(self, rhoR, rhoB):
         """f = w rho at rest, then the streaming the reference's loop starts with: the state is its first output"""
@@ -66,6 +75,11 @@ class CGPDense:
                 new[i] = np.where(src_fluid, shift(f[i], -L.e[i]), f[L.opp[i]])
             setattr(self, name, np.where(dom, new, 0.))
         self.rhoR = _qsum(self.fR); self.rhoB = _qsum(self.fB)
+        if self.bc is not None:
+            b = self.bc
+            b.fR, b.fB, b.rhoR, b.rhoB = self.fR, self.fB, self.rhoR, self.rhoB
+            b.boundaries()
+            self.fR, self.fB, self.rhoR, self.rhoB = b.fR, b.fB, b.rhoR, b.rhoB
         with np.errstate(invalid="ignore", divide="ignore"):
             rho = self.rhoB + self.rhoR
             self.u = np.zeros((3,) + self.shape)
@@ -96,7 +110,10 @@ class CGPDense:
                 m = np.tensordot(L.M, fT, axes=(1, 0)) - np.tensordot(L.M, fe, axes=(1, 0))
                 wF = 3. * L.w; wF[0] = 0.
                 force = np.stack([wF[i] * sum(ef[i, a] * self.bf[a] for a in range(L.D)) * np.ones(self.shape) for i in range(Q)])
-                fT = -np.tensordot(L.Mi, S * m, axes=(1, 0)) + force + fT
+                if self.relax == "SRT":
+                    fT = -(1. / tau) * (fT - fe) + force + fT
+                else:
+                    fT = -np.tensordot(L.Mi, S * m, axes=(1, 0)) + force + fT
                 # colour gradient: phi of the fluid neighbours, SolidColorDiff on solid ones
                 G = np.zeros((3,) + self.shape)
                 for k in range(1, Q):

@@ -16,8 +16,10 @@ simulator), on the reference class's own constants, index arrays and initial sta
     calRKCollision1GPU2DMRTNew                        (:1191-1199)
     calRKCollision23GPUNew                            (:1211-1219)
 The one reading under which the driver is self-consistent is taken:
-  * MRT only.  The SRT branch collides fR and fB separately (calRKCollision1GPU2DSRTNew) but the recolouring that
-    follows rebuilds both from the never-updated total population, i.e. the SRT collision is discarded.
+  * MRT.  The SRT branch collides fR and fB separately (calRKCollision1GPU2DSRTNew) but the recolouring that follows
+    rebuilds both from the never-updated total population, i.e. the SRT collision is discarded.  Case `block_srt` wires the
+    SRT kernel so that it counts (total population re-formed from its two outputs): the vector for the SRT relaxation the
+    reference's 3-D ini asks for.
   * calRecoloringProcess (:1220) is left out: with its never-written inputs zeroed it degenerates to `fR += 0, fB += 0`.
   * closed boxes only: the open-boundary kernels of this driver treat fR / fB AFTER the total population was formed
     (:1063 vs :1065-1118), so their effect never reaches the collision.
@@ -55,6 +57,11 @@ CASES = {
     "block_solidphi": (16, 16, base.geom_block,
                        lambda nx, ny, d, p: base.init_droplet(nx, ny, d, p, cx=nx / 2 + 1, cy=ny / 2 + 4, r=3.6),
                        dict(solidphi=0.4, tauR=0.9, tauB=1.1)),
+    # SRT: reference kernel calRKCollision1GPU2DSRTNew wired so that its result is used (the driver drops it, see the docstring);
+    # that kernel has no body-force term
+    "block_srt": (16, 16, base.geom_block,
+                  lambda nx, ny, d, p: base.init_droplet(nx, ny, d, p, cx=nx / 2 + 1, cy=ny / 2 + 4, r=3.6),
+                  dict(relax="SRT", solidphi=0.4, tauR=1.0, tauB=0.8, steps=24)),
 }
 
 
@@ -78,7 +85,8 @@ class RefCGP(base.RefCG):
         nodes, nb = d(self.fluidNodes), d(self.neighboringNodes)
         w, cR, cB = d(self.weightsCoeff), d(self.constantCR), d(self.constantCB)
         ex, ey, scheme, bnew = d(self.unitEX), d(self.unitEY), d(self.gradientScheme), d(self.constantBNew)
-        M, Mi, S = d(self.transformationM), d(self.invTransformationM), d(self.collisionS)
+        if self.relaxationType == "'MRT'":
+            M, Mi, S = d(self.transformationM), d(self.invTransformationM), d(self.collisionS)
         n = self.fluidNodes.size
         grid = (int(self.xDimension / self.threadNum), math.ceil(n / self.xDimension)); block = (self.threadNum, 1)
         xd = self.xDimension
@@ -100,8 +108,15 @@ class RefCGP(base.RefCG):
                 self.resultInHDF5(record)
                 record += 1
             RK.calPhaseFieldPhi[grid, block](n, xd, rhoR, rhoB, phi)
-            RK.calRKCollision1GPU2DMRTNew[grid, block](n, xd, self.deltaValue, self.tauR, self.tauB, self.bodyFX, self.bodyFY,
-                                                       ex, ey, cR, cB, w, vx, vy, rhoR, rhoB, phi, fT, M, Mi, S)
+            if self.relaxationType == "'SRT'":
+                # the reading under which the SRT branch is not discarded: the kernel's two per-colour collisions (:1166-1172)
+                # are summed into the total population the recolouring rebuilds both colours from
+                RK.calRKCollision1GPU2DSRTNew[grid, block](n, xd, self.deltaValue, self.tauR, self.tauB, ex, ey, cR, cB, w, vx, vy,
+                                                           rhoR, rhoB, phi, fR, fB, fRn, fBn)
+                RK.calTotalFluidPDF[grid, block](n, xd, fR, fB, fT)
+            else:
+                RK.calRKCollision1GPU2DMRTNew[grid, block](n, xd, self.deltaValue, self.tauR, self.tauB, self.bodyFX, self.bodyFY,
+                                                           ex, ey, cR, cB, w, vx, vy, rhoR, rhoB, phi, fT, M, Mi, S)
             RK.calRKCollision23GPUNew[grid, block](n, xd, self.betaThickness, self.AkR, self.AkB, self.solidPhi, nodes, nb,
                                                    bnew, w, ex, ey, scheme, rhoR, rhoB, phi, cR, cB, fR, fB, cgx, cgy, fT)
 

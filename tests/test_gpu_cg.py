@@ -184,3 +184,8 @@ def test_tracer_trajectory_vs_reference_kernels(path, chunk):
 def test_tracers_vs_dense_oracle(lattice, n, relax):
     m0, m1 = cases.case_tracer_dense(None, lattice, n, relax=relax, solid=True, steps=9 if n[0] < 20 else 14)
     np.testing.assert_allclose(m1, m0, rtol=1e-12)
+
+
+@pytest.mark.parametrize("lattice,n,inlet,outlet", [(19, (22, 8, 10), "Neumann", "Dirichlet"), (9, (26, 14), "Dirichlet", "Dirichlet")])
+def test_perturbation_open_boundaries_vs_oracle(lattice, n, inlet, outlet):
+    cases.case_cgp_open(None, lattice, n, inlet=inlet, outlet=outlet)

@@ -16,7 +16,7 @@ GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)),
 def sim_for_gold(g, p, lattice=None):
     sim = cgp_dense.CGPDense(lattice or cgp_dense.d2q9(), g["is_domain"], beta=float(p["beta"]), AkR=float(p["akr"]),
                              AkB=float(p["akb"]), tauR=float(p["tauR"]), tauB=float(p["tauB"]), solid_phi=float(p["solidphi"]),
-                             body_force=(float(p["bfx"]), float(p["bfy"])))
+                             body_force=(float(p["bfx"]), float(p["bfy"])), relax=p["relax"])
     dom, red, minor = g["is_domain"], g["red_mask"], float(g["minor"])
     sim.set_densities(np.where(dom, np.where(red, float(p["rhoR"]), minor), 0.0),
                       np.where(dom, np.where(red, minor, float(p["rhoB"])), 0.0))
