@@ -211,7 +211,7 @@ int lbm_total_mass(lbm_handle* h, double* mass, int32_t n_comp);
 
 /* ---- solute tracers riding on the colour-gradient CSF flow ------------------ */
 
-/* The numbers the reference reads from transportsetup.ini (Transport2DRK.py:96-391), NumberSchemes = 9.        */
+/* The numbers the reference reads from transportsetup.ini (Transport2DRK.py:96-391).                           */
 typedef struct lbm_tracer_config {
     int32_t n_tracers;         /* [TransportParameters] NumberTracers (1..4)                                    */
     int32_t relax;             /* [RelaxationType] Relaxation: LBM_RELAX_SRT | LBM_RELAX_MRT (MRT: D2Q9 only)   */
@@ -220,9 +220,21 @@ typedef struct lbm_tracer_config {
     double dxy[4], dyx[4];     /* [TransportMRT] DiffusionXY, DiffusionYX        (MRT)                          */
     double beta[4];            /* [TransportParameters] BetaInterface                                           */
     double criterion;          /* rho_R above which a node is outside the transport domain (0.5, :1167)         */
+    /* 5-velocity branch of the same driver (Transport2DRK.py:1344-1384), D2Q9 flow only, MRT only                */
+    int32_t n_schemes;         /* [SystemType] NumberSchemes: 9 (0 means 9) | 5                                 */
+    int32_t reaction;          /* [SystemType] Reaction: 1 = A + B -> C on tracers 0, 1, 2 (calReactionTracersGPU) */
+    int32_t inlet_type;        /* [BoundaryCondition] InletType: LBM_TR_NONE | LBM_TR_INLET_DIRICHLET           */
+    int32_t outlet_type;       /* [BoundaryCondition] OutletType: LBM_TR_NONE | LBM_TR_OUTLET_FREEFLOW          */
+    double reaction_rate;      /* [Reaction] ReactionRate (the first one; the kernel reads no other)            */
+    double diff_j[4];          /* [TransportParameters] DiffusionJ: rest share J_0 of the reaction source        */
+    double inlet_conc[4];      /* concentration held on the inlet row (Inamuro, calInamuroConstConcBoundary)     */
 } lbm_tracer_config;
+#define LBM_TR_NONE             0
+#define LBM_TR_INLET_DIRICHLET  1
+#define LBM_TR_OUTLET_FREEFLOW  1
 
-/* Attaches tracers to a colour-gradient CSF handle on a closed box.  Must precede lbm_init_equilibrium /
+/* Attaches tracers to a colour-gradient CSF handle (9-velocity tracers: closed boxes; 5-velocity tracers bring their own
+ * inlet / outlet rows and also ride on open channels).  Must precede lbm_init_equilibrium /
  * lbm_upload_state: the reference's transport loop STARTS with the streaming of the flow (Transport2DRK.py:1180-1200),
  * so a freshly set flow state is streamed once.  From then on every lbm_step iteration runs, between the colour
  * gradient and the flow collision, the tracer collision + interface term + streaming + concentration

@@ -2,10 +2,12 @@
 "transport" + "CG" (`Transport2DRK(ini).runTransport2DMPMCRK()`, main.py:66-68; RKCG2D/Transport2DRK.py).
 
 Upstream neither of its drivers runs as shipped.  This class keeps the constructor contract
-(`RKtwophasesetup2D.ini` for the flow + `transportsetup.ini`: [SystemType] Option = 'MPMC', NumberSchemes = 9;
-[TransportParameters] NumberTracers, Tau, BetaInterface; [TransportMRT] DiffusionX / Y / XY / YX; [RelaxationType]
-Relaxation; [InitialCondition] TracerConc) and runs the one tracer scheme whose kernels are self-consistent: the 9-velocity
-tracers of `runTransport2DMPMCRKNew` (Transport2DRK.py:1341-1425) on closed boxes, inside liblbmpm.so (lbm_tracer_*).
+(`RKtwophasesetup2D.ini` for the flow + `transportsetup.ini`: [SystemType] Option = 'MPMC', NumberSchemes = 9 | 5, Reaction;
+[TransportParameters] NumberTracers, Tau, BetaInterface, DiffusionJ; [TransportMRT] DiffusionX / Y / XY / YX; [RelaxationType]
+Relaxation; [InitialCondition] TracerConc; 5-velocity branch: [Reaction] ReactionRate, [BoundaryCondition] InletType /
+ConcentrationInlet / OutletType) and runs the tracer phase of `runTransport2DMPMCRKNew` (Transport2DRK.py:1341-1425) inside
+liblbmpm.so (lbm_tracer_*): 9-velocity tracers on closed boxes, 5-velocity tracers (MRT, reaction A + B -> C, Inamuro inlet
+row, free-flow outlet row) on closed boxes and open channels.
 Public arrays: `tracerConc[numTracers, ny, nx]` next to the flow class's `fluidsRhoR/B`, `physicalVX/VY`."""
 import time
 
@@ -25,14 +27,16 @@ class Transport2DRK(RKColorGradientLBM):
             raise IniError("only [SystemType] Option = 'MPMC' (tracers on the two-phase flow) is built")
         super().__init__(pathIniFile, verbose=verbose)
         self.reaction = ini.quoted("SystemType", "Reaction", default="no")
-        if self.reaction == "'yes'":
-            raise IniError("reactions between tracers act on the 5-velocity scheme of the reference only")
         self.numSchemes = ini.integer("SystemType", "NumberSchemes", default=9)
-        if self.numSchemes != 9:
-            raise IniError("NumberSchemes = 9 (the 5-velocity branch needs the reference's host-side transport-domain bookkeeping)")
+        if self.numSchemes not in (5, 9):
+            raise IniError("NumberSchemes must be 5 or 9")
+        if self.reaction == "'yes'" and self.numSchemes != 5:
+            raise IniError("reactions between tracers act on the 5-velocity scheme of the reference only")
         self.numTracers = nt = ini.integer("TransportParameters", "NumberTracers", default=1)
         if not 1 <= nt <= 4:
             raise IniError("1..4 tracers are supported")
+        if self.reaction == "'yes'" and nt != 3:
+            raise IniError("the reaction of the reference is A + B -> C on three tracers (calReactionTracersGPU)")
 
         def per_tracer(section, key, default):
             vals = ini.numbers(section, key, default=default)
@@ -51,11 +55,23 @@ class Transport2DRK(RKColorGradientLBM):
         self.diffusionYX = per_tracer("TransportMRT", "DiffusionYX", "0.0")
         self.initialTracerConc = per_tracer("InitialCondition", "TracerConc", "1.0")
         self.criteriaFluidRho = 0.5                               # Transport2DRK.py:1167
-        self.weightsCoeffTR = self.weightsCoeff.copy()
         if self.surfaceTensionType != "'CSF'":
             raise IniError("the tracers ride on the CSF flow (runTransport2DMPMCRKNew)")
-        if self.boundaryTypeInlet != "'Periodic'" or self.boundaryTypeOutlet != "'Periodic'":
-            raise IniError("the 9-velocity tracer branch of the reference has no inlet / outlet treatment: closed boxes only")
+        if self.numSchemes == 9:
+            self.weightsCoeffTR = self.weightsCoeff.copy()
+            if self.boundaryTypeInlet != "'Periodic'" or self.boundaryTypeOutlet != "'Periodic'":
+                raise IniError("the 9-velocity tracer branch of the reference has no inlet / outlet treatment: closed boxes only")
+        else:
+            # Transport2DRK.py:313-347 (lattice, weights), :82-89 (reaction), :124-127 (J_0), :147-192 (tracer boundary rows)
+            self.weightsCoeffTR = np.array([1. / 3., 1. / 6., 1. / 6., 1. / 6., 1. / 6.])
+            self.unitVX = np.array([0., 1., -1., 0., 0.]); self.unitVY = np.array([0., 0., 0., 1., -1.])
+            if self.relaxationTypeTR != "'MRT'":
+                raise IniError("the 5-velocity branch of the reference collides with MRT only ([RelaxationType] Relaxation = 'MRT')")
+            self.diffJ = per_tracer("TransportParameters", "DiffusionJ", "0.3333333333333333")
+            self.reactionRate = np.array(ini.numbers("Reaction", "ReactionRate", default="0.0"), float) if self.reaction == "'yes'" else np.zeros(0)
+            self.typeTracerInletBoundary = ini.quoted("BoundaryCondition", "InletType", default="Periodic")
+            self.typeTracerOutletBoundary = ini.quoted("BoundaryCondition", "OutletType", default="Periodic")
+            self.concTracerIn = per_tracer("BoundaryCondition", "ConcentrationInlet", "1.0")
         self._tracer_results = None
 
     def initializeTransportDomain(self):
@@ -70,9 +86,16 @@ class Transport2DRK(RKColorGradientLBM):
 
     def _make_engine(self):
         super()._make_engine()
+        extra = {}
+        if self.numSchemes == 5:
+            extra = dict(n_schemes=5, reaction=self.reaction == "'yes'", reaction_rate=float(self.reactionRate[0]) if self.reactionRate.size else 0.0,
+                         diff_j=self.diffJ, inlet_conc=self.concTracerIn,
+                         inlet_type=_lib.TR_INLET_DIRICHLET if self.typeTracerInletBoundary == "'Dirichlet'" else _lib.TR_NONE,
+                         # the reference's loop tests this spelling (Transport2DRK.py:1363; its parser mentions 'FreeFlow', :191)
+                         outlet_type=_lib.TR_OUTLET_FREEFLOW if self.typeTracerOutletBoundary in ("'Freeflow'", "'FreeFlow'") else _lib.TR_NONE)
         self.engine.tracer_setup(n_tracers=self.numTracers, relax=_lib.RELAX_MRT if self.relaxationTypeTR == "'MRT'" else _lib.RELAX_SRT,
                                  tau=self.transportTau, dxx=self.diffusionX, dyy=self.diffusionY, dxy=self.diffusionXY,
-                                 dyx=self.diffusionYX, beta=self.betaTracerArray, criterion=self.criteriaFluidRho)
+                                 dyx=self.diffusionYX, beta=self.betaTracerArray, criterion=self.criteriaFluidRho, **extra)
 
     def saveConcentrationHDF5(self, index):
         """Transport2DRK.py:651-661"""

@@ -47,7 +47,13 @@ class LbmTracerConfig(ctypes.Structure):
     """Mirror of `struct lbm_tracer_config` (include/lbmpm.h)."""
     _fields_ = [("n_tracers", ctypes.c_int32), ("relax", ctypes.c_int32), ("tau", ctypes.c_double * 4),
                 ("dxx", ctypes.c_double * 4), ("dyy", ctypes.c_double * 4), ("dxy", ctypes.c_double * 4),
-                ("dyx", ctypes.c_double * 4), ("beta", ctypes.c_double * 4), ("criterion", ctypes.c_double)]
+                ("dyx", ctypes.c_double * 4), ("beta", ctypes.c_double * 4), ("criterion", ctypes.c_double),
+                ("n_schemes", ctypes.c_int32), ("reaction", ctypes.c_int32), ("inlet_type", ctypes.c_int32),
+                ("outlet_type", ctypes.c_int32), ("reaction_rate", ctypes.c_double), ("diff_j", ctypes.c_double * 4),
+                ("inlet_conc", ctypes.c_double * 4)]
+
+
+TR_NONE, TR_INLET_DIRICHLET, TR_OUTLET_FREEFLOW = 0, 1, 1
 
 
 # name -> (restype, argtypes); every symbol include/lbmpm.h declares
@@ -262,11 +268,15 @@ class Engine:
 
     # -- solute tracers riding on the colour-gradient CSF flow ------------------------------------
     def tracer_setup(self, n_tracers=1, relax=RELAX_SRT, tau=(1.0,), dxx=(0.0,), dyy=(0.0,), dxy=(0.0,), dyx=(0.0,),
-                     beta=(0.0,), criterion=0.5):
+                     beta=(0.0,), criterion=0.5, n_schemes=9, reaction=False, reaction_rate=0.0, diff_j=(1. / 3.,),
+                     inlet_type=TR_NONE, inlet_conc=(0.0,), outlet_type=TR_NONE):
         """before init_equilibrium / upload_state (the transport loop starts with the flow's streaming)"""
         cfg = LbmTracerConfig()
         cfg.n_tracers, cfg.relax, cfg.criterion = int(n_tracers), int(relax), float(criterion)
-        for name, vals in (("tau", tau), ("dxx", dxx), ("dyy", dyy), ("dxy", dxy), ("dyx", dyx), ("beta", beta)):
+        cfg.n_schemes, cfg.reaction, cfg.reaction_rate = int(n_schemes), int(bool(reaction)), float(reaction_rate)
+        cfg.inlet_type, cfg.outlet_type = int(inlet_type), int(outlet_type)
+        for name, vals in (("tau", tau), ("dxx", dxx), ("dyy", dyy), ("dxy", dxy), ("dyx", dyx), ("beta", beta),
+                           ("diff_j", diff_j), ("inlet_conc", inlet_conc)):
             arr = getattr(cfg, name)
             vals = list(np.asarray(vals, float).ravel())
             for i in range(4):

@@ -23,6 +23,27 @@ struct TracerParams {
     double tau[TR_MAX], beta[TR_MAX];
     double sa[TR_MAX], sb[TR_MAX], sc[TR_MAX], sd[TR_MAX];   // S block of the flux moments: [[a, b], [c, d]] on (j_x, j_y); a also on q_x, d on q_y
     double criterion;
+    // 5-velocity branch (NumberSchemes = 5)
+    int schemes;                 // 9 (the flow lattice) | 5
+    int reaction;                // A + B -> C on tracers 0, 1, 2
+    double rate, j0[TR_MAX];     // reaction rate; J_0 of each tracer (rest share of the source; (1 - J_0)/4 on the others)
+    int inlet_row, outlet_row;   // local plane of the Inamuro inlet / of the free-flow outlet on this slab, -1: none here
+    double inlet_conc[TR_MAX];
+};
+
+// The reference's 5-velocity tracer lattice (Transport2DRK.py:60-61, 313-322): rest, +x, -x, +y, -y; the 2-D lattice lives on
+// array axes 0 and 2 like D2Q9.
+struct D2Q5 {
+    static constexpr int Q = 5;
+    static constexpr int D = 2;
+    LBM_HD static constexpr int cx(int i) { constexpr int t[5] = {0, 1, -1, 0, 0}; return t[i]; }
+    LBM_HD static constexpr int cy(int i) { constexpr int t[5] = {0, 0, 0, 1, -1}; return t[i]; }
+    LBM_HD static constexpr int d0(int i) { return cx(i); }
+    LBM_HD static constexpr int d1(int) { return 0; }
+    LBM_HD static constexpr int d2(int i) { return cy(i); }
+    LBM_HD static constexpr int c(int i, int a) { return a == 0 ? cx(i) : (a == 1 ? cy(i) : 0); }
+    LBM_HD static constexpr int opp(int i) { constexpr int t[5] = {0, 2, 1, 4, 3}; return t[i]; }
+    LBM_HD static constexpr double w(int i) { return i == 0 ? 1.0 / 3.0 : 1.0 / 6.0; }
 };
 
 struct TracerFields {
@@ -97,6 +118,81 @@ struct TracerCollideOp {
     }
 };
 
+// 5-velocity branch: MRT collision (calCollisionTransportLinearEqlMRTGPU :535-590 with M, S of Transport2DRK.py:313-347),
+// interface term (calTransportWithInterfaceD2Q5 :976-1013), reaction source (calReactionTracersGPU :95-112): g -> gC.
+// M rows: (1,1,1,1,1), j_x = (0,1,-1,0,0), j_y = (0,0,0,1,-1), (4,-1,-1,-1,-1), (0,1,1,-1,-1); squared norms 5, 2, 2, 20, 4.
+struct TracerCollideQ5Op {
+    CGFields c; TracerFields t;
+    LBM_HD void operator()(int64_t i) const {
+        using L = D2Q5;
+        const Grid& g = c.g;
+        const int64_t id = (int64_t)NG * g.plane + i, V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID)) return;
+        const double u[2] = {c.u[id], c.u[V + id]};
+        double ug[2] = {c.G[id], c.G[V + id]};
+        const double gn = sqrt(ug[0] * ug[0] + ug[1] * ug[1]);
+        double un = 0.0;
+        if (gn > 1.0e-8) {
+            ug[0] = -ug[0] / gn; ug[1] = -ug[1] / gn;
+            un = sqrt(ug[0] * ug[0] + ug[1] * ug[1]);
+        } else {
+            ug[0] = 0.0; ug[1] = 0.0;
+        }
+        const double value = c.rho[0][id] > t.p.criterion ? -0.0 : -1.0;
+        double src = 0.0;
+        if (t.p.reaction) src = t.p.rate * t.conc[id] * t.conc[V + id];
+        for (int k = 0; k < t.p.nt; ++k) {
+            const double C = t.conc[(int64_t)k * V + id];
+            double f[5], d[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                f[q] = t.g[((int64_t)k * 5 + q) * V + id];
+                d[q] = f[q] - C * L::w(q) * (1.0 + 3.0 * (L::cx(q) * u[0] + L::cy(q) * u[1]));
+            }
+            double m0 = (((d[0] + d[1]) + d[2]) + d[3]) + d[4];
+            const double mx = d[1] - d[2], my = d[3] - d[4];
+            double m3 = 4.0 * d[0] - (((d[1] + d[2]) + d[3]) + d[4]);
+            double m4 = (d[1] + d[2]) - (d[3] + d[4]);
+            const double a = t.p.sa[k], b = t.p.sb[k], cc = t.p.sc[k], dd = t.p.sd[k];
+            const double det = a * dd - b * cc;
+            const double rx = (dd * mx - b * my) / det * 0.5, ry = (a * my - cc * mx) / det * 0.5;
+            m0 *= 0.2; m3 *= 0.05; m4 *= 0.25;
+            f[0] -= m0 + 4.0 * m3;
+            f[1] -= m0 + rx - m3 + m4;
+            f[2] -= m0 - rx - m3 + m4;
+            f[3] -= m0 + ry - m3 - m4;
+            f[4] -= m0 - ry - m3 - m4;
+#pragma unroll
+            for (int q = 1; q < 5; ++q) {
+                const double eg = L::cx(q) * ug[0] + L::cy(q) * ug[1];
+                const double cosT = un > 1.0e-8 ? eg / un : 0.0;
+                f[q] = f[q] + t.p.beta[k] * value * (L::w(q) * C) * cosT;
+            }
+            if (t.p.reaction) {
+                const double sk = k == 2 ? src : -src, jr = (1.0 - t.p.j0[k]) / 4.0;
+                f[0] = f[0] + t.p.j0[k] * sk;
+#pragma unroll
+                for (int q = 1; q < 5; ++q) f[q] = f[q] + jr * sk;
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q) t.gC[((int64_t)k * 5 + q) * V + id] = f[q];
+        }
+    }
+};
+
+// free-flow outlet (calFreeConcBoundary3 :461-474): the outlet row takes the post-collision populations of the row above it
+// (where that node is solid the reference reads through index -1; here the node keeps its own)
+struct TracerFreeflowOp {
+    CGFields c; TracerFields t;
+    LBM_HD void operator()(int64_t i) const {       // i: node of the outlet plane
+        const Grid& g = c.g;
+        const int64_t id = (int64_t)(NG + t.p.outlet_row) * g.plane + i, up = id + g.plane, V = g.vol;
+        if (!(c.cls[id] & CLS_FLUID) || !(c.cls[up] & CLS_FLUID)) return;
+        for (int k = 0; k < t.p.nt; ++k)
+            for (int q = 0; q < 5; ++q) t.gC[((int64_t)k * 5 + q) * V + id] = t.gC[((int64_t)k * 5 + q) * V + up];
+    }
+};
+
 // pull streaming with half-way bounce back + concentration: gC -> g, conc
 template <class L>
 struct TracerStreamOp {
@@ -119,7 +215,8 @@ struct TracerStreamOp {
             gS[id] = v0; acc += v0;
 #pragma unroll
             for (int q = 1; q < L::Q; ++q) {
-                const double v = fl[q] ? gC[q * V + src[q]] : gC[L::opp(q) * V + id];
+                double v = fl[q] ? gC[q * V + src[q]] : gC[L::opp(q) * V + id];
+                if (L::Q == 5 && q == 4 && z == t.p.inlet_row) v = L::w(4) * ((t.p.inlet_conc[k] - acc) / L::w(4));      // Inamuro (calInamuroConstConcBoundary :682-698)
                 gS[q * V + id] = v;
                 acc += v;
             }

@@ -15,6 +15,17 @@ Restates the tracer part of the reference's `runTransport2DMPMCRKNew`, NumberSch
 The D2Q9 instantiation is PINNED against tests/golden/tr2d_*.npz (the reference's kernels executed verbatim,
 tests/golden/gen_goldens_tr2d.py; all-fluid periodic boxes -- next to wetting solids the reference's tracer streaming
 writes through a negative index, here it bounces back).  D3Q19: SRT by generalisation.
+NumberSchemes = 5 (`TracerDenseQ5`, branch :1344-1384 of the same driver; D2Q5 tracers on the D2Q9 flow):
+           MRT  g <- g - M^-1 S^-1 (M g - M g_eq), g_eq = C w_j (1 + 3 e_j.u), w = (1/3, 1/6 x4), rows of M: (1,1,1,1,1),
+                j_x, j_y, (4,-1,-1,-1,-1), (0,1,1,-1,-1); S = 1 except the flux block             calCollisionTransportLinearEqlMRTGPU :535-590, Transport2DRK.py:313-347
+           g_j += beta * indicator * w_j C cos(angle(e_j, -G)), j = 1..4                           calTransportWithInterfaceD2Q5 :976-1013
+           reaction A + B -> C on tracers 0, 1, 2: g_ij += J_ij (-/+) k C_0 C_1                     calReactionTracersGPU :95-112
+           free-flow outlet: row 0 copies the post-collision populations of row 1                    calFreeConcBoundary3 :461-474
+           streaming on the tracer lattice's own table: periodic in x AND y whatever the flow boundaries are, half-way
+           bounce back at solids, the rest population stays                                         fillNeighboringNodesTransport :51-75, calStreamingTransportGPU :139-192
+           Inamuro inlet: top row, g_4 = C_in - (g_0 + g_1 + g_2 + g_3)                             calInamuroConstConcBoundary :682-698
+           C = sum_j g_j
+PINNED against tests/golden/tr2d_q5_*.npz (reference kernels, solids + reaction + inlet/outlet rows included).
 Only tests/ may import it.
 """
 import numpy as np
@@ -79,4 +90,77 @@ class TracerDense:
                     for j in range(L.Q):
                         c = c + self.g[i, j]
                     self.conc[i] = c
+            f.body()
+
+
+class TracerDenseQ5:
+    E = np.array([[0, 0], [1, 0], [-1, 0], [0, 1], [0, -1]])
+    OPP = [0, 2, 1, 4, 3]
+    W = np.array([1. / 3., 1. / 6., 1. / 6., 1. / 6., 1. / 6.])
+
+    def __init__(self, flow, dxx=(0.05,), dyy=(0.08,), dxy=(0.0,), dyx=(0.0,), beta=(0.6,), criterion=0.5,
+                 reaction_rate=None, diff_j=None, inlet_conc=None, freeflow_outlet=False):
+        assert flow.L.D == 2, "the reference's 5-velocity tracer lattice is two-dimensional"
+        self.flow, self.criterion = flow, criterion
+        self.beta = np.asarray(beta, float)
+        self.nt = nt = self.beta.size
+        M = np.ones((5, 5)); M[1] = [0, 1, -1, 0, 0]; M[2] = [0, 0, 0, 1, -1]; M[3] = [4, -1, -1, -1, -1]; M[4] = [0, 1, 1, -1, -1]
+        self.M = M
+        self.A = []
+        for i in range(nt):
+            S = np.eye(5)
+            S[1, 1] = 0.5 + 3. * dxx[i]; S[2, 2] = 0.5 + 3. * dyy[i]; S[1, 2] = 3. * dxy[i]; S[2, 1] = 3. * dyx[i]
+            self.A.append(-np.dot(np.linalg.inv(M), np.linalg.inv(S)))
+        self.rate = reaction_rate
+        if reaction_rate is not None:
+            assert nt == 3, "the reference's reaction kernel is A + B -> C on three tracers"
+            dj = np.asarray(diff_j, float)
+            self.J = np.concatenate([dj[:, None], np.repeat((1. - dj)[:, None] / 4., 4, axis=1)], axis=1)
+        self.inlet_conc = None if inlet_conc is None else np.asarray(inlet_conc, float)
+        self.freeflow = freeflow_outlet
+
+    def set_concentrations(self, conc):
+        f = self.flow
+        self.conc = np.asarray(conc, float).reshape((self.nt,) + f.shape) * f.dom
+        self.g = self.W[None, :, None, None, None] * self.conc[:, None]
+        f.stream_only()
+
+    def step(self, n=1):
+        f = self.flow; dom = f.dom; ef = self.E.astype(float)
+        e3 = [(int(e[0]), int(e[1]), 0) for e in self.E]
+        for _ in range(n):
+            f.head()
+            G = f.gradient()
+            with np.errstate(invalid="ignore", divide="ignore"):
+                value = np.where(f.rhoR > self.criterion, -0.0, -1.0)
+                gn = np.sqrt((G * G).sum(0))
+                big = gn > 1.0e-8
+                ug = np.where(big, -G / np.where(big, gn, 1.), 0.)
+                un = np.sqrt((ug * ug).sum(0))
+                conc_lag = self.conc.copy()
+                for i in range(self.nt):
+                    C = conc_lag[i]
+                    geq = np.stack([C * self.W[j] * (1. + 3. * (ef[j, 0] * f.u[0] + ef[j, 1] * f.u[1])) for j in range(5)])
+                    diff = np.tensordot(self.M, self.g[i], axes=(1, 0)) - np.tensordot(self.M, geq, axes=(1, 0))
+                    g = self.g[i] + np.tensordot(self.A[i], diff, axes=(1, 0))
+                    for j in range(1, 5):
+                        ok = un > 1.0e-8
+                        cos = np.where(ok, (ef[j, 0] * ug[0] + ef[j, 1] * ug[1]) / np.where(ok, un, 1.), 0.)
+                        g[j] = g[j] + self.beta[i] * value * (self.W[j] * C) * cos
+                    if self.rate is not None:
+                        src = self.rate * conc_lag[0] * conc_lag[1] * (1.0 if i == 2 else -1.0)
+                        for j in range(5):
+                            g[j] = g[j] + self.J[i, j] * src
+                    if self.freeflow:
+                        ok = dom[0, 0] & dom[0, 1]          # (the reference reads through index -1 where row 1 is solid)
+                        g[:, 0, 0] = np.where(ok, g[:, 0, 1], g[:, 0, 0])
+                    new = np.empty_like(g)
+                    new[0] = g[0]
+                    for j in range(1, 5):
+                        src_fluid = shift(dom, tuple(-c for c in e3[j]))
+                        new[j] = np.where(src_fluid, shift(g[j], tuple(-c for c in e3[j])), g[self.OPP[j]])
+                    if self.inlet_conc is not None:
+                        new[4, 0, -1] = self.W[4] * ((self.inlet_conc[i] - (new[0, 0, -1] + new[1, 0, -1] + new[2, 0, -1] + new[3, 0, -1])) / self.W[4])
+                    self.g[i] = np.where(dom, new, 0.)
+                    self.conc[i] = ((((self.g[i, 0] + self.g[i, 1]) + self.g[i, 2]) + self.g[i, 3]) + self.g[i, 4])
             f.body()

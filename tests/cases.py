@@ -560,6 +560,76 @@ def tracer_pair(lattice, dom, rhoR, rhoB, conc, lib_path, flow=None, tr=None, **
     return eng, trs
 
 
+def tracer_pair_q5(dom, rhoR, rhoB, conc, lib_path, flow=None, tr=None, flow_bc=None, **extra):
+    """5-velocity tracers (NumberSchemes = 5) on the D2Q9 CSF flow -> (engine, oracle); `flow_bc`: open-channel keywords of
+    cg_dense.CGDense (inlet=, outlet=, v_inlet=, dBH= ...)"""
+    from oracle import tr_dense
+    flow = dict(dict(sigma=0.1, contact_angle_deg=60.0, wetting_type=2, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2), **(flow or {}))
+    tr = dict(dict(dxx=(0.05,), dyy=(0.08,), dxy=(0.01,), dyx=(0.02,), beta=(0.6,), criterion=0.5, reaction_rate=None, diff_j=None,
+                   inlet_conc=None, freeflow_outlet=False), **(tr or {}))
+    bc = dict(flow_bc or {})
+    sim = cg_dense.CGDense(cg_dense.d2q9(), dom, sigma=flow["sigma"], theta_deg=flow["contact_angle_deg"], wetting=flow["wetting_type"],
+                           beta=flow["beta"], delta=flow["delta"], tauR=flow["tauR"], tauB=flow["tauB"], tautype=flow["tau_type"], relax="MRT", **bc)
+    sim.set_densities(rhoR, rhoB)
+    trs = tr_dense.TracerDenseQ5(sim, **tr)
+    trs.set_concentrations(conc)
+    ekw = {}
+    if bc:
+        ekw = dict(inlet=INLET[bc.get("inlet", "Periodic")], outlet=OUTLET[bc.get("outlet", "Periodic")], inlet_velocity=bc.get("v_inlet", 0.0),
+                   rhoBH=bc.get("dBH", 5e-8), rhoRH=bc.get("dRH", 1.0), rhoBL=bc.get("dBL", 1.0), rhoRL=bc.get("dRL", 5e-8))
+    eng = _lib.Engine(9, dom.shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, lib_path=lib_path, **flow, **ekw, **extra)
+    nt = len(tr["beta"])
+    eng.tracer_setup(n_tracers=nt, relax=_lib.RELAX_MRT, dxx=tr["dxx"], dyy=tr["dyy"], dxy=tr["dxy"], dyx=tr["dyx"], beta=tr["beta"],
+                     criterion=tr["criterion"], n_schemes=5, reaction=tr["reaction_rate"] is not None, reaction_rate=tr["reaction_rate"] or 0.0,
+                     diff_j=tr["diff_j"] if tr["diff_j"] is not None else (1. / 3.,),
+                     inlet_type=_lib.TR_INLET_DIRICHLET if tr["inlet_conc"] is not None else _lib.TR_NONE,
+                     inlet_conc=tr["inlet_conc"] if tr["inlet_conc"] is not None else (0.0,),
+                     outlet_type=_lib.TR_OUTLET_FREEFLOW if tr["freeflow_outlet"] else _lib.TR_NONE)
+    eng.set_geometry(dom)
+    eng.init_equilibrium(np.where(dom, rhoR, 0.0), np.where(dom, rhoB, 0.0))
+    eng.tracer_init(*[np.where(dom, c, 0.0) for c in np.asarray(conc).reshape((nt,) + dom.shape)])
+    return eng, trs
+
+
+def case_tracer_q5_dense(lib_path, n=(26, 18), steps=9, channel=True, atol=1e-10, **extra):
+    """CUDA path vs oracle/tr_dense.py::TracerDenseQ5: three reacting tracers with an Inamuro inlet row and a free-flow outlet row, on
+    an open channel of the flow (velocity inlet, pressure outlet) with a wetting solid; concentrations after every chunk"""
+    import copy
+    rng = np.random.default_rng(43)
+    dom = np.ones(n, bool)
+    dom[10:13, 3:9] = False
+    if channel:
+        top = np.indices(n)[0] >= n[0] - 7
+        rhoR, rhoB = np.where(top, 1.0, 5e-8), np.where(top, 5e-8, 1.0)
+        bc = dict(inlet="Neumann", outlet="Dirichlet", v_inlet=-2.0e-3, dBL=1.0, dRL=5e-8)
+        # in the bulk of each phase the colour gradient is ~1e-7 (trace colour 5e-8): its direction, which the interface term
+        # of the tracers normalises, carries a relative rounding error of 1e-16 / 1e-7
+        atol = max(atol, 5e-9)
+    else:
+        rhoR = 0.5 + 0.4 * (rng.random(n) - 0.5); rhoB = 1.0 - rhoR
+        bc = None
+    nt = 3
+    conc = 0.2 + rng.random((nt,) + n)
+    tr = dict(dxx=(0.05, 0.1, 0.07), dyy=(0.08, 0.1, 0.07), dxy=(0.01, 0.0, 0.0), dyx=(0.02, 0.0, 0.0), beta=(0.6, 0.3, 0.0),
+              reaction_rate=0.04, diff_j=(0.3, 1. / 3., 0.4), inlet_conc=(0.7, 0.2, 0.0), freeflow_outlet=True)
+    eng, trs = tracer_pair_q5(dom, rhoR, rhoB, conc, lib_path, flow=dict(tauB=0.85, tau_type=1), tr=tr, flow_bc=bc, **extra)
+    done = 0
+    for k in (0, 1, 2, steps - 3):
+        eng.step(k); trs.step(k); done += k
+        conc_e = eng.tracer_download()
+        probe = copy.deepcopy(trs); probe.step(1)
+        for i in range(nt):
+            np.testing.assert_allclose(conc_e[i], probe.conc[i].reshape(n), rtol=0, atol=atol, err_msg="tracer %d after %d" % (i, done))
+        rho, u = eng.download_macros()
+        probe = copy.deepcopy(trs); probe.flow.head()
+        np.testing.assert_allclose(rho[0], probe.flow.rhoR.reshape(n), rtol=0, atol=atol, err_msg="rhoR after %d" % done)
+        np.testing.assert_allclose(u[1], probe.flow.u[1].reshape(n), rtol=0, atol=atol, err_msg="uy after %d" % done)
+    top_row = np.stack(conc_e)[:, -1][:, dom[-1]]
+    assert np.abs(top_row - np.array(tr["inlet_conc"])[:, None]).max() < 1e-13        # the inlet row holds the prescribed concentrations
+    eng.close()
+    return conc_e
+
+
 def case_tracer_dense(lib_path, lattice=9, n=(14, 18), steps=9, solid=True, relax="SRT", atol=1e-10, **extra):
     """CUDA path vs oracle/tr_dense.py: flow densities / velocity and tracer concentrations after every chunk"""
     rng = np.random.default_rng(41)
@@ -603,6 +673,14 @@ def case_tracer_dense(lib_path, lattice=9, n=(14, 18), steps=9, solid=True, rela
     return m0, m1
 
 
+def gold_initial_densities(g, p):
+    """the colour layout a golden file started from: an explicit pair of fields, or the red mask + minority value"""
+    if "rhoR0" in g.files:
+        return g["rhoR0"], g["rhoB0"]
+    red, minor = g["red_mask"], float(g["minor"])
+    return np.where(red, float(p["rhoR"]), minor), np.where(red, minor, float(p["rhoB"]))
+
+
 def check_tracer_vs_gold(path, lib_path, chunk=1):
     """flow snapshot k / tracer snapshot k of the golden file = what the reference's kernels hold at the two output
     points of loop iteration k (Transport2DRK.py:1300-1312 and :1427-1437)"""
@@ -610,10 +688,18 @@ def check_tracer_vs_gold(path, lib_path, chunk=1):
     dom, red, minor = g["is_domain"], g["red_mask"], float(g["minor"])
     flow = dict(sigma=float(p["sigma"]), contact_angle_deg=float(p["theta"]), wetting_type=int(p["wetting"]), beta=float(p["beta"]),
                 delta=float(p["delta"]), tauR=float(p["tauR"]), tauB=float(p["tauB"]), tau_type=int(p["tautype"]))
-    tr = dict(relax=p["tr_relax"], tau=(float(p["tr_tau"]),), dxx=(float(p["dxx"]),), dyy=(float(p["dyy"]),),
-              dxy=(float(p["dxy"]),), dyx=(float(p["dyx"]),), beta=(float(p["beta_tr"]),), criterion=0.5)
-    eng, trs = tracer_pair(9, dom, np.where(red, float(p["rhoR"]), minor), np.where(red, minor, float(p["rhoB"])), g["tracer0"], lib_path,
-                           flow=flow, tr=tr)
+    nt = int(p.get("nt", 1))
+    per = lambda key: (float(p[key]),) * nt
+    rho0 = gold_initial_densities(g, p)
+    if int(p.get("schemes", 9)) == 5:
+        tr = dict(dxx=per("dxx"), dyy=per("dyy"), dxy=per("dxy"), dyx=per("dyx"), beta=per("beta_tr"), criterion=0.5,
+                  reaction_rate=float(p["rate"]) if p["reaction"] == "yes" else None, diff_j=per("diffj"),
+                  inlet_conc=per("conc_in") if p["tr_inlet"] == "Dirichlet" else None, freeflow_outlet=p["tr_outlet"] == "Freeflow")
+        eng, trs = tracer_pair_q5(dom, rho0[0], rho0[1], g["tracer0"], lib_path, flow=flow, tr=tr)
+    else:
+        tr = dict(relax=p["tr_relax"], tau=per("tr_tau"), dxx=per("dxx"), dyy=per("dyy"), dxy=per("dxy"), dyx=per("dyx"), beta=per("beta_tr"),
+                  criterion=0.5)
+        eng, trs = tracer_pair(9, dom, rho0[0], rho0[1], g["tracer0"], lib_path, flow=flow, tr=tr)
     nsnap = g["rhoR"].shape[0]
     s = 0
     while True:
@@ -621,7 +707,8 @@ def check_tracer_vs_gold(path, lib_path, chunk=1):
         for k, a in (("rhoR", rho[0]), ("rhoB", rho[1]), ("ux", u[0]), ("uy", u[1])):
             np.testing.assert_allclose(a, g[k][s], rtol=0, atol=ATOL_GOLD, err_msg="%s snapshot %d" % (k, s))
         conc = eng.tracer_download()
-        np.testing.assert_allclose(conc[0], g["conc"][s][0], rtol=0, atol=ATOL_GOLD, err_msg="tracer snapshot %d" % s)
+        for i in range(nt):
+            np.testing.assert_allclose(conc[i], g["conc"][s][i], rtol=0, atol=ATOL_GOLD, err_msg="tracer %d snapshot %d" % (i, s))
         if s == nsnap - 1:
             break
         n = min(chunk, nsnap - 1 - s)

@@ -186,6 +186,11 @@ def test_tracers_vs_dense_oracle(lattice, n, relax):
     np.testing.assert_allclose(m1, m0, rtol=1e-12)
 
 
+@pytest.mark.parametrize("channel", [False, True])
+def test_five_velocity_tracers_vs_dense_oracle(channel):
+    cases.case_tracer_q5_dense(None, n=(40, 36), steps=12, channel=channel)
+
+
 @pytest.mark.parametrize("lattice,n,inlet,outlet", [(19, (22, 8, 10), "Neumann", "Dirichlet"), (9, (26, 14), "Dirichlet", "Dirichlet")])
 def test_perturbation_open_boundaries_vs_oracle(lattice, n, inlet, outlet):
     cases.case_cgp_open(None, lattice, n, inlet=inlet, outlet=outlet)

@@ -154,6 +154,30 @@ def test_reference_3d_ini_runs_the_perturbation_operator(hostlib):
     assert np.abs(sim.physicalVZ[-1][sim.isDomain[-1]] + 1.0e-3).max() < 1e-12        # the inlet plane carries the prescribed velocity
 
 
+def test_transport_class_five_velocity_branch(hostlib):
+    """NumberSchemes = 5 on an open channel: three reacting tracers, Inamuro inlet row, free-flow outlet row; equals the oracle"""
+    from openlbmpm_b200.Transport2DRK import Transport2DRK
+    from oracle import cg_dense, tr_dense
+    sim = Transport2DRK(os.path.join(REF_INI, "tr2d_q5"), verbose=False)
+    assert sim.numSchemes == 5 and sim.reaction == "'yes'" and sim.typeTracerOutletBoundary == "'Freeflow'"
+    yy, xx = np.indices((sim.yDomain, sim.xDomain))
+    sim.initialRedRegion = yy >= sim.yDomain - 12
+    sim.runTransport2DMPMCRK()
+    flow = cg_dense.CGDense(cg_dense.d2q9(), sim.isDomain, sigma=0.1, theta_deg=60.0, wetting=2, beta=0.7, delta=0.98, tauR=1.0,
+                            tauB=1.0, tautype=2, relax="MRT", inlet="Neumann", outlet="Dirichlet", v_inlet=-1.0e-3, dBL=1.0, dRL=5e-8)
+    red = sim.initialRedRegion & sim.isDomain
+    flow.set_densities(np.where(red, 1.0, 0.0) * sim.isDomain, np.where(red, 0.0, 1.0) * sim.isDomain)
+    tr = tr_dense.TracerDenseQ5(flow, dxx=(0.05, 0.1, 0.07), dyy=(0.08, 0.1, 0.07), dxy=(0.01, 0.0, 0.0), dyx=(0.02, 0.0, 0.0),
+                                beta=(0.6, 0.2, 0.0), reaction_rate=0.05, diff_j=(0.3, 0.3333, 0.4), inlet_conc=(0.7, 0.2, 0.0),
+                                freeflow_outlet=True)
+    reg = yy <= sim.yDomain - sim.numBufferingLayers
+    tr.set_concentrations(np.stack([np.where(reg, c, 0.0) for c in (1.0, 0.5, 0.1)]))
+    tr.step(sim.timeSteps + 1)
+    np.testing.assert_allclose(sim.tracerConc, tr.conc[:, 0], atol=5e-9)
+    assert np.abs(sim.tracerConc[:, -1][:, sim.isDomain[-1]] - np.array([[0.7], [0.2], [0.0]])).max() < 1e-13
+    assert sim.tracerConc[2].sum() > 0.1 * sim.isDomain.sum() * 1.0001        # the product C has been formed
+
+
 def test_transport_class_and_main(hostlib):
     """`Transport2DRK(ini).runTransport2DMPMCRK()` (main.py:66-68): flow + 2 tracers, MRT tracers; equals the oracle"""
     import main

@@ -217,9 +217,26 @@ def test_tracers_vs_dense_oracle(lattice, n, relax, solid, lib):
     np.testing.assert_allclose(m1, m0, rtol=1e-12)          # the tracer is conserved (half-way bounce back at the solids)
 
 
+@pytest.mark.parametrize("channel", [False, True])
+def test_five_velocity_tracers_vs_dense_oracle(channel, lib):
+    """NumberSchemes = 5: MRT, interface term, reaction A + B -> C, Inamuro inlet row, free-flow outlet row; closed box and
+    open channel of the flow, wetting solid"""
+    cases.case_tracer_q5_dense(lib, channel=channel)
+
+
 def test_tracer_setup_rejects_what_is_not_built(lib):
     from openlbmpm_b200 import _lib
     import numpy as np
+    eng = _lib.Engine(9, (8, 8), lib_path=lib)
+    for bad in (dict(n_schemes=7), dict(n_schemes=5, relax=_lib.RELAX_SRT), dict(n_schemes=5, relax=_lib.RELAX_MRT, reaction=True, n_tracers=2),
+                dict(n_schemes=9, relax=_lib.RELAX_MRT, inlet_type=_lib.TR_INLET_DIRICHLET), dict(n_schemes=5, relax=_lib.RELAX_MRT, outlet_type=4)):
+        with pytest.raises(_lib.LbmError):
+            eng.tracer_setup(**bad)
+    eng.close()
+    eng = _lib.Engine(19, (6, 6, 6), lib_path=lib)
+    with pytest.raises(_lib.LbmError):
+        eng.tracer_setup(n_schemes=5, relax=_lib.RELAX_MRT)         # the 5-velocity lattice is 2-D
+    eng.close()
     eng = _lib.Engine(19, (6, 6, 6), lib_path=lib)
     with pytest.raises(_lib.LbmError):
         eng.tracer_setup(relax=_lib.RELAX_MRT)                      # tracer MRT is D2Q9

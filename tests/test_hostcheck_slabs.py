@@ -224,7 +224,8 @@ def test_shan_chen_classes_on_slabs(which, monkeypatch, tmp_path):
 
 def test_tracers_on_slabs_bit_equal(lib):
     """flow + tracers on P = 2, 3 slabs vs one slab: concentrations bit-equal (tracer ghost planes travel with the flow's)"""
-    for lattice, shape, relax in ((9, (24, 12), _lib.RELAX_MRT), (19, (24, 6, 8), _lib.RELAX_SRT)):
+    q5 = dict(n_schemes=5, reaction=False, inlet_type=_lib.TR_INLET_DIRICHLET, inlet_conc=(0.7, 0.1), outlet_type=_lib.TR_OUTLET_FREEFLOW)
+    for lattice, shape, relax, trkw in ((9, (24, 12), _lib.RELAX_MRT, {}), (19, (24, 6, 8), _lib.RELAX_SRT, {}), (9, (24, 12), _lib.RELAX_MRT, q5)):
         dom = geometry(shape, True, False)
         rng = np.random.default_rng(9)
         rhoR = 0.5 + 0.3 * (rng.random(shape) - 0.5)
@@ -243,7 +244,7 @@ def test_tracers_on_slabs_bit_equal(lib):
                 try:
                     sl = slice(r * t, (r + 1) * t)
                     e = engines[r]
-                    e.tracer_setup(n_tracers=2, relax=relax, tau=(0.8, 1.1), dxx=(0.05, 0.1), dyy=(0.08, 0.1), beta=(0.6, 0.3))
+                    e.tracer_setup(n_tracers=2, relax=relax, tau=(0.8, 1.1), dxx=(0.05, 0.1), dyy=(0.08, 0.1), beta=(0.6, 0.3), **trkw)
                     e.set_geometry(dom[sl])
                     e.init_equilibrium(np.where(dom[sl], rhoR[sl], 0.0), np.where(dom[sl], 1.0 - rhoR[sl], 0.0))
                     e.tracer_init(*[np.where(dom[sl], c[sl], 0.0) for c in conc])
