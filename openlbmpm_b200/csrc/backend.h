@@ -168,9 +168,32 @@ inline void dev_d2h(void* h, const void* d, size_t bytes, stream_t) { memcpy(h, 
 inline void dev_d2d(void* d, const void* s_, size_t bytes, stream_t) { memmove(d, s_, bytes); }
 inline void dev_sync(stream_t) {}
 extern thread_local int64_t g_launch_counter;
+// Item order of a launch on the host (test hook).  On the GPU the items of one launch run in no particular order, so an
+// operator must not read what another item of the SAME launch writes; the forward loop would hide such a hazard.
+// LBM_HOST_ORDER=reverse | scatter runs the items backwards / in a strided permutation: the oracle comparisons of the CPU
+// tier then fail on any intra-launch dependence (tests/test_hostcheck_order.py).
+inline int host_launch_order() {
+    static const int order = [] {
+        const char* e = getenv("LBM_HOST_ORDER");
+        return !e ? 0 : (!strcmp(e, "reverse") ? 1 : (!strcmp(e, "scatter") ? 2 : 0));
+    }();
+    return order;
+}
 template <class Op>
 inline void launch(const Op& op, int64_t n, stream_t) {
-    for (int64_t i = 0; i < n; ++i) op(i);
+    const int order = host_launch_order();
+    if (order == 0) {
+        for (int64_t i = 0; i < n; ++i) op(i);
+    } else if (order == 1) {
+        for (int64_t i = n - 1; i >= 0; --i) op(i);
+    } else {
+        int64_t stride = 7919;                       // a prime; coprime to n unless n is a multiple of it
+        while (n % stride == 0) stride += 2;
+        auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+        while (n > 1 && gcd(stride, n) != 1) ++stride;
+        int64_t j = n / 3;
+        for (int64_t k = 0; k < n; ++k) { op(j); j += stride % n; if (j >= n) j -= n; }
+    }
     ++g_launch_counter;
 }
 inline bool g_prof_active() { return false; }
