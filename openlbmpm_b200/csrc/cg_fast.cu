@@ -7,6 +7,7 @@
 // consecutive lbm_step calls stay in factored form.
 #include "cg_fast_ops.cuh"
 #include "internal.h"
+#include <atomic>
 #include "coop.h"         // grid-wide barrier; on the host (test hook) also the CUDA vocabulary of the kernels below, cta_emu.h
 #ifndef LBM_HOSTCHECK
 #include <cuda_pipeline.h>
@@ -496,18 +497,15 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 static int tile_y_collide() {
-    static int ty = 0;
-    if (!ty) { ty = env_int("LBM_TILE_Y_COLLIDE", 4); if (ty != 4 && ty != 8 && ty != 16) ty = 4; }
+    static const int ty = [] { const int v = env_int("LBM_TILE_Y_COLLIDE", 4); return (v != 4 && v != 8 && v != 16) ? 4 : v; }();
     return ty;
 }
 static int tile_y_density() {
-    static int ty = 0;
-    if (!ty) { ty = env_int("LBM_TILE_Y_DENSITY", 8); if (ty != 4 && ty != 8 && ty != 16) ty = 8; }
+    static const int ty = [] { const int v = env_int("LBM_TILE_Y_DENSITY", 8); return (v != 4 && v != 8 && v != 16) ? 8 : v; }();
     return ty;
 }
 static int z_chunk(int n2) {
-    static int zc = 0;
-    if (!zc) { zc = env_int("LBM_ZCHUNK", 32); if (zc < 4) zc = 32; }
+    static const int zc = [] { const int v = env_int("LBM_ZCHUNK", 32); return v < 4 ? 32 : v; }();
     return n2 >= 2 * zc ? zc : n2;
 }
 static bool tiled_ok(const lbm_handle* h) {
@@ -527,7 +525,7 @@ static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s
 #ifdef LBM_HOSTCHECK
     cta_emu::launch(grid, block, smem, [&] { cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>(c, s, o, zchunk, z_lo, z_hi); });
 #else
-    static bool configured[64] = {};          // per device: the attribute belongs to the function on ONE device
+    static std::atomic<bool> configured[64];  // per device: the attribute belongs to the function on ONE device (zero-initialised)
     if (!configured[h->cfg.device & 63]) {
         LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -566,7 +564,7 @@ static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastF
 #ifdef LBM_HOSTCHECK
     cta_emu::launch(grid, block, smem, [&] { cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>(c, s, zchunk, z_lo, z_hi); });
 #else
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];
     if (!configured[h->cfg.device & 63]) {
         LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -599,10 +597,15 @@ static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFie
 // to travel upwards (c_z = +1) or downwards (c_z = -1) only, in-plane directions never cross a slab face
 template <class L>
 static const int8_t* factored_dirs() {
-    static int8_t d[L::Q + 4];
-    for (int q = 0; q < L::Q; ++q) d[q] = L::d2(q) == 0 ? 2 : (int8_t)L::d2(q);
-    for (int k = 0; k < 4; ++k) d[L::Q + k] = 0;
-    return d;
+    struct Table {
+        int8_t d[L::Q + 4];
+        Table() {
+            for (int q = 0; q < L::Q; ++q) d[q] = L::d2(q) == 0 ? 2 : (int8_t)L::d2(q);
+            for (int k = 0; k < 4; ++k) d[L::Q + k] = 0;
+        }
+    };
+    static const Table t;        // built once (several handles may step from several host threads)
+    return t.d;
 }
 
 // ---- open boundaries on the fast path -------------------------------------------------------------------------
@@ -819,14 +822,15 @@ static void launch_persistent_t(lbm_handle* h, int nsteps) {
 #ifdef LBM_HOSTCHECK
     cta_emu::launch_cooperative(dim3(3), dim3(32), [&] { cg_fast_persistent<L, SOLIDS>(c, b0, b1, rows, open, nsteps, cur0); });
 #else
-    static int grid_for_device[64] = {};
-    int& grid = grid_for_device[h->cfg.device & 63];
+    static std::atomic<int> grid_for_device[64];
+    int grid = grid_for_device[h->cfg.device & 63];
     if (!grid) {
         int per_sm = 0, sms = 0;
         LBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_fast_persistent<L, SOLIDS>, 256, 0));
         LBM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
         if (per_sm < 1) throw BackendError{"the persistent kernel does not fit on an SM"};
         grid = per_sm * sms;
+        grid_for_device[h->cfg.device & 63] = grid;
     }
     void* args[] = {&c, &b0, &b1, &rows, &open, &nsteps, &cur0};
     LBM_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)cg_fast_persistent<L, SOLIDS>, dim3(grid), dim3(256), args, 0, h->stream));

@@ -2,6 +2,7 @@
 // (original Shan-Chen: ShanChenD2Q9.py:1492-1629; explicit forcing SRT/MRT: ShanChenD2Q9.py:1714-2087).
 // D2Q9 follows the reference; D3Q19 (`ShanChenD3Q19.runOriginalSC3DGPU / runEFS4LBM3DGPU`, named by main.py:73-77
 // but absent upstream) runs the same lattice-generic operators, open boundaries included (oracle/sc_dense.py).
+#include <atomic>
 #include "coop.h"
 #include "internal.h"
 #include "sc_ops.cuh"
@@ -278,14 +279,15 @@ static void sc_launch_persistent(lbm_handle* h, int nsteps) {
 #ifdef LBM_HOSTCHECK
     cta_emu::launch_cooperative(dim3(3), dim3(32), [&] { sc_persistent<L>(c, efs, nsteps, do_in, do_out); });
 #else
-    static int grid_for_device[64] = {};
-    int& grid = grid_for_device[h->cfg.device & 63];
+    static std::atomic<int> grid_for_device[64];
+    int grid = grid_for_device[h->cfg.device & 63];
     if (!grid) {
         int per_sm = 0, sms = 0;
         LBM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sc_persistent<L>, 256, 0));
         LBM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
         if (per_sm < 1) throw BackendError{"the persistent kernel does not fit on an SM"};
         grid = per_sm * sms;
+        grid_for_device[h->cfg.device & 63] = grid;
     }
     void* args[] = {&c, &efs, &nsteps, &do_in, &do_out};
     LBM_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)sc_persistent<L>, dim3(grid), dim3(256), args, 0, h->stream));
