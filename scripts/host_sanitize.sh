@@ -26,5 +26,10 @@ for f in tests/test_hostcheck_tiled.py tests/test_hostcheck_slabs.py tests/test_
     echo "$f: ThreadSanitizer reports naming the hook: $(grep -c libhostcheck gpurun_out/host_tsan.log); $(tail -1 gpurun_out/host_tsan.log)"
     grep -q libhostcheck gpurun_out/host_tsan.log && status=1
 done
+# FMA contraction on (the closest host stand-in for nvcc's -fmad=true): the tolerances of the oracle / golden comparisons must hold
+g++ -O2 -std=c++17 -DLBM_HOSTCHECK -DLBM_HOST_FMA_TEST -march=native -mfma -ffp-contract=fast -fPIC -shared -pthread \
+    -x c++ $CS/lbm_api.cu $CS/sc_api.cu $CS/tr_api.cu $CS/cg_fast.cu $CS/host_stubs.cu -o tests/hostcheck/libhostcheck.so
+python -m pytest tests/test_hostcheck_cg.py tests/test_hostcheck_sc.py tests/test_hostcheck_tiled.py tests/test_hostcheck_properties.py \
+    tests/test_host_classes.py -q 2>&1 | tail -1 || status=1
 python tests/hostcheck/build.py --force > /dev/null
 exit $status
