@@ -81,3 +81,37 @@ def test_fast_path_equals_reference_ordered_kernels_on_random_masks(seed, lattic
     # parallel to the solid normal, where the Akai correction amplifies rounding by 1 / sin(theta') (seed 200, D2Q9,
     # porosity 0.5: one jump to 2e-10 at step 5 that decays afterwards) -- the bound is that of the ill-conditioned case
     np.testing.assert_allclose(out[0], out[1], rtol=0, atol=1e-8)
+
+
+@settings(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 10 ** 6), schemes=st.sampled_from([9, 5]), porosity=st.sampled_from([0.5, 0.8, 1.0]), react=st.booleans())
+def test_tracers_are_conserved_on_random_masks(seed, schemes, porosity, react):
+    """closed box, any solid layout: collision, interface term and half-way bounce back conserve every tracer; with the
+    reaction A + B -> C of the 5-velocity branch, A + C and B + C are conserved instead"""
+    rng = np.random.default_rng(seed)
+    shape = (int(rng.integers(4, 10)), int(rng.integers(4, 10)))
+    dom = rng.random(shape) < porosity
+    if dom.sum() < 2:
+        dom[:] = True
+    r = (0.2 + 0.6 * rng.random(shape)) * dom
+    react = react and schemes == 5
+    nt = 3 if react else 2
+    conc = [(0.1 + rng.random(shape)) * dom for _ in range(nt)]
+    eng = _lib.Engine(9, shape, lib_path=lib(), sigma=0.05, contact_angle_deg=70.0, tauR=1.0, tauB=0.8)
+    eng.tracer_setup(n_tracers=nt, relax=_lib.RELAX_MRT, dxx=(0.05, 0.1, 0.07), dyy=(0.08, 0.1, 0.07), dxy=(0.01, 0.0, 0.0),
+                     dyx=(0.02, 0.0, 0.0), beta=(0.6, 0.3, 0.1), n_schemes=schemes, reaction=react, reaction_rate=0.05,
+                     diff_j=(0.3, 1. / 3., 0.4))
+    eng.set_geometry(dom)
+    eng.init_equilibrium(r, (1.0 - r) * dom)
+    eng.tracer_init(*conc)
+    m0 = np.array([c.sum() for c in eng.tracer_download()])
+    eng.step(7)
+    out = eng.tracer_download()
+    eng.close()
+    m1 = np.array([c.sum() for c in out])
+    assert all(np.isfinite(c).all() and not c[~dom].any() for c in out)
+    if react:
+        np.testing.assert_allclose([m1[0] + m1[2], m1[1] + m1[2]], [m0[0] + m0[2], m0[1] + m0[2]], rtol=1e-12)
+        assert m1[2] > m0[2]
+    else:
+        np.testing.assert_allclose(m1, m0, rtol=1e-12)
