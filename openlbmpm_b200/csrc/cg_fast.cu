@@ -29,6 +29,8 @@ static FastFields fast_fields(const lbm_handle* h, int k) {
 
 static bool open_box(const lbm_handle* h) { return h->cfg.inlet != LBM_BC_PERIODIC || h->cfg.outlet != LBM_BC_PERIODIC; }
 
+static bool tiled_ok(const lbm_handle* h);
+
 bool cg_fast_eligible(const lbm_handle* h) {
     // open boundaries: the treated planes are patched around the two passes (fast_open_rows_*), which needs the
     // inlet and outlet planes of a slab to be apart.  WettingType 1 turns ANY non-zero |G| into a unit normal
@@ -36,7 +38,11 @@ bool cg_fast_eligible(const lbm_handle* h) {
     // outlet rows; the factored arithmetic rounds differently there, and that combination stays on the
     // reference-ordered kernels.
     if (h->cfg.model != LBM_MODEL_CG || (h->cfg.flags & LBM_FLAG_GENERIC_KERNELS) || h->cfg.surface_tension_type != LBM_ST_CSF) return false;
-    if (h->tracer) return false;      // tracers need G and u in memory between the two halves of the step: reference-ordered kernels
+    // Tracers read u, G and rho_R of the iteration, none of which the flow collision changes: on the one-thread-per-node fast
+    // path (closed boxes) their phase runs right after the collision pass, which then also stores u.  The tiled kernels keep G
+    // in shared memory, and the open-row patches rewrite u on a few planes: those combinations stay on the reference-ordered
+    // kernels.
+    if (h->tracer && (open_box(h) || tiled_ok(h))) return false;
     return !open_box(h) || (h->g.n2 >= 8 && h->cfg.wetting_type != 1);
 }
 
@@ -688,7 +694,9 @@ static void fast_enter(lbm_handle* h) {
     cg_generic_forces(h);
     CGFields c = h->fields();
     FastState* f = (FastState*)h->fast;
+    tracer_phase(h);          // no-op without tracers (or when a download already ran it for this iteration)
     launch(CollideFactoredOp<L>{c, fast_fields(h, f->cur)}, h->g.count(0), h->stream);
+    tracer_iteration_finished(h);
     h->head_done = false;
     h->fast_pending_stream = true;
 }
@@ -764,6 +772,7 @@ static void fast_one_step(lbm_handle* h) {
         launch(GradientOp<L>{c}, g.count(1), h->stream);
         if (h->has_solid) launch(PullCollideOp<L, true>{c, s, o}, g.count(0), h->stream);
         else launch(PullCollideOp<L, false>{c, s, o}, g.count(0), h->stream);
+        if (h->tracer) { tracer_phase(h); tracer_iteration_finished(h); }
     }
     if (open) fast_open_rows_post<L>(h, c, o, done);
     f->cur = 1 - f->cur;
@@ -809,7 +818,7 @@ cg_fast_persistent(const CGFields c, const FastFields b0, const FastFields b1, c
 }
 
 static bool persistent_ok(const lbm_handle* h) {
-    return (h->cfg.flags & LBM_FLAG_PERSISTENT) && h->nranks == 1 && h->g.wrap2 && !tiled_ok(h) && !g_prof_active();
+    return (h->cfg.flags & LBM_FLAG_PERSISTENT) && h->nranks == 1 && h->g.wrap2 && !tiled_ok(h) && !g_prof_active() && !h->tracer;
 }
 
 template <class L, bool SOLIDS>

@@ -181,6 +181,10 @@ struct PullCollideOp {
         cg_force_at<L>(c, x, y, z, id, G, n, F, &K);
 #pragma unroll
         for (int d = 0; d < L::D; ++d) c.F[d * V + id] = F[d];
+        if (c.store_u) {          // solute tracers ride on this step: their collision (after this pass) reads the velocity
+#pragma unroll
+            for (int d = 0; d < L::D; ++d) c.u[d * V + id] = u[d];
+        }
         const double tau = cg_tau(c.phi[id], rR, rB, c.p);
         cg_collide<L>(fT, rho, u, F, tau, c.p.relax);
         double kR, a[3];

@@ -22,6 +22,7 @@ struct CGFields {
     double* K;          // curvature
     const uint8_t* cls;
     const uint32_t* pull;   // [vol] pull masks (tiled kernels, lattices with solids)
+    int store_u;            // fast path: the collision pass also stores the velocity (tracers attached)
     const double* ns;   // [3][vol] solid normals
     // open boundaries (global plane numbers along axis 2; -1000 = not on this slab)
     int inlet, outlet;

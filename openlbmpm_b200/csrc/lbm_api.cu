@@ -51,6 +51,7 @@ CGFields lbm_handle::fields() const {
     c.rho[0] = rho; c.rho[1] = rho + g.vol;
     c.u = u; c.phi = phi; c.G = G; c.nrm = nrm; c.F = F; c.K = K;
     c.cls = cls; c.ns = ns; c.pull = pull;
+    c.store_u = tracer ? 1 : 0;
     c.inlet = cfg.inlet; c.outlet = cfg.outlet;
     // open-boundary rows in local plane numbers; the top rows live on the last rank, the bottom rows on rank 0
     const int off = -100000;

@@ -157,6 +157,7 @@ extern "C" int lbm_tracer_download(lbm_handle* h, double* const* conc, int32_t n
     if (!s || !s->has_state) { h->err = "no tracer state"; return LBM_ESTATE; }
     if (!conc || n != s->p.nt) { h->err = "one concentration array per tracer expected"; return LBM_EINVAL; }
     // the output point of the reference: after the tracer phase of the current iteration (Transport2DRK.py:1427-1437)
+    cg_fast_materialise(h);       // no-op unless the fast path left the streaming pending
     cg_ensure_head(h);
     cg_generic_forces(h);
     tracer_phase(h);

@@ -676,7 +676,7 @@ def gold_initial_densities(g, p):
     return np.where(red, float(p["rhoR"]), minor), np.where(red, minor, float(p["rhoB"]))
 
 
-def check_tracer_vs_gold(path, lib_path, chunk=1):
+def check_tracer_vs_gold(path, lib_path, chunk=1, **extra):
     """flow snapshot k / tracer snapshot k of the golden file = what the reference's kernels hold at the two output
     points of loop iteration k (Transport2DRK.py:1300-1312 and :1427-1437)"""
     g, p = load_gold(path)
@@ -690,11 +690,11 @@ def check_tracer_vs_gold(path, lib_path, chunk=1):
         tr = dict(dxx=per("dxx"), dyy=per("dyy"), dxy=per("dxy"), dyx=per("dyx"), beta=per("beta_tr"), criterion=0.5,
                   reaction_rate=float(p["rate"]) if p["reaction"] == "yes" else None, diff_j=per("diffj"),
                   inlet_conc=per("conc_in") if p["tr_inlet"] == "Dirichlet" else None, freeflow_outlet=p["tr_outlet"] == "Freeflow")
-        eng, trs = tracer_pair_q5(dom, rho0[0], rho0[1], g["tracer0"], lib_path, flow=flow, tr=tr)
+        eng, trs = tracer_pair_q5(dom, rho0[0], rho0[1], g["tracer0"], lib_path, flow=flow, tr=tr, **extra)
     else:
         tr = dict(relax=p["tr_relax"], tau=per("tr_tau"), dxx=per("dxx"), dyy=per("dyy"), dxy=per("dxy"), dyx=per("dyx"), beta=per("beta_tr"),
                   criterion=0.5)
-        eng, trs = tracer_pair(9, dom, rho0[0], rho0[1], g["tracer0"], lib_path, flow=flow, tr=tr)
+        eng, trs = tracer_pair(9, dom, rho0[0], rho0[1], g["tracer0"], lib_path, flow=flow, tr=tr, **extra)
     nsnap = g["rhoR"].shape[0]
     s = 0
     while True:

@@ -204,9 +204,39 @@ def test_baseline_configurations_run_small(k, scale, lib):
 
 # ---- solute tracers riding on the colour-gradient CSF flow ----
 @pytest.mark.parametrize("path", cases.GOLD_TR2D, ids=[os.path.basename(p)[5:-4] for p in cases.GOLD_TR2D])
-@pytest.mark.parametrize("chunk", [1, 9])
-def test_tracer_trajectory_vs_reference_kernels(path, chunk, lib):
-    cases.check_tracer_vs_gold(path, lib, chunk=chunk)
+@pytest.mark.parametrize("chunk,flags", [(1, 0), (9, 0), (9, 1)])
+def test_tracer_trajectory_vs_reference_kernels(path, chunk, flags, lib):
+    """flags = 0: the tracers ride on the factored fast path of the flow; 1: on the reference-ordered kernels"""
+    cases.check_tracer_vs_gold(path, lib, chunk=chunk, flags=flags)
+
+
+def test_tracers_ride_on_the_fast_path(lib):
+    """closed box: the flow keeps its factored fast path with tracers attached (3 flow + 2 tracer launches per step instead of the
+    reference-ordered sequence), same concentrations as on the reference-ordered kernels; downloads in between re-enter it"""
+    import numpy as np
+    from openlbmpm_b200 import _lib
+    shape = (24, 12)
+    dom = np.ones(shape, bool); dom[5:8, 3:7] = False
+    rng = np.random.default_rng(9)
+    rhoR = 0.5 + 0.3 * (rng.random(shape) - 0.5)
+    conc = 0.2 + rng.random((2,) + shape)
+    res = {}
+    for flags in (0, _lib.FLAG_GENERIC_KERNELS):
+        for schemes in (9, 5):
+            e = _lib.Engine(9, shape, lib_path=lib, contact_angle_deg=70.0, flags=flags)
+            e.tracer_setup(n_tracers=2, relax=_lib.RELAX_MRT, dxx=(0.05, 0.1), dyy=(0.08, 0.1), beta=(0.6, 0.3), n_schemes=schemes)
+            e.set_geometry(dom)
+            e.init_equilibrium(np.where(dom, rhoR, 0.0), np.where(dom, 1.0 - rhoR, 0.0))
+            e.tracer_init(*[np.where(dom, c, 0.0) for c in conc])
+            e.step(3); c1 = np.stack(e.tracer_download() + e.download_macros()[0])
+            e.step(10); launches = e.timing()["launches"]
+            res[(flags, schemes)] = (c1, np.stack(e.tracer_download() + e.download_macros()[0]), launches)
+            e.close()
+    for schemes in (9, 5):
+        fast, gen = res[(0, schemes)], res[(_lib.FLAG_GENERIC_KERNELS, schemes)]
+        np.testing.assert_allclose(fast[0], gen[0], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(fast[1], gen[1], rtol=0, atol=1e-13)
+        assert fast[2] < gen[2] and fast[2] <= 50, (fast[2], gen[2])
 
 
 @pytest.mark.parametrize("lattice,n,relax", [(9, (14, 18), "SRT"), (9, (14, 18), "MRT"), (19, (8, 10, 12), "SRT")])
