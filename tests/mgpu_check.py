@@ -14,18 +14,23 @@ import torch.distributed as dist
 from openlbmpm_b200 import _lib, slab
 
 
-def run(shape_global, dom, rhoR, steps, rank, world, **kw):
+def run(shape_global, dom, rhoR, steps, rank, world, tracers=None, **kw):
     nz = shape_global[0] // world
     sl = slice(rank * nz, (rank + 1) * nz)
-    eng = _lib.Engine(19, (nz,) + tuple(shape_global[1:]), device=int(os.environ.get("LOCAL_RANK", "0")), **kw)
+    eng = _lib.Engine(19 if len(shape_global) == 3 else 9, (nz,) + tuple(shape_global[1:]), device=int(os.environ.get("LOCAL_RANK", "0")), **kw)
     if world > 1:
         eng.comm_init(rank, world, slab.share_unique_id(dist, eng, rank, device="cuda"))
+    if tracers:
+        eng.tracer_setup(**tracers)
     eng.set_geometry(dom[sl])
     eng.init_equilibrium(np.where(dom[sl], rhoR[sl], 0.0), np.where(dom[sl], 1.0 - rhoR[sl], 0.0))
+    if tracers:
+        eng.tracer_init(*[np.where(dom[sl], 0.3 + 0.5 * rhoR[sl] * (k + 1) / tracers["n_tracers"], 0.0) for k in range(tracers["n_tracers"])])
     eng.step(steps)
     rho, u = eng.download_macros()
+    conc = eng.tracer_download() if tracers else []
     eng.close()
-    return np.stack(rho + u)
+    return np.stack(rho + u + conc)
 
 
 OPEN = dict(inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_CONVECTIVE, inlet_velocity=-2.0e-3)
@@ -61,9 +66,23 @@ def main():
                                    ("untiled fast path", (8 * world, 10, 12), True, dict(flags=2)),
                                    # cfg 5 layout: outlet planes on rank 0, inlet planes on the last rank, solids in between
                                    ("open channel tiled", (16 * world, 16, 32), True, dict(OPEN, contact_angle_deg=60.0)),
-                                   ("open channel general", (16 * world, 16, 32), True, dict(OPEN, flags=1))):
+                                   ("open channel general", (16 * world, 16, 32), True, dict(OPEN, flags=1)),
+                                   ("perturbation operator SRT, open", (16 * world, 16, 32), True,
+                                    dict(OPEN, surface_tension_type=_lib.ST_PERTURBATION, relax=_lib.RELAX_SRT, AkR=7e-3, AkB=7e-3, solid_phi=0.6)),
+                                   ("tracers, 3-D SRT", (8 * world, 10, 12), True,
+                                    dict(tracers=dict(n_tracers=2, relax=_lib.RELAX_SRT, tau=(0.8, 1.1), beta=(0.6, 0.3)))),
+                                   ("tracers, 2-D 9-velocity MRT", (16 * world, 40), True,
+                                    dict(tracers=dict(n_tracers=2, relax=_lib.RELAX_MRT, dxx=(0.05, 0.1), dyy=(0.08, 0.1), beta=(0.6, 0.3)))),
+                                   ("tracers, 2-D 5-velocity in/out", (16 * world, 40), True,
+                                    dict(tracers=dict(n_tracers=3, relax=_lib.RELAX_MRT, dxx=(0.05, 0.1, 0.07), dyy=(0.08, 0.1, 0.07),
+                                                      beta=(0.6, 0.3, 0.0), n_schemes=5, reaction=True, reaction_rate=0.04,
+                                                      diff_j=(0.3, 1. / 3., 0.4), inlet_type=_lib.TR_INLET_DIRICHLET,
+                                                      inlet_conc=(0.7, 0.2, 0.0), outlet_type=_lib.TR_OUTLET_FREEFLOW)))):
         dom = np.ones(shape, bool)
-        if solid:
+        if solid and len(shape) == 2:
+            yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+            dom = ((xx - 20) ** 2 + (yy - shape[0] / 2 + 0.5) ** 2) > 16.0
+        elif solid:
             z, y, x = np.mgrid[0:shape[0], 0:shape[1], 0:shape[2]]
             dom = ((x - shape[2] / 2) ** 2 + (y - shape[1] / 2) ** 2 + (z - shape[0] / 2 + 0.5) ** 2) > 9.0
             if "inlet" not in kw:      # a second solid straddling the periodic seam (open channels keep their end planes void)
@@ -77,7 +96,7 @@ def main():
             full = np.concatenate([t.cpu().numpy() for t in gathered], axis=1)
             single = run(shape, dom, rhoR, 7, 0, 1, **kw)
             same = np.array_equal(full, single)
-            print("%-22s P=%d bit-equal to P=1: %s  (max diff %.3e)" % (name, world, same, np.abs(full - single).max()), flush=True)
+            print("%-32s P=%d bit-equal to P=1: %s  (max diff %.3e)" % (name, world, same, np.abs(full - single).max()), flush=True)
             ok &= same
         dist.barrier()
     for name, kw in (("Shan-Chen", dict(model=_lib.MODEL_SC, relax=_lib.RELAX_SRT, sc_G=[0, 0.9, 0, 0, 0.9, 0])),
