@@ -113,7 +113,8 @@ def run_reference(args):
     v = float(np.median(vals))
     sample = "%s periodic spinodal box, %d steps per sample, oracle/cg_c (C + OpenMP restatement of the reference loop)" % (
         "x".join([str(n)] * (3 if lattice == 19 else 2)), args.cpu_steps)
-    line = {"impl": "reference", "metric": "MLUPS D3Q19 CG-MRT periodic box" if lattice == 19 else "MLUPS D2Q9 CG-MRT periodic box",
+    # the same metric string as the GPU arm prints for this workload (the sample the CPU actually ran is in config / cpu_baseline)
+    line = {"impl": "reference", "metric": metric_name(args, lattice, args.size, args.workload == "porous", 0),
             "value": v, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.median(per_step)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -121,6 +122,16 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def metric_name(args, Q, n, porous, cfg):
+    if cfg:
+        return "MLUPS (void nodes) BASELINE config %d" % cfg
+    if Q == 19 and n == 512 and not porous:
+        return "MLUPS D3Q19 CG-MRT 512^3"
+    if porous:
+        return "MLUPS (void nodes) D3Q19 CG-MRT porous"
+    return "MLUPS %s CG-MRT %d" % ("D3Q19" if Q == 19 else "D2Q9", n)
 
 
 def workload_name(args):
@@ -317,7 +328,7 @@ def main():
             cpu = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port", "sample": "unavailable: %r" % (e,)}
 
     ws_gb = 2 * 2 * Q * 8 * nodes_total / world / 1e9
-    line = {"metric": "MLUPS (void nodes) BASELINE config %d" % cfg if cfg else "MLUPS D3Q19 CG-MRT 512^3" if (Q == 19 and n == 512 and not porous) else "MLUPS (void nodes) D3Q19 CG-MRT porous" if porous else "MLUPS %s CG-MRT %d" % ("D3Q19" if Q == 19 else "D2Q9", n),
+    line = {"metric": metric_name(args, Q, n, porous, cfg),
             "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
