@@ -73,6 +73,9 @@ extern "C" {
 #define LBM_FLAG_GHOST_PLANES 64u     /* single slab: keep copying the periodic ghost planes every step instead of wrapping the flow axis by index arithmetic */
 #define LBM_FLAG_PERSISTENT 128u      /* single slab, one-thread-per-node fast path: all steps of an lbm_step call in ONE cooperative
                                         kernel (one grid-wide barrier between the phases of a step instead of a launch); opt-in */
+#define LBM_FLAG_PEER_EXCHANGE 256u    /* slab decomposition, factored fast path: the ghost planes are STORED into the neighbours' memory
+                                         (CUDA IPC peer pointers over NVLink) and a release / acquire flag pair replaces the
+                                         NCCL send / recv rendezvous of the two per-step exchanges (experimental, off by default) */
 #define LBM_FLAG_NO_CUDA_GRAPH 8u    /* small lattices: launch every kernel instead of replaying a captured graph */
 
 typedef struct lbm_handle lbm_handle;

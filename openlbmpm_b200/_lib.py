@@ -15,6 +15,7 @@ OUTLET_CONVECTIVE, OUTLET_PRESSURE = 1, 2
 FLAG_GENERIC_KERNELS = 1
 FLAG_GHOST_PLANES = 64
 FLAG_PERSISTENT = 128
+FLAG_PEER_EXCHANGE = 256
 ST_CSF, ST_PERTURBATION = 0, 1
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

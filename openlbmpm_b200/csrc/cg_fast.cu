@@ -737,6 +737,12 @@ static void fast_one_step_overlapped(lbm_handle* h) {
 }
 #endif
 
+// the two per-step exchanges of the fast path: NCCL send / recv, or (opt-in) stores into the neighbours' memory + flags
+static void fast_exchange(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs = nullptr) {
+    if (h->nranks > 1 && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE)) comm_peer_exchange_f64(h, base, stride, narr, gp, dirs);
+    else exchange_f64(h, base, stride, narr, gp, dirs);
+}
+
 template <class L>
 static void fast_one_step(lbm_handle* h) {
     FastState* f = (FastState*)h->fast;
@@ -749,7 +755,7 @@ static void fast_one_step(lbm_handle* h) {
 #endif
     CGFields c = h->fields();
     const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
-    exchange_f64(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
+    fast_exchange(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
     bool dens_done = false;
     if (tiled_ok(h) && !(h->cfg.flags & 4u)) {       // host test hook: the same kernels on host threads (cta_emu.h)
         if (h->has_solid) launch_density_tiled<true>(h, c, s); else launch_density_tiled<false>(h, c, s);
@@ -761,7 +767,7 @@ static void fast_one_step(lbm_handle* h) {
     }
     const bool open = open_box(h);
     if (open) fast_open_rows_pre<L>(h, c, s);
-    exchange_f64(h, c.phi, 0, 1, h->has_solid ? NG : 2);
+    fast_exchange(h, c.phi, 0, 1, h->has_solid ? NG : 2);
     if (h->has_solid && tiled_ok(h)) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);     // the tiled kernel stages phi, solids included
     bool done = false;
     if (tiled_ok(h)) {

@@ -6,6 +6,8 @@
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is bound at run time (see nccl_api)
 
+#include <vector>
+
 #include "internal.h"
 
 using namespace lbm;
@@ -201,6 +203,119 @@ void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, in
     launch(op, (int64_t)(op.n_up + op.n_dn) * per, st);
 }
 void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp) { ring_exchange<uint8_t>(h, base, 0, 1, gp, ncclUint8); }
+
+// ------------------------------------------------------------------------------------------------
+// One-sided exchange over peer memory (LBM_FLAG_PEER_EXCHANGE, experimental).  Every rank maps the neighbours' images of
+// an exchanged allocation once (cudaIpcGetMemHandle / cudaIpcOpenMemHandle; the 64-byte handles travel over the NCCL
+// communicator that exists anyway).  An exchange is then
+//     PeerPushOp   my boundary planes are STORED into the neighbours' ghost planes (NVLink stores)
+//     peer_signal  fence.sys, then the exchange number is released into the neighbours' flag words
+//     peer_wait    spins (acquire) until both neighbours' numbers have arrived in my flag words
+// on the handle's stream: no rendezvous, no staging.  Write-after-read safety on the fast path comes from its own schedule: the
+// factored state is double buffered and its exchange alternates with the exchange of phi, so the neighbour that overwrites a
+// ghost plane has waited for a signal its owner only sends after the kernels that read that plane (checked with
+// ThreadSanitizer on the thread-rank emulation, host_stubs.cu).  First run on the hardware: tests/mgpu_check.py with
+// LBM_TEST_FLAGS=256.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct PeerMap { const void* base; void* up; void* down; };
+struct PeerState {
+    std::vector<PeerMap> maps;
+    unsigned long long* flags = nullptr;          // [0]: written by the slab below, [1]: by the slab above
+    unsigned long long *up_flag = nullptr, *down_flag = nullptr;    // the neighbours' words I write
+    std::vector<void*> opened;
+};
+
+__global__ void peer_signal(unsigned long long* up_from_down, unsigned long long* down_from_up, unsigned long long epoch) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(up_from_down), "l"(epoch) : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(down_from_up), "l"(epoch) : "memory");
+}
+__global__ void peer_wait(const unsigned long long* flags, unsigned long long epoch) {
+    for (int k = 0; k < 2; ++k) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + k) : "memory");
+        } while (v < epoch);
+    }
+    __threadfence_system();
+}
+
+// swap one IPC handle with both ring neighbours and open theirs; -> {image in the slab above, image in the slab below}
+void peer_open(lbm_handle* h, PeerState* ps, void* mine, void** up_img, void** down_img) {
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    const int up = (h->rank + 1) % h->nranks, down = (h->rank + h->nranks - 1) % h->nranks;
+    cudaIpcMemHandle_t hm, hu, hd;
+    LBM_CUDA_CHECK(cudaIpcGetMemHandle(&hm, mine));
+    char* d = (char*)dev_alloc(3 * sizeof(hm));
+    try {
+        dev_h2d(d, &hm, sizeof(hm), h->stream);
+        LBM_NCCL_CHECK(ncclGroupStart());
+        LBM_NCCL_CHECK(ncclSend(d, sizeof(hm), ncclUint8, up, comm, h->stream));
+        LBM_NCCL_CHECK(ncclRecv(d + 2 * sizeof(hm), sizeof(hm), ncclUint8, down, comm, h->stream));
+        LBM_NCCL_CHECK(ncclSend(d, sizeof(hm), ncclUint8, down, comm, h->stream));
+        LBM_NCCL_CHECK(ncclRecv(d + sizeof(hm), sizeof(hm), ncclUint8, up, comm, h->stream));
+        LBM_NCCL_CHECK(ncclGroupEnd());
+        dev_d2h(&hu, d + sizeof(hm), sizeof(hm), h->stream);
+        dev_d2h(&hd, d + 2 * sizeof(hm), sizeof(hm), h->stream);
+    } catch (...) { dev_free(d); throw; }
+    dev_free(d);
+    LBM_CUDA_CHECK(cudaIpcOpenMemHandle(up_img, hu, cudaIpcMemLazyEnablePeerAccess));
+    ps->opened.push_back(*up_img);
+    if (up == down) { *down_img = *up_img; return; }       // two slabs: one neighbour, one mapping
+    LBM_CUDA_CHECK(cudaIpcOpenMemHandle(down_img, hd, cudaIpcMemLazyEnablePeerAccess));
+    ps->opened.push_back(*down_img);
+}
+}  // namespace
+
+void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+    if (narr > 48) throw BackendError{"peer exchange: too many arrays"};
+    PeerState* ps = (PeerState*)h->peer;
+    if (!ps) {
+        ps = new PeerState();
+        h->peer = ps;
+        ps->flags = (unsigned long long*)dev_alloc(2 * sizeof(unsigned long long));
+        dev_zero(ps->flags, 2 * sizeof(unsigned long long), h->stream);
+        dev_sync(h->stream);
+        void *fu = nullptr, *fd = nullptr;
+        peer_open(h, ps, ps->flags, &fu, &fd);
+        ps->up_flag = (unsigned long long*)fu;              // word [0] of the slab above: "from the slab below"
+        ps->down_flag = (unsigned long long*)fd + 1;        // word [1] of the slab below: "from the slab above"
+    }
+    const PeerMap* m = nullptr;
+    for (const PeerMap& k : ps->maps) if (k.base == base) m = &k;
+    if (!m) {
+        PeerMap n{base, nullptr, nullptr};
+        peer_open(h, ps, base, &n.up, &n.down);
+        ps->maps.push_back(n);
+        m = &ps->maps.back();
+    }
+    PeerPushOp op;
+    op.g = h->g; op.base = base; op.up = (double*)m->up; op.down = (double*)m->down; op.stride = stride; op.narr = narr; op.gp = gp;
+    for (int a = 0; a < 48; ++a) op.dirs[a] = (a < narr && dirs) ? dirs[a] : 0;
+    launch(op, op.items(), h->stream);
+    const unsigned long long epoch = ++h->peer_epoch;
+    peer_signal<<<1, 1, 0, h->stream>>>(ps->up_flag, ps->down_flag, epoch);
+    peer_wait<<<1, 1, 0, h->stream>>>(ps->flags, epoch);
+    LBM_CUDA_CHECK(cudaGetLastError());
+    g_launch_counter += 2;
+}
+
+static void peer_destroy(lbm_handle* h) {
+    PeerState* ps = (PeerState*)h->peer;
+    if (!ps) return;
+    cudaStreamSynchronize(h->stream);
+    for (void* p : ps->opened) cudaIpcCloseMemHandle(p);
+    // nobody frees an allocation its neighbours still have mapped: wait for every rank to have closed its mappings
+    try {
+        int* d = (int*)dev_alloc(sizeof(int));
+        if (nccl_api().AllReduce(d, d, 1, ncclInt32, ncclMax, (ncclComm_t)h->nccl, h->stream) == ncclSuccess) cudaStreamSynchronize(h->stream);
+        dev_free(d);
+    } catch (const BackendError&) {}
+    dev_free(ps->flags);
+    delete ps;
+    h->peer = nullptr;
+}
 // maximum of an integer over all slabs (used for decisions every rank must take identically)
 int comm_allreduce_max(lbm_handle* h, int v) {
     if (h->nranks <= 1) return v;
@@ -216,6 +331,7 @@ int comm_allreduce_max(lbm_handle* h, int v) {
 }
 
 void comm_destroy(lbm_handle* h) {
+    peer_destroy(h);
     if (h->nccl) {
         try { ncclCommDestroy((ncclComm_t)h->nccl); } catch (const BackendError&) {}
         h->nccl = nullptr;

@@ -77,6 +77,26 @@ struct GhostWrapOp {
     int64_t items() const { return (int64_t)narr * 2 * gp * g.plane; }
 };
 
+// One-sided ghost-plane exchange: store my boundary planes of `narr` arrays into the ghost planes of the neighbour slabs
+// (`up` / `down` are the neighbours' images of `base`).  item = (array, side, plane j, node in plane); dirs[a]: 0 both
+// ways, +1 only upwards, -1 only downwards, 2 none (comm.cu::ring_exchange has the same filter).
+struct PeerPushOp {
+    Grid g; const double* base; double* up; double* down; int64_t stride; int narr; int gp; int8_t dirs[48];
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t r = i % g.plane; int64_t q = i / g.plane;
+        const int j = (int)(q % gp); q /= gp;
+        const int side = (int)(q % 2); const int a = (int)(q / 2);
+        const int dir = dirs[a];
+        const double* f = base + a * stride;
+        if (side == 0) {            // my top planes -> low ghost of the slab above
+            if (dir == 0 || dir == 1) up[a * stride + (int64_t)(NG - gp + j) * g.plane + r] = f[(int64_t)(NG + g.n2 - gp + j) * g.plane + r];
+        } else {                    // my bottom planes -> high ghost of the slab below
+            if (dir == 0 || dir == -1) down[a * stride + (int64_t)(NG + g.n2 + j) * g.plane + r] = f[(int64_t)(NG + j) * g.plane + r];
+        }
+    }
+    int64_t items() const { return (int64_t)narr * 2 * gp * g.plane; }
+};
+
 // Node classes from the void mask (1 = void): the dense equivalent of optimizeFluidandSolidArray's
 // wetting-solid marking (RKD2Q9.py:677-689) and of sortOutFluidNodesToSolid (RKD2Q9.py:741-760).
 template <int D>

@@ -56,6 +56,8 @@ struct lbm_handle {
     size_t out_stage_bytes = 0;
 
     void* nccl = nullptr;       // ncclComm_t (host test hook: the in-process ring of host_stubs.cu)
+    void* peer = nullptr;       // PeerState of comm.cu / host_stubs.cu: peer pointers and flags of the one-sided exchange
+    uint64_t peer_epoch = 0;    // number of one-sided exchanges so far (identical on every rank)
 
     // measurement
     double last_ms = 0.0;

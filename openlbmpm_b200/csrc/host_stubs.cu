@@ -2,9 +2,13 @@
 // as CUDA code.  The tiled kernels are simply absent; the NCCL halo exchange is replaced by an in-process ring.
 #ifdef LBM_HOSTCHECK
 #include <pthread.h>
+#include <sched.h>
 
+#include <atomic>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <vector>
 
 #include "internal.h"
 
@@ -22,7 +26,11 @@ struct HostRing {
     std::vector<void*> pub;
     std::vector<int> ival;
     pthread_barrier_t bar;
+    // one-sided exchange: flag words of every slab ("from the slab below", "from the slab above")
+    std::unique_ptr<std::atomic<uint64_t>[]> from_down, from_up;
 };
+struct HostPeerMap { const void* base; double* up; double* down; };
+struct HostPeerState { std::vector<HostPeerMap> maps; };
 std::mutex g_ring_mutex;
 std::map<std::string, HostRing*> g_rings;
 uint64_t g_ring_counter = 0;
@@ -55,7 +63,37 @@ void comm_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, in
     host_ring_exchange(h, base, stride, narr, gp, dirs);
 }
 void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp) { host_ring_exchange(h, base, 0, 1, gp, nullptr); }
-void comm_destroy(lbm_handle*) {}
+// The one-sided exchange of comm.cu on thread ranks: the neighbours' arrays are plain pointers, the push is the same operator,
+// the flag words are std::atomic (release store / acquire spin).  Only the FIRST exchange of an array meets at a barrier (the
+// pointer swap that cudaIpc does on the GPU); after that the ranks synchronise through the flags alone, so ThreadSanitizer sees
+// the protocol as it is.
+void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+    HostRing* r = (HostRing*)h->nccl;
+    HostPeerState* ps = (HostPeerState*)h->peer;
+    if (!ps) { ps = new HostPeerState(); h->peer = ps; }
+    const int up = (h->rank + 1) % r->n, down = (h->rank + r->n - 1) % r->n;
+    const HostPeerMap* m = nullptr;
+    for (const HostPeerMap& k : ps->maps) if (k.base == base) m = &k;
+    if (!m) {
+        r->pub[h->rank] = base;
+        pthread_barrier_wait(&r->bar);
+        HostPeerMap n{base, (double*)r->pub[up], (double*)r->pub[down]};
+        pthread_barrier_wait(&r->bar);
+        ps->maps.push_back(n);
+        m = &ps->maps.back();
+    }
+    PeerPushOp op;
+    op.g = h->g; op.base = base; op.up = m->up; op.down = m->down; op.stride = stride; op.narr = narr; op.gp = gp;
+    for (int a = 0; a < 48; ++a) op.dirs[a] = (a < narr && dirs) ? dirs[a] : 0;
+    launch(op, op.items(), h->stream);
+    const uint64_t epoch = ++h->peer_epoch;
+    r->from_down[up].store(epoch, std::memory_order_release);        // signal
+    r->from_up[down].store(epoch, std::memory_order_release);
+    while (r->from_down[h->rank].load(std::memory_order_acquire) < epoch) sched_yield();      // wait
+    while (r->from_up[h->rank].load(std::memory_order_acquire) < epoch) sched_yield();
+    lbm::g_launch_counter += 2;
+}
+void comm_destroy(lbm_handle* h) { delete (HostPeerState*)h->peer; h->peer = nullptr; }
 int comm_allreduce_max(lbm_handle* h, int v) {
     if (h->nranks <= 1) return v;
     HostRing* r = (HostRing*)h->nccl;
@@ -87,6 +125,8 @@ extern "C" int lbm_comm_init(lbm_handle* h, int32_t rank, int32_t nranks, const 
             r = new HostRing();
             r->n = nranks; r->members.assign(nranks, nullptr); r->pub.assign(nranks, nullptr); r->ival.assign(nranks, 0);
             pthread_barrier_init(&r->bar, nullptr, (unsigned)nranks);
+            r->from_down.reset(new std::atomic<uint64_t>[nranks]); r->from_up.reset(new std::atomic<uint64_t>[nranks]);
+            for (int k = 0; k < nranks; ++k) { r->from_down[k].store(0); r->from_up[k].store(0); }
         }
         if (r->n != nranks) { h->err = "nranks differs between the members of one ring"; return LBM_EINVAL; }
         r->members[rank] = h;

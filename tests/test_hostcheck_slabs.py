@@ -111,6 +111,19 @@ def test_colour_gradient_slabs_bit_equal(lattice, shape, name, kw, lib):
     compare(lib, lattice, shape, [1, 2, 6], **kw)
 
 
+@pytest.mark.parametrize("lattice,shape", [(19, (24, 6, 8)), (9, (24, 10)), (19, (24, 8, 32))])
+@pytest.mark.parametrize("name,kw", [
+    ("fast path", dict(contact_angle_deg=70.0)),
+    ("open channel, velocity inlet + convective outlet", dict(OPEN, contact_angle_deg=60.0)),
+])
+def test_one_sided_exchange_slabs_bit_equal(lattice, shape, name, kw, lib):
+    """LBM_FLAG_PEER_EXCHANGE: the two per-step exchanges of the fast path as stores into the neighbours' ghost planes + a
+    release / acquire flag pair instead of the send / recv rendezvous (thread ranks: the neighbours' memory is a pointer, the
+    flags are std::atomic); P = 2, 3 slabs bit-equal to one slab, several lbm_step calls with downloads in between; (24, 8, 32)
+    runs the tiled kernels on every slab"""
+    compare(lib, lattice, shape, [1, 2, 6, 5], **dict(kw, flags=_lib.FLAG_PEER_EXCHANGE))
+
+
 def test_all_fluid_box_slabs_bit_equal(lib):
     compare(lib, 19, (24, 6, 8), [3, 5], solid=False, worlds=(2, 3, 6))
 
