@@ -75,7 +75,9 @@ extern "C" {
                                         kernel (one grid-wide barrier between the phases of a step instead of a launch); opt-in */
 #define LBM_FLAG_PEER_EXCHANGE 256u    /* slab decomposition, factored fast path: the ghost planes are STORED into the neighbours' memory
                                          (CUDA IPC peer pointers over NVLink) and a release / acquire flag pair replaces the
-                                         NCCL send / recv rendezvous of the two per-step exchanges (experimental, off by default) */
+                                         NCCL send / recv rendezvous of the two per-step exchanges; with the tiled kernels on closed
+                                         boxes the stores are issued by the collision / density passes themselves (experimental,
+                                         off by default) */
 #define LBM_FLAG_NO_CUDA_GRAPH 8u    /* small lattices: launch every kernel instead of replaying a captured graph */
 
 typedef struct lbm_handle lbm_handle;

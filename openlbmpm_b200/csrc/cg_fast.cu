@@ -18,6 +18,8 @@ namespace lbm {
 struct FastState {
     double* buf[2] = {nullptr, nullptr};   // each: gT [Q][vol], kR [vol], a [3][vol]
     int cur = 0;
+    bool pushed[2] = {false, false};       // one-sided exchange: the pass that wrote buf[k] has already stored its boundary planes
+                                           // into the neighbour slabs (only the flag handshake is left)
 };
 
 static FastFields fast_fields(const lbm_handle* h, int k) {
@@ -106,9 +108,18 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 // ------------------------------------------------------------------------------------------------
 // TMA = true: the phi planes are staged with TMA bulk copies (one cp.async.bulk per tile row, 288 B, issued by one
 // thread, completing on a per-slot mbarrier) instead of 8-byte cp.async copies issued by every thread.
-template <bool SOLIDS, int TX, int TY, bool TMA>
+// PEER = true (LBM_FLAG_PEER_EXCHANGE on slabs): the nodes of the slab's first / last plane store their results a second time,
+// through the peer pointers, into the ghost planes of the neighbour slabs -- the halo exchange rides on the pass that produces
+// the data (NVLink stores next to the HBM stores); only the flag handshake is left between the passes (comm.cu).
+struct PeerPtrs {
+    double* up;      // image of the written array in the slab above (its low ghost planes receive my top planes)
+    double* down;    // ... in the slab below (its high ghost planes receive my bottom planes)
+    int gp;          // ghost planes that travel
+};
+template <bool SOLIDS, int TX, int TY, bool TMA, bool PEER = false>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
-cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi) {
+cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi,
+                       const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
     using L = D3Q19;
     constexpr int NT = TX * TY;
     constexpr int PW = TX + 4, PH = TY + 4;     // phi tile
@@ -349,6 +360,28 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             o.a[d * V + id] = amp * sgn * n[d];
             c.F[d * V + id] = F[d];
         }
+        if (PEER) {
+            // the factored state travels one plane deep: populations moving up into the low ghost of the slab above, those moving
+            // down into the high ghost of the slab below, the four recolouring scalars both ways (factored_dirs)
+            if (z == g.n2 - 1) {
+                const int64_t gid = id - (int64_t)g.n2 * g.plane;
+#pragma unroll
+                for (int q = 1; q < L::Q; ++q)
+                    if (L::d2(q) == 1) pp.up[q * V + gid] = fT[q];
+                pp.up[L::Q * V + gid] = rR * irho;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pp.up[(L::Q + 1 + d) * V + gid] = amp * sgn * n[d];
+            }
+            if (z == 0) {
+                const int64_t gid = id + (int64_t)g.n2 * g.plane;
+#pragma unroll
+                for (int q = 1; q < L::Q; ++q)
+                    if (L::d2(q) == -1) pp.down[q * V + gid] = fT[q];
+                pp.down[L::Q * V + gid] = rR * irho;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pp.down[(L::Q + 1 + d) * V + gid] = amp * sgn * n[d];
+            }
+        }
     }
 }
 
@@ -361,9 +394,10 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 // ------------------------------------------------------------------------------------------------
 // TMA = true: the scalar planes are staged with TMA bulk copies (rows widened to a 2-node halo in x so that they start
 // 16-byte aligned), issued by four threads (one per field) and completing on a per-slot mbarrier.
-template <bool SOLIDS, int TX, int TY, bool TMA>
+template <bool SOLIDS, int TX, int TY, bool TMA, bool PEER = false>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
-cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, const int z_lo, const int z_hi) {
+cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, const int z_lo, const int z_hi,
+                       const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
     using L = D3Q19;
     constexpr int NT = TX * TY;
     constexpr int XH = TMA ? 2 : 1;                 // halo columns kept in shared memory
@@ -487,6 +521,10 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
             }
             c.rho[0][id] = accR; c.rho[1][id] = accB;
             c.phi[id] = (accR - accB) / (accR + accB);
+            if (PEER) {       // phi travels pp.gp planes deep, both ways
+                if (z >= g.n2 - pp.gp) pp.up[id - (int64_t)g.n2 * g.plane] = (accR - accB) / (accR + accB);
+                if (z < pp.gp) pp.down[id + (int64_t)g.n2 * g.plane] = (accR - accB) / (accR + accB);
+            }
         }
 #pragma unroll
         for (int q = 0; q < L::Q; ++q) cur[q] = nxt[q];
@@ -520,8 +558,9 @@ static bool tiled_ok(const lbm_handle* h) {
 
 bool cg_tiled_possible(const lbm_handle* h) { return h->cfg.model == LBM_MODEL_CG && tiled_ok(h); }
 
-template <bool SOLIDS, int TILE_Y, bool TMA>
-static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi) {
+template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER = false>
+static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi,
+                           const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
@@ -529,16 +568,16 @@ static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2) + 8);
 #ifdef LBM_HOSTCHECK
-    cta_emu::launch(grid, block, smem, [&] { cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>(c, s, o, zchunk, z_lo, z_hi); });
+    cta_emu::launch(grid, block, smem, [&] { cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER>(c, s, o, zchunk, z_lo, z_hi, pp); });
 #else
     static std::atomic<bool> configured[64];  // per device: the attribute belongs to the function on ONE device (zero-initialised)
     if (!configured[h->cfg.device & 63]) {
-        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
+        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[h->cfg.device & 63] = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tiled_d3q19<solids>" : "cg_collide_tiled_d3q19<all-fluid>", h->stream);
-    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi);
+    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi, pp);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -559,8 +598,9 @@ static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, 
     }
 }
 
-template <bool SOLIDS, int TILE_Y, bool TMA>
-static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo, int z_hi) {
+template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER = false>
+static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo, int z_hi,
+                                   const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
@@ -568,21 +608,37 @@ static void launch_density_tiled_t(lbm_handle* h, const CGFields& c, const FastF
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * 4 * (TILE_Y + 2) * (TILE_X + (TMA ? 4 : 2)) + 8);
 #ifdef LBM_HOSTCHECK
-    cta_emu::launch(grid, block, smem, [&] { cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>(c, s, zchunk, z_lo, z_hi); });
+    cta_emu::launch(grid, block, smem, [&] { cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER>(c, s, zchunk, z_lo, z_hi, pp); });
 #else
     static std::atomic<bool> configured[64];
     if (!configured[h->cfg.device & 63]) {
-        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA>,
+        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[h->cfg.device & 63] = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_density_tiled_d3q19<solids>" : "cg_density_tiled_d3q19<all-fluid>", h->stream);
-    cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA><<<grid, block, smem, h->stream>>>(c, s, zchunk, z_lo, z_hi);
+    cg_density_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER><<<grid, block, smem, h->stream>>>(c, s, zchunk, z_lo, z_hi, pp);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
     ++g_launch_counter;
 }
+// the variants that also store into the neighbour slabs exist for the default tile shapes only
+static bool peer_tiles_default() { return tile_y_collide() == 4 && tile_y_density() == 8; }
+template <bool SOLIDS>
+static void launch_tiled_peer(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, const PeerPtrs pp) {
+#ifdef LBM_HOSTCHECK
+    launch_tiled_t<SOLIDS, 4, false, true>(h, c, s, o, 0, -1, pp);
+#else
+    static const bool tma = env_int("LBM_PHI_TMA", 1) != 0;
+    if (tma) launch_tiled_t<SOLIDS, 4, true, true>(h, c, s, o, 0, -1, pp); else launch_tiled_t<SOLIDS, 4, false, true>(h, c, s, o, 0, -1, pp);
+#endif
+}
+template <bool SOLIDS>
+static void launch_density_tiled_peer(lbm_handle* h, const CGFields& c, const FastFields& s, const PeerPtrs pp) {
+    launch_density_tiled_t<SOLIDS, 8, false, true>(h, c, s, 0, -1, pp);
+}
+
 template <bool SOLIDS>
 static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, int z_lo = 0, int z_hi = -1) {
     // TMA bulk copies for the scalar planes exist (LBM_SCALAR_TMA=1) but measured 7.2 ms vs 4.7 ms per 512^3 launch:
@@ -695,6 +751,7 @@ static void fast_enter(lbm_handle* h) {
     CGFields c = h->fields();
     FastState* f = (FastState*)h->fast;
     tracer_phase(h);          // no-op without tracers (or when a download already ran it for this iteration)
+    f->pushed[f->cur] = false;
     launch(CollideFactoredOp<L>{c, fast_fields(h, f->cur)}, h->g.count(0), h->stream);
     tracer_iteration_finished(h);
     h->head_done = false;
@@ -755,23 +812,40 @@ static void fast_one_step(lbm_handle* h) {
 #endif
     CGFields c = h->fields();
     const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
-    fast_exchange(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
-    bool dens_done = false;
+    const bool open = open_box(h);
+    // one-sided exchange with the stores fused into the tiled passes (closed boxes: the open-row patches rewrite boundary planes
+    // after the collision pass)
+    const bool peer = h->nranks > 1 && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE);
+    const bool fused = peer && tiled_ok(h) && !(h->cfg.flags & 4u) && !open && peer_tiles_default();
+    if (peer && f->pushed[f->cur]) comm_peer_signal_wait(h);
+    else fast_exchange(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
+    f->pushed[f->cur] = false;
+    bool dens_done = false, phi_pushed = false;
     if (tiled_ok(h) && !(h->cfg.flags & 4u)) {       // host test hook: the same kernels on host threads (cta_emu.h)
-        if (h->has_solid) launch_density_tiled<true>(h, c, s); else launch_density_tiled<false>(h, c, s);
+        if (fused) {
+            PeerPtrs pp{nullptr, nullptr, h->has_solid ? NG : 2};
+            comm_peer_pointers(h, c.phi, &pp.up, &pp.down);
+            if (h->has_solid) launch_density_tiled_peer<true>(h, c, s, pp); else launch_density_tiled_peer<false>(h, c, s, pp);
+            phi_pushed = true;
+        } else if (h->has_solid) launch_density_tiled<true>(h, c, s); else launch_density_tiled<false>(h, c, s);
         dens_done = true;
     }
     if (!dens_done) {
         if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
         else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
     }
-    const bool open = open_box(h);
     if (open) fast_open_rows_pre<L>(h, c, s);
-    fast_exchange(h, c.phi, 0, 1, h->has_solid ? NG : 2);
+    if (phi_pushed) comm_peer_signal_wait(h);
+    else fast_exchange(h, c.phi, 0, 1, h->has_solid ? NG : 2);
     if (h->has_solid && tiled_ok(h)) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);     // the tiled kernel stages phi, solids included
     bool done = false;
     if (tiled_ok(h)) {
-        if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);
+        if (fused) {
+            PeerPtrs pp{nullptr, nullptr, 1};
+            comm_peer_pointers(h, f->buf[1 - f->cur], &pp.up, &pp.down);
+            if (h->has_solid) launch_tiled_peer<true>(h, c, s, o, pp); else launch_tiled_peer<false>(h, c, s, o, pp);
+            f->pushed[1 - f->cur] = true;
+        } else if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);
         done = true;
     }
     if (!done) {

@@ -268,37 +268,45 @@ void peer_open(lbm_handle* h, PeerState* ps, void* mine, void** up_img, void** d
 }
 }  // namespace
 
-void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
-    if (narr > 48) throw BackendError{"peer exchange: too many arrays"};
+static PeerState* peer_state(lbm_handle* h) {
     PeerState* ps = (PeerState*)h->peer;
-    if (!ps) {
-        ps = new PeerState();
-        h->peer = ps;
-        ps->flags = (unsigned long long*)dev_alloc(2 * sizeof(unsigned long long));
-        dev_zero(ps->flags, 2 * sizeof(unsigned long long), h->stream);
-        dev_sync(h->stream);
-        void *fu = nullptr, *fd = nullptr;
-        peer_open(h, ps, ps->flags, &fu, &fd);
-        ps->up_flag = (unsigned long long*)fu;              // word [0] of the slab above: "from the slab below"
-        ps->down_flag = (unsigned long long*)fd + 1;        // word [1] of the slab below: "from the slab above"
-    }
-    const PeerMap* m = nullptr;
-    for (const PeerMap& k : ps->maps) if (k.base == base) m = &k;
-    if (!m) {
-        PeerMap n{base, nullptr, nullptr};
-        peer_open(h, ps, base, &n.up, &n.down);
-        ps->maps.push_back(n);
-        m = &ps->maps.back();
-    }
-    PeerPushOp op;
-    op.g = h->g; op.base = base; op.up = (double*)m->up; op.down = (double*)m->down; op.stride = stride; op.narr = narr; op.gp = gp;
-    for (int a = 0; a < 48; ++a) op.dirs[a] = (a < narr && dirs) ? dirs[a] : 0;
-    launch(op, op.items(), h->stream);
+    if (ps) return ps;
+    ps = new PeerState();
+    h->peer = ps;
+    ps->flags = (unsigned long long*)dev_alloc(2 * sizeof(unsigned long long));
+    dev_zero(ps->flags, 2 * sizeof(unsigned long long), h->stream);
+    dev_sync(h->stream);
+    void *fu = nullptr, *fd = nullptr;
+    peer_open(h, ps, ps->flags, &fu, &fd);
+    ps->up_flag = (unsigned long long*)fu;              // word [0] of the slab above: "from the slab below"
+    ps->down_flag = (unsigned long long*)fd + 1;        // word [1] of the slab below: "from the slab above"
+    return ps;
+}
+void comm_peer_pointers(lbm_handle* h, double* base, double** up, double** down) {
+    PeerState* ps = peer_state(h);
+    for (const PeerMap& k : ps->maps)
+        if (k.base == base) { *up = (double*)k.up; *down = (double*)k.down; return; }
+    PeerMap n{base, nullptr, nullptr};
+    peer_open(h, ps, base, &n.up, &n.down);
+    ps->maps.push_back(n);
+    *up = (double*)n.up; *down = (double*)n.down;
+}
+void comm_peer_signal_wait(lbm_handle* h) {
+    PeerState* ps = peer_state(h);
     const unsigned long long epoch = ++h->peer_epoch;
     peer_signal<<<1, 1, 0, h->stream>>>(ps->up_flag, ps->down_flag, epoch);
     peer_wait<<<1, 1, 0, h->stream>>>(ps->flags, epoch);
     LBM_CUDA_CHECK(cudaGetLastError());
     g_launch_counter += 2;
+}
+void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+    if (narr > 48) throw BackendError{"peer exchange: too many arrays"};
+    PeerPushOp op;
+    comm_peer_pointers(h, base, &op.up, &op.down);
+    op.g = h->g; op.base = base; op.stride = stride; op.narr = narr; op.gp = gp;
+    for (int a = 0; a < 48; ++a) op.dirs[a] = (a < narr && dirs) ? dirs[a] : 0;
+    launch(op, op.items(), h->stream);
+    comm_peer_signal_wait(h);
 }
 
 static void peer_destroy(lbm_handle* h) {

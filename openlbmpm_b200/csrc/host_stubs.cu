@@ -67,31 +67,37 @@ void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp) { host_ring_exchange
 // the flag words are std::atomic (release store / acquire spin).  Only the FIRST exchange of an array meets at a barrier (the
 // pointer swap that cudaIpc does on the GPU); after that the ranks synchronise through the flags alone, so ThreadSanitizer sees
 // the protocol as it is.
-void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+void comm_peer_pointers(lbm_handle* h, double* base, double** up, double** down) {
     HostRing* r = (HostRing*)h->nccl;
     HostPeerState* ps = (HostPeerState*)h->peer;
     if (!ps) { ps = new HostPeerState(); h->peer = ps; }
+    for (const HostPeerMap& k : ps->maps)
+        if (k.base == base) { *up = k.up; *down = k.down; return; }
+    const int upr = (h->rank + 1) % r->n, downr = (h->rank + r->n - 1) % r->n;
+    r->pub[h->rank] = base;
+    pthread_barrier_wait(&r->bar);
+    HostPeerMap n{base, (double*)r->pub[upr], (double*)r->pub[downr]};
+    pthread_barrier_wait(&r->bar);
+    ps->maps.push_back(n);
+    *up = n.up; *down = n.down;
+}
+void comm_peer_signal_wait(lbm_handle* h) {
+    HostRing* r = (HostRing*)h->nccl;
     const int up = (h->rank + 1) % r->n, down = (h->rank + r->n - 1) % r->n;
-    const HostPeerMap* m = nullptr;
-    for (const HostPeerMap& k : ps->maps) if (k.base == base) m = &k;
-    if (!m) {
-        r->pub[h->rank] = base;
-        pthread_barrier_wait(&r->bar);
-        HostPeerMap n{base, (double*)r->pub[up], (double*)r->pub[down]};
-        pthread_barrier_wait(&r->bar);
-        ps->maps.push_back(n);
-        m = &ps->maps.back();
-    }
-    PeerPushOp op;
-    op.g = h->g; op.base = base; op.up = m->up; op.down = m->down; op.stride = stride; op.narr = narr; op.gp = gp;
-    for (int a = 0; a < 48; ++a) op.dirs[a] = (a < narr && dirs) ? dirs[a] : 0;
-    launch(op, op.items(), h->stream);
     const uint64_t epoch = ++h->peer_epoch;
     r->from_down[up].store(epoch, std::memory_order_release);        // signal
     r->from_up[down].store(epoch, std::memory_order_release);
     while (r->from_down[h->rank].load(std::memory_order_acquire) < epoch) sched_yield();      // wait
     while (r->from_up[h->rank].load(std::memory_order_acquire) < epoch) sched_yield();
     lbm::g_launch_counter += 2;
+}
+void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
+    PeerPushOp op;
+    comm_peer_pointers(h, base, &op.up, &op.down);
+    op.g = h->g; op.base = base; op.stride = stride; op.narr = narr; op.gp = gp;
+    for (int a = 0; a < 48; ++a) op.dirs[a] = (a < narr && dirs) ? dirs[a] : 0;
+    launch(op, op.items(), h->stream);
+    comm_peer_signal_wait(h);
 }
 void comm_destroy(lbm_handle* h) { delete (HostPeerState*)h->peer; h->peer = nullptr; }
 int comm_allreduce_max(lbm_handle* h, int v) {

@@ -12,6 +12,10 @@ void comm_exchange_u8(lbm_handle* h, uint8_t* base, int gp);
 // one-sided form (LBM_FLAG_PEER_EXCHANGE): boundary planes stored into the neighbours' ghost planes through peer pointers,
 // then signal (release) / wait (acquire) on a flag pair.  `base` must be the start of a device allocation.
 void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs);
+// its two halves, for passes that store into the neighbours themselves: the neighbours' images of an allocation (mapped on
+// first use), and the flag handshake that closes an exchange
+void comm_peer_pointers(lbm_handle* h, double* base, double** up, double** down);
+void comm_peer_signal_wait(lbm_handle* h);
 void comm_destroy(lbm_handle* h);
 int comm_allreduce_max(lbm_handle* h, int v);
 
