@@ -363,7 +363,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
         if (PEER) {
             // the factored state travels one plane deep: populations moving up into the low ghost of the slab above, those moving
             // down into the high ghost of the slab below, the four recolouring scalars both ways (factored_dirs)
-            if (z == g.n2 - 1) {
+            if (z == g.n2 - 1 && pp.up) {
                 const int64_t gid = id - (int64_t)g.n2 * g.plane;
 #pragma unroll
                 for (int q = 1; q < L::Q; ++q)
@@ -372,7 +372,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 #pragma unroll
                 for (int d = 0; d < 3; ++d) pp.up[(L::Q + 1 + d) * V + gid] = amp * sgn * n[d];
             }
-            if (z == 0) {
+            if (z == 0 && pp.down) {
                 const int64_t gid = id + (int64_t)g.n2 * g.plane;
 #pragma unroll
                 for (int q = 1; q < L::Q; ++q)
@@ -522,8 +522,8 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
             c.rho[0][id] = accR; c.rho[1][id] = accB;
             c.phi[id] = (accR - accB) / (accR + accB);
             if (PEER) {       // phi travels pp.gp planes deep, both ways
-                if (z >= g.n2 - pp.gp) pp.up[id - (int64_t)g.n2 * g.plane] = (accR - accB) / (accR + accB);
-                if (z < pp.gp) pp.down[id + (int64_t)g.n2 * g.plane] = (accR - accB) / (accR + accB);
+                if (z >= g.n2 - pp.gp && pp.up) pp.up[id - (int64_t)g.n2 * g.plane] = (accR - accB) / (accR + accB);
+                if (z < pp.gp && pp.down) pp.down[id + (int64_t)g.n2 * g.plane] = (accR - accB) / (accR + accB);
             }
         }
 #pragma unroll
@@ -794,6 +794,19 @@ static void fast_one_step_overlapped(lbm_handle* h) {
 }
 #endif
 
+// one direction of a one-sided exchange as a launch of its own: the planes an open-row patch rewrites after the pass that
+// stores the others (the outlet planes of the first slab travel down, the inlet planes of the last slab up)
+static void peer_push_one_way(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs, bool upwards) {
+    PeerPushOp op;
+    comm_peer_pointers(h, base, &op.up, &op.down);
+    op.g = h->g; op.base = base; op.stride = stride; op.narr = narr; op.gp = gp;
+    for (int a = 0; a < 48; ++a) {
+        const int d = (a < narr && dirs) ? dirs[a] : 0;
+        op.dirs[a] = a >= narr ? 2 : (upwards ? ((d == 0 || d == 1) ? 1 : 2) : ((d == 0 || d == -1) ? -1 : 2));
+    }
+    launch(op, op.items(), h->stream);
+}
+
 // the two per-step exchanges of the fast path: NCCL send / recv, or (opt-in) stores into the neighbours' memory + flags
 static void fast_exchange(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs = nullptr) {
     if (h->nranks > 1 && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE)) comm_peer_exchange_f64(h, base, stride, narr, gp, dirs);
@@ -813,10 +826,12 @@ static void fast_one_step(lbm_handle* h) {
     CGFields c = h->fields();
     const FastFields s = fast_fields(h, f->cur), o = fast_fields(h, 1 - f->cur);
     const bool open = open_box(h);
-    // one-sided exchange with the stores fused into the tiled passes (closed boxes: the open-row patches rewrite boundary planes
-    // after the collision pass)
+    // one-sided exchange with the stores fused into the tiled passes.  Open channels: the open-row patches rewrite the outlet
+    // planes of the first slab and the inlet planes of the last slab AFTER the passes, so those two slabs leave that direction
+    // to a one-way push behind the patch.
     const bool peer = h->nranks > 1 && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE);
-    const bool fused = peer && tiled_ok(h) && !(h->cfg.flags & 4u) && !open && peer_tiles_default();
+    const bool fused = peer && tiled_ok(h) && !(h->cfg.flags & 4u) && peer_tiles_default();
+    const bool late_down = fused && open && h->rank == 0, late_up = fused && open && h->rank == h->nranks - 1;
     if (peer && f->pushed[f->cur]) comm_peer_signal_wait(h);
     else fast_exchange(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
     f->pushed[f->cur] = false;
@@ -825,6 +840,8 @@ static void fast_one_step(lbm_handle* h) {
         if (fused) {
             PeerPtrs pp{nullptr, nullptr, h->has_solid ? NG : 2};
             comm_peer_pointers(h, c.phi, &pp.up, &pp.down);
+            if (late_up) pp.up = nullptr;
+            if (late_down) pp.down = nullptr;
             if (h->has_solid) launch_density_tiled_peer<true>(h, c, s, pp); else launch_density_tiled_peer<false>(h, c, s, pp);
             phi_pushed = true;
         } else if (h->has_solid) launch_density_tiled<true>(h, c, s); else launch_density_tiled<false>(h, c, s);
@@ -835,14 +852,19 @@ static void fast_one_step(lbm_handle* h) {
         else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
     }
     if (open) fast_open_rows_pre<L>(h, c, s);
-    if (phi_pushed) comm_peer_signal_wait(h);
-    else fast_exchange(h, c.phi, 0, 1, h->has_solid ? NG : 2);
+    if (phi_pushed) {
+        if (late_up) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, true);
+        if (late_down) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, false);
+        comm_peer_signal_wait(h);
+    } else fast_exchange(h, c.phi, 0, 1, h->has_solid ? NG : 2);
     if (h->has_solid && tiled_ok(h)) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);     // the tiled kernel stages phi, solids included
     bool done = false;
     if (tiled_ok(h)) {
         if (fused) {
             PeerPtrs pp{nullptr, nullptr, 1};
             comm_peer_pointers(h, f->buf[1 - f->cur], &pp.up, &pp.down);
+            if (late_up) pp.up = nullptr;
+            if (late_down) pp.down = nullptr;
             if (h->has_solid) launch_tiled_peer<true>(h, c, s, o, pp); else launch_tiled_peer<false>(h, c, s, o, pp);
             f->pushed[1 - f->cur] = true;
         } else if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);
@@ -855,6 +877,8 @@ static void fast_one_step(lbm_handle* h) {
         if (h->tracer) { tracer_phase(h); tracer_iteration_finished(h); }
     }
     if (open) fast_open_rows_post<L>(h, c, o, done);
+    if (late_up) peer_push_one_way(h, f->buf[1 - f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>(), true);
+    if (late_down) peer_push_one_way(h, f->buf[1 - f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>(), false);
     f->cur = 1 - f->cur;
 }
 
