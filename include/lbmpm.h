@@ -214,6 +214,12 @@ int lbm_download_fields(lbm_handle* h, double* phi, double* const* G, double* co
 /* Sum of each component's density over the void nodes (mass check).                        */
 int lbm_total_mass(lbm_handle* h, double* mass, int32_t n_comp);
 
+/* Checksum of the densities at the output point: per component the wrap-around uint64 sum of the bit patterns of rho over
+ * the slab's own nodes.  Sums of the slabs of a decomposed lattice add up (mod 2^64) to the sum of the undivided lattice
+ * iff the slabs are bit-equal to it -- bench.py prints the all-reduced value at every GPU count.  (No reference
+ * counterpart: the reference is single-GPU, RKD2Q9.py holds the whole lattice on one device.)                  */
+int lbm_state_checksum(lbm_handle* h, uint64_t* sums, int32_t n_comp);
+
 /* ---- solute tracers riding on the colour-gradient CSF flow ------------------ */
 
 /* The numbers the reference reads from transportsetup.ini (Transport2DRK.py:96-391).                           */

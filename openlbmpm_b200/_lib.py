@@ -86,6 +86,7 @@ PROTOTYPES = {
     "lbm_tracer_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_double_p), ctypes.c_int32]),
     "lbm_tracer_download": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_double_p), ctypes.c_int32]),
     "lbm_total_mass": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int32]),
+    "lbm_state_checksum": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32]),
     "lbm_get_timing": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_int64_p, c_int64_p]),
     "lbm_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "lbm_profile_report": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
@@ -339,6 +340,12 @@ class Engine:
         m = np.zeros(self.ncomp)
         self._check(self.lib.lbm_total_mass(self._h, m.ctypes.data_as(c_double_p), self.ncomp), "lbm_total_mass")
         return m
+
+    def checksum(self):
+        """per component: wrap-around uint64 sum of the bit patterns of rho at the output point (slab sums add up mod 2^64)"""
+        s = (ctypes.c_uint64 * self.ncomp)()
+        self._check(self.lib.lbm_state_checksum(self._h, s, self.ncomp), "lbm_state_checksum")
+        return [int(x) for x in s]
 
     def profile(self, on):
         self._check(self.lib.lbm_profile_enable(self._h, 1 if on else 0), "lbm_profile_enable")

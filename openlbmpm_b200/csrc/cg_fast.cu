@@ -50,6 +50,7 @@ bool cg_fast_eligible(const lbm_handle* h) {
 
 void cg_fast_free(lbm_handle* h) {
     FastState* f = (FastState*)h->fast;
+    if (f) comm_peer_release(h);            // the neighbour slabs have the buffers mapped (LBM_FLAG_PEER_EXCHANGE)
     if (f) { dev_free(f->buf[0]); dev_free(f->buf[1]); delete f; }
     h->fast = nullptr;
     h->fast_pending_stream = false;

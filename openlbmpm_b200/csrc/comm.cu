@@ -221,50 +221,87 @@ namespace {
 struct PeerMap { const void* base; void* up; void* down; };
 struct PeerState {
     std::vector<PeerMap> maps;
-    unsigned long long* flags = nullptr;          // [0]: written by the slab below, [1]: by the slab above
+    unsigned long long* flags = nullptr;          // [0]: written by the slab below, [1]: by the slab above, [2]: epoch of a timed-out wait
     unsigned long long *up_flag = nullptr, *down_flag = nullptr;    // the neighbours' words I write
-    std::vector<void*> opened;
+    std::vector<void*> opened;                    // mappings of the neighbours' exchanged arrays (dropped by comm_peer_release)
+    std::vector<void*> opened_flags;              // mappings of the neighbours' flag words (live as long as the handle)
 };
+// what travels between neighbours to map one allocation: the IPC handle of the driver allocation that CONTAINS the pointer
+// and the pointer's offset in it (cudaMalloc sub-allocates small requests from a larger block; the handle names the block)
+struct PeerTicket { cudaIpcMemHandle_t handle; unsigned long long offset; };
+unsigned long long offset_in_allocation(const void* p) {
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);      // cuMemGetAddressRange (driver API)
+    static range_fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+        return (range_fn)f;
+    }();
+    unsigned long long base = 0; size_t size = 0;
+    if (!fn || fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) throw BackendError{"cuMemGetAddressRange failed"};
+    return (unsigned long long)(uintptr_t)p - base;
+}
 
 __global__ void peer_signal(unsigned long long* up_from_down, unsigned long long* down_from_up, unsigned long long epoch) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(up_from_down), "l"(epoch) : "memory");
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(down_from_up), "l"(epoch) : "memory");
 }
-__global__ void peer_wait(const unsigned long long* flags, unsigned long long epoch) {
+// The wait is bounded (LBM_PEER_TIMEOUT_MS, default 20 s of the global timer): a neighbour that died or fell out of step must
+// not leave a kernel spinning on the GPU for ever.  A timeout is recorded in flags[2] and reported by the next synchronising call.
+__global__ void peer_wait(unsigned long long* flags, unsigned long long epoch, unsigned long long timeout_ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (int k = 0; k < 2; ++k) {
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + k) : "memory");
-        } while (v < epoch);
+            if (v >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) { flags[2] = epoch; return; }
+        } while (true);
     }
     __threadfence_system();
 }
 
-// swap one IPC handle with both ring neighbours and open theirs; -> {image in the slab above, image in the slab below}
-void peer_open(lbm_handle* h, PeerState* ps, void* mine, void** up_img, void** down_img) {
+// swap one ticket with both ring neighbours and open theirs; -> {image in the slab above, image in the slab below}
+void peer_open(lbm_handle* h, std::vector<void*>& opened, void* mine, void** up_img, void** down_img) {
     ncclComm_t comm = (ncclComm_t)h->nccl;
     const int up = (h->rank + 1) % h->nranks, down = (h->rank + h->nranks - 1) % h->nranks;
-    cudaIpcMemHandle_t hm, hu, hd;
-    LBM_CUDA_CHECK(cudaIpcGetMemHandle(&hm, mine));
-    char* d = (char*)dev_alloc(3 * sizeof(hm));
+    PeerTicket tm, tu, td;
+    memset(&tm, 0, sizeof(tm));
+    tm.offset = offset_in_allocation(mine);
+    LBM_CUDA_CHECK(cudaIpcGetMemHandle(&tm.handle, (char*)mine - tm.offset));
+    char* d = (char*)dev_alloc(3 * sizeof(tm));
     try {
-        dev_h2d(d, &hm, sizeof(hm), h->stream);
+        dev_h2d(d, &tm, sizeof(tm), h->stream);
         LBM_NCCL_CHECK(ncclGroupStart());
-        LBM_NCCL_CHECK(ncclSend(d, sizeof(hm), ncclUint8, up, comm, h->stream));
-        LBM_NCCL_CHECK(ncclRecv(d + 2 * sizeof(hm), sizeof(hm), ncclUint8, down, comm, h->stream));
-        LBM_NCCL_CHECK(ncclSend(d, sizeof(hm), ncclUint8, down, comm, h->stream));
-        LBM_NCCL_CHECK(ncclRecv(d + sizeof(hm), sizeof(hm), ncclUint8, up, comm, h->stream));
+        LBM_NCCL_CHECK(ncclSend(d, sizeof(tm), ncclUint8, up, comm, h->stream));
+        LBM_NCCL_CHECK(ncclRecv(d + 2 * sizeof(tm), sizeof(tm), ncclUint8, down, comm, h->stream));
+        LBM_NCCL_CHECK(ncclSend(d, sizeof(tm), ncclUint8, down, comm, h->stream));
+        LBM_NCCL_CHECK(ncclRecv(d + sizeof(tm), sizeof(tm), ncclUint8, up, comm, h->stream));
         LBM_NCCL_CHECK(ncclGroupEnd());
-        dev_d2h(&hu, d + sizeof(hm), sizeof(hm), h->stream);
-        dev_d2h(&hd, d + 2 * sizeof(hm), sizeof(hm), h->stream);
+        dev_d2h(&tu, d + sizeof(tm), sizeof(tm), h->stream);
+        dev_d2h(&td, d + 2 * sizeof(tm), sizeof(tm), h->stream);
     } catch (...) { dev_free(d); throw; }
     dev_free(d);
-    LBM_CUDA_CHECK(cudaIpcOpenMemHandle(up_img, hu, cudaIpcMemLazyEnablePeerAccess));
-    ps->opened.push_back(*up_img);
+    void* base_up = nullptr;
+    LBM_CUDA_CHECK(cudaIpcOpenMemHandle(&base_up, tu.handle, cudaIpcMemLazyEnablePeerAccess));
+    opened.push_back(base_up);
+    *up_img = (char*)base_up + tu.offset;
     if (up == down) { *down_img = *up_img; return; }       // two slabs: one neighbour, one mapping
-    LBM_CUDA_CHECK(cudaIpcOpenMemHandle(down_img, hd, cudaIpcMemLazyEnablePeerAccess));
-    ps->opened.push_back(*down_img);
+    void* base_down = nullptr;
+    LBM_CUDA_CHECK(cudaIpcOpenMemHandle(&base_down, td.handle, cudaIpcMemLazyEnablePeerAccess));
+    opened.push_back(base_down);
+    *down_img = (char*)base_down + td.offset;
+}
+// all slabs meet (nobody frees an allocation its neighbours still have mapped)
+void peer_barrier(lbm_handle* h) {
+    try {
+        int* d = (int*)dev_alloc(sizeof(int));
+        if (nccl_api().AllReduce(d, d, 1, ncclInt32, ncclMax, (ncclComm_t)h->nccl, h->stream) == ncclSuccess) cudaStreamSynchronize(h->stream);
+        dev_free(d);
+    } catch (const BackendError&) {}
 }
 }  // namespace
 
@@ -273,11 +310,11 @@ static PeerState* peer_state(lbm_handle* h) {
     if (ps) return ps;
     ps = new PeerState();
     h->peer = ps;
-    ps->flags = (unsigned long long*)dev_alloc(2 * sizeof(unsigned long long));
-    dev_zero(ps->flags, 2 * sizeof(unsigned long long), h->stream);
+    ps->flags = (unsigned long long*)dev_alloc(4 * sizeof(unsigned long long));
+    dev_zero(ps->flags, 4 * sizeof(unsigned long long), h->stream);
     dev_sync(h->stream);
     void *fu = nullptr, *fd = nullptr;
-    peer_open(h, ps, ps->flags, &fu, &fd);
+    peer_open(h, ps->opened_flags, ps->flags, &fu, &fd);
     ps->up_flag = (unsigned long long*)fu;              // word [0] of the slab above: "from the slab below"
     ps->down_flag = (unsigned long long*)fd + 1;        // word [1] of the slab below: "from the slab above"
     return ps;
@@ -287,7 +324,7 @@ void comm_peer_pointers(lbm_handle* h, double* base, double** up, double** down)
     for (const PeerMap& k : ps->maps)
         if (k.base == base) { *up = (double*)k.up; *down = (double*)k.down; return; }
     PeerMap n{base, nullptr, nullptr};
-    peer_open(h, ps, base, &n.up, &n.down);
+    peer_open(h, ps->opened, base, &n.up, &n.down);
     ps->maps.push_back(n);
     *up = (double*)n.up; *down = (double*)n.down;
 }
@@ -295,7 +332,11 @@ void comm_peer_signal_wait(lbm_handle* h) {
     PeerState* ps = peer_state(h);
     const unsigned long long epoch = ++h->peer_epoch;
     peer_signal<<<1, 1, 0, h->stream>>>(ps->up_flag, ps->down_flag, epoch);
-    peer_wait<<<1, 1, 0, h->stream>>>(ps->flags, epoch);
+    static const unsigned long long timeout_ns = [] {
+        const char* e = getenv("LBM_PEER_TIMEOUT_MS");
+        return (unsigned long long)(e ? atoll(e) : 20000) * 1000000ull;
+    }();
+    peer_wait<<<1, 1, 0, h->stream>>>(ps->flags, epoch, timeout_ns);
     LBM_CUDA_CHECK(cudaGetLastError());
     g_launch_counter += 2;
 }
@@ -309,17 +350,34 @@ void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int nar
     comm_peer_signal_wait(h);
 }
 
+// after a stream synchronisation: did a wait of the one-sided exchange give up?
+void comm_peer_check(lbm_handle* h) {
+    PeerState* ps = (PeerState*)h->peer;
+    if (!ps) return;
+    unsigned long long t = 0;
+    dev_d2h(&t, ps->flags + 2, sizeof(t), h->stream);
+    if (t) throw BackendError{"one-sided exchange " + std::to_string(t) + ": a neighbour slab's signal did not arrive within LBM_PEER_TIMEOUT_MS"};
+}
+void comm_peer_release(lbm_handle* h) {
+    PeerState* ps = (PeerState*)h->peer;
+    if (!ps || h->nranks <= 1 || ps->maps.empty()) return;
+    // the fused passes of the neighbours store into my ghost planes with the handshake deferred to the next step: close the
+    // protocol first (their signal is ordered behind their last stores), then drop what I have mapped of theirs
+    try { comm_peer_signal_wait(h); } catch (const BackendError&) {}      // (called from lbm_destroy too: never throws)
+    cudaStreamSynchronize(h->stream);
+    for (void* p : ps->opened) cudaIpcCloseMemHandle(p);
+    ps->opened.clear();
+    ps->maps.clear();
+    peer_barrier(h);
+}
+
 static void peer_destroy(lbm_handle* h) {
     PeerState* ps = (PeerState*)h->peer;
     if (!ps) return;
+    comm_peer_release(h);
     cudaStreamSynchronize(h->stream);
-    for (void* p : ps->opened) cudaIpcCloseMemHandle(p);
-    // nobody frees an allocation its neighbours still have mapped: wait for every rank to have closed its mappings
-    try {
-        int* d = (int*)dev_alloc(sizeof(int));
-        if (nccl_api().AllReduce(d, d, 1, ncclInt32, ncclMax, (ncclComm_t)h->nccl, h->stream) == ncclSuccess) cudaStreamSynchronize(h->stream);
-        dev_free(d);
-    } catch (const BackendError&) {}
+    for (void* p : ps->opened_flags) cudaIpcCloseMemHandle(p);
+    peer_barrier(h);
     dev_free(ps->flags);
     delete ps;
     h->peer = nullptr;

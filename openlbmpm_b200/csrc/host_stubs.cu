@@ -5,6 +5,7 @@
 #include <sched.h>
 
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -87,8 +88,11 @@ void comm_peer_signal_wait(lbm_handle* h) {
     const uint64_t epoch = ++h->peer_epoch;
     r->from_down[up].store(epoch, std::memory_order_release);        // signal
     r->from_up[down].store(epoch, std::memory_order_release);
-    while (r->from_down[h->rank].load(std::memory_order_acquire) < epoch) sched_yield();      // wait
-    while (r->from_up[h->rank].load(std::memory_order_acquire) < epoch) sched_yield();
+    // wait -- bounded, like comm.cu::peer_wait: a neighbour that died must not hang the others
+    const auto t0 = std::chrono::steady_clock::now();
+    auto late = [&] { return std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60); };
+    while (r->from_down[h->rank].load(std::memory_order_acquire) < epoch) { sched_yield(); if (late()) throw BackendError{"one-sided exchange: no signal from the slab below"}; }
+    while (r->from_up[h->rank].load(std::memory_order_acquire) < epoch) { sched_yield(); if (late()) throw BackendError{"one-sided exchange: no signal from the slab above"}; }
     lbm::g_launch_counter += 2;
 }
 void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs) {
@@ -99,6 +103,14 @@ void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int nar
     launch(op, op.items(), h->stream);
     comm_peer_signal_wait(h);
 }
+void comm_peer_release(lbm_handle* h) {
+    HostPeerState* ps = (HostPeerState*)h->peer;
+    if (!ps || h->nranks <= 1 || ps->maps.empty()) return;
+    try { comm_peer_signal_wait(h); } catch (const BackendError&) {}     // the neighbours' last stores into my ghost planes have landed
+    ps->maps.clear();
+    pthread_barrier_wait(&((HostRing*)h->nccl)->bar);   // nobody frees what a neighbour may still address
+}
+void comm_peer_check(lbm_handle*) {}     // the host wait throws by itself
 void comm_destroy(lbm_handle* h) { delete (HostPeerState*)h->peer; h->peer = nullptr; }
 int comm_allreduce_max(lbm_handle* h, int v) {
     if (h->nranks <= 1) return v;

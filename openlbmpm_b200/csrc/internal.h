@@ -16,6 +16,11 @@ void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int nar
 // first use), and the flag handshake that closes an exchange
 void comm_peer_pointers(lbm_handle* h, double* base, double** up, double** down);
 void comm_peer_signal_wait(lbm_handle* h);
+// An allocation the neighbours have mapped is about to be freed (re-initialisation, new geometry, destruction): one more
+// handshake (the neighbours' last stores into it have landed), every mapping of the neighbours' arrays is dropped, and all
+// slabs meet before anybody frees.  Collective like the calls that free; no-op without mappings.
+void comm_peer_release(lbm_handle* h);
+void comm_peer_check(lbm_handle* h);     // throws if a bounded wait of the one-sided exchange timed out (call after a stream sync)
 void comm_destroy(lbm_handle* h);
 int comm_allreduce_max(lbm_handle* h, int v);
 

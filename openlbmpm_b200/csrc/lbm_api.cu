@@ -156,6 +156,7 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
 }
 
 static void free_state(lbm_handle* h) {
+    comm_peer_release(h);       // one-sided exchange: phi and the factored buffers are mapped by the neighbour slabs
     double** arrs[] = {&h->fS, &h->fC, &h->rho, &h->u, &h->phi, &h->G, &h->nrm, &h->F, &h->K};
     for (double** p : arrs) { dev_free(*p); *p = nullptr; }
     cg_fast_free(h);
@@ -171,6 +172,9 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     cudaStreamSynchronize(h->stream);
 #endif
     graph_release(&h->graph, h->stream);
+#ifndef LBM_HOSTCHECK
+    g_prof.clear(); g_prof.on = false;      // the per-launch events are a per-thread switch: a destroyed handle must not leave it on
+#endif
     free_state(h);
     dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull); dev_free(h->out_stage);
     tracer_free(h);
@@ -205,6 +209,14 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
     h->g.wrap2 = 0;               // the geometry operators read the ghost planes of the mask (filled below)
     const Grid& g = h->g;
     const int64_t owned = g.plane * g.n2;
+    if (h->nranks > 1 && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE)) {
+        // the one-sided exchange addresses the neighbours' arrays with MY strides and ghost-plane offsets
+        const int same = comm_allreduce_max(h, g.n2) == g.n2 && comm_allreduce_max(h, -g.n2) == -g.n2 &&
+                         comm_allreduce_max(h, g.n0) == g.n0 && comm_allreduce_max(h, -g.n0) == -g.n0 &&
+                         comm_allreduce_max(h, g.n1) == g.n1 && comm_allreduce_max(h, -g.n1) == -g.n1;
+        if (comm_allreduce_max(h, same ? 0 : 1) != 0)
+            return fail(h, LBM_EINVAL, "LBM_FLAG_PEER_EXCHANGE needs slabs of equal extents on every rank");
+    }
     free_state(h);
     dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull);
     h->pull = nullptr;
@@ -536,6 +548,7 @@ extern "C" int lbm_synchronize(lbm_handle* h) {
     API_BEGIN(h)
     set_device(h);
     dev_sync(h->stream);
+    if (h->peer) comm_peer_check(h);
     API_END(h)
 }
 
@@ -713,6 +726,56 @@ extern "C" int lbm_total_mass(lbm_handle* h, double* mass, int32_t n_comp) {
         for (int64_t i = 0; i < owned; ++i) s += buf[i];
         mass[k] = (double)s;
     }
+    API_END(h)
+}
+
+namespace {
+// wrap-around uint64 sum of the bit patterns of an array: integer addition commutes, so the result does not depend on the
+// launch geometry, the reduction order or the number of slabs -- two runs agree in it iff (up to a 2^-64 accident) every
+// value agrees bit for bit.  item = one strip of the array
+struct ChecksumOp {
+    const double* a; int64_t n, strip; unsigned long long* out;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t lo = i * strip, hi = lo + strip < n ? lo + strip : n;
+        unsigned long long s = 0;
+        for (int64_t k = lo; k < hi; ++k) {
+            unsigned long long bits;
+            const double v = a[k];
+            memcpy(&bits, &v, 8);
+            s += bits;
+        }
+#ifdef __CUDA_ARCH__
+        atomicAdd(out, s);
+#else
+        __atomic_fetch_add(out, s, __ATOMIC_RELAXED);
+#endif
+    }
+};
+}  // namespace
+
+extern "C" int lbm_state_checksum(lbm_handle* h, uint64_t* sums, int32_t n_comp) {
+    API_BEGIN(h)
+    if (!h->has_state || !sums) return fail(h, LBM_ESTATE, "no state");
+    set_device(h);
+    const double* rho = nullptr; const double* u = nullptr;
+    if (h->cfg.model != LBM_MODEL_CG) {
+        if (n_comp != h->cfg.n_components) return fail(h, LBM_EINVAL, "one sum per component expected");
+        sc_output_pointers(h, &rho, &u);
+    } else {
+        if (n_comp != 2) return fail(h, LBM_EINVAL, "colour gradient has 2 components");
+        to_output_point(h);
+        rho = h->rho;
+    }
+    const Grid& g = h->g;
+    const int64_t owned = g.plane * g.n2, strip = 64;
+    unsigned long long* d = (unsigned long long*)dev_alloc((size_t)n_comp * 8);
+    try {
+        dev_zero(d, (size_t)n_comp * 8, h->stream);
+        for (int k = 0; k < n_comp; ++k)
+            launch(ChecksumOp{rho + k * g.vol + NG * g.plane, owned, strip, d + k}, (owned + strip - 1) / strip, h->stream);
+        dev_d2h(sums, d, (size_t)n_comp * 8, h->stream);
+    } catch (...) { dev_free(d); throw; }
+    dev_free(d);
     API_END(h)
 }
 

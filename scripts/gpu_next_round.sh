@@ -3,7 +3,7 @@
 # budget ran out, in the order DESIGN.md section 10 names.  Results land in gpurun_out/n_*.
 mkdir -p gpurun_out
 O=gpurun_out
-( timeout 420 python -u -m pytest tests -m gpu -q -rf --durations=8 > $O/n_pytest_gpu.log 2>&1; echo "rc=$?" >> $O/n_pytest_gpu.log ); tail -12 $O/n_pytest_gpu.log
+( timeout 700 python -u -m pytest tests -m gpu -q -rf --durations=8 > $O/n_pytest_gpu.log 2>&1; echo "rc=$?" >> $O/n_pytest_gpu.log ); tail -12 $O/n_pytest_gpu.log
 ( timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/n_smoke.log 2>&1; echo "rc=$?" >> $O/n_smoke.log ); tail -2 $O/n_smoke.log
 for w in cfg1 cfg2 cfg3; do
   ( timeout 120 python bench.py --workload $w --steps 2000 --warmup 50 > $O/n_bench_$w.json 2> $O/n_bench_$w.err ); python scripts/bench_brief.py $O/n_bench_$w.json || tail -3 $O/n_bench_$w.err

@@ -47,6 +47,7 @@ def run(lib, lattice, dom, rho, steps, world, **kw):
                 parts.append(np.stack(d + u))
             pdf = e.download_pdfs()
             out[r] = (parts, np.stack(pdf), e.total_mass())
+            e.close()                 # collective on slabs with the one-sided exchange (a last handshake): from the rank's own thread
         except Exception as ex:       # a rank that dies would leave the others in the barrier: report and bail out
             errors.append(ex)
             os._exit(3) if world > 1 else None
@@ -266,6 +267,7 @@ def test_tracers_on_slabs_bit_equal(lib):
                         e.step(n)
                         parts.append(np.stack(e.tracer_download() + e.download_macros()[0]))
                     out[r] = parts
+                    e.close()
                 except BaseException:
                     import traceback; traceback.print_exc()
                     os._exit(3)
