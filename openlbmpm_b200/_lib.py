@@ -16,6 +16,7 @@ FLAG_GENERIC_KERNELS = 1
 FLAG_GHOST_PLANES = 64
 FLAG_PERSISTENT = 128
 FLAG_PEER_EXCHANGE = 256
+FLAG_NCCL_EXCHANGE = 512
 ST_CSF, ST_PERTURBATION = 0, 1
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

@@ -18,8 +18,8 @@ namespace lbm {
 struct FastState {
     double* buf[2] = {nullptr, nullptr};   // each: gT [Q][vol], kR [vol], a [3][vol]
     int cur = 0;
-    bool pushed[2] = {false, false};       // one-sided exchange: the pass that wrote buf[k] has already stored its boundary planes
-                                           // into the neighbour slabs (only the flag handshake is left)
+    int pushed[2] = {0, 0};                // one-sided exchange: 1 = the pass that wrote buf[k] has already stored its boundary planes
+                                           // into the neighbour slabs (only the flag handshake is left), 2 = handshake done too
 };
 
 static FastFields fast_fields(const lbm_handle* h, int k) {
@@ -50,8 +50,10 @@ bool cg_fast_eligible(const lbm_handle* h) {
 
 void cg_fast_free(lbm_handle* h) {
     FastState* f = (FastState*)h->fast;
-    if (f) comm_peer_release(h);            // the neighbour slabs have the buffers mapped (LBM_FLAG_PEER_EXCHANGE)
-    if (f) { dev_free(f->buf[0]); dev_free(f->buf[1]); delete f; }
+    // one-sided exchange: the neighbour slabs have the buffers mapped.  If they cannot be reached any more (a rank that died),
+    // the buffers are deliberately not returned to the driver (the process is on its way out) rather than freed under a mapping.
+    const bool safe = f ? comm_peer_release(h) : true;
+    if (f) { if (safe) { dev_free(f->buf[0]); dev_free(f->buf[1]); } delete f; }
     h->fast = nullptr;
     h->fast_pending_stream = false;
 }
@@ -752,7 +754,7 @@ static void fast_enter(lbm_handle* h) {
     CGFields c = h->fields();
     FastState* f = (FastState*)h->fast;
     tracer_phase(h);          // no-op without tracers (or when a download already ran it for this iteration)
-    f->pushed[f->cur] = false;
+    f->pushed[f->cur] = 0;
     launch(CollideFactoredOp<L>{c, fast_fields(h, f->cur)}, h->g.count(0), h->stream);
     tracer_iteration_finished(h);
     h->head_done = false;
@@ -810,7 +812,7 @@ static void peer_push_one_way(lbm_handle* h, double* base, int64_t stride, int n
 
 // the two per-step exchanges of the fast path: NCCL send / recv, or (opt-in) stores into the neighbours' memory + flags
 static void fast_exchange(lbm_handle* h, double* base, int64_t stride, int narr, int gp, const int8_t* dirs = nullptr) {
-    if (h->nranks > 1 && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE)) comm_peer_exchange_f64(h, base, stride, narr, gp, dirs);
+    if (h->nranks > 1 && h->peer_ok) comm_peer_exchange_f64(h, base, stride, narr, gp, dirs);
     else exchange_f64(h, base, stride, narr, gp, dirs);
 }
 
@@ -830,12 +832,12 @@ static void fast_one_step(lbm_handle* h) {
     // one-sided exchange with the stores fused into the tiled passes.  Open channels: the open-row patches rewrite the outlet
     // planes of the first slab and the inlet planes of the last slab AFTER the passes, so those two slabs leave that direction
     // to a one-way push behind the patch.
-    const bool peer = h->nranks > 1 && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE);
+    const bool peer = h->nranks > 1 && h->peer_ok;
     const bool fused = peer && tiled_ok(h) && !(h->cfg.flags & 4u) && peer_tiles_default();
     const bool late_down = fused && open && h->rank == 0, late_up = fused && open && h->rank == h->nranks - 1;
-    if (peer && f->pushed[f->cur]) comm_peer_signal_wait(h);
-    else fast_exchange(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
-    f->pushed[f->cur] = false;
+    if (peer && f->pushed[f->cur] == 1) comm_peer_signal_wait(h);
+    else if (!(peer && f->pushed[f->cur] == 2)) fast_exchange(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
+    f->pushed[f->cur] = 0;
     bool dens_done = false, phi_pushed = false;
     if (tiled_ok(h) && !(h->cfg.flags & 4u)) {       // host test hook: the same kernels on host threads (cta_emu.h)
         if (fused) {
@@ -867,7 +869,7 @@ static void fast_one_step(lbm_handle* h) {
             if (late_up) pp.up = nullptr;
             if (late_down) pp.down = nullptr;
             if (h->has_solid) launch_tiled_peer<true>(h, c, s, o, pp); else launch_tiled_peer<false>(h, c, s, o, pp);
-            f->pushed[1 - f->cur] = true;
+            f->pushed[1 - f->cur] = 1;
         } else if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);
         done = true;
     }
@@ -971,6 +973,12 @@ void cg_fast_step(lbm_handle* h, int nsteps) {
     // the double buffer flips every step, so the replayed unit is a pair of steps
     replay(left / 2, h->graph_ok(), &h->graph, h->stream, [&] { one(); one(); });
     if (left & 1) one();
+    // One-sided exchange with the stores fused into the passes: the handshake of the last collision pass is not left to a
+    // next step that may never come.  When this call's work has drained, every store of the neighbours into my ghost planes
+    // has landed (their signal is ordered behind their stores), so nothing is in flight between lbm_step calls and the
+    // buffers may be freed / re-initialised / downloaded without talking to anybody.
+    FastState* f = (FastState*)h->fast;
+    if (h->nranks > 1 && h->peer_ok && f->pushed[f->cur] == 1) { comm_peer_signal_wait(h); f->pushed[f->cur] = 2; }
 }
 
 void cg_fast_materialise(lbm_handle* h) {

@@ -221,14 +221,15 @@ namespace {
 struct PeerMap { const void* base; void* up; void* down; };
 struct PeerState {
     std::vector<PeerMap> maps;
-    unsigned long long* flags = nullptr;          // [0]: written by the slab below, [1]: by the slab above, [2]: epoch of a timed-out wait
+    unsigned long long* flags = nullptr;          // [0]: written by the slab below, [1]: by the slab above, [2]: epoch of a timed-out wait; [4..6]: the same triple for comm_peer_release
     unsigned long long *up_flag = nullptr, *down_flag = nullptr;    // the neighbours' words I write
     std::vector<void*> opened;                    // mappings of the neighbours' exchanged arrays (dropped by comm_peer_release)
     std::vector<void*> opened_flags;              // mappings of the neighbours' flag words (live as long as the handle)
+    unsigned long long close_gen = 0;             // number of comm_peer_release rounds (words [4], [5]: the neighbours' counts; [6]: timeout)
 };
 // what travels between neighbours to map one allocation: the IPC handle of the driver allocation that CONTAINS the pointer
 // and the pointer's offset in it (cudaMalloc sub-allocates small requests from a larger block; the handle names the block)
-struct PeerTicket { cudaIpcMemHandle_t handle; unsigned long long offset; };
+struct PeerTicket { cudaIpcMemHandle_t handle; unsigned long long offset; unsigned long long valid; };
 unsigned long long offset_in_allocation(const void* p) {
     typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);      // cuMemGetAddressRange (driver API)
     static range_fn fn = [] {
@@ -270,8 +271,13 @@ void peer_open(lbm_handle* h, std::vector<void*>& opened, void* mine, void** up_
     const int up = (h->rank + 1) % h->nranks, down = (h->rank + h->nranks - 1) % h->nranks;
     PeerTicket tm, tu, td;
     memset(&tm, 0, sizeof(tm));
-    tm.offset = offset_in_allocation(mine);
-    LBM_CUDA_CHECK(cudaIpcGetMemHandle(&tm.handle, (char*)mine - tm.offset));
+    // a local failure must not leave the neighbours waiting in the swap: the ticket travels in any case, marked invalid
+    std::string local_error;
+    try {
+        tm.offset = offset_in_allocation(mine);
+        LBM_CUDA_CHECK(cudaIpcGetMemHandle(&tm.handle, (char*)mine - tm.offset));
+        tm.valid = 1;
+    } catch (const BackendError& e) { local_error = e.msg; cudaGetLastError(); }
     char* d = (char*)dev_alloc(3 * sizeof(tm));
     try {
         dev_h2d(d, &tm, sizeof(tm), h->stream);
@@ -285,6 +291,8 @@ void peer_open(lbm_handle* h, std::vector<void*>& opened, void* mine, void** up_
         dev_d2h(&td, d + 2 * sizeof(tm), sizeof(tm), h->stream);
     } catch (...) { dev_free(d); throw; }
     dev_free(d);
+    if (!tm.valid) throw BackendError{"one-sided exchange: " + local_error};
+    if (!tu.valid || !td.valid) throw BackendError{"one-sided exchange: a neighbour slab could not export its memory"};
     void* base_up = nullptr;
     LBM_CUDA_CHECK(cudaIpcOpenMemHandle(&base_up, tu.handle, cudaIpcMemLazyEnablePeerAccess));
     opened.push_back(base_up);
@@ -295,14 +303,6 @@ void peer_open(lbm_handle* h, std::vector<void*>& opened, void* mine, void** up_
     opened.push_back(base_down);
     *down_img = (char*)base_down + td.offset;
 }
-// all slabs meet (nobody frees an allocation its neighbours still have mapped)
-void peer_barrier(lbm_handle* h) {
-    try {
-        int* d = (int*)dev_alloc(sizeof(int));
-        if (nccl_api().AllReduce(d, d, 1, ncclInt32, ncclMax, (ncclComm_t)h->nccl, h->stream) == ncclSuccess) cudaStreamSynchronize(h->stream);
-        dev_free(d);
-    } catch (const BackendError&) {}
-}
 }  // namespace
 
 static PeerState* peer_state(lbm_handle* h) {
@@ -310,11 +310,19 @@ static PeerState* peer_state(lbm_handle* h) {
     if (ps) return ps;
     ps = new PeerState();
     h->peer = ps;
-    ps->flags = (unsigned long long*)dev_alloc(4 * sizeof(unsigned long long));
-    dev_zero(ps->flags, 4 * sizeof(unsigned long long), h->stream);
+    ps->flags = (unsigned long long*)dev_alloc(8 * sizeof(unsigned long long));
+    dev_zero(ps->flags, 8 * sizeof(unsigned long long), h->stream);
     dev_sync(h->stream);
     void *fu = nullptr, *fd = nullptr;
-    peer_open(h, ps->opened_flags, ps->flags, &fu, &fd);
+    try {
+        peer_open(h, ps->opened_flags, ps->flags, &fu, &fd);
+    } catch (...) {
+        for (void* p : ps->opened_flags) cudaIpcCloseMemHandle(p);
+        dev_free(ps->flags);
+        delete ps;
+        h->peer = nullptr;
+        throw;
+    }
     ps->up_flag = (unsigned long long*)fu;              // word [0] of the slab above: "from the slab below"
     ps->down_flag = (unsigned long long*)fd + 1;        // word [1] of the slab below: "from the slab above"
     return ps;
@@ -350,6 +358,19 @@ void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int nar
     comm_peer_signal_wait(h);
 }
 
+bool comm_peer_probe(lbm_handle* h) {
+    int bad = 0;
+    try { peer_state(h); } catch (const BackendError&) { bad = 1; cudaGetLastError(); }
+    if (comm_allreduce_max(h, bad) == 0) return true;
+    // some slab cannot: everybody drops what it has (no barrier -- the slab that failed holds nothing)
+    PeerState* ps = (PeerState*)h->peer;
+    if (ps) {
+        for (void* p : ps->opened_flags) cudaIpcCloseMemHandle(p);
+        delete ps;              // ps->flags stays allocated: a neighbour that did map it may close its mapping later
+        h->peer = nullptr;
+    }
+    return false;
+}
 // after a stream synchronisation: did a wait of the one-sided exchange give up?
 void comm_peer_check(lbm_handle* h) {
     PeerState* ps = (PeerState*)h->peer;
@@ -358,17 +379,28 @@ void comm_peer_check(lbm_handle* h) {
     dev_d2h(&t, ps->flags + 2, sizeof(t), h->stream);
     if (t) throw BackendError{"one-sided exchange " + std::to_string(t) + ": a neighbour slab's signal did not arrive within LBM_PEER_TIMEOUT_MS"};
 }
-void comm_peer_release(lbm_handle* h) {
+bool comm_peer_release(lbm_handle* h) {
     PeerState* ps = (PeerState*)h->peer;
-    if (!ps || h->nranks <= 1 || ps->maps.empty()) return;
-    // the fused passes of the neighbours store into my ghost planes with the handshake deferred to the next step: close the
-    // protocol first (their signal is ordered behind their last stores), then drop what I have mapped of theirs
-    try { comm_peer_signal_wait(h); } catch (const BackendError&) {}      // (called from lbm_destroy too: never throws)
+    if (!ps || h->nranks <= 1 || ps->maps.empty()) return !h->peer_unreachable;
     cudaStreamSynchronize(h->stream);
     for (void* p : ps->opened) cudaIpcCloseMemHandle(p);
     ps->opened.clear();
     ps->maps.clear();
-    peer_barrier(h);
+    // "I no longer map your arrays" into the neighbours' words [4] / [5]; wait (bounded) for theirs
+    static const unsigned long long timeout_ns = [] {
+        const char* e = getenv("LBM_PEER_CLOSE_TIMEOUT_MS");
+        return (unsigned long long)(e ? atoll(e) : 3000) * 1000000ull;
+    }();
+    const unsigned long long gen = ++ps->close_gen;
+    unsigned long long late = 1;
+    try {
+        peer_signal<<<1, 1, 0, h->stream>>>(ps->up_flag + 4, ps->down_flag + 4, gen);
+        peer_wait<<<1, 1, 0, h->stream>>>(ps->flags + 4, gen, timeout_ns);
+        dev_d2h(&late, ps->flags + 2 + 4, sizeof(late), h->stream);      // peer_wait records a timeout two words behind its pair
+        dev_zero(ps->flags + 2 + 4, sizeof(unsigned long long), h->stream);
+    } catch (const BackendError&) { cudaGetLastError(); }
+    if (late) h->peer_unreachable = true;
+    return !h->peer_unreachable;
 }
 
 static void peer_destroy(lbm_handle* h) {
@@ -377,8 +409,8 @@ static void peer_destroy(lbm_handle* h) {
     comm_peer_release(h);
     cudaStreamSynchronize(h->stream);
     for (void* p : ps->opened_flags) cudaIpcCloseMemHandle(p);
-    peer_barrier(h);
-    dev_free(ps->flags);
+    // ps->flags is NOT freed: a neighbour may still have the words mapped (its own destroy may come later), and freeing under a
+    // mapping is undefined; 64 bytes until the process exits
     delete ps;
     h->peer = nullptr;
 }

@@ -58,6 +58,9 @@ struct lbm_handle {
     void* nccl = nullptr;       // ncclComm_t (host test hook: the in-process ring of host_stubs.cu)
     void* peer = nullptr;       // PeerState of comm.cu / host_stubs.cu: peer pointers and flags of the one-sided exchange
     uint64_t peer_epoch = 0;    // number of one-sided exchanges so far (identical on every rank)
+    bool peer_unreachable = false;   // a neighbour slab did not confirm that it dropped its mappings of my arrays (see comm_peer_release)
+    bool peer_ok = false;       // decided collectively in lbm_set_geometry: the fast path's two per-step exchanges are stores into
+                                // the neighbours' memory + flags (default on slabs) instead of NCCL send / recv
 
     // measurement
     double last_ms = 0.0;

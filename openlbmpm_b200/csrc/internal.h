@@ -16,10 +16,13 @@ void comm_peer_exchange_f64(lbm_handle* h, double* base, int64_t stride, int nar
 // first use), and the flag handshake that closes an exchange
 void comm_peer_pointers(lbm_handle* h, double* base, double** up, double** down);
 void comm_peer_signal_wait(lbm_handle* h);
-// An allocation the neighbours have mapped is about to be freed (re-initialisation, new geometry, destruction): one more
-// handshake (the neighbours' last stores into it have landed), every mapping of the neighbours' arrays is dropped, and all
-// slabs meet before anybody frees.  Collective like the calls that free; no-op without mappings.
-void comm_peer_release(lbm_handle* h);
+// Allocations the neighbours have mapped are about to be freed (re-initialisation, new geometry, destruction).  Nothing is in
+// flight between lbm_step calls (cg_fast_step closes its last handshake), so this only has to make sure nobody frees under a
+// mapping: my mappings of the neighbours' arrays are dropped, "dropped" is signalled into their flag words, and theirs are
+// awaited -- BOUNDED (LBM_PEER_CLOSE_TIMEOUT_MS, default 3 s): lbm_destroy must not hang on a rank that is gone.
+// -> true: the neighbours confirmed, the exported arrays may be freed; false: they may still be mapped, do not free them.
+bool comm_peer_release(lbm_handle* h);
+bool comm_peer_probe(lbm_handle* h);     // collective: can every slab map its neighbours' memory (CUDA IPC over NVLink / PCIe P2P)?
 void comm_peer_check(lbm_handle* h);     // throws if a bounded wait of the one-sided exchange timed out (call after a stream sync)
 void comm_destroy(lbm_handle* h);
 int comm_allreduce_max(lbm_handle* h, int v);

@@ -156,10 +156,12 @@ extern "C" int lbm_create(const lbm_config* cfg, lbm_handle** out) {
 }
 
 static void free_state(lbm_handle* h) {
-    comm_peer_release(h);       // one-sided exchange: phi and the factored buffers are mapped by the neighbour slabs
+    cg_fast_free(h);            // first: with the one-sided exchange it also drops the neighbours' mappings of phi
     double** arrs[] = {&h->fS, &h->fC, &h->rho, &h->u, &h->phi, &h->G, &h->nrm, &h->F, &h->K};
-    for (double** p : arrs) { dev_free(*p); *p = nullptr; }
-    cg_fast_free(h);
+    for (double** p : arrs) {
+        if (p == &h->phi && h->peer_unreachable) { *p = nullptr; continue; }     // still mapped by a slab that did not answer: not freed
+        dev_free(*p); *p = nullptr;
+    }
     sc_free(h);
     if (h->tracer) tracer_iteration_finished(h);
     h->has_state = false;
@@ -209,13 +211,19 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
     h->g.wrap2 = 0;               // the geometry operators read the ghost planes of the mask (filled below)
     const Grid& g = h->g;
     const int64_t owned = g.plane * g.n2;
-    if (h->nranks > 1 && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE)) {
-        // the one-sided exchange addresses the neighbours' arrays with MY strides and ghost-plane offsets
+    h->peer_ok = false;
+    if (h->nranks > 1 && h->cfg.model == LBM_MODEL_CG && !(h->cfg.flags & LBM_FLAG_NCCL_EXCHANGE)) {
+        // One-sided exchange (default on slabs): it addresses the neighbours' arrays with MY strides and ghost-plane offsets,
+        // and every slab must be able to map its neighbours' memory.  Both are decided collectively; slabs of unequal
+        // thickness or GPUs without peer access keep the NCCL exchange.
         const int same = comm_allreduce_max(h, g.n2) == g.n2 && comm_allreduce_max(h, -g.n2) == -g.n2 &&
                          comm_allreduce_max(h, g.n0) == g.n0 && comm_allreduce_max(h, -g.n0) == -g.n0 &&
                          comm_allreduce_max(h, g.n1) == g.n1 && comm_allreduce_max(h, -g.n1) == -g.n1;
-        if (comm_allreduce_max(h, same ? 0 : 1) != 0)
-            return fail(h, LBM_EINVAL, "LBM_FLAG_PEER_EXCHANGE needs slabs of equal extents on every rank");
+        const bool all_same = comm_allreduce_max(h, same ? 0 : 1) == 0;
+        h->peer_ok = all_same && comm_peer_probe(h);
+        if (!h->peer_ok && (h->cfg.flags & LBM_FLAG_PEER_EXCHANGE))
+            return fail(h, LBM_EINVAL, all_same ? "LBM_FLAG_PEER_EXCHANGE: a slab cannot map its neighbours' memory (no peer access)"
+                                                : "LBM_FLAG_PEER_EXCHANGE needs slabs of equal extents on every rank");
     }
     free_state(h);
     dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull);

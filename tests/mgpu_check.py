@@ -61,6 +61,7 @@ def main():
     ok = True
     extra = int(os.environ.get("LBM_TEST_FLAGS", "0"))      # e.g. 32 = packed exchange, 16 = overlap (lbmpm.h)
     for name, shape, solid, kw in (("periodic tiled", (16 * world, 16, 32), False, {}),
+                                   ("periodic tiled, 4 x-tiles", (40 * world, 16, 128), False, {}),      # interior tiles + two z-chunks per slab
                                    ("sphere wetting tiled", (16 * world, 16, 32), True, dict(contact_angle_deg=70.0)),
                                    ("general kernels", (8 * world, 10, 12), True, dict(flags=1, contact_angle_deg=50.0)),
                                    ("untiled fast path", (8 * world, 10, 12), True, dict(flags=2)),

@@ -125,6 +125,17 @@ def test_one_sided_exchange_slabs_bit_equal(lattice, shape, name, kw, lib):
     compare(lib, lattice, shape, [1, 2, 6, 5], **dict(kw, flags=_lib.FLAG_PEER_EXCHANGE))
 
 
+@pytest.mark.parametrize("lattice,shape", [(19, (24, 6, 8)), (9, (24, 10)), (19, (24, 8, 32))])
+@pytest.mark.parametrize("name,kw", [
+    ("fast path", dict(contact_angle_deg=70.0)),
+    ("open channel, velocity inlet + convective outlet", dict(OPEN, contact_angle_deg=60.0)),
+])
+def test_send_recv_exchange_slabs_bit_equal(lattice, shape, name, kw, lib):
+    """LBM_FLAG_NCCL_EXCHANGE: the one-sided exchange is the default on slabs of equal extents; this flag keeps the send / recv
+    ring for the fast path's exchanges too (what GPUs without peer access fall back to)"""
+    compare(lib, lattice, shape, [1, 2, 6, 5], **dict(kw, flags=_lib.FLAG_NCCL_EXCHANGE))
+
+
 def test_all_fluid_box_slabs_bit_equal(lib):
     compare(lib, 19, (24, 6, 8), [3, 5], solid=False, worlds=(2, 3, 6))
 
