@@ -102,12 +102,48 @@ def cpu_oracle_mlups(lattice, n, steps, threads=None):
     return nodes * steps / dt / 1e6, threads, dt
 
 
+def reference_numba_cfg(cfg, scale, steps, warmup, target="cpu"):
+    """BASELINE configurations 1..3 through the UNMODIFIED reference (its drivers and Numba kernels from baseline/_ref, the
+    kernels re-targeted to numba.njit(parallel) on the host cores: oracle/ref_numba.py).  -> (MLUPS, ms per step, description)"""
+    from oracle import ref_numba
+    from openlbmpm_b200 import synthetic
+    dom, reg = synthetic.baseline_inputs_2d(cfg, scale)
+    ny, nx = dom.shape
+    total = warmup + steps + 1
+    if cfg == 2:
+        out = ref_numba.run_cg2d(nx, ny, total, target=target, dom=dom, red=reg)
+    elif cfg == 1:
+        out = ref_numba.run_sc2d(nx, ny, total, target=target, model="ShanChen", dom=dom, region0=reg)
+    else:
+        out = ref_numba.run_sc2d(nx, ny, total, target=target, model="EFS", dom=dom, region0=reg,
+                                 par=dict(relax="MRT", G=0.2, Gs0=-0.14, Gs1=0.14, inlet="Neumann", outlet="Dirichlet", vy1=-5.03e-4,
+                                          bg0=0.02, bg1=0.02))
+    dt = np.asarray(out["step_seconds"])[-steps:]          # the first iterations carry the JIT compilation
+    ms = float(dt.mean()) * 1e3
+    what = ("the reference's own driver (%s) and Numba kernels, unmodified, kernels re-targeted from cuda.jit to numba.njit(parallel) over "
+            "all threads of each launch (oracle/ref_numba.py), %d x %d, %d timed iterations after %d" % (
+                {1: "ShanChenD2Q9.runOptimizedLBM", 2: "RKColorGradientLBM.runRKColorGradient2DCSF", 3: "ShanChenD2Q9.runOptimizedEFLBM"}[cfg],
+                nx, ny, len(dt), total - 1 - len(dt)))
+    return out["n_fluid"] / (ms * 1e-3) / 1e6, ms, what, out["n_fluid"]
+
+
 def run_reference(args):
     """CPU arm.  A "step" here is one time step of the SAMPLE box (--cpu-size, default 256^3: the 512^3 box of the metric
     needs ~120 GB in the reference's kernel-per-phase AoS layout and 10 s per step); W untimed steps, then exactly K timed
     ones, each timed on its own.  MLUPS is size-normalised; the sample that ran is named at the top level of the line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload in ("cfg1", "cfg2", "cfg3"):
+        cfg = int(args.workload[3:])
+        cores = os.cpu_count()
+        v, ms, what, nodes = reference_numba_cfg(cfg, args.scale, max(1, args.steps), max(1, args.warmup))
+        print(json.dumps({"impl": "reference", "metric": "MLUPS (void nodes) BASELINE config %d" % cfg, "value": v, "unit": "MLUPS",
+                          "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, args.warmup), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "BASELINE configuration %d" % cfg, "sample": what, "void_nodes": nodes},
+                          "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": cores, "kind": "reference", "sample": what},
+                          "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     lattice = args.lattice
     n = args.cpu_size if lattice == 19 else args.size
@@ -355,6 +391,12 @@ def main():
             pass
 
     cpu = None
+    if not args.no_cpu and world == 1 and cfg in (1, 2, 3):
+        try:       # the reference itself on the host cores, same configuration and size (bounded: a few dozen iterations)
+            v, ms, what, _ = reference_numba_cfg(cfg, args.scale, 20 if cfg != 1 else 200, 5)
+            cpu = {"value": v, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "reference", "sample": what, "ms_per_step": ms}
+        except Exception as e:
+            cpu = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: %r" % (e,)}
     if not args.no_cpu and world == 1 and not porous:
         try:
             v, cores, dt = cpu_oracle_mlups(Q, args.cpu_size, args.cpu_steps)

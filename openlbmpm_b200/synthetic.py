@@ -48,6 +48,29 @@ def disc_pack(shape, seed=7, porosity=0.6, rmin=6.0, rmax=14.0, buffer_rows=40):
         dom[y0:y1, x0:x1] &= ((xx - cx) ** 2 + (yy - cy) ** 2) > r * r
 
 
+def baseline_inputs_2d(k, scale=1.0):
+    """void mask and initial region of the 2-D BASELINE configurations (1: droplet of fluid 0; 2: red band at the inlet;
+    3: fluid 0 below the inlet band), shared by the engine set-up below and by bench.py's reference arm"""
+    def ext(n):
+        return max(1, int(round(n * scale)))
+    if k == 1:
+        n = ext(128)
+        yy, xx = np.mgrid[0:n, 0:n]
+        return np.ones((n, n), bool), (xx - n / 2) ** 2 + (yy - n / 2) ** 2 <= (20 * n / 128.0) ** 2
+    if k == 2:
+        n = ext(512)
+        dom = np.ones((n, n), bool)
+        b = max(2, int(round(10 * scale)))
+        dom[b:-b, 0] = False; dom[b:-b, -1] = False
+        return dom, np.indices((n, n))[0] >= n - 2 * b
+    if k == 3:
+        n = ext(1024)
+        dom = disc_pack((n, n), buffer_rows=max(6, int(round(40 * scale))), rmin=max(2.0, 6.0 * min(1.0, 4 * scale)),
+                        rmax=max(4.0, 14.0 * min(1.0, 4 * scale)))
+        return dom, np.indices((n, n))[0] < n - max(4, int(round(10 * scale)))
+    raise ValueError("2-D configurations are 1..3")
+
+
 def baseline_config(k, scale=1.0, lib_path=None, device=0, flags=0):
     """Engine + initial state of BASELINE.json configuration `k` (1..5), lattice extents multiplied
     by `scale` (tests run them small).  -> (engine, number of void nodes, description).  Single slab; the slab-decomposed
@@ -57,21 +80,16 @@ def baseline_config(k, scale=1.0, lib_path=None, device=0, flags=0):
     def ext(n, multiple=1):
         return max(multiple, int(round(n * scale / multiple)) * multiple)
     if k == 1:      # D2Q9 original Shan-Chen, 128 x 128 periodic droplet (IniFiles/shanchen2D.ini)
-        n = ext(128)
-        yy, xx = np.mgrid[0:n, 0:n]
-        reg = (xx - n / 2) ** 2 + (yy - n / 2) ** 2 <= (20 * n / 128.0) ** 2
-        dom = np.ones((n, n), bool)
+        dom, reg = baseline_inputs_2d(1, scale)
+        n = dom.shape[0]
         eng = _lib.Engine(9, (n, n), model=_lib.MODEL_SC, relax=_lib.RELAX_SRT, n_components=2, sc_tau=[1.0, 1.0],
                           sc_G=[0, 3.8, 0, 0, 3.8, 0], sc_Gsolid=[-0.4, 0.4], lib_path=lib_path, device=device, flags=flags)
         eng.set_geometry(dom)
         eng.init_equilibrium(np.where(reg, 1.0, 0.06), np.where(reg, 0.06, 1.0))
         return eng, float(dom.sum()), "cfg 1: D2Q9 original Shan-Chen, %d x %d periodic droplet" % (n, n)
     if k == 2:      # D2Q9 CSF colour-gradient MRT, 512 x 512 capillary intrusion (RKtwophasesetup2D.ini)
-        n = ext(512)
-        dom = np.ones((n, n), bool)
-        b = max(2, int(round(10 * scale)))
-        dom[b:-b, 0] = False; dom[b:-b, -1] = False
-        red = np.indices((n, n))[0] >= n - 2 * b
+        dom, red = baseline_inputs_2d(2, scale)
+        n = dom.shape[0]
         eng = _lib.Engine(9, (n, n), relax=_lib.RELAX_MRT, sigma=0.1, contact_angle_deg=60.0, wetting_type=2, beta=0.7,
                           delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_PRESSURE,
                           inlet_velocity=-1.0e-4, rhoBL=1.0, rhoRL=5e-8, lib_path=lib_path, device=device, flags=flags)
@@ -79,10 +97,8 @@ def baseline_config(k, scale=1.0, lib_path=None, device=0, flags=0):
         eng.init_equilibrium(np.where(red, 1.0, 5e-8) * dom, np.where(red, 5e-8, 1.0) * dom)
         return eng, float(dom.sum()), "cfg 2: D2Q9 colour-gradient CSF MRT, %d x %d capillary intrusion, velocity inlet, pressure outlet" % (n, n)
     if k == 3:      # D2Q9 explicit-forcing Shan-Chen MRT, 1024 x 1024 porous drainage (efs2D.ini)
-        n = ext(1024)
-        dom = disc_pack((n, n), buffer_rows=max(6, int(round(40 * scale))), rmin=max(2.0, 6.0 * min(1.0, 4 * scale)),
-                        rmax=max(4.0, 14.0 * min(1.0, 4 * scale)))
-        reg = np.indices((n, n))[0] < n - max(4, int(round(10 * scale)))
+        dom, reg = baseline_inputs_2d(3, scale)
+        n = dom.shape[0]
         eng = _lib.Engine(9, (n, n), model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, n_components=2, sc_tau=[1.0, 1.0],
                           sc_G=[0, 0.2, 0, 0, 0.2, 0], sc_Gsolid=[-0.14, 0.14], inlet=_lib.INLET_VELOCITY,
                           outlet=_lib.OUTLET_PRESSURE, sc_inlet_velocity=[0.0, -5.03e-4], sc_rho_out=[1.0, 0.02],

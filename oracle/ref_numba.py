@@ -400,6 +400,8 @@ def run_cg2d(nx, ny, steps, target="cpu", dom=None, red=None, minor=5e-8, interv
         fh.write(CG_INI.format(**p))
     t_all = time.perf_counter()
     sink = io.StringIO()
+    keep_input = builtins.input
+    builtins.input = lambda *a, **k: ""          # the drivers pause for a key press (RKD2Q9.py:174)
     try:
         with contextlib.redirect_stdout(sink):
             sim = Ref(tmp)
@@ -407,8 +409,159 @@ def run_cg2d(nx, ny, steps, target="cpu", dom=None, red=None, minor=5e-8, interv
             t_setup = time.perf_counter() - t_all
             sim.runRKColorGradient2DCSF()
     finally:
+        builtins.input = keep_input
         rk.calRecoloringProcessM = orig
         shutil.rmtree(tmp, ignore_errors=True)
     dt = np.diff(np.array(stamps))
     return dict(snapshots=sim.snapshots, step_seconds=dt, setup_seconds=t_setup, total_seconds=time.perf_counter() - t_all,
                 n_fluid=int(sim.fluidNodes.size), kernels={k: tuple(v) for k, v in CpuKernel.launches.items()}, sim=sim)
+
+
+SC_BASIC = """
+[Scheme]
+Type = 'SRT'
+[Geometry]
+length = 1.0
+width = 1.0
+nx = {nx}
+ny = {ny}
+[Time]
+TimeLength = 1.0
+TimeStep = 1.0
+[InitialCondition]
+VelocityXLB = 0.0
+VelocityYLB = 0.0
+[BodyForce]
+gValue = 0.0
+[FlowDomain]
+xDomain = 0,{nx}
+yDomain = 0,{ny}
+"""
+SC_TWOPHASE = """
+[PictureSetup]
+Exist = 'no'
+[SeparationBorder]
+xGrid = {nx}
+yGrid = {ny}
+[FluidsTypes]
+NumberOfFluids = 2
+[InterType]
+InteractionType = '{model}'
+[Parallelism]
+Parallel = 'yes'
+xDimension = {xdim}
+ThreadsNum = 32
+[RelaxationType]
+Type = '{relax}'
+[DuplicateDomain]
+Option = 'no'
+[DICycles]
+Option = 'no'
+"""
+SC_MODEL = """
+[FluidProperties]
+InitialDensities = {rho0},{rho1}
+BackgroundDensities = {bg0},{bg1}
+FluidsTau = {tau0},{tau1}
+[{section}]
+InteractionFluid = {G}
+InteractionSolid = {Gs0},{Gs1}
+[ForceScheme]
+ExplicitScheme = {scheme}
+[BoundaryDefinition]
+BoundaryTypeInlet = '{inlet}'
+BoundaryMethod = 'ZouHe'
+BoundaryTypeOutlet = '{outlet}'
+[VelocityBoundary]
+velocityX = 0.0,0.0
+velocityY = {vy0},{vy1}
+[PressureBoundary]
+PressureInlet = 1.0,0.06
+PressureOutlet = 1.0,0.06
+[BodyForce]
+Option = 'no'
+[Time]
+numberTimeStep = {steps}
+"""
+
+
+def run_sc2d(nx, ny, steps, target="cpu", model="ShanChen", dom=None, region0=None, par=None, keep_states=False):
+    """BASELINE configurations 1 (model 'ShanChen': `runOptimizedLBM`, ShanChenD2Q9.py:1433-1629) and 3 (model 'EFS':
+    `runOptimizedEFLBM`, :1631-2087) through the reference's own driver.  The loops run `steps + 1` iterations.
+    -> dict(step_seconds (per iteration, from the launches of `calPhysicalVelocity`, the last kernel of an iteration), states)"""
+    ns = load(target)
+    SC = ns.SC
+    p = dict(relax="SRT", rho0=1.0, rho1=1.0, bg0=0.06, bg1=0.06, tau0=1.0, tau1=1.0, G=3.8, Gs0=-0.4, Gs1=0.4, inlet="Periodic",
+             outlet="Periodic", vy0=0.0, vy1=-1.0e-3, steps=steps, scheme=4, nx=nx, ny=ny, model=model,
+             xdim=128 if nx * ny >= 128 * 32 else 32)
+    p.update(par or {})
+    p["section"] = "ShanChenParameters" if model == "ShanChen" else "EFSParameters"
+    if dom is None:
+        dom = np.ones((ny, nx), bool)
+    if region0 is None:        # shanchen2D.ini's droplet of fluid 0
+        yy, xx = np.mgrid[0:ny, 0:nx]
+        region0 = (xx - nx // 2) ** 2 + (yy - ny // 2) ** 2 <= (min(nx, ny) * 20 // 128) ** 2
+    SC.defineGeometry = lambda x, y: (dom.copy(), ~dom)
+
+    class Ref(SC.ShanChenD2Q9):
+        def _ShanChenD2Q9__createHDF5File(self):
+            pass
+
+        def plotDensityDistributionOPT(self, *a, **k):
+            pass
+
+        def plotPhysicalVelocity(self, *a, **k):
+            pass
+
+        def resultInHDF5(self, *a, **k):
+            pass
+
+        def initializeDomainCondition(self):
+            # the reference's allocation (ShanChenD2Q9.py:740-745) and rest-equilibrium fill (:759-768) with the case's layout
+            n_y, n_x = self.ny, self.nx
+            d = np.stack([np.where(region0, self.initialDensities[0], self.backgroundDensities[0]),
+                          np.where(region0, self.backgroundDensities[1], self.initialDensities[1])]) * self.isDomain
+            self.fluidsDensity = d.astype(np.float64)
+            self.fluidPDF = self.fluidsDensity[..., None] * np.asarray(self.weightsCoeff)
+            self.physicalVX = np.zeros([n_y, n_x]); self.physicalVY = np.zeros([n_y, n_x])
+            self.forceX = np.zeros([self.typesFluids, n_y, n_x]); self.forceY = np.zeros([self.typesFluids, n_y, n_x])
+
+    stamps, states = [], []
+    real = SC.calPhysicalVelocity
+
+    class Tap:
+        def __getitem__(self, cfg):
+            inner = real[cfg]
+
+            def run(*a):
+                inner(*a)
+                if ns.target == "cuda":
+                    ns.cuda.synchronize()
+                stamps.append(time.perf_counter())
+                if keep_states:      # calPhysicalVelocity(totalNodes, numFluids, xDim, fluidPDF, fluidRho, forceX, forceY, physVX, physVY)
+                    states.append(dict(rho=a[4].copy_to_host(), ux=a[7].copy_to_host(), uy=a[8].copy_to_host()))
+            return run
+    SC.calPhysicalVelocity = Tap()
+    tmp = tempfile.mkdtemp()
+    for fname, text in (("basicsetup.ini", SC_BASIC), ("twophasesetup.ini", SC_TWOPHASE), ("shanchen2D.ini", SC_MODEL), ("efs2D.ini", SC_MODEL)):
+        with open(os.path.join(tmp, fname), "w") as fh:
+            fh.write(text.format(**p))
+    keep_input = builtins.input
+    builtins.input = lambda *a, **k: ""
+    t_all = time.perf_counter()
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim = Ref(tmp)
+            t_setup = time.perf_counter() - t_all
+            if model == "ShanChen":
+                sim.runOptimizedLBM()
+            else:
+                sim.runOptimizedEFLBM()
+    finally:
+        builtins.input = keep_input
+        SC.calPhysicalVelocity = real
+        shutil.rmtree(tmp, ignore_errors=True)
+    if model == "EFS":
+        stamps = stamps[1::2]; states = states[1::2]      # two launches per iteration (:1902 and :2016)
+    return dict(step_seconds=np.diff(np.array(stamps)), states=states, setup_seconds=t_setup, n_fluid=int(sim.fluidNodes.size),
+                total_seconds=time.perf_counter() - t_all, sim=sim, kernels={k: tuple(v) for k, v in CpuKernel.launches.items()})
