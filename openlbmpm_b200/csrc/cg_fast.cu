@@ -119,7 +119,11 @@ struct PeerPtrs {
     double* down;    // ... in the slab below (its high ghost planes receive my bottom planes)
     int gp;          // ghost planes that travel
 };
-template <bool SOLIDS, int TX, int TY, bool TMA, bool PEER = false>
+// AHEAD = how many planes the interface normals run ahead of the collision.  1: the normals of plane z + 1 are derived between
+// two barriers of plane step z (the first measured form: 28 % of all stall samples on those barriers).  2: the normals of
+// plane z + 2 are derived in step z into a ring of FOUR slots, so what the curvature stencil of plane z reads was written one
+// step earlier and a step needs ONE barrier, at its end (LBM_COLLIDE_AHEAD selects; default 2).
+template <bool SOLIDS, int TX, int TY, bool TMA, bool PEER = false, int AHEAD = 2>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
 cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi,
                        const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
@@ -129,8 +133,11 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     constexpr int NW = TX + 2, NH = TY + 2;     // normal tile
     LBM_DYN_SMEM(smem_dyn);
     double (*sphi)[PH][PW] = reinterpret_cast<double (*)[PH][PW]>(smem_dyn);                    // [5]
-    double (*sn)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn + 5 * PH * PW);  // [3][nx, ny, nz, |G|]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + 5 * PH * PW + 3 * 4 * NH * NW);     // [5] one mbarrier per phi slot
+    constexpr int NS = AHEAD + 2;               // slots of the normal ring
+    double (*sn)[4][NH][NW] = reinterpret_cast<double (*)[4][NH][NW]>(smem_dyn + 5 * PH * PW);  // [NS][nx, ny, nz, |G|]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + 5 * PH * PW + NS * 4 * NH * NW);     // [5] one mbarrier per phi slot
+    // SOLIDS: solid normals of the near-solid elements of the normal tile, two plane slots (copied one plane step ahead)
+    double (*sns)[3][NH][NW] = reinterpret_cast<double (*)[3][NH][NW]>(smem_dyn + 5 * PH * PW + NS * 4 * NH * NW + 8);   // [2]
     const Grid& g = c.g;
     const int64_t V = g.vol;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
@@ -181,8 +188,22 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 #pragma unroll
         for (int k = 0; k < NE; ++k) cl[k] = (SOLIDS && noff[k] >= 0) ? c.cls[(int64_t)(zp + NG) * g.plane + noff[k]] : (uint8_t)CLS_FLUID;
     };
-    auto normal_plane = [&](int zp, const uint8_t* cl) {
-        const int slot = (zp + 9) % 3;
+    // solid normals of plane zp -> shared memory (cp.async), for the elements whose class says "fluid next to a solid"
+    auto ns_plane = [&](int zp, const uint8_t* cl) {
+        const int slot = (zp + 8) & 1;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const int e = tid + k * NT;
+            if (e >= NH * NW || (cl[k] & (CLS_FLUID | CLS_NEAR)) != (CLS_FLUID | CLS_NEAR)) continue;
+            const int ly = e / NW, lx = e - ly * NW;
+            const int64_t id = (int64_t)(zp + NG) * g.plane + noff[k];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) __pipeline_memcpy_async(&sns[slot][d][ly][lx], c.ns + d * V + id, 8);
+        }
+    };
+    // STAGED: the solid normals were copied into shared memory one plane step ahead (ns_plane); otherwise they are read here
+    auto normal_plane = [&](int zp, const uint8_t* cl, const bool staged) {
+        const int slot = (zp + 12) % NS;
 #pragma unroll
         for (int k = 0; k < NE; ++k) {
             const int e = tid + k * NT;
@@ -206,7 +227,9 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
                 G[2] = (1.0 / 6.0) * (P(0, 0, 1) - P(0, 0, -1)) +
                        (1.0 / 12.0) * (((pxz - mxz) - (pmxz - mpxz)) + ((pyz - myz) - (pmyz - mpyz)));
                 if (SOLIDS && (cl[k] & CLS_NEAR)) {
-                    const double ns[3] = {c.ns[id], c.ns[V + id], c.ns[2 * V + id]};
+                    const int nsl = (zp + 8) & 1;
+                    const double ns[3] = {staged ? sns[nsl][0][ly][lx] : c.ns[id], staged ? sns[nsl][1][ly][lx] : c.ns[V + id],
+                                          staged ? sns[nsl][2][ly][lx] : c.ns[2 * V + id]};
                     if (c.p.exact_trig || c.p.wetting_type != 2) cg_wetting<3>(G, ns, c.p.cosT, c.p.sinT, c.p.wetting_type);
                     else cg_wetting_akai3_fast(G, ns, c.p.cosT, c.p.sinT);
                 }
@@ -236,27 +259,60 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
         }
         __syncthreads();
     }
-    for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) load_phi_plane(zp);
-    __pipeline_commit();
-    load_phi_plane(z_begin + 2);
-    __pipeline_commit();
-    __pipeline_wait_prior(1);
-    for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) wait_phi_plane(zp);
-    __syncthreads();
-    uint8_t ncl[NE];
-    class_plane(z_begin - 1, ncl);
-    normal_plane(z_begin - 1, ncl);
-    class_plane(z_begin, ncl);
-    normal_plane(z_begin, ncl);
-    // the first asynchronous copy of the loop lands in the slot of plane z_begin - 2, which normal_plane(z_begin - 1)
-    // has just read: every thread must be done with it first (found as a run-to-run difference at 256^3)
-    __syncthreads();
+    // Node classes of the normal tile run two plane steps ahead of their use, in registers (1 byte per element): at plane step z
+    // cl1 = plane z + AHEAD (consumed by normal_plane in this step), cl2 = plane z + AHEAD + 1 (says which solid normals
+    // ns_plane copies in this step), ncl = plane z + AHEAD + 2 (requested in this step).  Before: the class byte and the
+    // normals were loaded where they were used, between the two barriers of a plane step -- 30 % of all stall samples of the
+    // porous workload sat on those two loads.
+    uint8_t ncl[NE], cl1[NE], cl2[NE];
+    if (AHEAD == 1) {
+        for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) load_phi_plane(zp);
+        __pipeline_commit();
+        load_phi_plane(z_begin + 2);
+        class_plane(z_begin + 1, cl1);
+        if (SOLIDS) ns_plane(z_begin + 1, cl1);
+        __pipeline_commit();
+        class_plane(z_begin + 2, cl2);
+        __pipeline_wait_prior(1);
+        for (int zp = z_begin - 2; zp <= z_begin + 1; ++zp) wait_phi_plane(zp);
+        __syncthreads();
+        class_plane(z_begin - 1, ncl);
+        normal_plane(z_begin - 1, ncl, false);
+        class_plane(z_begin, ncl);
+        normal_plane(z_begin, ncl, false);
+        // the first asynchronous copy of the loop lands in the slot of plane z_begin - 2, which normal_plane(z_begin - 1)
+        // has just read: every thread must be done with it first (found as a run-to-run difference at 256^3)
+        __syncthreads();
+    } else {
+        for (int zp = z_begin - 2; zp <= z_begin + 2; ++zp) load_phi_plane(zp);      // all five slots
+        class_plane(z_begin + 2, cl1);
+        if (SOLIDS && z_begin + 2 <= z_end) ns_plane(z_begin + 2, cl1);
+        __pipeline_commit();
+        class_plane(z_begin + 3, cl2);
+        __pipeline_wait_prior(0);
+        for (int zp = z_begin - 2; zp <= z_begin + 2; ++zp) wait_phi_plane(zp);
+        __syncthreads();
+        class_plane(z_begin - 1, ncl);
+        normal_plane(z_begin - 1, ncl, false);
+        __syncthreads();                                // every thread is done with phi(z_begin - 2): its slot takes plane z_begin + 3
+        if (z_begin + 2 <= z_end) load_phi_plane(z_begin + 3);
+        __pipeline_commit();
+        class_plane(z_begin, ncl);
+        normal_plane(z_begin, ncl, false);
+        class_plane(z_begin + 1, ncl);
+        normal_plane(z_begin + 1, ncl, false);
+        __pipeline_wait_prior(0);
+        if (z_begin + 2 <= z_end) wait_phi_plane(z_begin + 3);
+        __syncthreads();
+    }
 
     const double sgn = c.p.wetting_type == 1 ? 1.0 : -1.0;
     uint32_t pm_next = 1u;
     if (SOLIDS) pm_next = c.pull[(int64_t)(z_begin + NG) * g.plane + yo[1] + xo[1]];
     for (int z = z_begin; z < z_end; ++z) {
-        if (z + 1 < z_end) load_phi_plane(z + 3);       // needed by the NEXT plane step
+        const bool more_phi = z + AHEAD + 1 <= z_end;   // the next step derives the normals of plane z + AHEAD + 1
+        if (more_phi) load_phi_plane(z + AHEAD + 2);
+        if (SOLIDS && more_phi) ns_plane(z + AHEAD + 1, cl2);
         __pipeline_commit();
         // ---- requests to HBM first: pulled populations, densities, lagged force ----
         const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
@@ -267,7 +323,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             if (z + 1 < z_end) pm_next = c.pull[id + g.plane];
         }
         const bool fluid = pm & 1u;
-        class_plane(z + 1, ncl);                        // node classes of the normal tile of the next plane
+        if (z + AHEAD + 2 <= z_end) class_plane(z + AHEAD + 2, ncl);     // node classes of the normal tile, two plane steps ahead
         double fT[L::Q];
         double rR = 1.0, rB = 1.0, Fl[3] = {0.0, 0.0, 0.0}, phi0 = 0.0;
         if (fluid) {
@@ -283,12 +339,18 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 #pragma unroll
             for (int d = 0; d < 3; ++d) Fl[d] = c.F[d * V + id];
         }
-        __pipeline_wait_prior(1);                       // plane z + 2 (requested one step ago) has landed
-        wait_phi_plane(z + 2);
-        __syncthreads();
-        normal_plane(z + 1, ncl);
-        __syncthreads();
-        if (!fluid) continue;
+        if (AHEAD == 1) {
+            __pipeline_wait_prior(1);                   // plane z + 2 (requested one step ago) has landed
+            wait_phi_plane(z + 2);
+            __syncthreads();
+            normal_plane(z + 1, cl1, true);
+            __syncthreads();
+        } else if (z + AHEAD <= z_end) {
+            normal_plane(z + AHEAD, cl1, true);         // reads phi up to plane z + AHEAD + 1: landed and published at the end of the last step
+        }
+#pragma unroll
+        for (int k = 0; k < NE; ++k) { cl1[k] = cl2[k]; cl2[k] = ncl[k]; }
+        if (fluid) {
         if (SOLIDS) {
             // The requests above sit in a conditional block; without this fence the compiler sinks the first
             // arithmetic on the loaded values (0.5 * F, the first moment sums) into that block, i.e. in FRONT of the
@@ -304,13 +366,13 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
         }
         phi0 = sphi[(z + 10) % 5][ty + 2][tx + 2];
         // ---- curvature and force from the normals in shared memory ----
-        const int sl = (z + 9) % 3;
+        const int sl = (z + 12) % NS;
         double n[3] = {sn[sl][0][ty + 1][tx + 1], sn[sl][1][ty + 1][tx + 1], sn[sl][2][ty + 1][tx + 1]};
         const double gn = sn[sl][3][ty + 1][tx + 1];
         double dn[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
 #pragma unroll
         for (int q = 1; q < L::Q; ++q) {
-            const int sq = (z + L::d2(q) + 9) % 3;
+            const int sq = (z + L::d2(q) + 12) % NS;
             double nk[3];
 #pragma unroll
             for (int b = 0; b < 3; ++b) nk[b] = sn[sq][b][ty + 1 + L::d1(q)][tx + 1 + L::d0(q)];
@@ -384,6 +446,14 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
 #pragma unroll
                 for (int d = 0; d < 3; ++d) pp.down[(L::Q + 1 + d) * V + gid] = amp * sgn * n[d];
             }
+        }
+        }   // fluid
+        if (AHEAD != 1) {
+            // the copies requested at the top of this step (phi plane, solid normals) have had the whole step to land; after
+            // the barrier they are visible to every thread, and everybody is done with the slots the next step overwrites
+            __pipeline_wait_prior(0);
+            if (more_phi) wait_phi_plane(z + AHEAD + 2);
+            __syncthreads();
         }
     }
 }
@@ -561,30 +631,42 @@ static bool tiled_ok(const lbm_handle* h) {
 
 bool cg_tiled_possible(const lbm_handle* h) { return h->cfg.model == LBM_MODEL_CG && tiled_ok(h); }
 
-template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER = false>
-static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi,
-                           const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
+template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER, int AHEAD>
+static void launch_tiled_a(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi, const PeerPtrs pp) {
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
     if (z_hi <= z_lo) return;
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
-    constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + 3 * 4 * (TILE_Y + 2) * (TILE_X + 2) + 8);
+    constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + (AHEAD + 2) * 4 * (TILE_Y + 2) * (TILE_X + 2) + 8 +
+                                              (SOLIDS ? 2 * 3 * (TILE_Y + 2) * (TILE_X + 2) : 0));
 #ifdef LBM_HOSTCHECK
-    cta_emu::launch(grid, block, smem, [&] { cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER>(c, s, o, zchunk, z_lo, z_hi, pp); });
+    cta_emu::launch(grid, block, smem, [&] { cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD>(c, s, o, zchunk, z_lo, z_hi, pp); });
 #else
     static std::atomic<bool> configured[64];  // per device: the attribute belongs to the function on ONE device (zero-initialised)
     if (!configured[h->cfg.device & 63]) {
-        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER>,
+        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[h->cfg.device & 63] = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tiled_d3q19<solids>" : "cg_collide_tiled_d3q19<all-fluid>", h->stream);
-    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi, pp);
+    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi, pp);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
     ++g_launch_counter;
+}
+
+// normals one plane ahead (two barriers per plane step) or two planes ahead (one barrier): LBM_COLLIDE_AHEAD = 1 | 2
+static int collide_ahead() {
+    static const int a = [] { const int v = env_int("LBM_COLLIDE_AHEAD", 2); return v == 1 ? 1 : 2; }();
+    return a;
+}
+template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER = false>
+static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi,
+                           const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
+    if (collide_ahead() == 1) launch_tiled_a<SOLIDS, TILE_Y, TMA, PEER, 1>(h, c, s, o, z_lo, z_hi, pp);
+    else launch_tiled_a<SOLIDS, TILE_Y, TMA, PEER, 2>(h, c, s, o, z_lo, z_hi, pp);
 }
 
 template <bool SOLIDS>
@@ -860,7 +942,10 @@ static void fast_one_step(lbm_handle* h) {
         if (late_down) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, false);
         comm_peer_signal_wait(h);
     } else fast_exchange(h, c.phi, 0, 1, h->has_solid ? NG : 2);
-    if (h->has_solid && tiled_ok(h)) launch(PhiSolidOp<L>{c}, g.count(2), h->stream);     // the tiled kernel stages phi, solids included
+    if (h->has_solid && tiled_ok(h)) {      // the tiled kernel stages phi, wetting solids included
+        if (h->pull) launch(PhiSolidListOp<L>{c, h->wet_list}, h->n_wet_list, h->stream);
+        else launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
+    }
     bool done = false;
     if (tiled_ok(h)) {
         if (fused) {

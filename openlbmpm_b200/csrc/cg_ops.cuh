@@ -308,6 +308,20 @@ struct PhiSolidOp {
     }
 };
 
+// the same over the compact list of wetting solids (grid.cuh::WetFillOp)
+template <class L>
+struct PhiSolidListOp {
+    CGFields c; const int64_t* list;
+    LBM_HD void operator()(int64_t i) const {
+        const Grid& g = c.g;
+        const int64_t id = list[i];
+        const int z = (int)(id / g.plane) - NG;
+        const int r = (int)(id % g.plane);
+        const int y = r / g.n0, x = r - y * g.n0;
+        c.phi[id] = cg_phi_on_solid<L>(c, x, y, z);
+    }
+};
+
 // calRKInitialGradient (1582-1632) + updateColorGradientOnWetting[New] (1637-1679 / 2428-2492) and the
 // unit normal that the curvature stencil gathers; planes [-1, n2+1)
 template <class L>

@@ -177,6 +177,30 @@ struct PullMaskOp {
     }
 };
 
+// ---- compact list of the wetting-solid nodes of planes [-2, n2 + 2), grouped by plane ------------------------------
+// (the tiled kernels stage phi with bulk copies, so the colour a wetting solid shows has to be IN the phi array; evaluating it
+// over a list of the few per cent of nodes that are wetting solids replaces a pass over the whole lattice)
+LBM_HD int64_t lbm_atomic_inc(int64_t* p) {
+#ifdef __CUDA_ARCH__
+    return (int64_t)atomicAdd((unsigned long long*)p, 1ull);
+#else
+    return (*p)++;
+#endif
+}
+struct WetCountOp {      // counts[plane + 2] += 1 for every wetting solid; item = node of planes [-2, n2 + 2)
+    Grid g; const uint8_t* cls; int64_t* counts;
+    LBM_HD void operator()(int64_t i) const {
+        if (cls[(int64_t)(NG - 2) * g.plane + i] & CLS_WET) lbm_atomic_inc(counts + i / g.plane);
+    }
+};
+struct WetFillOp {       // list[cursor[plane]++] = flat id (unordered inside a plane: the items are independent)
+    Grid g; const uint8_t* cls; int64_t* cursor; int64_t* list;
+    LBM_HD void operator()(int64_t i) const {
+        const int64_t id = (int64_t)(NG - 2) * g.plane + i;
+        if (cls[id] & CLS_WET) list[lbm_atomic_inc(cursor + i / g.plane)] = id;
+    }
+};
+
 // ---- export of the reference's compact index structures (single slab; bit-exact contract) -------
 struct FlagOp {          // flag[i] = 1 where the owned node has all bits of `mask` set, row-major order
     Grid g; const uint8_t* cls; uint8_t mask; int64_t* flag;

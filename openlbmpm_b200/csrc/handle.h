@@ -20,6 +20,8 @@ struct lbm_handle {
     uint8_t* cls = nullptr;     // [vol] node classes
     double* ns = nullptr;       // [3][vol]
     uint32_t* pull = nullptr;   // [vol] pull masks of the tiled kernels (grid.cuh::PullMaskOp; D3Q19 with solids only)
+    int64_t* wet_list = nullptr;   // flat ids of the wetting solids of planes [-2, n2 + 2) (tiled kernels with solids only)
+    int64_t n_wet_list = 0;
     int64_t n_fluid = 0, n_wet = 0, n_near = 0;
     bool has_geometry = false;
     bool has_solid = false;     // any solid node in the slab or its ghost planes

@@ -178,7 +178,7 @@ extern "C" int lbm_destroy(lbm_handle* h) {
     g_prof.clear(); g_prof.on = false;      // the per-launch events are a per-thread switch: a destroyed handle must not leave it on
 #endif
     free_state(h);
-    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull); dev_free(h->out_stage);
+    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull); dev_free(h->wet_list); dev_free(h->out_stage);
     tracer_free(h);
     comm_destroy(h);
 #ifndef LBM_HOSTCHECK
@@ -226,8 +226,8 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
                                                 : "LBM_FLAG_PEER_EXCHANGE needs slabs of equal extents on every rank");
     }
     free_state(h);
-    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull);
-    h->pull = nullptr;
+    dev_free(h->dom); dev_free(h->cls); dev_free(h->ns); dev_free(h->pull); dev_free(h->wet_list);
+    h->pull = nullptr; h->wet_list = nullptr; h->n_wet_list = 0;
     h->dom = (uint8_t*)dev_alloc(g.vol); h->cls = (uint8_t*)dev_alloc(g.vol);
     h->ns = (double*)dev_alloc(3 * g.vol * sizeof(double));
     dev_zero(h->dom, g.vol, h->stream); dev_zero(h->cls, g.vol, h->stream);
@@ -257,6 +257,25 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
             h->pull = (uint32_t*)dev_alloc((size_t)g.vol * sizeof(uint32_t));
             dev_zero(h->pull, (size_t)g.vol * sizeof(uint32_t), h->stream);
             launch(PullMaskOp<D3Q19>{g, h->cls, h->pull}, g.count(0), h->stream);
+            // wetting solids of planes [-2, n2 + 2), grouped by plane
+            const int np = g.n2 + 4;
+            int64_t* counts = (int64_t*)dev_alloc((size_t)np * 8);
+            try {
+                dev_zero(counts, (size_t)np * 8, h->stream);
+                launch(WetCountOp{g, h->cls, counts}, g.count(2), h->stream);
+                std::vector<int64_t> cnt((size_t)np), cur((size_t)np);
+                dev_d2h(cnt.data(), counts, (size_t)np * 8, h->stream);
+                int64_t total = 0;
+                for (int k = 0; k < np; ++k) { cur[k] = total; total += cnt[k]; }
+                h->n_wet_list = total;
+                if (total > 0) {
+                    h->wet_list = (int64_t*)dev_alloc((size_t)total * 8);
+                    dev_h2d(counts, cur.data(), (size_t)np * 8, h->stream);
+                    launch(WetFillOp{g, h->cls, counts, h->wet_list}, g.count(2), h->stream);
+                    dev_sync(h->stream);
+                }
+            } catch (...) { dev_free(counts); throw; }
+            dev_free(counts);
         }
     }
     dev_sync(h->stream);
