@@ -119,11 +119,14 @@ struct PeerPtrs {
     double* down;    // ... in the slab below (its high ghost planes receive my bottom planes)
     int gp;          // ghost planes that travel
 };
-// AHEAD = how many planes the interface normals run ahead of the collision.  1: the normals of plane z + 1 are derived between
-// two barriers of plane step z (the first measured form: 28 % of all stall samples on those barriers).  2: the normals of
-// plane z + 2 are derived in step z into a ring of FOUR slots, so what the curvature stencil of plane z reads was written one
-// step earlier and a step needs ONE barrier, at its end (LBM_COLLIDE_AHEAD selects; default 2).
-template <bool SOLIDS, int TX, int TY, bool TMA, bool PEER = false, int AHEAD = 2>
+// AHEAD = how many planes the interface normals run ahead of the collision.  1 (default): the normals of plane z + 1 are derived
+// between two barriers of plane step z.  2 (LBM_COLLIDE_AHEAD=2): the normals of plane z + 2 are derived in step z into a ring of
+// FOUR slots, so what the curvature stencil of plane z reads was written one step earlier and a step needs ONE barrier, at its
+// end.  Measured on the B200 (round 2): the one-barrier form halves the barrier stalls (2.55 -> 1.19 warps per issue) and is
+// SLOWER -- 10.87 vs 10.25 ms per 512^3 launch, 3.40 vs 3.18 ms on the porous workload: the wait at the first barrier was where
+// the 24 HBM requests of a plane landed, without it the same latency shows up as long-scoreboard stalls on the first use of the
+// populations (1.55 -> 1.92).  The kernel is bound by requests in flight per SM (16 warps at 126 registers), not by the barriers.
+template <bool SOLIDS, int TX, int TY, bool TMA, bool PEER = false, int AHEAD = 1>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
 cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi,
                        const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
@@ -559,14 +562,16 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
     double cur[L::Q], nxt[L::Q];
     unsigned mcur = 0, mnxt = 0;
     bool fcur = true, fnxt = true;
-    uint32_t pm1 = pull_mask(z_begin + 1), pm2 = 0u;
+    // the pull masks run TWO plane steps ahead of the requests they steer (a plane step of this pass is short: one step ahead
+    // left 15 % of all stall samples of the porous workload on the mask's arrival)
+    uint32_t pm1 = pull_mask(z_begin + 1), pm2 = pull_mask(z_begin + 2), pm3 = 0u;
     request(z_begin, pull_mask(z_begin), cur, mcur, fcur);
     for (int z = z_begin; z < z_end; ++z) {
         if (z + 1 < z_end) load_scalar_plane(z + 2);    // cp.async, needed by the next plane step
         __pipeline_commit();
-        pm2 = pull_mask(z + 2);
+        pm3 = pull_mask(z + 3);
         if (z + 1 < z_end) request(z + 1, pm1, nxt, mnxt, fnxt);
-        pm1 = pm2;
+        pm1 = pm2; pm2 = pm3;
         __pipeline_wait_prior(1);                       // plane z + 1 has landed
         wait_scalar_plane(z + 1, z_begin - 1);
         __syncthreads();
@@ -659,7 +664,7 @@ static void launch_tiled_a(lbm_handle* h, const CGFields& c, const FastFields& s
 
 // normals one plane ahead (two barriers per plane step) or two planes ahead (one barrier): LBM_COLLIDE_AHEAD = 1 | 2
 static int collide_ahead() {
-    static const int a = [] { const int v = env_int("LBM_COLLIDE_AHEAD", 2); return v == 1 ? 1 : 2; }();
+    static const int a = [] { const int v = env_int("LBM_COLLIDE_AHEAD", 1); return v == 2 ? 2 : 1; }();
     return a;
 }
 template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER = false>
