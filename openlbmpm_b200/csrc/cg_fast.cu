@@ -745,6 +745,234 @@ static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFie
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// D2Q9: the two passes on TX x TY tiles, one thread per node (no marching: the 2-D configurations are a few hundred thousand
+// nodes and live in the L2, so a step is bounded by how many dependent round trips to the L2 a CTA makes and by how many CTAs
+// fit on an SM, not by bandwidth).  Everything a tile needs is requested up front -- the phi window (halo 2) and the recolouring
+// scalars (halo 1) with cp.async into shared memory, the node's nine pulled populations into registers, with solids BOTH
+// candidates of every direction (the upstream node's and the node's own opposite one; the pull mask picks afterwards) -- so a
+// tile makes ONE round trip, then works out of shared memory and registers.  The collision pass derives the colour gradient
+// and the unit normals of the tile + 1 ring in shared memory (the arithmetic of GradientOp, operation for operation: the
+// results are bit-equal to the three one-thread-per-node launches this replaces) and never writes G / n to memory.
+// Rows wrap by index arithmetic on a single slab (Grid::wrap2) or reach into the ghost rows of a slab decomposition.
+// ------------------------------------------------------------------------------------------------
+constexpr int T2X = 32, T2Y = 8;
+template <int TX, int TY>
+struct Tile2D {
+    const Grid& g; int x0, z0;
+    __device__ __forceinline__ int wx(int v) const { return v < 0 ? v + g.n0 : (v >= g.n0 ? v - g.n0 : v); }
+    __device__ __forceinline__ int wz(int v) const { return g.wrap2 ? (v < 0 ? v + g.n2 : (v >= g.n2 ? v - g.n2 : v)) : v; }
+    // flat id of tile-relative node (lx, lz), any halo depth
+    __device__ __forceinline__ int64_t id(int lx, int lz) const { return (int64_t)(wz(z0 + lz) + NG) * g.plane + wx(x0 + lx); }
+};
+
+template <bool SOLIDS, int TX, int TY>
+__global__ void __launch_bounds__(TX* TY)
+cg_density_tile_d2q9(const CGFields c, const FastFields s) {
+    using L = D2Q9;
+    constexpr int NT = TX * TY, NW = TX + 2, NH = TY + 2;
+    LBM_DYN_SMEM(smem_dyn);
+    double (*ss)[NH][NW] = reinterpret_cast<double (*)[NH][NW]>(smem_dyn);     // [3]: kR, ax, ay of the tile + 1 ring
+    const Grid& g = c.g;
+    const int64_t V = g.vol;
+    const int tx = threadIdx.x, tz = threadIdx.y, tid = tz * TX + tx;
+    const Tile2D<TX, TY> t{g, (int)blockIdx.x * TX, (int)blockIdx.y * TY};
+    for (int e = tid; e < NH * NW; e += NT) {
+        const int lz = e / NW, lx = e - lz * NW;
+        const int64_t src = t.id(lx - 1, lz - 1);
+        __pipeline_memcpy_async(&ss[0][lz][lx], s.kR + src, 8);
+        __pipeline_memcpy_async(&ss[1][lz][lx], s.a + src, 8);
+        __pipeline_memcpy_async(&ss[2][lz][lx], s.a + V + src, 8);
+    }
+    __pipeline_commit();
+    const int64_t id = t.id(tx, tz);
+    const uint32_t pm = SOLIDS ? c.pull[id] : 0xFFFFFFFFu;
+    double up[L::Q], own[L::Q];
+    up[0] = s.gT[id];
+#pragma unroll
+    for (int q = 1; q < L::Q; ++q) {
+        up[q] = s.gT[q * V + t.id(tx - L::d0(q), tz - L::d2(q))];
+        if (SOLIDS) own[q] = s.gT[L::opp(q) * V + id];
+    }
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    if (!(pm & 1u)) return;
+    const double kR0 = ss[0][tz + 1][tx + 1];
+    const double a0[3] = {ss[1][tz + 1][tx + 1], ss[2][tz + 1][tx + 1], 0.0};
+    double accR = kR0 * up[0], accB = up[0] - accR;
+#pragma unroll
+    for (int q = 1; q < L::Q; ++q) {
+        double gt, fr;
+        if (!SOLIDS || (pm & (1u << q))) {
+            const int lz = tz + 1 - L::d2(q), lx = tx + 1 - L::d0(q);
+            gt = up[q];
+            const double an[3] = {ss[1][lz][lx], ss[2][lz][lx], 0.0};
+            fr = cg_red_part<L>(q, gt, ss[0][lz][lx], an);
+        } else {
+            gt = own[q];
+            fr = cg_red_part<L>(L::opp(q), gt, kR0, a0);
+        }
+        accR += fr; accB += gt - fr;
+    }
+    c.rho[0][id] = accR; c.rho[1][id] = accB;
+    c.phi[id] = (accR - accB) / (accR + accB);
+}
+
+template <bool SOLIDS, int TX, int TY>
+__global__ void __launch_bounds__(TX* TY)
+cg_collide_tile_d2q9(const CGFields c, const FastFields s, const FastFields o) {
+    using L = D2Q9;
+    constexpr int NT = TX * TY, PW = TX + 4, PH = TY + 4, NW = TX + 2, NH = TY + 2;
+    constexpr int NE = (NH * NW + NT - 1) / NT;
+    LBM_DYN_SMEM(smem_dyn);
+    double (*sphi)[PW] = reinterpret_cast<double (*)[PW]>(smem_dyn);                                  // phi, halo 2
+    double (*sg)[NH][NW] = reinterpret_cast<double (*)[NH][NW]>(smem_dyn + PH * PW);                  // [4]: Gx, Gy, nx, ny, halo 1
+    const Grid& g = c.g;
+    const int64_t V = g.vol;
+    const int tx = threadIdx.x, tz = threadIdx.y, tid = tz * TX + tx;
+    const Tile2D<TX, TY> t{g, (int)blockIdx.x * TX, (int)blockIdx.y * TY};
+    for (int e = tid; e < PH * PW; e += NT) {
+        const int lz = e / PW, lx = e - lz * PW;
+        __pipeline_memcpy_async(&sphi[lz][lx], c.phi + t.id(lx - 2, lz - 2), 8);
+    }
+    __pipeline_commit();
+    // ---- everything else this thread will need, requested before anything is waited for ----
+    const int64_t id = t.id(tx, tz);
+    const uint32_t pm = SOLIDS ? c.pull[id] : 0xFFFFFFFFu;
+    double fT[L::Q], own[L::Q];
+    fT[0] = s.gT[id];
+#pragma unroll
+    for (int q = 1; q < L::Q; ++q) {
+        fT[q] = s.gT[q * V + t.id(tx - L::d0(q), tz - L::d2(q))];
+        if (SOLIDS) own[q] = s.gT[L::opp(q) * V + id];
+    }
+    const double rR = c.rho[0][id], rB = c.rho[1][id];
+    const double Fl[2] = {c.F[id], c.F[V + id]};
+    uint8_t cl[NE];
+    double nsx[NE], nsy[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int e = tid + k * NT, lz = e / NW, lx = e - lz * NW;
+        cl[k] = CLS_FLUID; nsx[k] = 0.0; nsy[k] = 0.0;
+        if (SOLIDS && e < NH * NW) {
+            const int64_t nid = t.id(lx - 1, lz - 1);
+            cl[k] = c.cls[nid]; nsx[k] = c.ns[nid]; nsy[k] = c.ns[V + nid];
+        }
+    }
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    // ---- colour gradient and unit normal of the tile + 1 ring: GradientOp's arithmetic from the phi window ----
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int e = tid + k * NT;
+        if (e >= NH * NW) break;
+        const int lz = e / NW, lx = e - lz * NW;
+        double G[3] = {0.0, 0.0, 0.0}, n[3] = {0.0, 0.0, 0.0};
+        if (cl[k] & CLS_FLUID) {
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                const double v = mul_rn(L::w(q), sphi[lz + 1 + L::d2(q)][lx + 1 + L::d0(q)]);
+#pragma unroll
+                for (int a = 0; a < L::D; ++a)
+                    if (L::c(q, a) != 0) G[a] = add_rn(G[a], L::c(q, a) > 0 ? v : -v);
+            }
+            G[0] *= 3.0; G[1] *= 3.0;
+            if (SOLIDS && (cl[k] & CLS_NEAR)) {
+                double ns[3] = {nsx[k], nsy[k], 0.0};
+                cg_wetting<2>(G, ns, c.p.cosT, c.p.sinT, c.p.wetting_type);
+            }
+            cg_unit_normal<2>(G, c.p.wetting_type, n);
+        }
+        sg[0][lz][lx] = G[0]; sg[1][lz][lx] = G[1]; sg[2][lz][lx] = n[0]; sg[3][lz][lx] = n[1];
+    }
+    __syncthreads();
+    if (!(pm & 1u)) return;
+    if (SOLIDS) {
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q)
+            if (!(pm & (1u << q))) fT[q] = own[q];          // half-way bounce back
+    }
+    // ---- PullCollideOp from here on, with the normals in shared memory ----
+    const double rho = rB + rR;
+    double mom[3] = {0.0, 0.0, 0.0}, u[3] = {0, 0, 0}, G[3] = {0, 0, 0}, n[3] = {0, 0, 0}, F[3] = {0, 0, 0};
+#pragma unroll
+    for (int q = 1; q < L::Q; ++q)
+#pragma unroll
+        for (int d = 0; d < L::D; ++d)
+            if (L::c(q, d) != 0) mom[d] += L::c(q, d) * fT[q];
+#pragma unroll
+    for (int d = 0; d < L::D; ++d) {
+        u[d] = (mom[d] + 0.5 * Fl[d]) / rho;                // force of the previous step
+        G[d] = sg[d][tz + 1][tx + 1]; n[d] = sg[2 + d][tz + 1][tx + 1];
+    }
+    double dn[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};   // cg_force_at
+#pragma unroll
+    for (int q = 1; q < L::Q; ++q) {
+        const int lz = tz + 1 + L::d2(q), lx = tx + 1 + L::d0(q);
+        const double nk[2] = {sg[2][lz][lx], sg[3][lz][lx]};
+#pragma unroll
+        for (int a = 0; a < L::D; ++a)
+            if (L::c(q, a) != 0)
+#pragma unroll
+                for (int b = 0; b < L::D; ++b) dn[a][b] = add_rn(dn[a][b], mul_rn(3.0 * L::w(q) * L::c(q, a), nk[b]));
+    }
+    double K = 0.0, nn = 0.0, div = 0.0;
+#pragma unroll
+    for (int a = 0; a < L::D; ++a) {
+        nn += n[a] * n[a]; div += dn[a][a];
+#pragma unroll
+        for (int b = 0; b < L::D; ++b) K += n[a] * n[b] * dn[a][b];
+    }
+    K -= nn * div;
+    const double sgn = c.p.wetting_type == 1 ? 0.5 : -0.5;
+#pragma unroll
+    for (int a = 0; a < L::D; ++a) { F[a] = sgn * c.p.sigma * K * G[a]; c.F[a * V + id] = F[a]; }
+    const double tau = cg_tau(sphi[tz + 2][tx + 2], rR, rB, c.p);
+    cg_collide<L>(fT, rho, u, F, tau, c.p.relax);
+    double kR, a[3];
+    cg_recolour_coeffs<L>(rR, rB, G, c.p.beta, &kR, a);
+#pragma unroll
+    for (int q = 0; q < L::Q; ++q) o.gT[q * V + id] = fT[q];
+    o.kR[id] = kR;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) o.a[d * V + id] = a[d];
+}
+
+static bool tiled2d_ok(const lbm_handle* h) {
+    static const bool off = env_int("LBM_TILE_2D", 1) == 0;
+    return h->Q == 9 && !off && h->g.n0 % T2X == 0 && h->g.n2 % T2Y == 0 && !(h->cfg.flags & 2u) && !h->tracer && (!h->has_solid || h->pull);
+}
+template <bool SOLIDS>
+static void launch_density_tile2d(lbm_handle* h, const CGFields& c, const FastFields& s) {
+    const Grid& g = h->g;
+    dim3 grid(g.n0 / T2X, g.n2 / T2Y), block(T2X, T2Y);
+    constexpr size_t smem = sizeof(double) * 3 * (T2Y + 2) * (T2X + 2);
+#ifdef LBM_HOSTCHECK
+    cta_emu::launch(grid, block, smem, [&] { cg_density_tile_d2q9<SOLIDS, T2X, T2Y>(c, s); });
+#else
+    if (g_prof.on) g_prof.begin(SOLIDS ? "cg_density_tile_d2q9<solids>" : "cg_density_tile_d2q9<all-fluid>", h->stream);
+    cg_density_tile_d2q9<SOLIDS, T2X, T2Y><<<grid, block, smem, h->stream>>>(c, s);
+    if (g_prof.on) g_prof.end(h->stream);
+    LBM_CUDA_CHECK(cudaGetLastError());
+#endif
+    ++g_launch_counter;
+}
+template <bool SOLIDS>
+static void launch_collide_tile2d(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o) {
+    const Grid& g = h->g;
+    dim3 grid(g.n0 / T2X, g.n2 / T2Y), block(T2X, T2Y);
+    constexpr size_t smem = sizeof(double) * ((T2Y + 4) * (T2X + 4) + 4 * (T2Y + 2) * (T2X + 2));
+#ifdef LBM_HOSTCHECK
+    cta_emu::launch(grid, block, smem, [&] { cg_collide_tile_d2q9<SOLIDS, T2X, T2Y>(c, s, o); });
+#else
+    if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tile_d2q9<solids>" : "cg_collide_tile_d2q9<all-fluid>", h->stream);
+    cg_collide_tile_d2q9<SOLIDS, T2X, T2Y><<<grid, block, smem, h->stream>>>(c, s, o);
+    if (g_prof.on) g_prof.end(h->stream);
+    LBM_CUDA_CHECK(cudaGetLastError());
+#endif
+    ++g_launch_counter;
+}
+
 // which ghost planes of the factored state are ever read: population q is pulled from z - c_z(q), so it has
 // to travel upwards (c_z = +1) or downwards (c_z = -1) only, in-plane directions never cross a slab face
 template <class L>
@@ -937,8 +1165,10 @@ static void fast_one_step(lbm_handle* h) {
         } else if (h->has_solid) launch_density_tiled<true>(h, c, s); else launch_density_tiled<false>(h, c, s);
         dens_done = true;
     }
+    const bool tile2d = L::Q == 9 && tiled2d_ok(h);
     if (!dens_done) {
-        if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
+        if (tile2d) { if (h->has_solid) launch_density_tile2d<true>(h, c, s); else launch_density_tile2d<false>(h, c, s); }
+        else if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
         else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
     }
     if (open) fast_open_rows_pre<L>(h, c, s);
@@ -947,7 +1177,7 @@ static void fast_one_step(lbm_handle* h) {
         if (late_down) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, false);
         comm_peer_signal_wait(h);
     } else fast_exchange(h, c.phi, 0, 1, h->has_solid ? NG : 2);
-    if (h->has_solid && tiled_ok(h)) {      // the tiled kernel stages phi, wetting solids included
+    if (h->has_solid && (tiled_ok(h) || tile2d)) {      // the tiled kernels stage phi, wetting solids included
         if (h->pull) launch(PhiSolidListOp<L>{c, h->wet_list}, h->n_wet_list, h->stream);
         else launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
     }
@@ -961,6 +1191,10 @@ static void fast_one_step(lbm_handle* h) {
             if (h->has_solid) launch_tiled_peer<true>(h, c, s, o, pp); else launch_tiled_peer<false>(h, c, s, o, pp);
             f->pushed[1 - f->cur] = 1;
         } else if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);
+        done = true;
+    }
+    if (!done && tile2d) {
+        if (h->has_solid) launch_collide_tile2d<true>(h, c, s, o); else launch_collide_tile2d<false>(h, c, s, o);
         done = true;
     }
     if (!done) {

@@ -253,30 +253,32 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
     } else {
         launch(ClassifyOp<3>{g, h->dom, h->cls}, g.count(NG), h->stream);
         launch(SolidNormalOp<3>{g, h->dom, h->cls, h->ns}, g.count(1), h->stream);
-        if (h->has_solid) {
-            h->pull = (uint32_t*)dev_alloc((size_t)g.vol * sizeof(uint32_t));
-            dev_zero(h->pull, (size_t)g.vol * sizeof(uint32_t), h->stream);
-            launch(PullMaskOp<D3Q19>{g, h->cls, h->pull}, g.count(0), h->stream);
-            // wetting solids of planes [-2, n2 + 2), grouped by plane
-            const int np = g.n2 + 4;
-            int64_t* counts = (int64_t*)dev_alloc((size_t)np * 8);
-            try {
-                dev_zero(counts, (size_t)np * 8, h->stream);
-                launch(WetCountOp{g, h->cls, counts}, g.count(2), h->stream);
-                std::vector<int64_t> cnt((size_t)np), cur((size_t)np);
-                dev_d2h(cnt.data(), counts, (size_t)np * 8, h->stream);
-                int64_t total = 0;
-                for (int k = 0; k < np; ++k) { cur[k] = total; total += cnt[k]; }
-                h->n_wet_list = total;
-                if (total > 0) {
-                    h->wet_list = (int64_t*)dev_alloc((size_t)total * 8);
-                    dev_h2d(counts, cur.data(), (size_t)np * 8, h->stream);
-                    launch(WetFillOp{g, h->cls, counts, h->wet_list}, g.count(2), h->stream);
-                    dev_sync(h->stream);
-                }
-            } catch (...) { dev_free(counts); throw; }
-            dev_free(counts);
-        }
+    }
+    if (h->has_solid && h->cfg.model == LBM_MODEL_CG) {
+        // what the tiled kernels of the fast path read instead of gathering node classes: one pull mask per node, and the
+        // wetting solids of planes [-2, n2 + 2) as a list grouped by plane
+        h->pull = (uint32_t*)dev_alloc((size_t)g.vol * sizeof(uint32_t));
+        dev_zero(h->pull, (size_t)g.vol * sizeof(uint32_t), h->stream);
+        if (h->D == 2) launch(PullMaskOp<D2Q9>{g, h->cls, h->pull}, g.count(0), h->stream);
+        else launch(PullMaskOp<D3Q19>{g, h->cls, h->pull}, g.count(0), h->stream);
+        const int np = g.n2 + 4;
+        int64_t* counts = (int64_t*)dev_alloc((size_t)np * 8);
+        try {
+            dev_zero(counts, (size_t)np * 8, h->stream);
+            launch(WetCountOp{g, h->cls, counts}, g.count(2), h->stream);
+            std::vector<int64_t> cnt((size_t)np), cur((size_t)np);
+            dev_d2h(cnt.data(), counts, (size_t)np * 8, h->stream);
+            int64_t total = 0;
+            for (int k = 0; k < np; ++k) { cur[k] = total; total += cnt[k]; }
+            h->n_wet_list = total;
+            if (total > 0) {
+                h->wet_list = (int64_t*)dev_alloc((size_t)total * 8);
+                dev_h2d(counts, cur.data(), (size_t)np * 8, h->stream);
+                launch(WetFillOp{g, h->cls, counts, h->wet_list}, g.count(2), h->stream);
+                dev_sync(h->stream);
+            }
+        } catch (...) { dev_free(counts); throw; }
+        dev_free(counts);
     }
     dev_sync(h->stream);
     h->n_wet = h->n_near = -1;

@@ -776,3 +776,48 @@ def case_cgp_open(lib_path, lattice=19, n=(22, 8, 10), steps=9, inlet="Neumann",
     pdf = eng.download_pdfs()
     np.testing.assert_allclose(pdf[0], np.moveaxis(sim.fR, 0, -1).reshape(n + (L.Q,)), rtol=0, atol=atol)
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# D2Q9 tile kernels of the fast path (cg_fast.cu::cg_density_tile_d2q9 / cg_collide_tile_d2q9)
+# ---------------------------------------------------------------------------------------------------
+def check_d2q9_tile_kernels(lib_path, tol=0.0):
+    """lattices whose extents admit the 32 x 8 tiles: the tile kernels (default) against the one-thread-per-node operators they
+    replace (LBM_FLAG_NO_TILED_KERNEL) -- same arithmetic operation for operation, so the comparison is bit for bit (tol = 0) --
+    and against the dense oracle; periodic box, obstacles with both wetting types, open channel with walls"""
+    rng = np.random.default_rng(21)
+    shape = (48, 64)
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    obst = np.ones(shape, bool)
+    obst[10:14, 5:20] = False; obst[30:33, 40:70] = False; obst[0:2, 30:34] = False          # one obstacle on the periodic seam
+    obst &= (xx - 50) ** 2 + (yy - 20) ** 2 > 30.0
+    walls = np.ones(shape, bool); walls[6:-6, 0] = False; walls[6:-6, -1] = False; walls[20:23, 20:30] = False
+    top = yy >= shape[0] - 12
+    noise = 0.5 + 0.4 * (rng.random(shape) - 0.5)
+    runs = [("periodic", np.ones(shape, bool), noise, dict()),
+            ("obstacles, WettingType 2", obst, noise, dict(contact_angle_deg=65.0)),
+            ("obstacles, WettingType 1, SRT", obst, noise, dict(contact_angle_deg=120.0, wetting_type=1, relax=_lib.RELAX_SRT, tauR=0.9, tauB=1.1)),
+            ("channel, velocity inlet + pressure outlet", walls, np.where(top, 1.0, 5e-8),
+             dict(contact_angle_deg=60.0, inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_PRESSURE, inlet_velocity=-1e-3, rhoBL=1.0, rhoRL=5e-8)),
+            ("channel, pressure inlet + convective outlet", walls, np.where(top, 1.0, 5e-8),
+             dict(contact_angle_deg=100.0, inlet=_lib.INLET_PRESSURE, outlet=_lib.OUTLET_CONVECTIVE, rhoRH=1.003, rhoBH=5e-8))]
+    for name, dom, rhoR, kw in runs:
+        rhoB = np.where(rhoR > 0.99, 5e-8, 1.0 - rhoR) if rhoR.max() > 0.99 else 1.0 - rhoR
+        out = []
+        for flags in (0, 2):
+            eng = _lib.Engine(9, shape, lib_path=lib_path, flags=flags, **kw)
+            eng.set_geometry(dom)
+            eng.init_equilibrium(rhoR * dom, rhoB * dom)
+            snaps = []
+            for n in (1, 2, 9):
+                eng.step(n)
+                rho, u = eng.download_macros()
+                snaps.append(np.stack(rho + u))
+            snaps.append(np.stack([p.sum(-1) for p in eng.download_pdfs()]))
+            out.append(snaps)
+            eng.close()
+        for k, (a, b) in enumerate(zip(out[0], out[1])):
+            d = float(np.abs(a - b).max())
+            assert d <= tol, "%s: tile kernels differ from the one-thread-per-node operators in snapshot %d by %.3e" % (name, k, d)
+    # ... and against the dense oracle (periodic box with obstacles; closed box)
+    run_dense_case(9, obst, noise, 1.0 - noise, 12, lib_path, relax="MRT", chunk=[3, 9], contact_angle_deg=65.0)

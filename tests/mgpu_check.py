@@ -63,6 +63,8 @@ def main():
     for name, shape, solid, kw in (("periodic tiled", (16 * world, 16, 32), False, {}),
                                    ("periodic tiled, 4 x-tiles", (40 * world, 16, 128), False, {}),      # interior tiles + two z-chunks per slab
                                    ("sphere wetting tiled", (16 * world, 16, 32), True, dict(contact_angle_deg=70.0)),
+                                   ("D2Q9 tile kernels", (16 * world, 64), True, dict(contact_angle_deg=65.0)),
+                                   ("D2Q9 tile kernels, open channel", (16 * world, 64), True, dict(OPEN, contact_angle_deg=60.0)),
                                    ("general kernels", (8 * world, 10, 12), True, dict(flags=1, contact_angle_deg=50.0)),
                                    ("untiled fast path", (8 * world, 10, 12), True, dict(flags=2)),
                                    # cfg 5 layout: outlet planes on rank 0, inlet planes on the last rank, solids in between

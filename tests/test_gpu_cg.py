@@ -194,3 +194,11 @@ def test_five_velocity_tracers_vs_dense_oracle(channel):
 @pytest.mark.parametrize("lattice,n,inlet,outlet", [(19, (22, 8, 10), "Neumann", "Dirichlet"), (9, (26, 14), "Dirichlet", "Dirichlet")])
 def test_perturbation_open_boundaries_vs_oracle(lattice, n, inlet, outlet):
     cases.case_cgp_open(None, lattice, n, inlet=inlet, outlet=outlet)
+
+
+def test_d2q9_tile_kernels_equal_the_operators_they_replace():
+    """cg_density_tile_d2q9 / cg_collide_tile_d2q9 on the GPU: the one-thread-per-node fast path and the dense oracle.  On the
+    host the two forms are bit-equal (same operations in the same order, tests/test_hostcheck_tiled.py); nvcc contracts
+    multiply-adds kernel by kernel, so on the GPU they differ in the last bit (3e-16 measured) -- 1e-12 here.  BASELINE
+    configuration 2 at 512^2 gives the same density checksum with and without the tile kernels (profiles/r02_cfg2_*.json)."""
+    cases.check_d2q9_tile_kernels(None, tol=1e-12)

@@ -136,6 +136,16 @@ def test_send_recv_exchange_slabs_bit_equal(lattice, shape, name, kw, lib):
     compare(lib, lattice, shape, [1, 2, 6, 5], **dict(kw, flags=_lib.FLAG_NCCL_EXCHANGE))
 
 
+@pytest.mark.parametrize("name,kw", [
+    ("closed box", dict(contact_angle_deg=70.0)),
+    ("open channel, velocity inlet + convective outlet", dict(OPEN, contact_angle_deg=60.0)),
+    ("send / recv ring", dict(contact_angle_deg=70.0, flags=_lib.FLAG_NCCL_EXCHANGE)),
+])
+def test_d2q9_tile_kernels_on_slabs_bit_equal(name, kw, lib):
+    """2-D lattice whose slabs admit the 32 x 8 tile kernels (ghost rows instead of the index wrap of a single slab)"""
+    compare(lib, 9, (48, 32), [1, 2, 6], worlds=(2, 3), **kw)
+
+
 def test_all_fluid_box_slabs_bit_equal(lib):
     compare(lib, 19, (24, 6, 8), [3, 5], solid=False, worlds=(2, 3, 6))
 

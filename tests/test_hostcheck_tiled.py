@@ -106,3 +106,8 @@ def test_persistent_kernel_equals_launched_form(lib):
 def test_colour_gradient_trajectories_persistent_kernel(path, lib):
     """the reference's own vectors through the persistent kernel (19 steps per call)"""
     cases.check_trajectory_vs_gold(path, lib, chunk=19, flags=_lib.FLAG_PERSISTENT)
+
+
+def test_d2q9_tile_kernels_equal_the_operators_they_replace(lib):
+    """the D2Q9 tile kernels on host threads (cta_emu.h): bit-equal to the one-thread-per-node fast path, equal to the oracle"""
+    cases.check_d2q9_tile_kernels(lib)
