@@ -177,6 +177,8 @@ def metric_name(args, Q, n, porous, cfg):
         return "MLUPS (void nodes) BASELINE config %d" % cfg
     if Q == 19 and n == 512 and not porous:
         return "MLUPS D3Q19 CG-MRT 512^3"
+    if args.workload == "ini3d":
+        return "MLUPS D3Q19 CG perturbation-operator SRT open channel %d^3" % n
     if porous:
         return "MLUPS (void nodes) D3Q19 CG-MRT porous"
     return "MLUPS %s CG-MRT %d" % ("D3Q19" if Q == 19 else "D2Q9", n)
@@ -185,6 +187,9 @@ def metric_name(args, Q, n, porous, cfg):
 def workload_name(args):
     if args.workload.startswith("cfg"):
         return getattr(args, "cfg_description", "BASELINE configuration %s" % args.workload[3:])
+    if args.workload == "ini3d":
+        return ("D3Q19 colour gradient with the perturbation operator, SRT, velocity inlet + pressure outlet (the variant the reference's "
+                "IniFiles/RKtwophasesetup3D.ini selects), %d^3 all-fluid box" % args.size)
     if args.workload == "porous":
         return ("D3Q19 colour-gradient CSF MRT, %d x %d x %d sphere pack (seed 7, porosity ~0.6, half-way bounce back, contact "
                 "angle 60), velocity inlet along -z, convective outlet (BASELINE config 5 geometry)" % (args.size, args.size, args.nz or args.size))
@@ -210,15 +215,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="lbm_config.flags (LBM_FLAG_*), for A/B measurements")
-    ap.add_argument("--workload", default="box", choices=["box", "porous", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+    ap.add_argument("--workload", default="box", choices=["box", "porous", "ini3d", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="box: the metric's periodic spinodal box; porous: sphere pack with velocity inlet + convective outlet (cfg 5 "
                          "geometry, any size, slab-decomposable); cfgN: BASELINE.json configuration N at its own size on one GPU "
                          "(--scale shrinks it)")
     ap.add_argument("--scale", type=float, default=1.0, help="cfgN: factor on the lattice extents")
     ap.add_argument("--nz", type=int, default=0, help="porous: planes along the flow axis (default: --size)")
     args = ap.parse_args()
-    if args.workload == "porous":
+    if args.workload in ("porous", "ini3d"):
         args.lattice = 19
+    if args.workload == "ini3d" and args.size == 512:
+        args.size = 256
     if args.impl == "reference":
         return run_reference(args)
 
@@ -242,7 +249,8 @@ def main():
     if cfg:
         args.lattice = 9 if cfg <= 3 else 19
     Q, n = args.lattice, args.size
-    porous = args.workload == "porous" or cfg > 0        # no host-buffer round trip / CPU arm for these lines
+    ini3d = args.workload == "ini3d"
+    porous = args.workload == "porous" or cfg > 0 or ini3d        # no host-buffer round trip / CPU arm for these lines
     nz = (args.nz or n) if porous else n
     if nz % world:
         raise SystemExit("size must be divisible by the number of GPUs")
@@ -250,18 +258,28 @@ def main():
     shape = (nloc, n, n) if Q == 19 else (nloc, n)
     flags = (_lib.FLAG_GENERIC_KERNELS if args.general else 0) | args.flags
     bc = dict(inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_CONVECTIVE, inlet_velocity=-5.0e-4, contact_angle_deg=60.0) if porous else {}
+    par = dict(relax=_lib.RELAX_MRT, sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2)
+    if ini3d:       # what IniFiles/RKtwophasesetup3D.ini parameterises (its :9-25, :28-40, :55), on a box of --size^3 instead of 32 x 32 x 96
+        bc = dict(inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_PRESSURE, inlet_velocity=-1.0e-4, rhoBL=1.0, rhoRL=1.0e-8)
+        par = dict(relax=_lib.RELAX_SRT, surface_tension_type=_lib.ST_PERTURBATION, beta=1.0, AkR=7.0e-3, AkB=7.0e-3, tauR=1.0, tauB=1.0,
+                   delta=0.98, solid_phi=0.7)
     if cfg:
         from openlbmpm_b200 import synthetic
         eng, nodes_total, args.cfg_description = synthetic.baseline_config(cfg, scale=args.scale, device=local, flags=flags)
         shape = eng.shape
     else:
-        eng = _lib.Engine(Q, shape, model=_lib.MODEL_CG, relax=_lib.RELAX_MRT, device=local, flags=flags,
-                          sigma=0.1, beta=0.7, delta=0.98, tauR=1.0, tauB=1.0, tau_type=2, wetting_type=2, **bc)
+        eng = _lib.Engine(Q, shape, model=_lib.MODEL_CG, device=local, flags=flags, **par, **bc)
     if world > 1:
         from openlbmpm_b200 import slab
         eng.comm_init(rank, world, slab.share_unique_id(dist, eng, rank, device="cuda"))
     if cfg:
         pass
+    elif ini3d:
+        sl = slice(rank * nloc, (rank + 1) * nloc)
+        eng.set_geometry(np.ones(shape, np.uint8))
+        red = np.broadcast_to((np.arange(nz)[sl] >= nz - nz // 8)[:, None, None], shape)      # the invading fluid fills the top eighth
+        eng.init_equilibrium(np.where(red, 1.0, 1e-8), np.where(red, 1e-8, 1.0))
+        nodes_total = float(n) * n * nz
     elif porous:
         from openlbmpm_b200 import synthetic
         sl = slice(rank * nloc, (rank + 1) * nloc)

@@ -39,7 +39,9 @@ bool cg_fast_eligible(const lbm_handle* h) {
     // (AcceleratedRKGPU2D.py:1700-1706), so its trajectories hang on the exact cancellation of phi between the copied
     // outlet rows; the factored arithmetic rounds differently there, and that combination stays on the
     // reference-ordered kernels.
-    if (h->cfg.model != LBM_MODEL_CG || (h->cfg.flags & LBM_FLAG_GENERIC_KERNELS) || h->cfg.surface_tension_type != LBM_ST_CSF) return false;
+    if (h->cfg.model != LBM_MODEL_CG || (h->cfg.flags & LBM_FLAG_GENERIC_KERNELS)) return false;
+    // the perturbation-operator model has its own collision pass (PullPerturbCollideOp); tracers ride on the CSF flow only
+    if (h->cfg.surface_tension_type != LBM_ST_CSF && h->tracer) return false;
     // Tracers read u, G and rho_R of the iteration, none of which the flow collision changes: on the one-thread-per-node fast
     // path (closed boxes) their phase runs right after the collision pass, which then also stores u.  The tiled kernels keep G
     // in shared memory, and the open-row patches rewrite u on a few planes: those combinations stay on the reference-ordered
@@ -559,6 +561,7 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
     __pipeline_commit();
     wait_scalar_plane(z_begin - 1, z_begin - 1);
     wait_scalar_plane(z_begin, z_begin - 1);
+    const bool pert = c.p.st_type == LBM_ST_PERTURBATION;      // recolouring weights w_i / |e_i| (cg_fast_ops.cuh::cg_red_part)
     double cur[L::Q], nxt[L::Q];
     unsigned mcur = 0, mnxt = 0;
     bool fcur = true, fnxt = true;
@@ -591,9 +594,9 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
 #pragma unroll
                     for (int d = 0; d < 3; ++d)
                         if (L::c(q, d) != 0) ea += L::c(q, d) * ss[sq][1 + d][ly][lx];
-                    fr = ss[sq][0][ly][lx] * cur[q] + L::w(q) * ea;
+                    fr = ss[sq][0][ly][lx] * cur[q] + cg_red_weight<L>(q, pert) * ea;
                 } else {
-                    fr = cg_red_part<L>(L::opp(q), cur[q], kR0, a0);
+                    fr = cg_red_part<L>(L::opp(q), cur[q], kR0, a0, pert);
                 }
                 accR += fr; accB += cur[q] - fr;
             }
@@ -607,6 +610,99 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
 #pragma unroll
         for (int q = 0; q < L::Q; ++q) cur[q] = nxt[q];
         mcur = mnxt; fcur = fnxt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled collision pass of the PERTURBATION-operator model for D3Q19 (what the reference's RKtwophasesetup3D.ini selects).
+// Same column-marching layout as cg_collide_tiled_d3q19, but this model needs no normals and no curvature: the colour gradient
+// of a node comes straight from a rolling window of phi planes (halo 1, four slots, 8-byte cp.async one plane step ahead), so
+// a plane step has ONE barrier and the only shared-memory traffic is the 18-point phi stencil.  Solid neighbours show
+// SolidColorDiff; which neighbours are solid is read off the node's pull mask (bit opp(q) = "x + e_q is fluid").  The node
+// arithmetic is cg_fast_ops.cuh::cgp_collide_factored, the gradient that of cgp_gradient_at operation for operation.
+// ------------------------------------------------------------------------------------------------
+template <bool SOLIDS, int TX, int TY>
+__global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
+cgp_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi) {
+    using L = D3Q19;
+    constexpr int NT = TX * TY, NW = TX + 2, NH = TY + 2;
+    LBM_DYN_SMEM(smem_dyn);
+    double (*sphi)[NH][NW] = reinterpret_cast<double (*)[NH][NW]>(smem_dyn);      // [4] planes
+    const Grid& g = c.g;
+    const int64_t V = g.vol;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int z_begin = z_lo + blockIdx.z * zchunk;
+    const int z_end = min(z_begin + zchunk, z_hi);
+    const int x = x0 + tx, y = y0 + ty;
+    auto wrapx = [&](int v) { return v < 0 ? v + g.n0 : (v >= g.n0 ? v - g.n0 : v); };
+    auto wrapy = [&](int v) { return v < 0 ? v + g.n1 : (v >= g.n1 ? v - g.n1 : v); };
+    auto load_phi_plane = [&](int zp) {
+        const int slot = (zp + 8) & 3;
+        const double* src = c.phi + (int64_t)(zp + NG) * g.plane;
+        for (int e = tid; e < NH * NW; e += NT) {
+            const int ly = e / NW, lx = e - ly * NW;
+            __pipeline_memcpy_async(&sphi[slot][ly][lx], src + (int64_t)wrapy(y0 + ly - 1) * g.n0 + wrapx(x0 + lx - 1), 8);
+        }
+    };
+    const int64_t xo[3] = {(int64_t)wrapx(x - 1), (int64_t)x, (int64_t)wrapx(x + 1)};
+    const int64_t yo[3] = {(int64_t)wrapy(y - 1) * g.n0, (int64_t)y * g.n0, (int64_t)wrapy(y + 1) * g.n0};
+    for (int zp = z_begin - 1; zp <= z_begin + 1; ++zp) load_phi_plane(zp);
+    __pipeline_commit();
+    uint32_t pm_next = 1u;
+    if (SOLIDS) pm_next = c.pull[(int64_t)(z_begin + NG) * g.plane + yo[1] + xo[1]];
+    for (int z = z_begin; z < z_end; ++z) {
+        const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
+        uint32_t pm = 0xFFFFFFFFu;
+        if (SOLIDS) {
+            pm = pm_next;
+            if (z + 1 < z_end) pm_next = c.pull[id + g.plane];
+        }
+        const bool fluid = pm & 1u;
+        double fT[L::Q];
+        double rR = 1.0, rB = 1.0;
+        if (fluid) {
+            fT[0] = __ldcs(s.gT + id);
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) {
+                const int64_t src = (int64_t)(z - L::d2(q) + NG) * g.plane + yo[1 - L::d1(q)] + xo[1 - L::d0(q)];
+                int64_t addr = q * V + src;
+                if (SOLIDS && !(pm & (1u << q))) addr = L::opp(q) * V + id;      // half-way bounce back
+                fT[q] = __ldcs(s.gT + addr);
+            }
+            rR = c.rho[0][id]; rB = c.rho[1][id];
+        }
+        __pipeline_wait_prior(0);           // phi plane z + 1, requested during the last step (the prologue's planes for the first)
+        __syncthreads();
+        // the slot of plane z - 2 is free now: every thread has left step z - 1, the last reader of that plane
+        if (z + 1 < z_end) load_phi_plane(z + 2);
+        __pipeline_commit();
+        if (!fluid) continue;
+        double G[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            double pk = sphi[(z + L::d2(q) + 8) & 3][ty + 1 + L::d1(q)][tx + 1 + L::d0(q)];
+            if (SOLIDS && !(pm & (1u << L::opp(q)))) pk = c.p.solid_phi;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (L::c(q, k) != 0) G[k] = add_rn(G[k], mul_rn(3.0 * L::w(q) * L::c(q, k), pk));
+        }
+        const double phi0 = sphi[(z + 8) & 3][ty + 1][tx + 1];
+        const double rho = rB + rR;
+        double mom[3] = {0.0, 0.0, 0.0}, u[3], kR, a[3];
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (L::c(q, k) != 0) mom[k] += L::c(q, k) * fT[q];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) u[k] = mom[k] / rho;
+        cgp_collide_factored<L>(fT, rR, rB, phi0, u, G, c.p, &kR, a);
+#pragma unroll
+        for (int q = 0; q < L::Q; ++q) __stcs(o.gT + q * V + id, fT[q]);
+        o.kR[id] = kR;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { o.a[k * V + id] = a[k]; c.G[k * V + id] = G[k]; }
     }
 }
 
@@ -686,6 +782,24 @@ static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, 
         case 16: launch_tiled_t<SOLIDS, 16, false>(h, c, s, o, z_lo, z_hi); break;
         default: if (tma) launch_tiled_t<SOLIDS, 8, true>(h, c, s, o, z_lo, z_hi); else launch_tiled_t<SOLIDS, 8, false>(h, c, s, o, z_lo, z_hi);
     }
+}
+
+template <bool SOLIDS>
+static void launch_perturb_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o) {
+    const Grid& g = h->g;
+    constexpr int TILE_Y = 4;
+    const int zchunk = z_chunk(g.n2);
+    dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
+    constexpr size_t smem = sizeof(double) * 4 * (TILE_Y + 2) * (TILE_X + 2);
+#ifdef LBM_HOSTCHECK
+    cta_emu::launch(grid, block, smem, [&] { cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y>(c, s, o, zchunk, 0, g.n2); });
+#else
+    if (g_prof.on) g_prof.begin(SOLIDS ? "cgp_collide_tiled_d3q19<solids>" : "cgp_collide_tiled_d3q19<all-fluid>", h->stream);
+    cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, 0, g.n2);
+    if (g_prof.on) g_prof.end(h->stream);
+    LBM_CUDA_CHECK(cudaGetLastError());
+#endif
+    ++g_launch_counter;
 }
 
 template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER = false>
@@ -797,6 +911,7 @@ cg_density_tile_d2q9(const CGFields c, const FastFields s) {
     __pipeline_wait_prior(0);
     __syncthreads();
     if (!(pm & 1u)) return;
+    const bool pert = c.p.st_type == LBM_ST_PERTURBATION;
     const double kR0 = ss[0][tz + 1][tx + 1];
     const double a0[3] = {ss[1][tz + 1][tx + 1], ss[2][tz + 1][tx + 1], 0.0};
     double accR = kR0 * up[0], accB = up[0] - accR;
@@ -807,10 +922,10 @@ cg_density_tile_d2q9(const CGFields c, const FastFields s) {
             const int lz = tz + 1 - L::d2(q), lx = tx + 1 - L::d0(q);
             gt = up[q];
             const double an[3] = {ss[1][lz][lx], ss[2][lz][lx], 0.0};
-            fr = cg_red_part<L>(q, gt, ss[0][lz][lx], an);
+            fr = cg_red_part<L>(q, gt, ss[0][lz][lx], an, pert);
         } else {
             gt = own[q];
-            fr = cg_red_part<L>(L::opp(q), gt, kR0, a0);
+            fr = cg_red_part<L>(L::opp(q), gt, kR0, a0, pert);
         }
         accR += fr; accB += gt - fr;
     }
@@ -1050,6 +1165,10 @@ template <class L>
 static void fast_open_rows_post(lbm_handle* h, const CGFields& c, const FastFields& o, bool need_gradient) {
     const OpenRows r = open_rows(c);
     if (!r.n) return;
+    if (c.p.st_type == LBM_ST_PERTURBATION) {     // this model's collision evaluates its gradient itself
+        launch_plane_ranges(h, PerturbCollideFactoredOp<L>{c, o}, 0, r.n, r.mod_lo, r.mod_hi);
+        return;
+    }
     if (need_gradient) {      // the tiled collision pass keeps G and the normals in shared memory: evaluate them around the patched planes
         int lo[2], hi[2];
         for (int k = 0; k < r.n; ++k) {
@@ -1065,6 +1184,16 @@ static void fast_open_rows_post(lbm_handle* h, const CGFields& c, const FastFiel
 template <class L>
 static void fast_enter(lbm_handle* h) {
     cg_ensure_head(h);
+    if (h->cfg.surface_tension_type == LBM_ST_PERTURBATION) {
+        CGFields c = h->fields();
+        FastState* f = (FastState*)h->fast;
+        exchange_f64(h, c.phi, 0, 1, 1);
+        f->pushed[f->cur] = 0;
+        launch(PerturbCollideFactoredOp<L>{c, fast_fields(h, f->cur)}, h->g.count(0), h->stream);
+        h->head_done = false;
+        h->fast_pending_stream = true;
+        return;
+    }
     cg_generic_forces(h);
     CGFields c = h->fields();
     FastState* f = (FastState*)h->fast;
@@ -1136,7 +1265,8 @@ static void fast_one_step(lbm_handle* h) {
     FastState* f = (FastState*)h->fast;
     const Grid& g = h->g;
 #ifndef LBM_HOSTCHECK
-    if (h->nranks > 1 && !h->has_solid && !open_box(h) && tiled_ok(h) && g.n2 >= 8 && (h->cfg.flags & 16u) && !(h->cfg.flags & 4u)) {
+    if (h->nranks > 1 && !h->has_solid && !open_box(h) && tiled_ok(h) && g.n2 >= 8 && (h->cfg.flags & 16u) && !(h->cfg.flags & 4u) &&
+        h->cfg.surface_tension_type == LBM_ST_CSF) {
         fast_one_step_overlapped(h);
         return;
     }
@@ -1148,7 +1278,8 @@ static void fast_one_step(lbm_handle* h) {
     // planes of the first slab and the inlet planes of the last slab AFTER the passes, so those two slabs leave that direction
     // to a one-way push behind the patch.
     const bool peer = h->nranks > 1 && h->peer_ok;
-    const bool fused = peer && tiled_ok(h) && !(h->cfg.flags & 4u) && peer_tiles_default();
+    const bool pert = h->cfg.surface_tension_type == LBM_ST_PERTURBATION;
+    const bool fused = peer && tiled_ok(h) && !(h->cfg.flags & 4u) && peer_tiles_default() && !pert;
     const bool late_down = fused && open && h->rank == 0, late_up = fused && open && h->rank == h->nranks - 1;
     if (peer && f->pushed[f->cur] == 1) comm_peer_signal_wait(h);
     else if (!(peer && f->pushed[f->cur] == 2)) fast_exchange(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
@@ -1165,7 +1296,7 @@ static void fast_one_step(lbm_handle* h) {
         } else if (h->has_solid) launch_density_tiled<true>(h, c, s); else launch_density_tiled<false>(h, c, s);
         dens_done = true;
     }
-    const bool tile2d = L::Q == 9 && tiled2d_ok(h);
+    const bool tile2d = L::Q == 9 && tiled2d_ok(h) && !pert;
     if (!dens_done) {
         if (tile2d) { if (h->has_solid) launch_density_tile2d<true>(h, c, s); else launch_density_tile2d<false>(h, c, s); }
         else if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
@@ -1177,12 +1308,19 @@ static void fast_one_step(lbm_handle* h) {
         if (late_down) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, false);
         comm_peer_signal_wait(h);
     } else fast_exchange(h, c.phi, 0, 1, h->has_solid ? NG : 2);
-    if (h->has_solid && (tiled_ok(h) || tile2d)) {      // the tiled kernels stage phi, wetting solids included
+    if (h->has_solid && (tiled_ok(h) || tile2d) && !pert) {      // the tiled kernels stage phi, wetting solids included
         if (h->pull) launch(PhiSolidListOp<L>{c, h->wet_list}, h->n_wet_list, h->stream);
         else launch(PhiSolidOp<L>{c}, g.count(2), h->stream);
     }
     bool done = false;
-    if (tiled_ok(h)) {
+    if (pert) {
+        if (tiled_ok(h) && h->g.n1 % 4 == 0 && (!h->has_solid || h->pull)) {
+            if (h->has_solid) launch_perturb_tiled<true>(h, c, s, o); else launch_perturb_tiled<false>(h, c, s, o);
+        } else if (h->has_solid) launch(PullPerturbCollideOp<L, true>{c, s, o}, g.count(0), h->stream);
+        else launch(PullPerturbCollideOp<L, false>{c, s, o}, g.count(0), h->stream);
+        done = true;
+    }
+    if (!done && tiled_ok(h)) {
         if (fused) {
             PeerPtrs pp{nullptr, nullptr, 1};
             comm_peer_pointers(h, f->buf[1 - f->cur], &pp.up, &pp.down);
@@ -1249,7 +1387,8 @@ cg_fast_persistent(const CGFields c, const FastFields b0, const FastFields b1, c
 }
 
 static bool persistent_ok(const lbm_handle* h) {
-    return (h->cfg.flags & LBM_FLAG_PERSISTENT) && h->nranks == 1 && h->g.wrap2 && !tiled_ok(h) && !g_prof_active() && !h->tracer;
+    return (h->cfg.flags & LBM_FLAG_PERSISTENT) && h->nranks == 1 && h->g.wrap2 && !tiled_ok(h) && !g_prof_active() && !h->tracer &&
+           h->cfg.surface_tension_type == LBM_ST_CSF;
 }
 
 template <class L, bool SOLIDS>

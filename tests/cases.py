@@ -356,13 +356,13 @@ def cgp_clean_snapshots(g, p):
     return nsnap
 
 
-def check_cgp_vs_gold(path, lib_path, chunk=1):
+def check_cgp_vs_gold(path, lib_path, chunk=1, **extra):
     """snapshot k of the golden file = what the reference's kernels hold at the output point of loop iteration k"""
     g, p = load_gold(path)
     clean = cgp_clean_snapshots(g, p)
     dom, red, minor = g["is_domain"], g["red_mask"], float(g["minor"])
     eng = cgp_engine(9, dom, lib_path, float(p["beta"]), float(p["akr"]), float(p["akb"]), float(p["tauR"]), float(p["tauB"]),
-                     float(p["solidphi"]), (float(p["bfx"]), float(p["bfy"])), relax=p["relax"])
+                     float(p["solidphi"]), (float(p["bfx"]), float(p["bfy"])), relax=p["relax"], **extra)
     eng.init_equilibrium(np.where(dom, np.where(red, float(p["rhoR"]), minor), 0.0),
                          np.where(dom, np.where(red, minor, float(p["rhoB"])), 0.0))
     nsnap = g["rhoR"].shape[0]
@@ -399,9 +399,11 @@ def case_cgp_dense(lib_path, lattice=19, n=(10, 12, 14), steps=8, solid=True, at
     par = dict(beta=0.8, AkR=1.0e-2, AkB=1.6e-2, tauR=1.0, tauB=0.85, solid_phi=0.3,
                body_force=(1.0e-5, -2.0e-5, 3.0e-5)[:3 if lattice == 19 else 2])
     L = cgp_dense.d3q19() if lattice == 19 else cgp_dense.d2q9()
-    sim = cgp_dense.CGPDense(L, dom, **par)
+    par.update({k: extra.pop(k) for k in ("body_force",) if k in extra})
+    relax = extra.pop("relax", "MRT")
+    sim = cgp_dense.CGPDense(L, dom, relax=relax, **par)
     sim.set_densities(rhoR, 1.0 - rhoR)
-    eng = cgp_engine(lattice, dom, lib_path, **par, **extra)
+    eng = cgp_engine(lattice, dom, lib_path, relax=relax, **par, **extra)
     eng.init_equilibrium(np.where(dom, rhoR, 0.0), np.where(dom, 1.0 - rhoR, 0.0))
     done = 0
     for k in (0, 1, 2, steps - 3):

@@ -159,6 +159,7 @@ def test_trajectory_vs_reference_graph_replay(path, flags):
 @pytest.mark.parametrize("chunk", [1, 13])
 def test_perturbation_trajectory_vs_reference_kernels(path, chunk):
     cases.check_cgp_vs_gold(path, None, chunk=chunk)
+    cases.check_cgp_vs_gold(path, None, chunk=chunk, flags=1)        # the reference-ordered kernels
 
 
 @pytest.mark.parametrize("lattice,n", [(19, (10, 12, 14)), (9, (14, 18)), (19, (24, 20, 36))])
@@ -202,3 +203,10 @@ def test_d2q9_tile_kernels_equal_the_operators_they_replace():
     multiply-adds kernel by kernel, so on the GPU they differ in the last bit (3e-16 measured) -- 1e-12 here.  BASELINE
     configuration 2 at 512^2 gives the same density checksum with and without the tile kernels (profiles/r02_cfg2_*.json)."""
     cases.check_d2q9_tile_kernels(None, tol=1e-12)
+
+
+def test_perturbation_fast_path_tiled_density_vs_oracle():
+    """the perturbation model on the factored fast path with the tiled density pass (D3Q19, extents admit the tiles)"""
+    cases.case_cgp_dense(None, 19, (10, 16, 32), solid=True)
+    cases.case_cgp_dense(None, 19, (40, 16, 64), solid=False, steps=10)
+    cases.case_cgp_dense(None, 19, (10, 16, 32), solid=True, flags=1)

@@ -135,9 +135,10 @@ def test_fast_wetting_form_of_the_tiled_kernels_equals_the_reference_ordered_for
 
 # ---- perturbation surface-tension operator ----
 @pytest.mark.parametrize("path", cases.GOLD_CGP2D, ids=[os.path.basename(p)[6:-4] for p in cases.GOLD_CGP2D])
-@pytest.mark.parametrize("chunk", [1, 7])
-def test_perturbation_trajectory_vs_reference_kernels(path, chunk, lib):
-    clean = cases.check_cgp_vs_gold(path, lib, chunk=chunk)
+@pytest.mark.parametrize("chunk,flags", [(1, 0), (7, 0), (7, 1)])
+def test_perturbation_trajectory_vs_reference_kernels(path, chunk, flags, lib):
+    """flags = 0: the factored fast path (density pass + PullPerturbCollideOp); 1: the reference-ordered kernels"""
+    clean = cases.check_cgp_vs_gold(path, lib, chunk=chunk, flags=flags)
     # the centred droplet loses its conditioning when both colours meet at its antipode (cases.cgp_clean_snapshots);
     # the asymmetric cases are compared over all 40 snapshots
     assert clean == (24 if "block_srt" in path else 40) or "cgp2d_droplet.npz" in path
@@ -145,8 +146,9 @@ def test_perturbation_trajectory_vs_reference_kernels(path, chunk, lib):
 
 @pytest.mark.parametrize("lattice,n", [(19, (10, 12, 14)), (9, (14, 18))])
 @pytest.mark.parametrize("solid", [False, True])
-def test_perturbation_vs_dense_oracle(lattice, n, solid, lib):
-    m, m_ref = cases.case_cgp_dense(lib, lattice, n, solid=solid)
+@pytest.mark.parametrize("flags", [0, 1])
+def test_perturbation_vs_dense_oracle(lattice, n, solid, flags, lib):
+    m, m_ref = cases.case_cgp_dense(lib, lattice, n, solid=solid, flags=flags)
     assert abs(m[0] - m_ref[0]) < 1e-9 and abs(m[1] - m_ref[1]) < 1e-9
 
 
@@ -289,3 +291,25 @@ def test_tracer_setup_rejects_what_is_not_built(lib):
 def test_perturbation_open_boundaries_vs_oracle(lattice, n, inlet, outlet, lib):
     """the perturbation operator with the open rows of the CSF loop: what the reference's 3-D ini parameterises"""
     cases.case_cgp_open(lib, lattice, n, inlet=inlet, outlet=outlet)
+
+
+def test_perturbation_fast_path_launches_and_tiled_density(lib):
+    """the perturbation model on the factored fast path: 2 launches per step on a closed 2-D box (3 on the reference-ordered
+    kernels), and a D3Q19 box whose extents admit the tiled density pass (recolouring weights w_i / |e_i|) against the oracle"""
+    import numpy as np
+    from openlbmpm_b200 import _lib
+    shape = (20, 24)
+    dom = np.ones(shape, bool); dom[5:8, 3:7] = False
+    rng = np.random.default_rng(4)
+    r = 0.5 + 0.3 * (rng.random(shape) - 0.5)
+    got = {}
+    for flags in (0, 1):
+        eng = cases.cgp_engine(9, dom, lib, 0.7, 8e-3, 1e-2, 1.0, 0.9, 0.4, flags=flags)
+        eng.init_equilibrium(r * dom, (1 - r) * dom)
+        eng.step(2); eng.step(10)
+        got[flags] = (eng.timing()["launches"] / 10, np.stack(eng.download_macros()[0]))
+        eng.close()
+    assert got[0][0] == 2 and got[1][0] == 3, (got[0][0], got[1][0])
+    np.testing.assert_allclose(got[0][1], got[1][1], rtol=0, atol=1e-12)
+    cases.case_cgp_dense(lib, 19, (10, 16, 32), solid=True)
+    cases.case_cgp_dense(lib, 19, (10, 16, 32), solid=False, relax="SRT", body_force=(0.0, 0.0, 0.0))

@@ -111,3 +111,13 @@ def test_colour_gradient_trajectories_persistent_kernel(path, lib):
 def test_d2q9_tile_kernels_equal_the_operators_they_replace(lib):
     """the D2Q9 tile kernels on host threads (cta_emu.h): bit-equal to the one-thread-per-node fast path, equal to the oracle"""
     cases.check_d2q9_tile_kernels(lib)
+
+
+def test_perturbation_tiled_kernels_on_slabs(lib):
+    """the perturbation-operator model with the tiled density pass and cgp_collide_tiled_d3q19 on every slab: P = 2, 3 bit-equal to
+    one slab, closed box with solids and the open channel of the reference's 3-D ini"""
+    import test_hostcheck_slabs as S
+    pert = dict(surface_tension_type=_lib.ST_PERTURBATION, AkR=7e-3, AkB=9e-3, solid_phi=0.7, beta=1.0)
+    S.compare(lib, 19, (24, 8, 32), [1, 2, 4], **pert)
+    S.compare(lib, 19, (48, 8, 32), [1, 3], worlds=(2, 3), relax=_lib.RELAX_SRT,
+              inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_PRESSURE, inlet_velocity=-1e-3, rhoBL=1.0, rhoRL=1e-8, **pert)
