@@ -128,7 +128,11 @@ struct PeerPtrs {
 // SLOWER -- 10.87 vs 10.25 ms per 512^3 launch, 3.40 vs 3.18 ms on the porous workload: the wait at the first barrier was where
 // the 24 HBM requests of a plane landed, without it the same latency shows up as long-scoreboard stalls on the first use of the
 // populations (1.55 -> 1.92).  The kernel is bound by requests in flight per SM (16 warps at 126 registers), not by the barriers.
-template <bool SOLIDS, int TX, int TY, bool TMA, bool PEER = false, int AHEAD = 1>
+// PF (all-fluid lattices, LBM_POP_PREFETCH): the 24 per-node inputs of plane z + 1 (19 pulled populations, rhoR, rhoB, lagged force)
+// are requested during plane step z with 8-byte cp.async into THREAD-PRIVATE shared-memory slots (no barrier: a thread only ever
+// reads what it copied itself) and picked up at the top of step z + 1 -- a request pipeline one full plane step deep that costs no
+// registers, where the plain loads of a step have only the shared-memory phase of the same step to land.
+template <bool SOLIDS, int TX, int TY, bool TMA, bool PEER = false, int AHEAD = 1, bool PF = false>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
 cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi,
                        const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
@@ -143,6 +147,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + 5 * PH * PW + NS * 4 * NH * NW);     // [5] one mbarrier per phi slot
     // SOLIDS: solid normals of the near-solid elements of the normal tile, two plane slots (copied one plane step ahead)
     double (*sns)[3][NH][NW] = reinterpret_cast<double (*)[3][NH][NW]>(smem_dyn + 5 * PH * PW + NS * 4 * NH * NW + 8);   // [2]
+    double* spop = smem_dyn + 5 * PH * PW + NS * 4 * NH * NW + 8 + (SOLIDS ? 2 * 3 * NH * NW : 0);    // PF: [24][NT] thread-private
     const Grid& g = c.g;
     const int64_t V = g.vol;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
@@ -314,7 +319,41 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
     const double sgn = c.p.wetting_type == 1 ? 1.0 : -1.0;
     uint32_t pm_next = 1u;
     if (SOLIDS) pm_next = c.pull[(int64_t)(z_begin + NG) * g.plane + yo[1] + xo[1]];
+    // PF: request the per-node inputs of plane zp into this thread's slots
+    auto prefetch_inputs = [&](int zp) {
+        const int64_t pid = (int64_t)(zp + NG) * g.plane + yo[1] + xo[1];
+        __pipeline_memcpy_async(&spop[tid], s.gT + pid, 8);
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            const int64_t src = (int64_t)(zp - L::d2(q) + NG) * g.plane + yo[1 - L::d1(q)] + xo[1 - L::d0(q)];
+            __pipeline_memcpy_async(&spop[q * NT + tid], s.gT + q * V + src, 8);
+        }
+        __pipeline_memcpy_async(&spop[19 * NT + tid], c.rho[0] + pid, 8);
+        __pipeline_memcpy_async(&spop[20 * NT + tid], c.rho[1] + pid, 8);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) __pipeline_memcpy_async(&spop[(21 + d) * NT + tid], c.F + d * V + pid, 8);
+    };
+    if (PF) { prefetch_inputs(z_begin); __pipeline_commit(); }
     for (int z = z_begin; z < z_end; ++z) {
+        double fT[L::Q];
+        double rR = 1.0, rB = 1.0, Fl[3] = {0.0, 0.0, 0.0}, phi0 = 0.0;
+        if (PF) {
+            __pipeline_wait_prior(0);                   // this thread's inputs of plane z (and every older copy) have landed
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) fT[q] = spop[q * NT + tid];
+            rR = spop[19 * NT + tid]; rB = spop[20 * NT + tid];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) Fl[d] = spop[(21 + d) * NT + tid];
+#ifndef LBM_HOSTCHECK
+            // the values are in registers before the slots are handed to the next copies
+            asm volatile("" : "+d"(fT[0]), "+d"(fT[1]), "+d"(fT[2]), "+d"(fT[3]), "+d"(fT[4]), "+d"(fT[5]), "+d"(fT[6]),
+                              "+d"(fT[7]), "+d"(fT[8]), "+d"(fT[9]), "+d"(fT[10]), "+d"(fT[11]), "+d"(fT[12]), "+d"(fT[13]),
+                              "+d"(fT[14]), "+d"(fT[15]), "+d"(fT[16]), "+d"(fT[17]), "+d"(fT[18]), "+d"(rR), "+d"(rB),
+                              "+d"(Fl[0]), "+d"(Fl[1]), "+d"(Fl[2]));
+#endif
+            if (z + 1 < z_end) prefetch_inputs(z + 1);
+            __pipeline_commit();
+        }
         const bool more_phi = z + AHEAD + 1 <= z_end;   // the next step derives the normals of plane z + AHEAD + 1
         if (more_phi) load_phi_plane(z + AHEAD + 2);
         if (SOLIDS && more_phi) ns_plane(z + AHEAD + 1, cl2);
@@ -329,9 +368,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
         }
         const bool fluid = pm & 1u;
         if (z + AHEAD + 2 <= z_end) class_plane(z + AHEAD + 2, ncl);     // node classes of the normal tile, two plane steps ahead
-        double fT[L::Q];
-        double rR = 1.0, rB = 1.0, Fl[3] = {0.0, 0.0, 0.0}, phi0 = 0.0;
-        if (fluid) {
+        if (fluid && !PF) {
             fT[0] = __ldcs(s.gT + id);
 #pragma unroll
             for (int q = 1; q < L::Q; ++q) {
@@ -345,7 +382,7 @@ cg_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o,
             for (int d = 0; d < 3; ++d) Fl[d] = c.F[d * V + id];
         }
         if (AHEAD == 1) {
-            __pipeline_wait_prior(1);                   // plane z + 2 (requested one step ago) has landed
+            if (!PF) __pipeline_wait_prior(1);          // plane z + 2 (requested one step ago) has landed (PF: waited for at the top)
             wait_phi_plane(z + 2);
             __syncthreads();
             normal_plane(z + 1, cl1, true);
@@ -732,7 +769,7 @@ static bool tiled_ok(const lbm_handle* h) {
 
 bool cg_tiled_possible(const lbm_handle* h) { return h->cfg.model == LBM_MODEL_CG && tiled_ok(h); }
 
-template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER, int AHEAD>
+template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER, int AHEAD, bool PF = false>
 static void launch_tiled_a(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi, const PeerPtrs pp) {
     const Grid& g = h->g;
     if (z_hi < 0) z_hi = g.n2;
@@ -740,18 +777,18 @@ static void launch_tiled_a(lbm_handle* h, const CGFields& c, const FastFields& s
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (z_hi - z_lo + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * (5 * (TILE_Y + 4) * (TILE_X + 4) + (AHEAD + 2) * 4 * (TILE_Y + 2) * (TILE_X + 2) + 8 +
-                                              (SOLIDS ? 2 * 3 * (TILE_Y + 2) * (TILE_X + 2) : 0));
+                                              (SOLIDS ? 2 * 3 * (TILE_Y + 2) * (TILE_X + 2) : 0) + (PF ? 24 * TILE_X * TILE_Y : 0));
 #ifdef LBM_HOSTCHECK
-    cta_emu::launch(grid, block, smem, [&] { cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD>(c, s, o, zchunk, z_lo, z_hi, pp); });
+    cta_emu::launch(grid, block, smem, [&] { cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD, PF>(c, s, o, zchunk, z_lo, z_hi, pp); });
 #else
     static std::atomic<bool> configured[64];  // per device: the attribute belongs to the function on ONE device (zero-initialised)
     if (!configured[h->cfg.device & 63]) {
-        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD>,
+        LBM_CUDA_CHECK(cudaFuncSetAttribute(cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD, PF>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[h->cfg.device & 63] = true;
     }
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tiled_d3q19<solids>" : "cg_collide_tiled_d3q19<all-fluid>", h->stream);
-    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi, pp);
+    cg_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, TMA, PEER, AHEAD, PF><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, z_lo, z_hi, pp);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -766,6 +803,8 @@ static int collide_ahead() {
 template <bool SOLIDS, int TILE_Y, bool TMA, bool PEER = false>
 static void launch_tiled_t(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, int z_lo, int z_hi,
                            const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
+    static const bool pf = env_int("LBM_POP_PREFETCH", 0) != 0;
+    if (!SOLIDS && TILE_Y == 4 && pf && collide_ahead() == 1) { launch_tiled_a<false, 4, TMA, PEER, 1, true>(h, c, s, o, z_lo, z_hi, pp); return; }
     if (collide_ahead() == 1) launch_tiled_a<SOLIDS, TILE_Y, TMA, PEER, 1>(h, c, s, o, z_lo, z_hi, pp);
     else launch_tiled_a<SOLIDS, TILE_Y, TMA, PEER, 2>(h, c, s, o, z_lo, z_hi, pp);
 }
