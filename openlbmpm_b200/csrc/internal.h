@@ -41,6 +41,7 @@ bool cg_tiled_possible(const lbm_handle* h);     // lattice extents and flags ad
 void cg_fast_step(lbm_handle* h, int nsteps);
 void cg_fast_materialise(lbm_handle* h);
 void cg_fast_free(lbm_handle* h);
+void cg_fast_reset(lbm_handle* h);     // new state on the same geometry: keep the factored buffers, forget their contents
 
 // Shan-Chen / explicit-forcing models (sc_api.cu)
 int sc_init_equilibrium(lbm_handle* h, const double* const* rho, int32_t n_comp);

@@ -415,7 +415,7 @@ extern "C" int lbm_init_equilibrium(lbm_handle* h, const double* const* rho, int
     set_device(h);
     if (h->cfg.model != LBM_MODEL_CG) return sc_init_equilibrium(h, rho, n_comp);
     if (n_comp != 2 || !rho || !rho[0] || !rho[1]) return fail(h, LBM_EINVAL, "colour gradient needs rho[0] = rhoR and rho[1] = rhoB");
-    cg_fast_free(h);
+    cg_fast_reset(h);
     cg_alloc_state(h);
     const int64_t owned = h->g.plane * h->g.n2;
     double* tmp = (double*)dev_alloc(2 * owned * 8);
@@ -439,7 +439,7 @@ extern "C" int lbm_upload_state(lbm_handle* h, const double* const* pdf, const d
     set_device(h);
     if (h->cfg.model != LBM_MODEL_CG) return sc_upload_state(h, pdf, rho, n_comp);
     if (n_comp != 2 || !pdf || !pdf[0] || !pdf[1]) return fail(h, LBM_EINVAL, "colour gradient needs pdf[0] = fluidPDFR and pdf[1] = fluidPDFB");
-    cg_fast_free(h);
+    cg_fast_reset(h);
     cg_alloc_state(h);
     const Grid& g = h->g;
     const int64_t owned = g.plane * g.n2;
@@ -859,7 +859,7 @@ extern "C" int lbm_init_spinodal_device(lbm_handle* h, double amplitude, uint64_
     if (!h->has_geometry) return fail(h, LBM_ESTATE, "lbm_set_geometry has not been called");
     if (h->cfg.model != LBM_MODEL_CG) return fail(h, LBM_EINVAL, "colour-gradient initialiser");
     set_device(h);
-    cg_fast_free(h);
+    cg_fast_reset(h);
     cg_alloc_state(h);
     const int64_t owned = h->g.plane * h->g.n2;
     CGFields c = h->fields();

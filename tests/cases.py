@@ -783,7 +783,7 @@ def case_cgp_open(lib_path, lattice=19, n=(22, 8, 10), steps=9, inlet="Neumann",
 # ---------------------------------------------------------------------------------------------------
 # D2Q9 tile kernels of the fast path (cg_fast.cu::cg_density_tile_d2q9 / cg_collide_tile_d2q9)
 # ---------------------------------------------------------------------------------------------------
-def check_d2q9_tile_kernels(lib_path, tol=0.0):
+def check_d2q9_tile_kernels(lib_path, tol=0.0, only=None):
     """lattices whose extents admit the 32 x 8 tiles: the tile kernels (default) against the one-thread-per-node operators they
     replace (LBM_FLAG_NO_TILED_KERNEL) -- same arithmetic operation for operation, so the comparison is bit for bit (tol = 0) --
     and against the dense oracle; periodic box, obstacles with both wetting types, open channel with walls"""
@@ -804,6 +804,8 @@ def check_d2q9_tile_kernels(lib_path, tol=0.0):
             ("channel, pressure inlet + convective outlet", walls, np.where(top, 1.0, 5e-8),
              dict(contact_angle_deg=100.0, inlet=_lib.INLET_PRESSURE, outlet=_lib.OUTLET_CONVECTIVE, rhoRH=1.003, rhoBH=5e-8))]
     for name, dom, rhoR, kw in runs:
+        if only is not None and not any(o in name for o in only):
+            continue
         rhoB = np.where(rhoR > 0.99, 5e-8, 1.0 - rhoR) if rhoR.max() > 0.99 else 1.0 - rhoR
         out = []
         for flags in (0, 2):
