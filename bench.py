@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--lattice", type=int, default=19)
-    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--size", type=int, default=0, help="lattice extent (default: 512; ini3d: 256)")
     ap.add_argument("--general", action="store_true", help="force the general (unfused) kernels")
     ap.add_argument("--cpu-size", type=int, default=256)
     ap.add_argument("--cpu-steps", type=int, default=10)
@@ -224,8 +224,8 @@ def main():
     args = ap.parse_args()
     if args.workload in ("porous", "ini3d"):
         args.lattice = 19
-    if args.workload == "ini3d" and args.size == 512:
-        args.size = 256
+    if not args.size:
+        args.size = 256 if args.workload == "ini3d" else 512
     if args.impl == "reference":
         return run_reference(args)
 
