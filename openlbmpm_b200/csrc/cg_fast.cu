@@ -668,9 +668,10 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
 // SolidColorDiff; which neighbours are solid is read off the node's pull mask (bit opp(q) = "x + e_q is fluid").  The node
 // arithmetic is cg_fast_ops.cuh::cgp_collide_factored, the gradient that of cgp_gradient_at operation for operation.
 // ------------------------------------------------------------------------------------------------
-template <bool SOLIDS, int TX, int TY>
+template <bool SOLIDS, int TX, int TY, bool PEER = false>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
-cgp_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi) {
+cgp_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi,
+                        const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
     using L = D3Q19;
     constexpr int NT = TX * TY, NW = TX + 2, NH = TY + 2;
     LBM_DYN_SMEM(smem_dyn);
@@ -750,6 +751,26 @@ cgp_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o
         o.kR[id] = kR;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { o.a[k * V + id] = a[k]; c.G[k * V + id] = G[k]; }
+        if (PEER) {         // the slab's first / last plane also goes into the neighbour slabs' ghost planes (see cg_collide_tiled_d3q19)
+            if (z == g.n2 - 1 && pp.up) {
+                const int64_t gid = id - (int64_t)g.n2 * g.plane;
+#pragma unroll
+                for (int q = 1; q < L::Q; ++q)
+                    if (L::d2(q) == 1) pp.up[q * V + gid] = fT[q];
+                pp.up[L::Q * V + gid] = kR;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pp.up[(L::Q + 1 + k) * V + gid] = a[k];
+            }
+            if (z == 0 && pp.down) {
+                const int64_t gid = id + (int64_t)g.n2 * g.plane;
+#pragma unroll
+                for (int q = 1; q < L::Q; ++q)
+                    if (L::d2(q) == -1) pp.down[q * V + gid] = fT[q];
+                pp.down[L::Q * V + gid] = kR;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pp.down[(L::Q + 1 + k) * V + gid] = a[k];
+            }
+        }
     }
 }
 
@@ -833,18 +854,19 @@ static void launch_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, 
     }
 }
 
-template <bool SOLIDS>
-static void launch_perturb_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o) {
+template <bool SOLIDS, bool PEER = false>
+static void launch_perturb_tiled(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o,
+                                 const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
     const Grid& g = h->g;
     constexpr int TILE_Y = 4;
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
     constexpr size_t smem = sizeof(double) * 4 * (TILE_Y + 2) * (TILE_X + 2);
 #ifdef LBM_HOSTCHECK
-    cta_emu::launch(grid, block, smem, [&] { cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y>(c, s, o, zchunk, 0, g.n2); });
+    cta_emu::launch(grid, block, smem, [&] { cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER>(c, s, o, zchunk, 0, g.n2, pp); });
 #else
     if (g_prof.on) g_prof.begin(SOLIDS ? "cgp_collide_tiled_d3q19<solids>" : "cgp_collide_tiled_d3q19<all-fluid>", h->stream);
-    cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, 0, g.n2);
+    cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, 0, g.n2, pp);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -1328,7 +1350,8 @@ static void fast_one_step(lbm_handle* h) {
     // to a one-way push behind the patch.
     const bool peer = h->nranks > 1 && h->peer_ok;
     const bool pert = h->cfg.surface_tension_type == LBM_ST_PERTURBATION;
-    const bool fused = peer && tiled_ok(h) && !(h->cfg.flags & 4u) && peer_tiles_default() && !pert;
+    const bool pert_tiled = pert && tiled_ok(h) && h->g.n1 % 4 == 0 && (!h->has_solid || h->pull);
+    const bool fused = peer && tiled_ok(h) && !(h->cfg.flags & 4u) && peer_tiles_default() && (!pert || pert_tiled);
     const bool late_down = fused && open && h->rank == 0, late_up = fused && open && h->rank == h->nranks - 1;
     if (peer && f->pushed[f->cur] == 1) comm_peer_signal_wait(h);
     else if (!(peer && f->pushed[f->cur] == 2)) fast_exchange(h, f->buf[f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>());
@@ -1363,7 +1386,14 @@ static void fast_one_step(lbm_handle* h) {
     }
     bool done = false;
     if (pert) {
-        if (tiled_ok(h) && h->g.n1 % 4 == 0 && (!h->has_solid || h->pull)) {
+        if (pert_tiled && fused) {
+            PeerPtrs pp{nullptr, nullptr, 1};
+            comm_peer_pointers(h, f->buf[1 - f->cur], &pp.up, &pp.down);
+            if (late_up) pp.up = nullptr;
+            if (late_down) pp.down = nullptr;
+            if (h->has_solid) launch_perturb_tiled<true, true>(h, c, s, o, pp); else launch_perturb_tiled<false, true>(h, c, s, o, pp);
+            f->pushed[1 - f->cur] = 1;
+        } else if (pert_tiled) {
             if (h->has_solid) launch_perturb_tiled<true>(h, c, s, o); else launch_perturb_tiled<false>(h, c, s, o);
         } else if (h->has_solid) launch(PullPerturbCollideOp<L, true>{c, s, o}, g.count(0), h->stream);
         else launch(PullPerturbCollideOp<L, false>{c, s, o}, g.count(0), h->stream);
