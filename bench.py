@@ -422,8 +422,8 @@ def main():
             v, cores, dt = cpu_oracle_mlups(Q, args.cpu_size, args.cpu_steps)
             cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port",
                    "sample": "%d^%d periodic spinodal box x %d steps (%.1f s), oracle/cg_c: C + OpenMP restatement of the "
-                             "reference's kernel-per-phase loop (the reference has no D3Q19 code and its Numba-CUDA "
-                             "kernels cannot run on host cores)" % (args.cpu_size, 3 if Q == 19 else 2, args.cpu_steps, dt)}
+                             "reference's kernel-per-phase loop (the reference has no D3Q19 code; where it has code -- BASELINE configurations "
+                             "1-3 -- the CPU leg is the reference itself, oracle/ref_numba.py)" % (args.cpu_size, 3 if Q == 19 else 2, args.cpu_steps, dt)}
         except Exception as e:       # the oracle is a checker; its absence must not hide the GPU number
             cpu = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "port", "sample": "unavailable: %r" % (e,)}
 
