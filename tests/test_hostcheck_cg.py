@@ -343,3 +343,32 @@ def test_reinitialisation_reuses_the_factored_buffers(lib):
         fresh.upload_state(pdf); fresh.step(3)
         assert np.array_equal(third, np.stack(fresh.download_macros()[0])), (lattice, shape)
         fresh.close()
+
+
+def test_open_rows_of_wide_planes_use_parallel_launches(lib):
+    """planes of >= 16384 nodes: the open-row chain of the fast path runs as three fully parallel launches (materialise | row
+    operators | head) instead of one thread per column -- same arithmetic, checked against the reference-ordered kernels"""
+    import numpy as np
+    from openlbmpm_b200 import _lib
+    shape = (10, 128, 128)
+    rng = np.random.default_rng(2)
+    dom = np.ones(shape, bool); dom[4:6, 20:40, 30:60] = False
+    top = np.indices(shape)[0] >= 7
+    noise = rng.random(shape)
+    kw = dict(contact_angle_deg=60.0, inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_CONVECTIVE, inlet_velocity=-1e-3)
+    out = []
+    for flags in (2, 1):          # one-thread-per-node fast path (the emulated tiled kernels would take minutes here) | general
+        eng = _lib.Engine(19, shape, lib_path=lib, flags=flags, **kw)
+        eng.set_geometry(dom)
+        # (a generic colour field: a 5e-8 trace colour puts |G| next to the reference's 1e-8 threshold, and a flat interface over
+        # the flat top of the block aligns G with the solid normal -- both are knife-edges of the reference's wetting kernel
+        # where two equivalent arithmetic orders part ways at 1e-8, see tests/test_gpu_baseline_sizes.py)
+        rR = (np.where(top, 0.8, 0.2) + 0.1 * (noise - 0.5)) * dom
+        eng.init_equilibrium(rR, (1.0 - rR) * dom)
+        eng.step(2); eng.step(4)
+        rho, u = eng.download_macros()
+        out.append(np.stack(rho + u))
+        if flags == 2:
+            assert eng.timing()["launches"] / 4 == 7       # density | materialise, row operators, head | gradient | collision | patched planes (5 with the single-launch chain)
+        eng.close()
+    np.testing.assert_allclose(out[0], out[1], rtol=0, atol=1e-10)
