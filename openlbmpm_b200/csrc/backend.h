@@ -103,6 +103,24 @@ inline void launch(const Op& op, int64_t n, stream_t s) {
     ++g_launch_counter;
 }
 
+// ... with at least MINB resident 256-thread CTAs per SM (a register cap for bandwidth-bound operators that hold many values)
+template <class Op, int MINB>
+__global__ void __launch_bounds__(256, MINB) node_kernel_occ(const Op op, const int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) op(i);
+}
+template <int MINB, class Op>
+inline void launch_occ(const Op& op, int64_t n, stream_t s) {
+    if (n <= 0) return;
+    const int block = 256;
+    const int64_t grid = (n + block - 1) / block;
+    if (g_prof.on) g_prof.begin(typeid(Op).name(), s);
+    node_kernel_occ<Op, MINB><<<(unsigned)grid, block, 0, s>>>(op, n);
+    if (g_prof.on) g_prof.end(s);
+    LBM_CUDA_CHECK(cudaGetLastError());
+    ++g_launch_counter;
+}
+
 // Replay of a launch-bound unit of work: small lattices (the 2-D configurations) spend their time in launch
 // overhead, so `body` (which only enqueues kernels on `s`) is captured once into a CUDA graph and the graph is
 // launched `reps` times.  The executable graph is parked in *keep and destroyed by the next call / the owner.
@@ -196,6 +214,8 @@ inline void launch(const Op& op, int64_t n, stream_t) {
     }
     ++g_launch_counter;
 }
+template <int MINB, class Op>
+inline void launch_occ(const Op& op, int64_t n, stream_t s) { launch(op, n, s); }
 inline bool g_prof_active() { return false; }
 struct GraphKeep { int unused = 0; };
 inline void graph_release(GraphKeep*, stream_t) {}

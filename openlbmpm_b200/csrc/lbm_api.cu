@@ -254,13 +254,16 @@ extern "C" int lbm_set_geometry(lbm_handle* h, const uint8_t* is_domain) {
         launch(ClassifyOp<3>{g, h->dom, h->cls}, g.count(NG), h->stream);
         launch(SolidNormalOp<3>{g, h->dom, h->cls, h->ns}, g.count(1), h->stream);
     }
-    if (h->has_solid && h->cfg.model == LBM_MODEL_CG) {
-        // what the tiled kernels of the fast path read instead of gathering node classes: one pull mask per node, and the
-        // wetting solids of planes [-2, n2 + 2) as a list grouped by plane
+    if (h->has_solid) {
+        // what the fused passes (tiled colour-gradient kernels, two-pass Shan-Chen loops) read instead of gathering node
+        // classes: one pull mask per node
         h->pull = (uint32_t*)dev_alloc((size_t)g.vol * sizeof(uint32_t));
         dev_zero(h->pull, (size_t)g.vol * sizeof(uint32_t), h->stream);
         if (h->D == 2) launch(PullMaskOp<D2Q9>{g, h->cls, h->pull}, g.count(0), h->stream);
         else launch(PullMaskOp<D3Q19>{g, h->cls, h->pull}, g.count(0), h->stream);
+    }
+    if (h->has_solid && h->cfg.model == LBM_MODEL_CG) {
+        // ... and the wetting solids of planes [-2, n2 + 2) as a list grouped by plane
         const int np = g.n2 + 4;
         int64_t* counts = (int64_t*)dev_alloc((size_t)np * 8);
         try {

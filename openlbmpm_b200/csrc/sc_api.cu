@@ -5,7 +5,7 @@
 #include <atomic>
 #include "coop.h"
 #include "internal.h"
-#include "sc_ops.cuh"
+#include "sc_fast.cuh"
 
 namespace lbm {
 
@@ -145,8 +145,8 @@ static void sc_ensure_head(lbm_handle* h) {
     s->head_done = true;
 }
 
-// one iteration of runOptimizedLBM's loop (ShanChenD2Q9.py:1492-1629)
-static void sc_iteration(lbm_handle* h) {
+// one iteration of runOptimizedLBM's loop (ShanChenD2Q9.py:1492-1629), in two halves: what precedes the streaming ...
+static void sc_head_collide(lbm_handle* h) {
     SCState* s = (SCState*)h->sc;
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
@@ -164,6 +164,12 @@ static void sc_iteration(lbm_handle* h) {
     }
     exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
     SC_LAUNCH(g.count(0), ScCollideOp, c);                  // interactionCollisionProcess
+}
+// ... and the streaming with what follows it
+static void sc_tail(lbm_handle* h) {
+    SCState* s = (SCState*)h->sc;
+    const Grid& g = h->g;
+    SCFields c = sc_fields(h);
     exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
     SC_LAUNCH(g.count(0), ScStreamOp, c);                   // calStreaming1GPU/2GPU (+ densities)
     if (c.p.outlet == LBM_OUTLET_CONVECTIVE && owns_outlet(h))      // convectiveOutletGPU / Ghost2 / Ghost3
@@ -171,6 +177,10 @@ static void sc_iteration(lbm_handle* h) {
     // calPhysicalVelocity: an output, nothing in the loop reads it -> evaluated when somebody asks (sc_ensure_velocity)
     s->uph_valid = false;
     s->head_done = false;
+}
+static void sc_iteration(lbm_handle* h) {
+    sc_head_collide(h);
+    sc_tail(h);
 }
 
 // the physical velocity of the last finished iteration of the original Shan-Chen loop (ShanChenD2Q9.py:1561-1573); must
@@ -206,13 +216,18 @@ static void efs_prepare(lbm_handle* h) {
     s->efs_prepared = true;
 }
 
-// one iteration of runOptimizedEFLBM's loop (ShanChenD2Q9.py:1852-2087)
-static void efs_iteration(lbm_handle* h) {
+// one iteration of runOptimizedEFLBM's loop (ShanChenD2Q9.py:1852-2087), in two halves: the collision ...
+static void efs_collide(lbm_handle* h) {
     const Grid& g = h->g;
     SCFields c = sc_fields(h);
     const bool convective = c.p.outlet == LBM_OUTLET_CONVECTIVE;
     if (convective && owns_outlet(h)) SC_LAUNCH(3 * g.plane, ScSaveRowsOp, c);   // savePDFLastStep
     SC_LAUNCH(g.count(0), EfsCollideOp, c);
+}
+// ... and the streaming, the boundary rows and the force of the next collision
+static void efs_tail(lbm_handle* h) {
+    const Grid& g = h->g;
+    SCFields c = sc_fields(h);
     exchange_f64(h, c.fC, g.vol, c.p.nc * h->Q, 1);
     SC_LAUNCH(g.count(0), ScStreamOp, c);
     // boundary rows (convective-each | pressure outlet, velocity inlet) and calFluidRhoGPU after them: the streaming and the
@@ -225,6 +240,81 @@ static void efs_iteration(lbm_handle* h) {
     }
     exchange_f64(h, c.rho, g.vol, c.p.nc, c.p.scheme == 4 ? 1 : NG);
     SC_LAUNCH(g.count(0), EfsForceOp, c);               // also the physical velocity of the output point (:2016-2027)
+}
+static void efs_iteration(lbm_handle* h) {
+    efs_collide(h);
+    efs_tail(h);
+}
+
+// ---- two-pass form (sc_fast.cuh) ---------------------------------------------------------------------------------------
+// Two components, isotropy 4, no convective outlet under explicit forcing (its rows read the populations of the previous
+// iteration and the physical velocity of plane 3, which the two-pass form does not keep); everything else -- solids, velocity
+// inlet, pressure outlet (explicit forcing) / convective outlet (original Shan-Chen), D2Q9 and D3Q19, slabs -- runs on it.
+static bool sc_fast_eligible(const lbm_handle* h) {
+    const lbm_config& cfg = h->cfg;
+    if (cfg.flags & LBM_FLAG_GENERIC_KERNELS) return false;
+    if (cfg.n_components != 2) return false;
+    if (cfg.model == LBM_MODEL_EFS) {
+        if (cfg.sc_isotropy == 8 || cfg.sc_isotropy == 10) return false;
+        if (cfg.outlet == LBM_OUTLET_CONVECTIVE) return false;
+    }
+    return !h->has_solid || h->pull != nullptr;
+}
+
+// `m` >= 2 iterations; the state is the reference-ordered one (streamed populations, densities, force) at entry and at exit:
+// the first collision and the last streaming run on the reference-ordered operators, the m - 1 streaming + collision pairs in
+// between on the two passes.  The two population buffers of the state alternate as source and destination.
+// resident 256-thread CTAs per SM the collision pass is compiled for: D2Q9 holds 2 x 9 populations and 2 x 8 neighbour densities
+// (120 / 148 registers uncapped; 2 CTAs = a 128-register cap cost the explicit-forcing operator 64 bytes of spills), D3Q19 holds
+// 2 x 19 + 2 x 18 values and spills hundreds of bytes under any cap.  LBM_SC_OCC = 1 | 2 | 3 overrides (measurement aid).
+static int sc_occupancy(int Q) {
+    static const int forced = [] { const char* e = getenv("LBM_SC_OCC"); return e ? atoi(e) : 0; }();
+    if (forced >= 1 && forced <= 3) return forced;
+    return Q == 9 ? 2 : 1;
+}
+template <class Op>
+static void sc_launch_collide(lbm_handle* h, const Op& op) {
+    const int64_t n = h->g.count(0);
+    switch (sc_occupancy(h->Q)) {
+        case 3: launch_occ<3>(op, n, h->stream); break;
+        case 2: launch_occ<2>(op, n, h->stream); break;
+        default: launch(op, n, h->stream);
+    }
+}
+template <class L>
+static void sc_fast_iterations(lbm_handle* h, int m) {
+    SCState* s = (SCState*)h->sc;
+    const Grid& g = h->g;
+    const bool efs = h->cfg.model == LBM_MODEL_EFS;
+    if (efs) efs_collide(h); else sc_head_collide(h);
+    const SCFields c = sc_fields(h);
+    const int do_in = (c.p.inlet == LBM_INLET_VELOCITY && owns_inlet(h)) ? 1 : 0;
+    const int do_out = ((efs ? c.p.outlet == LBM_OUTLET_PRESSURE : c.p.outlet == LBM_OUTLET_CONVECTIVE) && owns_outlet(h)) ? 1 : 0;
+    ScFast f;
+    f.pull = h->has_solid ? h->pull : nullptr;
+    f.mat_lo = do_out ? (efs ? c.z_out + 1 : 4) : 0;       // pressure outlet: planes 0 .. z_out; convective copies: 3 -> 2 -> 1 -> 0
+    f.mat_hi = do_in ? g.n2 - c.z_in : 0;                  // velocity inlet: planes z_in .. n2 - 1
+    auto fused = [&](double* src, double* dst) {
+        exchange_f64(h, src, g.vol, c.p.nc * h->Q, 1);
+        f.src = src; f.dst = dst;
+        launch(ScPullDensityOp<L>{c, f}, g.count(0), h->stream);
+        if (do_in || do_out) {
+            SCFields r = c;
+            r.fS = dst;
+            launch(ScOpenRowsOp<L>{r, efs ? 1 : 0, efs ? 0 : 3, do_in, do_out, 1}, 2 * g.plane, h->stream);
+        }
+        exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
+        if (efs) sc_launch_collide(h, EfsPullCollideOp<L, 2>{c, f});
+        else sc_launch_collide(h, ScPullCollideOp<L, 2>{c, f});
+    };
+    double *A = s->fC, *B = s->fS;
+    const int n = m - 1;
+    replay(n / 2, h->graph_ok(), &h->graph, h->stream, [&] { fused(A, B); fused(B, A); });
+    if (n & 1) {
+        fused(A, B);
+        s->fC = B; s->fS = A;
+    }
+    if (efs) efs_tail(h); else sc_tail(h);
 }
 
 // Persistent form of both loops (LBM_FLAG_PERSISTENT, opt-in; see cg_fast.cu::cg_fast_persistent): every iteration of an
@@ -303,6 +393,10 @@ void sc_step(lbm_handle* h, int nsteps) {
     one();      // outside the graph: whether the inlet treatment of this iteration is still due depends on the host state
     if (nsteps > 1 && (h->cfg.flags & LBM_FLAG_PERSISTENT) && h->nranks == 1 && h->g.wrap2 && !g_prof_active()) {
         if (h->Q == 9) sc_launch_persistent<D2Q9>(h, nsteps - 1); else sc_launch_persistent<D3Q19>(h, nsteps - 1);
+        return;
+    }
+    if (nsteps > 2 && sc_fast_eligible(h)) {
+        if (h->Q == 9) sc_fast_iterations<D2Q9>(h, nsteps - 1); else sc_fast_iterations<D3Q19>(h, nsteps - 1);
         return;
     }
     replay(nsteps - 1, h->graph_ok(), &h->graph, h->stream, one);

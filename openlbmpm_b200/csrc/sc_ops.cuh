@@ -262,7 +262,8 @@ struct ScConvectiveEachOp {
 // so one thread runs them back to back: same arithmetic, same order.  `efs`: the explicit-forcing loop
 // (ShanChenD2Q9.py:1933-2014: convective-each / pressure outlet, inlet, then calFluidRhoGPU -- of which only the two
 // Zou-He planes are not already sums); otherwise the original loop's pieces selected by `part`:
-// 1 = inlet at the top of an iteration (+ calFluidRhoGPU on its plane), 2 = convective outlet copies after the streaming.
+// 1 = inlet at the top of an iteration (+ calFluidRhoGPU on its plane), 2 = convective outlet copies after the streaming
+// (3 = both: the two-pass form treats the rows of iteration k's end and iteration k + 1's top between its passes).
 template <class L>
 struct ScOpenRowsOp {
     SCFields c; int efs, part, do_in, do_out, rho_after_inlet;
@@ -284,12 +285,12 @@ struct ScOpenRowsOp {
                     for (int zr = c.z_out; zr > 0; --zr) ScRowCopyOp<L>{c, zr - 1, zr}(i);
                     ScRhoOp<L>{c}((int64_t)c.z_out * plane + i);
                 }
-            } else if (part == 2 && c.p.outlet == LBM_OUTLET_CONVECTIVE) {
+            } else if ((part & 2) && c.p.outlet == LBM_OUTLET_CONVECTIVE) {
                 ScRowCopyOp<L>{c, 2, 3}(i); ScRowCopyOp<L>{c, 1, 2}(i); ScRowCopyOp<L>{c, 0, 1}(i);
             }
         } else {
             if (!do_in || c.p.inlet != LBM_INLET_VELOCITY) return;
-            if (efs || part == 1) inlet_column(i - plane);
+            if (efs || (part & 1)) inlet_column(i - plane);
         }
     }
 };
@@ -529,12 +530,7 @@ struct EfsForceOp {
 // equilibrium and force distributions of component k at a node (calEquilibriumFuncEFGPU 227-248,
 // calForceDistrGPU 255-272)
 template <class L>
-LBM_HD void efs_feq_ff(const SCFields& c, int k, int64_t id, double* feq, double* ff) {
-    const int64_t V = c.g.vol;
-    const double r = c.rho[k * V + id];
-    double u[3] = {0.0, 0.0, 0.0}, F[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int a = 0; a < L::D; ++a) { u[a] = c.ueq[a * V + id]; F[a] = c.Fc(k, a, id); }
+LBM_HD void efs_feq_ff_at(double r, const double* u, const double* F, double* feq, double* ff) {
 #pragma unroll
     for (int q = 0; q < L::Q; ++q) {
         feq[q] = sc_feq<L>(q, r, u);
@@ -543,6 +539,15 @@ LBM_HD void efs_feq_ff(const SCFields& c, int k, int64_t id, double* feq, double
         for (int a = 0; a < L::D; ++a) s += F[a] * (L::c(q, a) - u[a]);
         ff[q] = s * feq[q] / (1.0 / 3.0 * r);
     }
+}
+template <class L>
+LBM_HD void efs_feq_ff(const SCFields& c, int k, int64_t id, double* feq, double* ff) {
+    const int64_t V = c.g.vol;
+    const double r = c.rho[k * V + id];
+    double u[3] = {0.0, 0.0, 0.0}, F[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < L::D; ++a) { u[a] = c.ueq[a * V + id]; F[a] = c.Fc(k, a, id); }
+    efs_feq_ff_at<L>(r, u, F, feq, ff);
 }
 // transformPDFGPU (ExplicitD2Q9GPU.py:278-287), once before the first iteration: f <- f - fF / 2
 template <class L>

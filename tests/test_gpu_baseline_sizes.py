@@ -122,3 +122,52 @@ def test_porous_d3q19_fast_path_equals_general_kernels():
                      expect=("cg_collide_tiled",), contact_angle_deg=60.0, inlet=_lib.INLET_VELOCITY,
                      outlet=_lib.OUTLET_CONVECTIVE, inlet_velocity=-5.0e-4, **PAR)
     assert worst[0] < 1e-9 and max(worst) < 1e-6, worst
+
+
+def sc_pair(shape, dom, rho, chunks, expect, **par):
+    """the two-pass form (csrc/sc_fast.cuh) and LBM_FLAG_GENERIC_KERNELS on the same input -> max |difference| over the
+    densities, the velocity and the populations"""
+    outs = []
+    for flags in (0, _lib.FLAG_GENERIC_KERNELS):
+        eng = _lib.Engine(9, shape, flags=flags, **par)
+        eng.set_geometry(dom)
+        eng.init_equilibrium(rho[0], rho[1])
+        eng.profile(True)
+        snaps = []
+        for n in chunks:
+            eng.step(n)
+            r, u = eng.download_macros()
+            snaps.append(np.stack(r + u))
+        snaps.append(np.stack(eng.download_pdfs()))
+        names = ran_kernels(eng)
+        eng.profile(False)
+        assert (expect in names) == (flags == 0), names
+        outs.append(snaps)
+        eng.close()
+    return max(np.abs(a - b).max() for a, b in zip(*outs))
+
+
+def test_cfg3_1024_squared_two_pass_form_equals_reference_ordered_operators():
+    """BASELINE config 3 at its own size (D2Q9 explicit forcing MRT, disc pack, velocity inlet + pressure outlet, 1024 x 1024):
+    the two-pass form against the reference-ordered operators (pinned to the reference's vectors), every field, 1e-11 --
+    the two differ by nvcc's multiply-add contraction per kernel only"""
+    from test_gpu_fullsize import discs
+    shape = (1024, 1024)
+    dom = discs(shape)
+    reg = np.indices(shape)[0] < shape[0] - 10
+    rho = np.stack([np.where(reg, 1.0, 0.02), np.where(reg, 0.02, 1.0)]) * dom
+    par = dict(model=_lib.MODEL_EFS, relax=_lib.RELAX_MRT, n_components=2, sc_tau=[1.0, 1.0], sc_G=[0, 0.2, 0, 0, 0.2, 0],
+               sc_Gsolid=[-0.14, 0.14], inlet=_lib.INLET_VELOCITY, outlet=_lib.OUTLET_PRESSURE,
+               sc_inlet_velocity=[0.0, -5.03e-4], sc_rho_out=[1.0, 0.02])
+    assert sc_pair(shape, dom, rho, [1, 30, 69], "EfsPullCollideOp", **par) < 1e-11
+
+
+def test_cfg1_128_squared_two_pass_form_equals_reference_ordered_operators():
+    """BASELINE config 1 (D2Q9 original Shan-Chen, 128 x 128 periodic droplet), 60 steps: 1e-10 (the segregating droplet amplifies rounding differences)"""
+    n = (128, 128)
+    yy, xx = np.mgrid[0:128, 0:128]
+    reg = (xx - 64) ** 2 + (yy - 64) ** 2 <= 20 ** 2
+    rho = np.stack([np.where(reg, 1.0, 0.06), np.where(reg, 0.06, 1.0)])
+    par = dict(model=_lib.MODEL_SC, relax=_lib.RELAX_SRT, n_components=2, sc_tau=[1.0, 1.0], sc_G=[0, 3.8, 0, 0, 3.8, 0],
+               sc_Gsolid=[-0.4, 0.4])
+    assert sc_pair(n, np.ones(n, bool), rho, [1, 20, 39], "ScPullCollideOp", **par) < 1e-10
