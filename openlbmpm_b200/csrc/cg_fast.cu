@@ -941,6 +941,22 @@ static void launch_density_tiled(lbm_handle* h, const CGFields& c, const FastFie
 // results are bit-equal to the three one-thread-per-node launches this replaces) and never writes G / n to memory.
 // Rows wrap by index arithmetic on a single slab (Grid::wrap2) or reach into the ghost rows of a slab decomposition.
 // ------------------------------------------------------------------------------------------------
+struct OpenRows {
+    int n = 0;
+    int mat_lo[2], mat_hi[2];     // planes whose streamed populations the row operators read
+    int mod_lo[2], mod_hi[2];     // planes they modify
+};
+static OpenRows open_rows(const CGFields& c) {
+    OpenRows r;
+    if (c.outlet != LBM_BC_PERIODIC && c.z_out >= 0) {
+        const bool conv = c.outlet == LBM_OUTLET_CONVECTIVE;      // rows 2 <- 3, 1 <- 2, 0 <- 1 | row 1 treated, 0 <- 1
+        r.mat_lo[r.n] = 0; r.mat_hi[r.n] = conv ? 4 : 2; r.mod_lo[r.n] = 0; r.mod_hi[r.n] = conv ? 3 : 2; ++r.n;
+    }
+    if (c.inlet != LBM_BC_PERIODIC && c.z_in >= 0) {
+        r.mat_lo[r.n] = r.mod_lo[r.n] = c.z_in; r.mat_hi[r.n] = r.mod_hi[r.n] = c.z_in_ghost + 1; ++r.n;
+    }
+    return r;
+}
 constexpr int T2X = 32, T2Y = 8;
 template <int TX, int TY>
 struct Tile2D {
@@ -1006,7 +1022,7 @@ cg_density_tile_d2q9(const CGFields c, const FastFields s) {
 
 template <bool SOLIDS, int TX, int TY>
 __global__ void __launch_bounds__(TX* TY)
-cg_collide_tile_d2q9(const CGFields c, const FastFields s, const FastFields o) {
+cg_collide_tile_d2q9(const CGFields c, const FastFields s, const FastFields o, const OpenRows rows) {
     using L = D2Q9;
     constexpr int NT = TX * TY, PW = TX + 4, PH = TY + 4, NW = TX + 2, NH = TY + 2;
     constexpr int NE = (NH * NW + NT - 1) / NT;
@@ -1026,11 +1042,21 @@ cg_collide_tile_d2q9(const CGFields c, const FastFields s, const FastFields o) {
     const int64_t id = t.id(tx, tz);
     const uint32_t pm = SOLIDS ? c.pull[id] : 0xFFFFFFFFu;
     double fT[L::Q], own[L::Q];
-    fT[0] = s.gT[id];
+    // open-boundary rows: their streamed populations were materialised and treated by the row operators (FastOpenPreOp), the
+    // node collides those instead of pulling -- what used to be two launches behind this one (gradient + collision of the rows)
+    const int zrow = (int)blockIdx.y * TY + tz;
+    const bool treated = (rows.n > 0 && zrow >= rows.mod_lo[0] && zrow < rows.mod_hi[0]) ||
+                         (rows.n > 1 && zrow >= rows.mod_lo[1] && zrow < rows.mod_hi[1]);
+    if (treated) {
 #pragma unroll
-    for (int q = 1; q < L::Q; ++q) {
-        fT[q] = s.gT[q * V + t.id(tx - L::d0(q), tz - L::d2(q))];
-        if (SOLIDS) own[q] = s.gT[L::opp(q) * V + id];
+        for (int q = 0; q < L::Q; ++q) { fT[q] = c.fS[0][q * V + id] + c.fS[1][q * V + id]; own[q] = 0.0; }
+    } else {
+        fT[0] = s.gT[id];
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            fT[q] = s.gT[q * V + t.id(tx - L::d0(q), tz - L::d2(q))];
+            if (SOLIDS) own[q] = s.gT[L::opp(q) * V + id];
+        }
     }
     const double rR = c.rho[0][id], rB = c.rho[1][id];
     const double Fl[2] = {c.F[id], c.F[V + id]};
@@ -1073,7 +1099,7 @@ cg_collide_tile_d2q9(const CGFields c, const FastFields s, const FastFields o) {
     }
     __syncthreads();
     if (!(pm & 1u)) return;
-    if (SOLIDS) {
+    if (SOLIDS && !treated) {
 #pragma unroll
         for (int q = 1; q < L::Q; ++q)
             if (!(pm & (1u << q))) fT[q] = own[q];          // half-way bounce back
@@ -1144,15 +1170,15 @@ static void launch_density_tile2d(lbm_handle* h, const CGFields& c, const FastFi
     ++g_launch_counter;
 }
 template <bool SOLIDS>
-static void launch_collide_tile2d(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o) {
+static void launch_collide_tile2d(lbm_handle* h, const CGFields& c, const FastFields& s, const FastFields& o, const OpenRows& rows) {
     const Grid& g = h->g;
     dim3 grid(g.n0 / T2X, g.n2 / T2Y), block(T2X, T2Y);
     constexpr size_t smem = sizeof(double) * ((T2Y + 4) * (T2X + 4) + 4 * (T2Y + 2) * (T2X + 2));
 #ifdef LBM_HOSTCHECK
-    cta_emu::launch(grid, block, smem, [&] { cg_collide_tile_d2q9<SOLIDS, T2X, T2Y>(c, s, o); });
+    cta_emu::launch(grid, block, smem, [&] { cg_collide_tile_d2q9<SOLIDS, T2X, T2Y>(c, s, o, rows); });
 #else
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tile_d2q9<solids>" : "cg_collide_tile_d2q9<all-fluid>", h->stream);
-    cg_collide_tile_d2q9<SOLIDS, T2X, T2Y><<<grid, block, smem, h->stream>>>(c, s, o);
+    cg_collide_tile_d2q9<SOLIDS, T2X, T2Y><<<grid, block, smem, h->stream>>>(c, s, o, rows);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -1191,22 +1217,6 @@ static void launch_plane_ranges(lbm_handle* h, const Op& op, int ext, int n, con
         const int64_t cnt0 = (int64_t)(hi[0] - lo[0]) * plane, cnt1 = (int64_t)(hi[1] - lo[1]) * plane;
         launch(TwoRangeOp<Op>{op, (int64_t)(lo[0] + ext) * plane, cnt0, (int64_t)(lo[1] + ext) * plane}, cnt0 + cnt1, h->stream);
     }
-}
-struct OpenRows {
-    int n = 0;
-    int mat_lo[2], mat_hi[2];     // planes whose streamed populations the row operators read
-    int mod_lo[2], mod_hi[2];     // planes they modify
-};
-static OpenRows open_rows(const CGFields& c) {
-    OpenRows r;
-    if (c.outlet != LBM_BC_PERIODIC && c.z_out >= 0) {
-        const bool conv = c.outlet == LBM_OUTLET_CONVECTIVE;      // rows 2 <- 3, 1 <- 2, 0 <- 1 | row 1 treated, 0 <- 1
-        r.mat_lo[r.n] = 0; r.mat_hi[r.n] = conv ? 4 : 2; r.mod_lo[r.n] = 0; r.mod_hi[r.n] = conv ? 3 : 2; ++r.n;
-    }
-    if (c.inlet != LBM_BC_PERIODIC && c.z_in >= 0) {
-        r.mat_lo[r.n] = r.mod_lo[r.n] = c.z_in; r.mat_hi[r.n] = r.mod_hi[r.n] = c.z_in_ghost + 1; ++r.n;
-    }
-    return r;
 }
 // One thread per column and side: materialise the streamed populations of the column's open rows from the factored state
 // (read-only neighbours), run the row operators on them, re-evaluate velocity (lagged force) and phi there.  Every step of
@@ -1418,9 +1428,14 @@ static void fast_one_step(lbm_handle* h) {
         } else if (h->has_solid) launch_tiled<true>(h, c, s, o); else launch_tiled<false>(h, c, s, o);
         done = true;
     }
+    bool rows_done = false;
     if (!done && tile2d) {
-        if (h->has_solid) launch_collide_tile2d<true>(h, c, s, o); else launch_collide_tile2d<false>(h, c, s, o);
+        // the tile kernel collides the treated open rows itself (LBM_TILE_2D_ROWS=0: the two patch launches behind it, as before)
+        static const bool fold_rows = env_int("LBM_TILE_2D_ROWS", 1) != 0;
+        const OpenRows rows = (open && fold_rows) ? open_rows(c) : OpenRows();
+        if (h->has_solid) launch_collide_tile2d<true>(h, c, s, o, rows); else launch_collide_tile2d<false>(h, c, s, o, rows);
         done = true;
+        rows_done = open && fold_rows;
     }
     if (!done) {
         launch(GradientOp<L>{c}, g.count(1), h->stream);
@@ -1428,7 +1443,7 @@ static void fast_one_step(lbm_handle* h) {
         else launch(PullCollideOp<L, false>{c, s, o}, g.count(0), h->stream);
         if (h->tracer) { tracer_phase(h); tracer_iteration_finished(h); }
     }
-    if (open) fast_open_rows_post<L>(h, c, o, done);
+    if (open && !rows_done) fast_open_rows_post<L>(h, c, o, done);
     if (late_up) peer_push_one_way(h, f->buf[1 - f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>(), true);
     if (late_down) peer_push_one_way(h, f->buf[1 - f->cur], g.vol, L::Q + 4, 1, factored_dirs<L>(), false);
     f->cur = 1 - f->cur;

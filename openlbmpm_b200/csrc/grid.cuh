@@ -39,9 +39,16 @@ struct Grid {
     }
     // item i of a launch over planes [-ext, n2 + ext)
     LBM_HD void decode(int64_t i, int ext, int& x, int& y, int& z) const {
-        z = (int)(i / plane) - ext;
-        const int r = (int)(i % plane);
-        y = r / n0;
+        int r;
+        if ((uint64_t)(i | plane) >> 31 == 0) {     // every lattice below 2^31 nodes: one 32-bit division instead of an emulated 64-bit one
+            const uint32_t ii = (uint32_t)i, p = (uint32_t)plane, zz = ii / p;
+            z = (int)zz - ext;
+            r = (int)(ii - zz * p);
+        } else {
+            z = (int)(i / plane) - ext;
+            r = (int)(i % plane);
+        }
+        y = n1 == 1 ? 0 : r / n0;
         x = r - y * n0;
     }
     LBM_HD int64_t count(int ext) const { return plane * (int64_t)(n2 + 2 * ext); }

@@ -39,17 +39,17 @@ struct ScPullDensityOp {
         const uint32_t m = s.pull ? s.pull[id] : 0xFFFFFFFFu;
         if (!(m & 1u)) return;
         const bool mat = s.materialised(g, z);
-        int64_t up[L::Q];
+        int64_t from[L::Q];     // where population q comes from: the upstream node, or the node's own opposite direction
 #pragma unroll
-        for (int q = 1; q < L::Q; ++q) up[q] = g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q));
+        for (int q = 1; q < L::Q; ++q)
+            from[q] = (m >> q & 1u) ? (int64_t)q * g.vol + g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q)) : (int64_t)L::opp(q) * g.vol + id;
         for (int k = 0; k < c.p.nc; ++k) {
             const double* fk = s.src + (int64_t)k * L::Q * g.vol;
             double* dk = s.dst + (int64_t)k * L::Q * g.vol;
             double v[L::Q];
             v[0] = fk[id];
 #pragma unroll
-            for (int q = 1; q < L::Q; ++q)
-                v[q] = (m >> q & 1u) ? fk[(int64_t)q * g.vol + up[q]] : fk[(int64_t)L::opp(q) * g.vol + id];
+            for (int q = 1; q < L::Q; ++q) v[q] = fk[from[q]];
             double acc = v[0];
 #pragma unroll
             for (int q = 1; q < L::Q; ++q) acc += v[q];
@@ -74,16 +74,16 @@ LBM_HD void sc_fast_gather(const SCFields& c, const ScFast& s, int x, int y, int
             for (int q = 0; q < L::Q; ++q) f[k][q] = s.dst[((int64_t)k * L::Q + q) * g.vol + id];
         return;
     }
-    int64_t up[L::Q];
+    int64_t from[L::Q];
 #pragma unroll
-    for (int q = 1; q < L::Q; ++q) up[q] = g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q));
+    for (int q = 1; q < L::Q; ++q)
+        from[q] = (m >> q & 1u) ? (int64_t)q * g.vol + g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q)) : (int64_t)L::opp(q) * g.vol + id;
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
         const double* fk = s.src + (int64_t)k * L::Q * g.vol;
         f[k][0] = fk[id];
 #pragma unroll
-        for (int q = 1; q < L::Q; ++q)
-            f[k][q] = (m >> q & 1u) ? fk[(int64_t)q * g.vol + up[q]] : fk[(int64_t)L::opp(q) * g.vol + id];
+        for (int q = 1; q < L::Q; ++q) f[k][q] = fk[from[q]];
     }
 }
 
@@ -107,7 +107,7 @@ struct ScPullCollideOp {
             fl[q] = m >> L::opp(q) & 1u;
             const int64_t nb = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
 #pragma unroll
-            for (int k = 0; k < NC; ++k) rn[k][q] = fl[q] ? c.rho[k * V + nb] : 0.0;
+            for (int k = 0; k < NC; ++k) rn[k][q] = c.rho[k * V + nb];      // only used where fl[q] (a solid node holds 0)
         }
         double f[NC][L::Q];
         sc_fast_gather<L, NC>(c, s, x, y, z, id, m, f);
@@ -189,7 +189,7 @@ struct EfsPullCollideOp {
             fl[q] = m >> L::opp(q) & 1u;
             const int64_t nb = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
 #pragma unroll
-            for (int k = 0; k < NC; ++k) rn[k][q] = fl[q] ? c.rho[k * V + nb] : 0.0;
+            for (int k = 0; k < NC; ++k) rn[k][q] = c.rho[k * V + nb];      // only used where fl[q] (a solid node holds 0)
         }
         double f[NC][L::Q];
         sc_fast_gather<L, NC>(c, s, x, y, z, id, m, f);
