@@ -297,7 +297,7 @@ static void sc_fast_iterations(lbm_handle* h, int m) {
     auto fused = [&](double* src, double* dst) {
         exchange_f64(h, src, g.vol, c.p.nc * h->Q, 1);
         f.src = src; f.dst = dst;
-        launch(ScPullDensityOp<L>{c, f}, g.count(0), h->stream);
+        launch(ScPullDensityOp<L, 2>{c, f}, g.count(0), h->stream);
         if (do_in || do_out) {
             SCFields r = c;
             r.fS = dst;

@@ -29,34 +29,41 @@ struct ScFast {
 };
 
 // streaming + densities, nothing else written (calStreaming1GPU/2GPU + calFluidRhoGPU, OptimizedD2Q9GPU.py:450-548, 84-93)
-template <class L>
+template <class L, int NC>
 struct ScPullDensityOp {
     SCFields c; ScFast s;
     LBM_HD void operator()(int64_t i) const {
         const Grid& g = c.g;
         int x, y, z; g.decode(i, 0, x, y, z);
-        const int64_t id = g.at(x, y, z);
+        const int64_t id = g.at(x, y, z), V = g.vol;
         const uint32_t m = s.pull ? s.pull[id] : 0xFFFFFFFFu;
         if (!(m & 1u)) return;
         const bool mat = s.materialised(g, z);
+        const NbTable nb(g, x, y, z);
         int64_t from[L::Q];     // where population q comes from: the upstream node, or the node's own opposite direction
 #pragma unroll
-        for (int q = 1; q < L::Q; ++q)
-            from[q] = (m >> q & 1u) ? (int64_t)q * g.vol + g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q)) : (int64_t)L::opp(q) * g.vol + id;
-        for (int k = 0; k < c.p.nc; ++k) {
-            const double* fk = s.src + (int64_t)k * L::Q * g.vol;
-            double* dk = s.dst + (int64_t)k * L::Q * g.vol;
-            double v[L::Q];
-            v[0] = fk[id];
+        for (int q = 1; q < L::Q; ++q) {
+            const int64_t pulled = (int64_t)q * V + nb(-L::d0(q), -L::d1(q), -L::d2(q)), own = (int64_t)L::opp(q) * V + id;
+            from[q] = (m >> q & 1u) ? pulled : own;
+        }
+        double v[NC][L::Q];     // both components requested before either is summed
 #pragma unroll
-            for (int q = 1; q < L::Q; ++q) v[q] = fk[from[q]];
-            double acc = v[0];
+        for (int k = 0; k < NC; ++k) {
+            const double* fk = s.src + (int64_t)k * L::Q * V;
+            v[k][0] = fk[id];
 #pragma unroll
-            for (int q = 1; q < L::Q; ++q) acc += v[q];
-            c.rho[k * g.vol + id] = acc;
+            for (int q = 1; q < L::Q; ++q) v[k][q] = fk[from[q]];
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            double acc = v[k][0];
+#pragma unroll
+            for (int q = 1; q < L::Q; ++q) acc += v[k][q];
+            c.rho[k * V + id] = acc;
             if (mat) {
+                double* dk = s.dst + (int64_t)k * L::Q * V;
 #pragma unroll
-                for (int q = 0; q < L::Q; ++q) dk[(int64_t)q * g.vol + id] = v[q];
+                for (int q = 0; q < L::Q; ++q) dk[(int64_t)q * V + id] = v[k][q];
             }
         }
     }
@@ -65,7 +72,7 @@ struct ScPullDensityOp {
 // the streamed populations of a node, all components: pulled from the post-collision buffer, or -- on the open-boundary
 // planes -- what the row operators left in the destination buffer
 template <class L, int NC>
-LBM_HD void sc_fast_gather(const SCFields& c, const ScFast& s, int x, int y, int z, int64_t id, uint32_t m, double (*f)[L::Q]) {
+LBM_HD void sc_fast_gather(const SCFields& c, const ScFast& s, const NbTable& nb, int z, int64_t id, uint32_t m, double (*f)[L::Q]) {
     const Grid& g = c.g;
     if (s.materialised(g, z)) {
 #pragma unroll
@@ -76,8 +83,10 @@ LBM_HD void sc_fast_gather(const SCFields& c, const ScFast& s, int x, int y, int
     }
     int64_t from[L::Q];
 #pragma unroll
-    for (int q = 1; q < L::Q; ++q)
-        from[q] = (m >> q & 1u) ? (int64_t)q * g.vol + g.nb(x, y, z, -L::d0(q), -L::d1(q), -L::d2(q)) : (int64_t)L::opp(q) * g.vol + id;
+    for (int q = 1; q < L::Q; ++q) {
+        const int64_t pulled = (int64_t)q * g.vol + nb(-L::d0(q), -L::d1(q), -L::d2(q)), own = (int64_t)L::opp(q) * g.vol + id;
+        from[q] = (m >> q & 1u) ? pulled : own;
+    }
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
         const double* fk = s.src + (int64_t)k * L::Q * g.vol;
@@ -98,6 +107,7 @@ struct ScPullCollideOp {
         const uint32_t m = s.pull ? s.pull[id] : 0xFFFFFFFFu;
         if (!(m & 1u)) return;
         // densities of the node and of its neighbours; x + e_q is fluid <=> the upstream node of direction opp(q) is
+        const NbTable nb(g, x, y, z);
         double rho[NC], rn[NC][L::Q];
         bool fl[L::Q];
 #pragma unroll
@@ -105,12 +115,12 @@ struct ScPullCollideOp {
 #pragma unroll
         for (int q = 1; q < L::Q; ++q) {
             fl[q] = m >> L::opp(q) & 1u;
-            const int64_t nb = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
+            const int64_t nq = nb(L::d0(q), L::d1(q), L::d2(q));
 #pragma unroll
-            for (int k = 0; k < NC; ++k) rn[k][q] = c.rho[k * V + nb];      // only used where fl[q] (a solid node holds 0)
+            for (int k = 0; k < NC; ++k) rn[k][q] = c.rho[k * V + nq];      // only used where fl[q] (a solid node holds 0)
         }
         double f[NC][L::Q];
-        sc_fast_gather<L, NC>(c, s, x, y, z, id, m, f);
+        sc_fast_gather<L, NC>(c, s, nb, z, id, m, f);
         double vt[3] = {0.0, 0.0, 0.0}, rt = 0.0;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -180,6 +190,7 @@ struct EfsPullCollideOp {
         const int64_t id = g.at(x, y, z), V = g.vol;
         const uint32_t m = s.pull ? s.pull[id] : 0xFFFFFFFFu;
         if (!(m & 1u)) return;
+        const NbTable nb(g, x, y, z);
         double rho[NC], rn[NC][L::Q];
         bool fl[L::Q];
 #pragma unroll
@@ -187,12 +198,12 @@ struct EfsPullCollideOp {
 #pragma unroll
         for (int q = 1; q < L::Q; ++q) {
             fl[q] = m >> L::opp(q) & 1u;
-            const int64_t nb = g.nb(x, y, z, L::d0(q), L::d1(q), L::d2(q));
+            const int64_t nq = nb(L::d0(q), L::d1(q), L::d2(q));
 #pragma unroll
-            for (int k = 0; k < NC; ++k) rn[k][q] = c.rho[k * V + nb];      // only used where fl[q] (a solid node holds 0)
+            for (int k = 0; k < NC; ++k) rn[k][q] = c.rho[k * V + nq];      // only used where fl[q] (a solid node holds 0)
         }
         double f[NC][L::Q];
-        sc_fast_gather<L, NC>(c, s, x, y, z, id, m, f);
+        sc_fast_gather<L, NC>(c, s, nb, z, id, m, f);
         double F[NC][3];
         double mt[3] = {0.0, 0.0, 0.0}, rt = 0.0;
 #pragma unroll
