@@ -668,7 +668,11 @@ cg_density_tiled_d3q19(const CGFields c, const FastFields s, const int zchunk, c
 // SolidColorDiff; which neighbours are solid is read off the node's pull mask (bit opp(q) = "x + e_q is fluid").  The node
 // arithmetic is cg_fast_ops.cuh::cgp_collide_factored, the gradient that of cgp_gradient_at operation for operation.
 // ------------------------------------------------------------------------------------------------
-template <bool SOLIDS, int TX, int TY, bool PEER = false>
+// PF (LBM_PERT_PREFETCH): the 21 per-node inputs of plane z + 1 (19 pulled populations, rhoR, rhoB) are requested during step z with
+// 8-byte cp.async into thread-private shared-memory slots -- no registers, no barrier -- and picked up at the top of step z + 1.  The
+// same idea lost on the CSF kernel (its ~95 shared-memory instructions per node already saturate the MIO queue); this kernel issues
+// ~20, and its profile shows the plane's loads landing on the first use of the populations (long-scoreboard at `rho = rB + rR`).
+template <bool SOLIDS, int TX, int TY, bool PEER = false, bool PF = false>
 __global__ void __launch_bounds__(TX* TY, 512 / (TX * TY) > 0 ? 512 / (TX * TY) : 1)
 cgp_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o, const int zchunk, const int z_lo, const int z_hi,
                         const PeerPtrs pp = PeerPtrs{nullptr, nullptr, 0}) {
@@ -676,6 +680,7 @@ cgp_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o
     constexpr int NT = TX * TY, NW = TX + 2, NH = TY + 2;
     LBM_DYN_SMEM(smem_dyn);
     double (*sphi)[NH][NW] = reinterpret_cast<double (*)[NH][NW]>(smem_dyn);      // [4] planes
+    double* spop = smem_dyn + 4 * NH * NW;                                        // PF: [21][NT] thread-private slots
     const Grid& g = c.g;
     const int64_t V = g.vol;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
@@ -696,20 +701,42 @@ cgp_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o
     const int64_t xo[3] = {(int64_t)wrapx(x - 1), (int64_t)x, (int64_t)wrapx(x + 1)};
     const int64_t yo[3] = {(int64_t)wrapy(y - 1) * g.n0, (int64_t)y * g.n0, (int64_t)wrapy(y + 1) * g.n0};
     for (int zp = z_begin - 1; zp <= z_begin + 1; ++zp) load_phi_plane(zp);
+    uint32_t pm_next = 0xFFFFFFFFu, pm_next2 = 0xFFFFFFFFu;      // PF: the masks run two planes ahead (they steer the requests of z + 1)
+    if (SOLIDS) {
+        pm_next = c.pull[(int64_t)(z_begin + NG) * g.plane + yo[1] + xo[1]];
+        if (PF && z_begin + 1 < z_end) pm_next2 = c.pull[(int64_t)(z_begin + 1 + NG) * g.plane + yo[1] + xo[1]];
+    }
+    // PF: request the per-node inputs of plane zp (pull mask pmz) into this thread's slots
+    auto prefetch_inputs = [&](int zp, uint32_t pmz) {
+        if (!(pmz & 1u)) return;
+        const int64_t pid = (int64_t)(zp + NG) * g.plane + yo[1] + xo[1];
+        __pipeline_memcpy_async(&spop[tid], s.gT + pid, 8);
+#pragma unroll
+        for (int q = 1; q < L::Q; ++q) {
+            const int64_t src = (int64_t)(zp - L::d2(q) + NG) * g.plane + yo[1 - L::d1(q)] + xo[1 - L::d0(q)];
+            int64_t addr = q * V + src;
+            if (SOLIDS && !(pmz & (1u << q))) addr = L::opp(q) * V + pid;        // half-way bounce back
+            __pipeline_memcpy_async(&spop[q * NT + tid], s.gT + addr, 8);
+        }
+        __pipeline_memcpy_async(&spop[19 * NT + tid], c.rho[0] + pid, 8);
+        __pipeline_memcpy_async(&spop[20 * NT + tid], c.rho[1] + pid, 8);
+    };
+    if (PF) prefetch_inputs(z_begin, pm_next);
     __pipeline_commit();
-    uint32_t pm_next = 1u;
-    if (SOLIDS) pm_next = c.pull[(int64_t)(z_begin + NG) * g.plane + yo[1] + xo[1]];
     for (int z = z_begin; z < z_end; ++z) {
         const int64_t id = (int64_t)(z + NG) * g.plane + yo[1] + xo[1];
         uint32_t pm = 0xFFFFFFFFu;
         if (SOLIDS) {
             pm = pm_next;
-            if (z + 1 < z_end) pm_next = c.pull[id + g.plane];
+            if (PF) {
+                pm_next = pm_next2;
+                if (z + 2 < z_end) pm_next2 = c.pull[id + 2 * g.plane];
+            } else if (z + 1 < z_end) pm_next = c.pull[id + g.plane];
         }
         const bool fluid = pm & 1u;
         double fT[L::Q];
         double rR = 1.0, rB = 1.0;
-        if (fluid) {
+        if (!PF && fluid) {
             fT[0] = __ldcs(s.gT + id);
 #pragma unroll
             for (int q = 1; q < L::Q; ++q) {
@@ -720,10 +747,22 @@ cgp_collide_tiled_d3q19(const CGFields c, const FastFields s, const FastFields o
             }
             rR = c.rho[0][id]; rB = c.rho[1][id];
         }
-        __pipeline_wait_prior(0);           // phi plane z + 1, requested during the last step (the prologue's planes for the first)
+        __pipeline_wait_prior(0);           // phi plane z + 1 (and, PF, this thread's inputs of plane z), requested during the last step
+        if (PF && fluid) {
+#pragma unroll
+            for (int q = 0; q < L::Q; ++q) fT[q] = spop[q * NT + tid];
+            rR = spop[19 * NT + tid]; rB = spop[20 * NT + tid];
+#ifndef LBM_HOSTCHECK
+            // the values are in registers before the slots are handed to the next copies
+            asm volatile("" : "+d"(fT[0]), "+d"(fT[1]), "+d"(fT[2]), "+d"(fT[3]), "+d"(fT[4]), "+d"(fT[5]), "+d"(fT[6]),
+                              "+d"(fT[7]), "+d"(fT[8]), "+d"(fT[9]), "+d"(fT[10]), "+d"(fT[11]), "+d"(fT[12]), "+d"(fT[13]),
+                              "+d"(fT[14]), "+d"(fT[15]), "+d"(fT[16]), "+d"(fT[17]), "+d"(fT[18]), "+d"(rR), "+d"(rB));
+#endif
+        }
         __syncthreads();
         // the slot of plane z - 2 is free now: every thread has left step z - 1, the last reader of that plane
         if (z + 1 < z_end) load_phi_plane(z + 2);
+        if (PF && z + 1 < z_end) prefetch_inputs(z + 1, pm_next);
         __pipeline_commit();
         if (!fluid) continue;
         double G[3] = {0.0, 0.0, 0.0};
@@ -861,12 +900,15 @@ static void launch_perturb_tiled(lbm_handle* h, const CGFields& c, const FastFie
     constexpr int TILE_Y = 4;
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
-    constexpr size_t smem = sizeof(double) * 4 * (TILE_Y + 2) * (TILE_X + 2);
+    static const bool pf = env_int("LBM_PERT_PREFETCH", 0) != 0;
+    const size_t smem = sizeof(double) * (4 * (TILE_Y + 2) * (TILE_X + 2) + (pf ? 21 * TILE_X * TILE_Y : 0));
 #ifdef LBM_HOSTCHECK
-    cta_emu::launch(grid, block, smem, [&] { cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER>(c, s, o, zchunk, 0, g.n2, pp); });
+    if (pf) cta_emu::launch(grid, block, smem, [&] { cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER, true>(c, s, o, zchunk, 0, g.n2, pp); });
+    else cta_emu::launch(grid, block, smem, [&] { cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER>(c, s, o, zchunk, 0, g.n2, pp); });
 #else
     if (g_prof.on) g_prof.begin(SOLIDS ? "cgp_collide_tiled_d3q19<solids>" : "cgp_collide_tiled_d3q19<all-fluid>", h->stream);
-    cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, 0, g.n2, pp);
+    if (pf) cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER, true><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, 0, g.n2, pp);
+    else cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER><<<grid, block, smem, h->stream>>>(c, s, o, zchunk, 0, g.n2, pp);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -1240,7 +1282,9 @@ template <class L>
 static void fast_open_rows_pre(lbm_handle* h, const CGFields& c, const FastFields& s) {
     const OpenRows r = open_rows(c);
     if (!r.n) return;
-    if (h->g.plane >= (int64_t)1 << 14) {
+    // LBM_OPEN_PRE_SPLIT = 0 | 1 forces the single launch / the three launches (measurement aid)
+    static const int split = env_int("LBM_OPEN_PRE_SPLIT", -1);
+    if (split >= 0 ? split != 0 : h->g.plane >= (int64_t)1 << 14) {
         // wide planes (3-D): three fully parallel launches beat one thread per column walking its rows (0.31 ms for the two end
         // slabs of BASELINE config 5 on 8 GPUs); the 2-D lattices are launch-bound and keep the single launch
         launch_plane_ranges(h, PullMaterialiseOp<L>{c, s}, 0, r.n, r.mat_lo, r.mat_hi);
