@@ -62,8 +62,40 @@ inline void dev_d2d(void* d, const void* s_, size_t bytes, stream_t s) {
 }
 inline void dev_sync(stream_t s) { LBM_CUDA_CHECK(cudaStreamSynchronize(s)); }
 
+// Programmatic dependent launch (sm_90+, LBM_PDL=1): a kernel launched with the attribute may have its CTAs scheduled while
+// the kernel in front of it on the stream is still running -- as soon as every CTA of that one has executed
+// `griddepcontrol.launch_dependents` -- and blocks in `griddepcontrol.wait` until that kernel has completed and its writes are
+// visible.  Every kernel of this library that takes part executes both instructions before it touches memory, so the order of
+// all memory operations is that of the plain stream; what overlaps is launch latency and CTA scheduling, which is what the
+// launch-bound 2-D configurations (2-6 kernels of a few microseconds per step, replayed from a graph) spend their time on.
+// Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("LBM_PDL"); return e ? atoi(e) != 0 : false; }();
+    return on;
+}
+template <class... KArgs, class... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const Args&... args) {
+    if (!pdl_enabled()) {
+        kernel<<<grid, block, smem, s>>>(args...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (e != cudaSuccess) throw BackendError{std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e)};
+}
+
 template <class Op>
 __global__ void __launch_bounds__(256) node_kernel(const Op op, const int64_t n) {
+    pdl_prologue();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) op(i);
 }
@@ -97,7 +129,7 @@ inline void launch(const Op& op, int64_t n, stream_t s) {
     const int block = 256;
     const int64_t grid = (n + block - 1) / block;
     if (g_prof.on) g_prof.begin(typeid(Op).name(), s);
-    node_kernel<Op><<<(unsigned)grid, block, 0, s>>>(op, n);
+    launch_kernel(node_kernel<Op>, dim3((unsigned)grid), dim3(block), 0, s, op, n);
     if (g_prof.on) g_prof.end(s);
     LBM_CUDA_CHECK(cudaGetLastError());
     ++g_launch_counter;
@@ -106,6 +138,7 @@ inline void launch(const Op& op, int64_t n, stream_t s) {
 // ... with at least MINB resident 256-thread CTAs per SM (a register cap for bandwidth-bound operators that hold many values)
 template <class Op, int MINB>
 __global__ void __launch_bounds__(256, MINB) node_kernel_occ(const Op op, const int64_t n) {
+    pdl_prologue();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) op(i);
 }
@@ -115,7 +148,7 @@ inline void launch_occ(const Op& op, int64_t n, stream_t s) {
     const int block = 256;
     const int64_t grid = (n + block - 1) / block;
     if (g_prof.on) g_prof.begin(typeid(Op).name(), s);
-    node_kernel_occ<Op, MINB><<<(unsigned)grid, block, 0, s>>>(op, n);
+    launch_kernel(node_kernel_occ<Op, MINB>, dim3((unsigned)grid), dim3(block), 0, s, op, n);
     if (g_prof.on) g_prof.end(s);
     LBM_CUDA_CHECK(cudaGetLastError());
     ++g_launch_counter;

@@ -87,8 +87,10 @@ inline void bulk_g2s(void*, const void*, uint32_t, uint64_t*) {}
 inline void mbar_wait(uint64_t*, uint32_t) {}
 #define LBM_DYN_SMEM(name) double* name = cta_emu::tls().shared
 #define LBM_OPAQUE(...) ((void)0)
+#define LBM_PDL_PROLOGUE() ((void)0)
 #else
 #define LBM_DYN_SMEM(name) extern __shared__ __align__(128) double name[]
+#define LBM_PDL_PROLOGUE() pdl_prologue()       // backend.h: programmatic dependent launch
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -900,7 +902,9 @@ static void launch_perturb_tiled(lbm_handle* h, const CGFields& c, const FastFie
     constexpr int TILE_Y = 4;
     const int zchunk = z_chunk(g.n2);
     dim3 grid(g.n0 / TILE_X, g.n1 / TILE_Y, (g.n2 + zchunk - 1) / zchunk), block(TILE_X, TILE_Y);
-    static const bool pf = env_int("LBM_PERT_PREFETCH", 0) != 0;
+    // measured on the B200 (profiles/r02b_ini3d_*): 1.567 -> 1.432 ms per 256^3 launch, 7 174 -> 7 614 MLUPS for the reference's 3-D ini
+    // configuration (8.0 -> 8.6 GLUPS = 0.82 of the roofline at 256 x 256 x 512); LBM_PERT_PREFETCH=0 selects the plain loads
+    static const bool pf = env_int("LBM_PERT_PREFETCH", 1) != 0;
     const size_t smem = sizeof(double) * (4 * (TILE_Y + 2) * (TILE_X + 2) + (pf ? 21 * TILE_X * TILE_Y : 0));
 #ifdef LBM_HOSTCHECK
     if (pf) cta_emu::launch(grid, block, smem, [&] { cgp_collide_tiled_d3q19<SOLIDS, TILE_X, TILE_Y, PEER, true>(c, s, o, zchunk, 0, g.n2, pp); });
@@ -1013,6 +1017,7 @@ template <bool SOLIDS, int TX, int TY>
 __global__ void __launch_bounds__(TX* TY)
 cg_density_tile_d2q9(const CGFields c, const FastFields s) {
     using L = D2Q9;
+    LBM_PDL_PROLOGUE();
     constexpr int NT = TX * TY, NW = TX + 2, NH = TY + 2;
     LBM_DYN_SMEM(smem_dyn);
     double (*ss)[NH][NW] = reinterpret_cast<double (*)[NH][NW]>(smem_dyn);     // [3]: kR, ax, ay of the tile + 1 ring
@@ -1066,6 +1071,7 @@ template <bool SOLIDS, int TX, int TY>
 __global__ void __launch_bounds__(TX* TY)
 cg_collide_tile_d2q9(const CGFields c, const FastFields s, const FastFields o, const OpenRows rows) {
     using L = D2Q9;
+    LBM_PDL_PROLOGUE();
     constexpr int NT = TX * TY, PW = TX + 4, PH = TY + 4, NW = TX + 2, NH = TY + 2;
     constexpr int NE = (NH * NW + NT - 1) / NT;
     LBM_DYN_SMEM(smem_dyn);
@@ -1205,7 +1211,7 @@ static void launch_density_tile2d(lbm_handle* h, const CGFields& c, const FastFi
     cta_emu::launch(grid, block, smem, [&] { cg_density_tile_d2q9<SOLIDS, T2X, T2Y>(c, s); });
 #else
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_density_tile_d2q9<solids>" : "cg_density_tile_d2q9<all-fluid>", h->stream);
-    cg_density_tile_d2q9<SOLIDS, T2X, T2Y><<<grid, block, smem, h->stream>>>(c, s);
+    launch_kernel(cg_density_tile_d2q9<SOLIDS, T2X, T2Y>, grid, block, smem, h->stream, c, s);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -1220,7 +1226,7 @@ static void launch_collide_tile2d(lbm_handle* h, const CGFields& c, const FastFi
     cta_emu::launch(grid, block, smem, [&] { cg_collide_tile_d2q9<SOLIDS, T2X, T2Y>(c, s, o, rows); });
 #else
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_collide_tile_d2q9<solids>" : "cg_collide_tile_d2q9<all-fluid>", h->stream);
-    cg_collide_tile_d2q9<SOLIDS, T2X, T2Y><<<grid, block, smem, h->stream>>>(c, s, o, rows);
+    launch_kernel(cg_collide_tile_d2q9<SOLIDS, T2X, T2Y>, grid, block, smem, h->stream, c, s, o, rows);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -1282,11 +1288,13 @@ template <class L>
 static void fast_open_rows_pre(lbm_handle* h, const CGFields& c, const FastFields& s) {
     const OpenRows r = open_rows(c);
     if (!r.n) return;
-    // LBM_OPEN_PRE_SPLIT = 0 | 1 forces the single launch / the three launches (measurement aid)
-    static const int split = env_int("LBM_OPEN_PRE_SPLIT", -1);
-    if (split >= 0 ? split != 0 : h->g.plane >= (int64_t)1 << 14) {
-        // wide planes (3-D): three fully parallel launches beat one thread per column walking its rows (0.31 ms for the two end
-        // slabs of BASELINE config 5 on 8 GPUs); the 2-D lattices are launch-bound and keep the single launch
+    // Three fully parallel launches (materialise the planes | row operators | velocity and phi of the treated planes) beat ONE launch
+    // whose threads walk the rows of their column: the chain of one column is a few thousand dependent instructions and ~8 round
+    // trips to the L2, and that latency -- not the launch count -- is what a replayed graph pays for.  BASELINE config 2: 64 -> 47 us
+    // per step (4 101 -> 5 541 MLUPS, profiles/r02b_cfg2_split{0,1}.json); the end slabs of config 5 on 8 GPUs: 0.31 ms.
+    // LBM_OPEN_PRE_SPLIT=0 selects the single launch (FastOpenPreOp).
+    static const int split = env_int("LBM_OPEN_PRE_SPLIT", 1);
+    if (split != 0) {
         launch_plane_ranges(h, PullMaterialiseOp<L>{c, s}, 0, r.n, r.mat_lo, r.mat_hi);
         launch(OpenRowsOp<L>{c}, 2 * h->g.plane, h->stream);
         launch_plane_ranges(h, HeadOp<L>{c}, 0, r.n, r.mod_lo, r.mod_hi);

@@ -200,11 +200,12 @@ def test_baseline_configurations_run_small(k, scale, lib):
         np.testing.assert_allclose(m1, m0, rtol=1e-12)
     eng.step(3); eng.step(10)             # the second call finds the lattice in its steady form (no entry / exit work)
     # launches per step: the launch-bound 2-D configurations live on few, fat launches
-    # (cfg 2 on the D2Q9 tile kernels: density tile | open rows | colour of the wetting solids (list) | collision tile with the
-    # gradient in shared memory, treated open rows included; cfg 1 and cfg 3 on the two-pass form of the Shan-Chen loops:
+    # (cfg 2 on the D2Q9 tile kernels: density tile | open rows as three parallel launches: materialise, row operators, head |
+    # colour of the wetting solids (list) | collision tile with the gradient in shared memory, treated open rows included;
+    # cfg 1 and cfg 3 on the two-pass form of the Shan-Chen loops:
     # pull-density | [open rows] | pull-collide, between one reference-ordered iteration at the start of a call (2 | 4 launches),
     # its first collision (1) and the streaming + rows + force at its end (1 | 3))
-    assert eng.timing()["launches"] == {1: 2 + 1 + 8 * 2 + 1, 2: 40, 3: 4 + 1 + 8 * 3 + 3, 4: 30, 5: 50}[k]
+    assert eng.timing()["launches"] == {1: 2 + 1 + 8 * 2 + 1, 2: 60, 3: 4 + 1 + 8 * 3 + 3, 4: 30, 5: 70}[k]
     eng.close()
 
 
