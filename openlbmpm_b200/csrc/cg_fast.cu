@@ -1015,7 +1015,7 @@ struct Tile2D {
 
 template <bool SOLIDS, int TX, int TY>
 __global__ void __launch_bounds__(TX* TY)
-cg_density_tile_d2q9(const CGFields c, const FastFields s) {
+cg_density_tile_d2q9(const CGFields c, const FastFields s, const OpenRows skip) {
     using L = D2Q9;
     LBM_PDL_PROLOGUE();
     constexpr int NT = TX * TY, NW = TX + 2, NH = TY + 2;
@@ -1045,6 +1045,10 @@ cg_density_tile_d2q9(const CGFields c, const FastFields s) {
     __pipeline_wait_prior(0);
     __syncthreads();
     if (!(pm & 1u)) return;
+    {   // forked open-row chain (fast_one_step): the planes it materialises get their densities and phi from that chain
+        const int zrow = (int)blockIdx.y * TY + tz;
+        if ((skip.n > 0 && zrow >= skip.mat_lo[0] && zrow < skip.mat_hi[0]) || (skip.n > 1 && zrow >= skip.mat_lo[1] && zrow < skip.mat_hi[1])) return;
+    }
     const bool pert = c.p.st_type == LBM_ST_PERTURBATION;
     const double kR0 = ss[0][tz + 1][tx + 1];
     const double a0[3] = {ss[1][tz + 1][tx + 1], ss[2][tz + 1][tx + 1], 0.0};
@@ -1203,15 +1207,15 @@ static bool tiled2d_ok(const lbm_handle* h) {
     return h->Q == 9 && !off && h->g.n0 % T2X == 0 && h->g.n2 % T2Y == 0 && !(h->cfg.flags & 2u) && !h->tracer && (!h->has_solid || h->pull);
 }
 template <bool SOLIDS>
-static void launch_density_tile2d(lbm_handle* h, const CGFields& c, const FastFields& s) {
+static void launch_density_tile2d(lbm_handle* h, const CGFields& c, const FastFields& s, const OpenRows& skip = OpenRows()) {
     const Grid& g = h->g;
     dim3 grid(g.n0 / T2X, g.n2 / T2Y), block(T2X, T2Y);
     constexpr size_t smem = sizeof(double) * 3 * (T2Y + 2) * (T2X + 2);
 #ifdef LBM_HOSTCHECK
-    cta_emu::launch(grid, block, smem, [&] { cg_density_tile_d2q9<SOLIDS, T2X, T2Y>(c, s); });
+    cta_emu::launch(grid, block, smem, [&] { cg_density_tile_d2q9<SOLIDS, T2X, T2Y>(c, s, skip); });
 #else
     if (g_prof.on) g_prof.begin(SOLIDS ? "cg_density_tile_d2q9<solids>" : "cg_density_tile_d2q9<all-fluid>", h->stream);
-    launch_kernel(cg_density_tile_d2q9<SOLIDS, T2X, T2Y>, grid, block, smem, h->stream, c, s);
+    launch_kernel(cg_density_tile_d2q9<SOLIDS, T2X, T2Y>, grid, block, smem, h->stream, c, s, skip);
     if (g_prof.on) g_prof.end(h->stream);
     LBM_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -1285,9 +1289,15 @@ struct FastOpenPreOp {
     }
 };
 template <class L>
-static void fast_open_rows_pre(lbm_handle* h, const CGFields& c, const FastFields& s) {
+static void fast_open_rows_pre(lbm_handle* h, const CGFields& c, const FastFields& s, bool head_on_materialised = false) {
     const OpenRows r = open_rows(c);
     if (!r.n) return;
+    if (head_on_materialised) {     // forked chain: nobody else writes phi of the materialised planes
+        launch_plane_ranges(h, PullMaterialiseOp<L>{c, s}, 0, r.n, r.mat_lo, r.mat_hi);
+        launch(OpenRowsOp<L>{c}, 2 * h->g.plane, h->stream);
+        launch_plane_ranges(h, HeadOp<L>{c}, 0, r.n, r.mat_lo, r.mat_hi);
+        return;
+    }
     // Three fully parallel launches (materialise the planes | row operators | velocity and phi of the treated planes) beat ONE launch
     // whose threads walk the rows of their column: the chain of one column is a few thousand dependent instructions and ~8 round
     // trips to the L2, and that latency -- not the launch count -- is what a replayed graph pays for.  BASELINE config 2: 64 -> 47 us
@@ -1401,6 +1411,29 @@ static void fast_exchange(lbm_handle* h, double* base, int64_t stride, int narr,
     else exchange_f64(h, base, stride, narr, gp, dirs);
 }
 
+// a second stream beside the handle's for work that is independent of what the main stream runs next (captured into the same
+// graph as a parallel branch when the step is being captured); created on first use, destroyed with the handle (comm_destroy)
+#ifdef LBM_HOSTCHECK
+static void side_stream_fork(lbm_handle*) {}
+static void side_stream_swap(lbm_handle*) {}
+static void side_stream_join(lbm_handle*) {}
+#else
+static void side_stream_fork(lbm_handle* h) {
+    if (!h->comm_stream) {
+        LBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+        LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+    }
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_main, h->stream));
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
+}
+static void side_stream_swap(lbm_handle* h) { std::swap(h->stream, h->comm_stream); }
+static void side_stream_join(lbm_handle* h) {
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_comm, h->comm_stream));
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+}
+#endif
+
 template <class L>
 static void fast_one_step(lbm_handle* h) {
     FastState* f = (FastState*)h->fast;
@@ -1439,12 +1472,25 @@ static void fast_one_step(lbm_handle* h) {
         dens_done = true;
     }
     const bool tile2d = L::Q == 9 && tiled2d_ok(h) && !pert;
+    // D2Q9 tiles on one slab, open box (LBM_OPEN_FORK=1): the open-row chain only reads the factored state, so it runs BESIDE the
+    // density tile (a second stream / a parallel branch of the replayed graph) once the tile leaves the materialised planes alone
+    static const bool fork_wanted = env_int("LBM_OPEN_FORK", 0) != 0;
+    const bool fork = fork_wanted && tile2d && open && !dens_done && h->nranks == 1;
     if (!dens_done) {
-        if (tile2d) { if (h->has_solid) launch_density_tile2d<true>(h, c, s); else launch_density_tile2d<false>(h, c, s); }
+        if (tile2d) {
+            const OpenRows skip = fork ? open_rows(c) : OpenRows();
+            if (fork) side_stream_fork(h);
+            if (h->has_solid) launch_density_tile2d<true>(h, c, s, skip); else launch_density_tile2d<false>(h, c, s, skip);
+        }
         else if (h->has_solid) launch(PullDensityOp<L, true>{c, s}, g.count(0), h->stream);
         else launch(PullDensityOp<L, false>{c, s}, g.count(0), h->stream);
     }
-    if (open) fast_open_rows_pre<L>(h, c, s);
+    if (fork) {
+        side_stream_swap(h);
+        fast_open_rows_pre<L>(h, c, s, true);
+        side_stream_swap(h);
+        side_stream_join(h);
+    } else if (open) fast_open_rows_pre<L>(h, c, s);
     if (phi_pushed) {
         if (late_up) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, true);
         if (late_down) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, false);
