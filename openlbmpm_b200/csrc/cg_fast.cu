@@ -1411,29 +1411,6 @@ static void fast_exchange(lbm_handle* h, double* base, int64_t stride, int narr,
     else exchange_f64(h, base, stride, narr, gp, dirs);
 }
 
-// a second stream beside the handle's for work that is independent of what the main stream runs next (captured into the same
-// graph as a parallel branch when the step is being captured); created on first use, destroyed with the handle (comm_destroy)
-#ifdef LBM_HOSTCHECK
-static void side_stream_fork(lbm_handle*) {}
-static void side_stream_swap(lbm_handle*) {}
-static void side_stream_join(lbm_handle*) {}
-#else
-static void side_stream_fork(lbm_handle* h) {
-    if (!h->comm_stream) {
-        LBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
-        LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
-        LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
-    }
-    LBM_CUDA_CHECK(cudaEventRecord(h->ev_main, h->stream));
-    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
-}
-static void side_stream_swap(lbm_handle* h) { std::swap(h->stream, h->comm_stream); }
-static void side_stream_join(lbm_handle* h) {
-    LBM_CUDA_CHECK(cudaEventRecord(h->ev_comm, h->comm_stream));
-    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
-}
-#endif
-
 template <class L>
 static void fast_one_step(lbm_handle* h) {
     FastState* f = (FastState*)h->fast;
@@ -1472,9 +1449,10 @@ static void fast_one_step(lbm_handle* h) {
         dens_done = true;
     }
     const bool tile2d = L::Q == 9 && tiled2d_ok(h) && !pert;
-    // D2Q9 tiles on one slab, open box (LBM_OPEN_FORK=1): the open-row chain only reads the factored state, so it runs BESIDE the
+    // D2Q9 tiles on one slab, open box: the open-row chain only reads the factored state, so it runs BESIDE the
     // density tile (a second stream / a parallel branch of the replayed graph) once the tile leaves the materialised planes alone
-    static const bool fork_wanted = env_int("LBM_OPEN_FORK", 0) != 0;
+    // BASELINE config 2, same box, A B A B: 5 262 / 5 335 -> 5 844 / 5 937 MLUPS (profiles/r02b_cfg2_fork{0,1}.json); LBM_OPEN_FORK=0: serial order
+    static const bool fork_wanted = env_int("LBM_OPEN_FORK", 1) != 0;
     const bool fork = fork_wanted && tile2d && open && !dens_done && h->nranks == 1;
     if (!dens_done) {
         if (tile2d) {
@@ -1487,7 +1465,7 @@ static void fast_one_step(lbm_handle* h) {
     }
     if (fork) {
         side_stream_swap(h);
-        fast_open_rows_pre<L>(h, c, s, true);
+        try { fast_open_rows_pre<L>(h, c, s, true); } catch (...) { side_stream_swap(h); throw; }
         side_stream_swap(h);
         side_stream_join(h);
     } else if (open) fast_open_rows_pre<L>(h, c, s);

@@ -27,6 +27,14 @@ void comm_peer_check(lbm_handle* h);     // throws if a bounded wait of the one-
 void comm_destroy(lbm_handle* h);
 int comm_allreduce_max(lbm_handle* h, int v);
 
+// A second stream beside the handle's for work that is independent of what the main stream runs next (captured into the same
+// graph as a parallel branch when the step is being captured); created on first use, destroyed with the handle (comm_destroy).
+// fork: the side stream waits for what the main stream has been given so far; swap: launches that go to h->stream go to the
+// side stream (swap again to restore); join: the main stream waits for the side stream.  No-ops on the host test hook.
+void side_stream_fork(lbm_handle* h);
+void side_stream_swap(lbm_handle* h);
+void side_stream_join(lbm_handle* h);
+
 // general colour-gradient path (lbm_api.cu)
 void cg_alloc_state(lbm_handle* h);
 void cg_alloc_postcollision(lbm_handle* h);

@@ -7,6 +7,7 @@
 #include <new>
 
 #include "handle.h"
+#include <utility>
 #include "internal.h"
 
 namespace lbm {
@@ -77,6 +78,27 @@ void lbm::exchange_u8(lbm_handle* h, uint8_t* base, int gp) {
     GhostWrapOp<uint8_t> op{h->g, base, 0, 1, gp};
     launch(op, op.items(), h->stream);
 }
+
+#ifdef LBM_HOSTCHECK
+void lbm::side_stream_fork(lbm_handle*) {}
+void lbm::side_stream_swap(lbm_handle*) {}
+void lbm::side_stream_join(lbm_handle*) {}
+#else
+void lbm::side_stream_fork(lbm_handle* h) {
+    if (!h->comm_stream) {
+        LBM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+        LBM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+    }
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_main, h->stream));
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
+}
+void lbm::side_stream_swap(lbm_handle* h) { std::swap(h->stream, h->comm_stream); }
+void lbm::side_stream_join(lbm_handle* h) {
+    LBM_CUDA_CHECK(cudaEventRecord(h->ev_comm, h->comm_stream));
+    LBM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // lifetime

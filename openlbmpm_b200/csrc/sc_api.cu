@@ -294,14 +294,32 @@ static void sc_fast_iterations(lbm_handle* h, int m) {
     f.pull = h->has_solid ? h->pull : nullptr;
     f.mat_lo = do_out ? (efs ? c.z_out + 1 : 4) : 0;       // pressure outlet: planes 0 .. z_out; convective copies: 3 -> 2 -> 1 -> 0
     f.mat_hi = do_in ? g.n2 - c.z_in : 0;                  // velocity inlet: planes z_in .. n2 - 1
+    // One slab with open ends: the planes next to them are pulled and treated on a second stream (a parallel branch of the replayed
+    // graph) BESIDE the density pass of the other planes -- both only read the source buffer and write disjoint planes -- so the
+    // serial chain of the row operators (one thread per column, ~10 us) is off the critical path.  LBM_SC_FORK=0: serial order.
+    static const bool fork_wanted = [] { const char* e = getenv("LBM_SC_FORK"); return e ? atoi(e) != 0 : true; }();
+    const bool fork = fork_wanted && h->nranks == 1 && (do_in || do_out) && g.n2 > f.mat_lo + f.mat_hi;
     auto fused = [&](double* src, double* dst) {
         exchange_f64(h, src, g.vol, c.p.nc * h->Q, 1);
         f.src = src; f.dst = dst;
-        launch(ScPullDensityOp<L, 2>{c, f}, g.count(0), h->stream);
-        if (do_in || do_out) {
-            SCFields r = c;
-            r.fS = dst;
-            launch(ScOpenRowsOp<L>{r, efs ? 1 : 0, efs ? 0 : 3, do_in, do_out, 1}, 2 * g.plane, h->stream);
+        SCFields r = c;
+        r.fS = dst;
+        const ScOpenRowsOp<L> rows{r, efs ? 1 : 0, efs ? 0 : 3, do_in, do_out, 1};
+        if (fork) {
+            const ScPullDensityOp<L, 2> dens{c, f};
+            side_stream_fork(h);
+            launch(PlaneRangeOp<ScPullDensityOp<L, 2>>{dens, (int64_t)f.mat_lo * g.plane}, (int64_t)(g.n2 - f.mat_lo - f.mat_hi) * g.plane, h->stream);
+            side_stream_swap(h);
+            try {
+                const int64_t cnt0 = (int64_t)f.mat_lo * g.plane, cnt1 = (int64_t)f.mat_hi * g.plane;
+                launch(TwoRangeOp<ScPullDensityOp<L, 2>>{dens, 0, cnt0, (int64_t)(g.n2 - f.mat_hi) * g.plane}, cnt0 + cnt1, h->stream);
+                launch(rows, 2 * g.plane, h->stream);
+            } catch (...) { side_stream_swap(h); throw; }
+            side_stream_swap(h);
+            side_stream_join(h);
+        } else {
+            launch(ScPullDensityOp<L, 2>{c, f}, g.count(0), h->stream);
+            if (do_in || do_out) launch(rows, 2 * g.plane, h->stream);
         }
         exchange_f64(h, c.rho, g.vol, c.p.nc, 1);
         if (efs) sc_launch_collide(h, EfsPullCollideOp<L, 2>{c, f});
