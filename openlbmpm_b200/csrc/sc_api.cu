@@ -296,8 +296,10 @@ static void sc_fast_iterations(lbm_handle* h, int m) {
     f.mat_hi = do_in ? g.n2 - c.z_in : 0;                  // velocity inlet: planes z_in .. n2 - 1
     // One slab with open ends: the planes next to them are pulled and treated on a second stream (a parallel branch of the replayed
     // graph) BESIDE the density pass of the other planes -- both only read the source buffer and write disjoint planes -- so the
-    // serial chain of the row operators (one thread per column, ~10 us) is off the critical path.  LBM_SC_FORK=0: serial order.
-    static const bool fork_wanted = [] { const char* e = getenv("LBM_SC_FORK"); return e ? atoi(e) != 0 : true; }();
+    // serial chain of the row operators (one thread per column, ~10 us) is off the critical path.  Measured on BASELINE config 3:
+    // 4 808 (forked) vs 4 871 MLUPS (serial) -- the chain is 7 % of that step and a second density launch costs what it hides, so the
+    // serial order stays the default here (the colour-gradient D2Q9 tiles gained 11 % from the same move); LBM_SC_FORK=1 selects it.
+    static const bool fork_wanted = [] { const char* e = getenv("LBM_SC_FORK"); return e ? atoi(e) != 0 : false; }();
     const bool fork = fork_wanted && h->nranks == 1 && (do_in || do_out) && g.n2 > f.mat_lo + f.mat_hi;
     auto fused = [&](double* src, double* dst) {
         exchange_f64(h, src, g.vol, c.p.nc * h->Q, 1);

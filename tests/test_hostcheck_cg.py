@@ -203,9 +203,9 @@ def test_baseline_configurations_run_small(k, scale, lib):
     # (cfg 2 on the D2Q9 tile kernels: density tile | open rows as three parallel launches: materialise, row operators, head |
     # colour of the wetting solids (list) | collision tile with the gradient in shared memory, treated open rows included;
     # cfg 1 and cfg 3 on the two-pass form of the Shan-Chen loops:
-    # pull-density | [pull-density of the planes next to the open ends | open rows: beside it on a second stream] | pull-collide, between one reference-ordered iteration at the start of a call (2 | 4 launches),
+    # pull-density | [open rows] | pull-collide, between one reference-ordered iteration at the start of a call (2 | 4 launches),
     # its first collision (1) and the streaming + rows + force at its end (1 | 3))
-    assert eng.timing()["launches"] == {1: 2 + 1 + 8 * 2 + 1, 2: 60, 3: 4 + 1 + 8 * 4 + 3, 4: 30, 5: 70}[k]
+    assert eng.timing()["launches"] == {1: 2 + 1 + 8 * 2 + 1, 2: 60, 3: 4 + 1 + 8 * 3 + 3, 4: 30, 5: 70}[k]
     eng.close()
 
 
