@@ -1468,7 +1468,9 @@ static void fast_one_step(lbm_handle* h) {
         try { fast_open_rows_pre<L>(h, c, s, true); } catch (...) { side_stream_swap(h); throw; }
         side_stream_swap(h);
         side_stream_join(h);
-    } else if (open) fast_open_rows_pre<L>(h, c, s);
+    } else if (open) fast_open_rows_pre<L>(h, c, s, tile2d);     // D2Q9 tiles: phi of the materialised planes from the head operator in
+                                                                 // EVERY schedule (forked or not, one slab or many), so that slabs stay
+                                                                 // bit-equal to one GPU under nvcc's per-kernel multiply-add contraction
     if (phi_pushed) {
         if (late_up) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, true);
         if (late_down) peer_push_one_way(h, c.phi, 0, 1, h->has_solid ? NG : 2, nullptr, false);
